@@ -1,0 +1,174 @@
+/* rspt_gpu.h -- C ABI of the B200-native signal-packer library (librspt_gpu.so).
+ *
+ * This is the drop-in boundary for rspt's packer hot path.  The reference has no FFI of its own:
+ * its only plugin interface is the C++ abstract class i_signal_packer
+ * (/root/reference/lib_rspt/signal_packer.h:29-73).  The entry points below are what a binding
+ * for that path needs: one handle per packer instance (= one `new_*` factory call), batched
+ * compress / decompress over many independent fixed-shape frames, and the size bound.  The C++
+ * class in include/signal_packer.h is implemented on top of exactly these calls
+ * (rspt_b200/csrc/signal_packer_gpu.cpp); INTEGRATION.md shows the binding stubs.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * RSPT_E_* code and never throws; `d_` pointers are CUDA device pointers on the handle's device,
+ * `h_` pointers are host pointers.  Batch calls are asynchronous on the handle's stream unless
+ * stated otherwise.  A handle is not thread-safe; distinct handles are independent
+ * (reference: instances are not re-entrant either, signal_packer_base.h:20-21).
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef RSPT_GPU_H_
+#define RSPT_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSPT_GPU_ABI_VERSION 1
+
+/* packer kinds <-> reference factories */
+enum {
+    RSPT_XDELTA_HZR = 0, /* i_signal_packer::new_xdelta_hzr, signal_packer.h:59 */
+    RSPT_HZR = 1,        /* i_signal_packer::new_hzr,        signal_packer.h:62 */
+    RSPT_HADAMARD = 2,   /* i_signal_packer::new_hadamard,   signal_packer.h:68 */
+    RSPT_DCT = 3         /* i_signal_packer::new_dct,        signal_packer.h:65 */
+};
+
+enum {
+    RSPT_OK = 0,
+    RSPT_E_ARG = -1,      /* bad argument / unsupported shape */
+    RSPT_E_CUDA = -2,     /* CUDA runtime error (see rspt_gpu_last_error) */
+    RSPT_E_CAPACITY = -3, /* destination or batch capacity too small */
+    RSPT_E_STREAM = -4,   /* malformed compressed stream */
+    RSPT_E_NOGPU = -5     /* no usable CUDA device: the library refuses to run */
+};
+
+typedef struct rspt_gpu_packer rspt_gpu_packer;
+
+/* Replaces the constructor behind new_xdelta_hzr / new_hzr / new_hadamard / new_dct
+ * (signal_packer_xdelta_hzr.cpp:42-50, signal_packer_hzr.cpp, signal_packer_hadamard.cpp:47-55,
+ * signal_packer_dct.cpp:49-58).  `nb` = nr_bytes_to_encode, used by RSPT_XDELTA_HZR only.
+ * `stream` is a cudaStream_t (NULL = the CUDA default stream); all work of the handle is ordered on it.  `max_batch_frames` sizes the
+ * device scratch (planes, histograms, code tables); batches larger than that are rejected. */
+int rspt_gpu_create(int kind, size_t bytes_per_sample, size_t nr_channels, size_t nr_samples,
+                    size_t nb, int device, void* stream, size_t max_batch_frames,
+                    rspt_gpu_packer** out);
+
+/* Replaces delete_xdelta_hzr / delete_hzr / delete_hadamard / delete_dct (signal_packer.h:60-69). */
+int rspt_gpu_destroy(rspt_gpu_packer* p);
+
+size_t rspt_gpu_frame_bytes(const rspt_gpu_packer* p); /* bps * ch * ns */
+size_t rspt_gpu_header_bytes(const rspt_gpu_packer* p); /* 3*ch for hadamard/dct, else 0 */
+
+/* Worst-case bytes of ONE compressed frame: 1 + header + planes * (4 + hzr_max_compressed_size(ch*ns))
+ * (signal_packer_base.cpp:83-95, hzr_encode.c:489-497), with `planes` the largest count the
+ * instance can reach (xdelta_hzr may escalate up to bytes_per_sample). */
+size_t rspt_gpu_max_compressed_size(const rspt_gpu_packer* p);
+
+/* Current plane count: the reference's nr_bytes_to_compress_ (signal_packer_xdelta_hzr.cpp:39,66).
+ * Synchronises the handle's stream. */
+int rspt_gpu_nb(rspt_gpu_packer* p, unsigned* nb);
+
+/* Replaces i_signal_packer::compress (signal_packer.h:44) for `n_frames` frames at once.
+ *   d_src      [n_frames][frame_bytes]  interleaved little-endian samples ([ns][ch][bps])
+ *   d_dst      the frames' streams, concatenated back to back, each byte-identical to what the
+ *              reference writes for that frame
+ *   d_offsets  [n_frames + 1] byte offset of every frame in d_dst; d_offsets[n_frames] = total
+ *   d_frame_nb [n_frames] planes used per frame (the reference does not store this in the
+ *              stream; decompress needs it); may be NULL
+ *   d_sidecar  optional out-of-band decode index (rspt_gpu_sidecar_bytes(p, n_frames) bytes);
+ *              NULL = not produced.  The stream itself never depends on it.
+ * Frames are processed as if by ONE reference instance in order: the xdelta_hzr plane count
+ * carries from frame to frame and from batch to batch (signal_packer_xdelta_hzr.cpp:63-69). */
+int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src, size_t n_frames,
+                            uint8_t* d_dst, size_t dst_capacity, uint64_t* d_offsets,
+                            uint8_t* d_frame_nb, void* d_sidecar);
+
+/* Replaces i_signal_packer::decompress (signal_packer.h:57) for `n_frames` frames.
+ *   d_src      concatenated frames; d_offsets [n_frames + 1] as produced by compress (frames are
+ *              self-delimiting but carry no index, signal_packer_base.cpp:121)
+ *   d_frame_nb per-frame plane count or NULL = the handle's current count for every frame
+ *   d_sidecar  optional decode index produced by compress_batch for these same frames, or NULL
+ *              (streams from the CPU reference): decode then walks each hzr block serially
+ *   d_dst      [n_frames][frame_bytes]
+ *   d_status   [n_frames] 0 = ok, else RSPT_E_STREAM-style code; may be NULL */
+int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets,
+                              size_t n_frames, const uint8_t* d_frame_nb, const void* d_sidecar,
+                              uint8_t* d_dst, int32_t* d_status);
+
+size_t rspt_gpu_sidecar_bytes(const rspt_gpu_packer* p, size_t n_frames);
+
+/* Single-frame convenience with HOST buffers -- the exact shape of the reference calls
+ * (signal_packer.h:44,57): stages host<->device, runs the batch path with n_frames = 1 and
+ * synchronises.  decompress reports the consumed length through *src_len like the reference. */
+int rspt_gpu_compress_host(rspt_gpu_packer* p, const uint8_t* h_src, uint8_t* h_dst,
+                           size_t dst_max_len, size_t* dst_len);
+int rspt_gpu_decompress_host(rspt_gpu_packer* p, const uint8_t* h_src, size_t* src_len, uint8_t* h_dst);
+
+/* Host-buffer batch (what bench.py times as the end-to-end leg): H2D of the frames, the batch
+ * path, D2H of offsets and payload.  h_offsets [n_frames + 1]. */
+int rspt_gpu_compress_batch_host(rspt_gpu_packer* p, const uint8_t* h_src, size_t n_frames,
+                                 uint8_t* h_dst, size_t dst_capacity, uint64_t* h_offsets);
+int rspt_gpu_decompress_batch_host(rspt_gpu_packer* p, const uint8_t* h_src, const uint64_t* h_offsets,
+                                   size_t n_frames, uint8_t* h_dst);
+
+int rspt_gpu_sync(rspt_gpu_packer* p);
+const char* rspt_gpu_last_error(const rspt_gpu_packer* p);
+
+/* Counters since creation (never silent). Synchronises. */
+typedef struct {
+    uint64_t frames_compressed, frames_decompressed;
+    uint64_t raw_bytes_in, compressed_bytes_out;
+    uint64_t blocks_copy, blocks_huff, blocks_fill;
+    uint64_t escalations;    /* "Compression needs one more byte to encode." events */
+    uint64_t kernel_launches;
+} rspt_gpu_counters;
+int rspt_gpu_get_counters(rspt_gpu_packer* p, rspt_gpu_counters* out);
+
+/* Per-stage device timing (CUDA events recorded on the handle's stream around each kernel group).
+ * Off by default.  get: accumulated milliseconds and launch-group counts since the last reset;
+ * synchronises the stream. */
+enum {
+    RSPT_STAGE_TRANSFORM = 0, /* samples -> byte planes (xdelta / fwht / dct) */
+    RSPT_STAGE_HIST = 1,      /* per-block token histogram */
+    RSPT_STAGE_TREE = 2,      /* Huffman tree + code tables + block plan */
+    RSPT_STAGE_LAYOUT = 3,    /* frame sizes + offset scan */
+    RSPT_STAGE_ENCODE = 4,    /* bit packing + CRC-32C + framing */
+    RSPT_STAGE_PARSE = 5,     /* decode: frame / block header walk */
+    RSPT_STAGE_DECODE = 6,    /* decode: hzr blocks -> planes */
+    RSPT_STAGE_INVERSE = 7,   /* decode: planes -> samples */
+    RSPT_STAGE_COUNT = 8
+};
+int rspt_gpu_set_stage_timing(rspt_gpu_packer* p, int enable);
+int rspt_gpu_get_stage_times(rspt_gpu_packer* p, double* ms /*[RSPT_STAGE_COUNT]*/,
+                             uint64_t* calls /*[RSPT_STAGE_COUNT]*/, int reset);
+
+/* Stage-level entry points used by the parity tests (same device code as the batch path). */
+int rspt_gpu_debug_planes(rspt_gpu_packer* p, const uint8_t* d_src, size_t n_frames,
+                          uint8_t* d_planes /*[n][planes][ch*ns]*/, uint8_t* d_header /*[n][hdr]*/);
+int rspt_gpu_debug_hzr_tables(rspt_gpu_packer* p, const uint8_t* d_block, size_t n,
+                              uint32_t* d_hist /*[261]*/, uint32_t* d_codes /*[261]: code | len<<27*/,
+                              uint32_t* d_info /*[4]: mode, payload_len, tree_nbits, n_used*/);
+int rspt_gpu_crc32c(const uint8_t* d_data, size_t n, uint32_t* h_crc, void* stream);
+
+/* Synthetic ECG-like workload (include/rspt_synth.h), frames [first_frame, first_frame + n). */
+int rspt_gpu_synth_ecg(uint8_t* d_dst, uint64_t first_frame, size_t n_frames, int bps, int ch, int ns,
+                       uint64_t seed, int32_t amplitude, int32_t sigma, void* stream);
+
+/* Quality metric on device: PRDN as printed by the reference's test harness
+ * (lib_rspt_test/rspt_test.cpp:98-111), accumulated over n_frames.  h_out = {sum_sq_err, sum_sq_dev}. */
+int rspt_gpu_prdn_terms(const uint8_t* d_orig, const uint8_t* d_dec, size_t n_frames, int bps, int ch,
+                        int ns, double* h_out, void* stream);
+
+/* Multi-GPU placement of the concatenated stream: given every rank's compressed byte total
+ * (exchanged by the caller with ONE all-gather of a uint64 per rank -- ncclAllGather through
+ * torch.distributed in rspt_b200, or rspt_nccl_allgather_totals below), rebase this rank's
+ * frame offsets by the exclusive prefix of the totals.  d_all_totals [world]. */
+int rspt_gpu_rebase_offsets(uint64_t* d_offsets, size_t n_frames_plus_1, const uint64_t* d_all_totals,
+                            int rank, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

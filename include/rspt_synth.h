@@ -78,7 +78,6 @@ RSPT_HD int32_t rspt_synth_sample(const rspt_synth_params* p, const rspt_synth_c
     return (int32_t)v;
 }
 
-#ifndef __CUDA_ARCH__
 #include <math.h>
 /* Host-side table construction (double math, rounded once). */
 static inline void rspt_synth_build_tables(int32_t* beat, int32_t* sine)
@@ -96,6 +95,5 @@ static inline void rspt_synth_build_tables(int32_t* beat, int32_t* sine)
         sine[i] = (int32_t)lrint(sin(2.0 * 3.14159265358979323846 * t) * 16384.0);
     }
 }
-#endif
 
 #endif

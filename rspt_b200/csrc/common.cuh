@@ -1,0 +1,227 @@
+// Shared definitions for the sm_100a signal-packer kernels.
+//
+// Vocabulary (follows the reference): a FRAME is one compress() call's input,
+// [ns][ch][bps] interleaved little-endian samples; its N = ch*ns sample words are split into
+// `nb` byte PLANES (signal_packer_base.cpp:40-68); each plane is an hzr stream cut into BLOCKS
+// of <= 65536 bytes (hzr_encode.c:528-539).  Inside a block, work is divided into 64-byte
+// STRIPS, one per thread.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rspt {
+
+constexpr int kNumSymbols = 261;       // hzr_internal.h:114
+constexpr int kSymStride = 264;        // padded row for per-block tables
+constexpr int kTreeWords = 92;         // >= ceil((11*261-1)/32)
+constexpr uint32_t kBlock = 65536;     // HZR_MAX_BLOCK_SIZE, hzr_internal.h:109
+constexpr uint32_t kRunCap = 16662;    // hzr_encode.c:149
+constexpr int kStrip = 64;             // bytes per thread-strip
+constexpr int kSegStrips = 4;          // strips per decode segment (sidecar granularity: 256 B)
+constexpr int kSegBytes = kStrip * kSegStrips;
+constexpr int kMaxSegs = kBlock / kSegBytes;  // 256 per block
+
+enum : uint32_t { MODE_COPY = 0, MODE_HUFF = 1, MODE_FILL = 2 };  // hzr_internal.h:98-101
+
+// Per-block plan written by the tree kernel and consumed by layout + encode.
+struct BlkInfo {
+    uint32_t payload_len;  // bytes after the 7-byte block header
+    uint32_t total_bits;   // tree bits + token bits (HUFF)
+    uint16_t tree_nbits;
+    uint8_t mode;
+    uint8_t fill;
+    uint32_t n_used;       // symbols with a non-zero count
+};
+
+struct Shape {
+    int kind;
+    int bps, ch, ns;
+    uint32_t N;             // ch * ns
+    uint32_t nblk;          // hzr blocks per plane
+    uint32_t nb_init;       // planes the instance starts with
+    uint32_t nb_alloc;      // planes reserved per frame in scratch (max reachable)
+    uint32_t hdr_bytes;     // 3*ch for hadamard/dct
+    uint32_t plane_stride;  // N rounded up to 16
+    uint32_t frame_bytes;   // bps * N
+    uint32_t method;        // frame method byte (0 hzr/xdelta, 1 dct, 2 hadamard)
+};
+
+__host__ __device__ __forceinline__ uint32_t blk_len(const Shape& s, uint32_t b)
+{
+    uint32_t off = b * kBlock;
+    return s.N - off < kBlock ? s.N - off : kBlock;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+
+// Extra bits carried by the zero-run symbols 256..260 (hzr_internal.h:117-121).
+__device__ __forceinline__ uint32_t sym_extra_bits(uint32_t sym)
+{
+    // 256:0 257:2 258:4 259:8 260:14
+    return sym < 257 ? 0u : (sym == 257 ? 2u : (sym == 258 ? 4u : (sym == 259 ? 8u : 14u)));
+}
+
+// Classify a zero-run chunk z in [1, 16662] -> (symbol, extra value); hzr_encode.c:152-166.
+__device__ __forceinline__ void run_token(uint32_t z, uint32_t& sym, uint32_t& ev, uint32_t& eb)
+{
+    if (z <= 2) { sym = z == 1 ? 0u : 256u; ev = 0; eb = 0; }
+    else if (z <= 6) { sym = 257; ev = z - 3; eb = 2; }
+    else if (z <= 22) { sym = 258; ev = z - 7; eb = 4; }
+    else if (z <= 278) { sym = 259; ev = z - 23; eb = 8; }
+    else { sym = 260; ev = z - 279; eb = 14; }
+}
+
+// ---- strip loading -----------------------------------------------------------------------
+// blk is 16-byte aligned (plane rows are padded to 16 and blocks start at multiples of 65536).
+// Bytes at or beyond `valid` are forced to zero so that az/tz can be computed on whole words;
+// the token walk itself never looks past `valid`.
+__device__ __forceinline__ int load_strip(const uint8_t* __restrict__ blk, uint32_t n, uint32_t t,
+                                          uint32_t (&w)[16])
+{
+    int valid = (int)n - (int)(t * kStrip);
+    valid = valid < 0 ? 0 : (valid > kStrip ? kStrip : valid);
+    const uint4* p = reinterpret_cast<const uint4*>(blk + (size_t)t * kStrip);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q * 16 < valid) v = __ldg(p + q);
+        w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+    if (valid < kStrip) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            int nbv = valid - 4 * j;
+            uint32_t m = nbv >= 4 ? 0xFFFFFFFFu : (nbv <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 8 * nbv)));
+            w[j] &= m;
+        }
+    }
+    return valid;
+}
+
+// trailing zero bytes of a 64-byte strip (64 when it is all zero)
+__device__ __forceinline__ uint32_t strip_trailing_zeros(const uint32_t (&w)[16])
+{
+    uint32_t tz = 64;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (w[j]) tz = 4u * (15 - j) + ((uint32_t)__clz((int)w[j]) >> 3);
+    return tz;
+}
+
+// Zero bytes immediately preceding this thread's strip inside the block (the pending run that
+// the first non-zero byte of the strip will have to emit).  Block-wide; s_wtz/s_waz are
+// shared arrays of 32 words each.  Contains one __syncthreads().
+__device__ __forceinline__ uint32_t strip_carry_in(uint32_t tz, bool az, uint32_t* s_wtz, uint32_t* s_waz)
+{
+    const uint32_t lane = lane_id(), wid = warp_id();
+    const uint32_t azm = __ballot_sync(0xFFFFFFFFu, az);
+    const uint32_t lower = ~azm & ((1u << lane) - 1u);
+    const int p = 31 - __clz((int)lower);  // nearest preceding lane with a non-zero byte, -1 = none
+    const uint32_t tz_p = __shfl_sync(0xFFFFFFFFu, tz, p < 0 ? 0 : p);
+    uint32_t carry = p >= 0 ? tz_p + (uint32_t)kStrip * (lane - 1 - p) : (uint32_t)kStrip * lane;
+    // warp summary: zeros at the end of the warp's 2048-byte range
+    const int q = 31 - __clz((int)~azm);
+    const uint32_t tz_q = __shfl_sync(0xFFFFFFFFu, tz, q < 0 ? 0 : q);
+    if (lane == 0) {
+        s_wtz[wid] = q >= 0 ? tz_q + (uint32_t)kStrip * (31 - q) : 32u * kStrip;
+        s_waz[wid] = q < 0;
+    }
+    __syncthreads();
+    if (p < 0) {
+        for (int v = (int)wid - 1; v >= 0; --v) {
+            carry += s_wtz[v];
+            if (!s_waz[v]) break;
+        }
+    }
+    return carry;
+}
+
+// ---- token walk --------------------------------------------------------------------------
+// Emits, in stream order, the tokens OWNED by this strip: every literal in the strip, each
+// preceded by the zero run that ends right before it (which may have started in earlier
+// strips: `carry`), plus -- for the last strip of the block -- the run that reaches the block
+// end.  Concatenated over strips this is exactly the reference token sequence
+// (hzr_encode.c:410-457: greedy chunks of <= 16662 zeros).
+template <class Sink>
+__device__ __forceinline__ void emit_run(uint32_t z, Sink& sink)
+{
+    while (z > kRunCap) {
+        sink.token(260u, kRunCap - 279u, 14u);
+        z -= kRunCap;
+    }
+    uint32_t sym, ev, eb;
+    run_token(z, sym, ev, eb);
+    sink.token(sym, ev, eb);
+}
+
+template <class Sink>
+__device__ __forceinline__ void walk_strip(const uint32_t (&w)[16], int valid, uint32_t carry,
+                                           bool last_strip, Sink& sink)
+{
+    uint32_t zrun = carry;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int nbv = valid - 4 * j;
+        if (nbv > 0) {
+            const uint32_t x = w[j];
+            if (x == 0) {
+                zrun += nbv >= 4 ? 4u : (uint32_t)nbv;
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (b < nbv) {
+                        const uint32_t v = (x >> (8 * b)) & 0xFFu;
+                        if (v) {
+                            if (zrun) {
+                                emit_run(zrun, sink);
+                                zrun = 0;
+                            }
+                            sink.token(v, 0u, 0u);
+                        } else {
+                            ++zrun;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (last_strip && zrun) emit_run(zrun, sink);
+}
+
+// ---- block-wide exclusive scan of one uint32 per thread (blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /*[33]*/, uint32_t* total)
+{
+    const uint32_t lane = lane_id(), wid = warp_id(), nw = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (uint32_t)o) inc += y;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t x = lane < nw ? s_warp[lane] : 0u;
+        uint32_t xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xi, o);
+            if (lane >= (uint32_t)o) xi += y;
+        }
+        s_warp[lane] = xi - x;  // exclusive warp offsets
+        if (lane == 31) s_warp[32] = xi;
+    }
+    __syncthreads();
+    if (total) *total = s_warp[32];
+    return s_warp[wid] + inc - v;
+}
+
+#define RSPT_CUDA_CHECK(call)                                      \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return rspt::fail_cuda(p, e_, #call); \
+    } while (0)
+
+}  // namespace rspt

@@ -1,0 +1,650 @@
+// hzr encoder for sm_100a: per-block histogram -> batched tree build -> sized layout -> bit
+// packing with CRC-32C.  Replaces lib_hzr/hzr_encode.c (Histogram :133-173, MakeTree :222-283,
+// StoreTree :177-219, OnlySingleCode :285-305, EncodeSingleBlock :369-487, PlainCopy :307-339,
+// EncodeFill :341-367, hzr_encode :499-544) and the framing half of compress_i32
+// (lib_signalpacker/signal_packer_base.cpp:69-95).  The output is byte-identical to the
+// reference's.
+#pragma once
+
+#include "common.cuh"
+
+namespace rspt {
+
+// CRC-32C constants, built on the host at library load (crc_tables.cpp) and kept in global
+// memory: byte table, the per-lane multipliers x^(32(j+1)) and, for every supported CTA width
+// T, the 4x256 table of Z^(4T) (advance the register by 4T zero bytes).
+struct CrcConst {
+    uint32_t byte_tab[256];
+    uint32_t lane_mul[1024];
+    uint32_t zt[4][4][256];  // [log2(T/128)][byte][value]
+};
+
+__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b)
+{
+    // product of two polynomials mod P in the reflected representation (bit 31 = x^0)
+    uint32_t p = 0;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+        p ^= b & (0u - ((a >> (31 - i)) & 1u));
+        b = (b >> 1) ^ (0x82F63B78u & (0u - (b & 1u)));
+    }
+    return p;
+}
+
+// CRC-32C of `len` bytes that start at the WORD-ALIGNED shared-memory address `words`
+// (hzr_crc32c.c:77-84 semantics: init ~0, final ~).  All threads of the CTA must call it;
+// the result is returned to every thread.  s_zt is the CTA's copy of zt[log2(T/128)],
+// s_red holds 33 words.  blockDim.x must be 128, 256, 512 or 1024.
+__device__ __forceinline__ uint32_t block_crc32c(const uint32_t* words, uint32_t len, const uint32_t* s_zt,
+                                                 const CrcConst* __restrict__ cc, uint32_t* s_red)
+{
+    const uint32_t T = blockDim.x, j = threadIdx.x;
+    uint32_t part = 0;
+    if (len >= 8) {
+        const uint32_t W = len >> 2;
+        if (j < W) {
+            uint32_t S = 0;
+            for (uint32_t i = (W - 1 - j) % T; i < W; i += T) {
+                uint32_t w = words[i];
+                if (i == 0) w = ~w;  // init 0xFFFFFFFF == complement of the first four bytes
+                S = s_zt[S & 255u] ^ s_zt[256 + ((S >> 8) & 255u)] ^ s_zt[512 + ((S >> 16) & 255u)] ^
+                    s_zt[768 + (S >> 24)] ^ w;
+            }
+            part = crc_mulmod(__ldg(&cc->lane_mul[j]), S);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xFFFFFFFFu, part, o);
+    __syncthreads();
+    if (lane_id() == 0) s_red[warp_id()] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (uint32_t w = 0; w < (T >> 5); ++w) s ^= s_red[w];
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
+        uint32_t q = len & ~3u;
+        if (len < 8) {
+            s = 0xFFFFFFFFu;
+            q = 0;
+        }
+        for (; q < len; ++q) s = (s >> 8) ^ __ldg(&cc->byte_tab[(s ^ bytes[q]) & 255u]);
+        s_red[32] = ~s;
+    }
+    __syncthreads();
+    return s_red[32];
+}
+
+// ------------------------------------------------------------------------------------------
+// Block addressing: blk = (f * nb_alloc + k) * nblk + b
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void blk_decode(const Shape& s, uint32_t blk, uint32_t& f, uint32_t& k, uint32_t& b)
+{
+    b = blk % s.nblk;
+    uint32_t fk = blk / s.nblk;
+    k = fk % s.nb_alloc;
+    f = fk / s.nb_alloc;
+}
+
+__device__ __forceinline__ const uint8_t* blk_ptr(const uint8_t* planes, const Shape& s, uint32_t f, uint32_t k, uint32_t b)
+{
+    return planes + ((size_t)f * s.nb_alloc + k) * s.plane_stride + (size_t)b * kBlock;
+}
+
+// ------------------------------------------------------------------------------------------
+// 1. histogram: one CTA per block, one 64-byte strip per thread
+// ------------------------------------------------------------------------------------------
+struct HistSink {
+    uint32_t* sh;
+    __device__ __forceinline__ void token(uint32_t sym, uint32_t, uint32_t) { atomicAdd(&sh[sym], 1u); }
+};
+
+__global__ void __launch_bounds__(1024) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
+                                                    const uint8_t* __restrict__ frame_nb,
+                                                    uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t sh[kSymStride];
+    __shared__ uint32_t s_wtz[32], s_waz[32];
+    uint32_t f, k, b;
+    const uint32_t blk = blockIdx.x;
+    blk_decode(s, blk, f, k, b);
+    if (k >= frame_nb[f]) return;
+    const uint32_t n = blk_len(s, b);
+    for (uint32_t i = threadIdx.x; i < kSymStride; i += blockDim.x) sh[i] = 0;
+    const uint32_t nstrips = (n + kStrip - 1) / kStrip;
+    uint32_t w[16];
+    const uint8_t* src = blk_ptr(planes, s, f, k, b);
+    for (uint32_t base = 0; base < nstrips; base += blockDim.x) {
+        // (blocks are at most 1024 strips, so with blockDim.x == 1024 this loop runs once;
+        // narrower CTAs are used for small shapes and also run it once)
+        const uint32_t t = base + threadIdx.x;
+        const int valid = load_strip(src, n, t, w);
+        const uint32_t tz = strip_trailing_zeros(w);
+        const uint32_t carry = strip_carry_in(tz, tz == 64, s_wtz, s_waz);
+        HistSink sink{sh};
+        if (valid > 0 && !(tz == 64 && t != nstrips - 1)) walk_strip(w, valid, carry, t == nstrips - 1, sink);
+    }
+    __syncthreads();
+    uint32_t* out = hist + (size_t)blk * kSymStride;
+    for (uint32_t i = threadIdx.x; i < kSymStride; i += blockDim.x) out[i] = sh[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. tree build: a warp owns 32 blocks.  Phase A (warp-cooperative, one block at a time):
+// classify, compact and sort the used symbols by (count asc, symbol desc).  Phase B (one lane
+// per block): two-queue merge that reproduces MakeTree's selection order -- internal nodes
+// win ties against leaves and, among equal-weight internal nodes, the most recently created
+// wins (hzr_encode.c:247-261).  Phase C (one lane per block): pre-order walk that assigns the
+// LSB-first codes, serialises the tree (StoreTree) and totals the payload bits.
+// ------------------------------------------------------------------------------------------
+constexpr int kTreeWarps = 3;
+struct TreeSmem {
+    uint32_t leaf[kNumSymbols][32];  // sorted keys: count << 9 | (511 - symbol)
+    uint32_t icnt[260][32];          // internal node weights; reused as the DFS stack
+    uint32_t tmp[512];
+};
+
+struct Counters {
+    unsigned long long frames_compressed, frames_decompressed, raw_bytes_in, compressed_bytes_out;
+    unsigned long long blocks_copy, blocks_huff, blocks_fill, escalations;
+};
+
+__global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __restrict__ hist, Shape s,
+                                                               const uint8_t* __restrict__ frame_nb,
+                                                               uint32_t total_blocks,
+                                                               uint32_t* __restrict__ codes,
+                                                               uint32_t* __restrict__ tree,
+                                                               uint32_t* __restrict__ children,
+                                                               BlkInfo* __restrict__ info,
+                                                               Counters* __restrict__ ctr)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    TreeSmem& S = reinterpret_cast<TreeSmem*>(smem_raw)[warp_id()];
+    const uint32_t lane = lane_id();
+    const uint32_t base = (blockIdx.x * kTreeWarps + warp_id()) * 32u;
+    if (base >= total_blocks) return;
+
+    int myL = 0;         // leaves of this lane's tree (0 = nothing to build)
+    uint32_t myn = 0;    // block length
+    uint32_t n_copy = 0, n_huff = 0, n_fill = 0;
+
+    // ---- phase A
+    for (uint32_t jj = 0; jj < 32; ++jj) {
+        const uint32_t blk = base + jj;
+        if (blk >= total_blocks) break;
+        uint32_t f, k, b;
+        blk_decode(s, blk, f, k, b);
+        if (k >= frame_nb[f]) continue;
+        const uint32_t n = blk_len(s, b);
+        const uint32_t* h = hist + (size_t)blk * kSymStride;
+        uint32_t key[9];
+        uint32_t L = 0, nz = 0, nzsym = 0, zero_class = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const uint32_t sym = r * 32 + lane;
+            const uint32_t c = sym < kNumSymbols ? __ldg(h + sym) : 0u;
+            if (sym < kSymStride) codes[(size_t)blk * kSymStride + sym] = 0;
+            const bool used = c != 0;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, used);
+            const uint32_t pos = L + __popc(m & ((1u << lane) - 1u));
+            key[r] = (c << 9) | (511u - sym);
+            if (used) S.tmp[pos] = key[r];
+            L += __popc(m);
+            if (r == 0) {
+                zero_class |= m & 1u;
+                const uint32_t mm = m & ~1u;
+                nz += __popc(mm);
+                if (mm) nzsym = __ffs(mm) - 1;
+            } else if (r < 8) {
+                nz += __popc(m);
+                if (m && !nzsym) nzsym = r * 32 + __ffs(m) - 1;
+            } else {
+                zero_class |= m != 0;
+            }
+        }
+        if (nz + (zero_class ? 1u : 0u) == 1u) {
+            // single value class -> FILL (OnlySingleCode); payload is in[0]
+            if (lane == 0) {
+                BlkInfo bi;
+                bi.payload_len = 1; bi.total_bits = 8; bi.tree_nbits = 0;
+                bi.mode = MODE_FILL; bi.fill = (uint8_t)(nz ? nzsym : 0u); bi.n_used = L;
+                info[blk] = bi;
+            }
+            ++n_fill;
+            continue;
+        }
+        // pad to a power of two >= 32 and bitonic-sort ascending in shared memory
+        uint32_t P = 32;
+        while (P < L) P <<= 1;
+        for (uint32_t i = L + lane; i < P; i += 32) S.tmp[i] = 0xFFFFFFFFu;
+        __syncwarp();
+        for (uint32_t kk = 2; kk <= P; kk <<= 1)
+            for (uint32_t jx = kk >> 1; jx > 0; jx >>= 1) {
+                for (uint32_t idx = lane; idx < (P >> 1); idx += 32) {
+                    const uint32_t i = ((idx & ~(jx - 1)) << 1) | (idx & (jx - 1));
+                    const uint32_t ixj = i | jx;
+                    const uint32_t a = S.tmp[i], c2 = S.tmp[ixj];
+                    const bool up = (i & kk) == 0;
+                    if ((a > c2) == up) {
+                        S.tmp[i] = c2;
+                        S.tmp[ixj] = a;
+                    }
+                }
+                __syncwarp();
+            }
+        for (uint32_t i = lane; i < L; i += 32) S.leaf[i][jj] = S.tmp[i];
+        __syncwarp();
+        if (lane == jj) {
+            myL = (int)L;
+            myn = n;
+        }
+    }
+    __syncwarp();
+
+    // ---- phase B: two-queue merge, one lane per tree
+    const uint32_t blk = base + lane;
+    uint32_t* my_children = children + (size_t)blk * 260;
+    {
+        int maxL = myL;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxL = max(maxL, __shfl_xor_sync(0xFFFFFFFFu, maxL, o));
+        uint32_t li = 0, fr = 0, top = 0, run_end = 0, ni = 0;
+        bool started = false;
+        for (int round = 0; round + 1 < maxL; ++round) {
+            if (round + 1 < myL) {
+                uint32_t id[2], wt[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const uint32_t lc = li < (uint32_t)myL ? (S.leaf[li][lane] >> 9) : 0xFFFFFFFFu;
+                    const uint32_t ic = fr < ni ? S.icnt[fr][lane] : 0xFFFFFFFFu;
+                    if (ic <= lc) {
+                        if (!started) {
+                            top = fr + 1;
+                            while (top < ni && S.icnt[top][lane] == ic) ++top;
+                            run_end = top;
+                            started = true;
+                        }
+                        --top;
+                        id[q] = 512u + top;
+                        wt[q] = ic;
+                        if (top == fr) {
+                            fr = run_end;
+                            started = false;
+                        }
+                    } else {
+                        id[q] = li;
+                        wt[q] = lc;
+                        ++li;
+                    }
+                }
+                S.icnt[ni][lane] = wt[0] + wt[1];
+                my_children[ni] = id[0] | (id[1] << 16);
+                ++ni;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- phase C: pre-order walk (child_a first), codes + tree bits + payload size
+    {
+        uint32_t sp = 0;
+        if (myL >= 2) {
+            S.icnt[0][lane] = 512u + (uint32_t)(myL - 2);  // root = last internal node, depth 0
+            S.icnt[128][lane] = 0;
+            sp = 1;
+        }
+        unsigned long long acc = 0;
+        uint32_t nacc = 0, wi = 0, token_bits = 0, too_deep = 0;
+        uint32_t* my_tree = tree + (size_t)blk * kTreeWords;
+        uint32_t* my_codes = codes + (size_t)blk * kSymStride;
+        while (__any_sync(0xFFFFFFFFu, sp > 0)) {
+            if (sp > 0) {
+                --sp;
+                const uint32_t e = S.icnt[sp][lane];
+                const uint32_t code = S.icnt[128 + sp][lane];
+                const uint32_t id = e & 0xFFFFu, depth = e >> 16;
+                if (id < 512u) {
+                    const uint32_t kv = S.leaf[id][lane];
+                    const uint32_t sym = 511u - (kv & 511u), cnt = kv >> 9;
+                    acc |= (unsigned long long)(1u | (sym << 1)) << nacc;
+                    nacc += 10;
+                    my_codes[sym] = code | (depth << 27);
+                    token_bits += cnt * (depth + sym_extra_bits(sym));
+                    too_deep |= depth > 27u;
+                } else {
+                    nacc += 1;
+                    const uint32_t ch = my_children[id - 512u];
+                    S.icnt[sp][lane] = (ch >> 16) | ((depth + 1) << 16);  // child_b: bit `depth` = 1
+                    S.icnt[128 + sp][lane] = code | (1u << depth);
+                    ++sp;
+                    S.icnt[sp][lane] = (ch & 0xFFFFu) | ((depth + 1) << 16);  // child_a on top
+                    S.icnt[128 + sp][lane] = code;
+                    ++sp;
+                }
+                if (nacc >= 32) {
+                    my_tree[wi++] = (uint32_t)acc;
+                    acc >>= 32;
+                    nacc -= 32;
+                }
+            }
+        }
+        if (myL >= 2) {
+            if (nacc) my_tree[wi++] = (uint32_t)acc;
+            BlkInfo bi;
+            bi.tree_nbits = (uint16_t)(11 * myL - 1);
+            bi.total_bits = bi.tree_nbits + token_bits;
+            const uint32_t bytes = (bi.total_bits + 7u) >> 3;
+            // capped block stream (hzr_encode.c:377-382) and 16-bit size field (:466-467)
+            const bool copy = bytes > myn || bytes >= kBlock || too_deep;
+            bi.mode = copy ? MODE_COPY : MODE_HUFF;
+            bi.payload_len = copy ? myn : bytes;
+            bi.fill = 0;
+            bi.n_used = (uint32_t)myL;
+            info[blk] = bi;
+            if (copy) ++n_copy; else ++n_huff;
+        }
+    }
+    // counters (n_fill is warp-uniform; n_copy / n_huff are per lane)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_copy += __shfl_xor_sync(0xFFFFFFFFu, n_copy, o);
+        n_huff += __shfl_xor_sync(0xFFFFFFFFu, n_huff, o);
+    }
+    if (lane == 0) {
+        if (n_copy) atomicAdd(&ctr->blocks_copy, (unsigned long long)n_copy);
+        if (n_huff) atomicAdd(&ctr->blocks_huff, (unsigned long long)n_huff);
+        if (n_fill) atomicAdd(&ctr->blocks_fill, (unsigned long long)n_fill);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. layout: per-frame plane count (prefix max of `need`, the reference's sticky
+// nr_bytes_to_compress_++), frame sizes, exclusive scan -> byte offset of every frame.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_frame_nb(const uint32_t* __restrict__ need, uint32_t n_frames,
+                                                    uint32_t* __restrict__ nb_state, uint8_t* __restrict__ frame_nb,
+                                                    Counters* __restrict__ ctr)
+{
+    __shared__ uint32_t s_w[33];
+    uint32_t carry = *nb_state;
+    const uint32_t start_nb = carry;
+    for (uint32_t base = 0; base < n_frames; base += blockDim.x) {
+        const uint32_t f = base + threadIdx.x;
+        uint32_t v = f < n_frames ? need[f] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if (lane_id() >= (uint32_t)o) v = max(v, y);
+        }
+        if (lane_id() == 31) s_w[warp_id()] = v;
+        __syncthreads();
+        uint32_t pre = carry;
+        for (uint32_t w = 0; w < warp_id(); ++w) pre = max(pre, s_w[w]);
+        v = max(v, pre);
+        if (f < n_frames) frame_nb[f] = (uint8_t)v;
+        uint32_t all = carry;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) all = max(all, s_w[w]);
+        carry = all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *nb_state = carry;
+        if (carry > start_nb) atomicAdd(&ctr->escalations, (unsigned long long)(carry - start_nb));
+    }
+}
+
+__device__ __forceinline__ uint32_t chunk_bytes(const BlkInfo* info, const Shape& s, uint32_t f, uint32_t k)
+{
+    // hzr stream of one plane: 4-byte decoded size + blocks of 7 + payload (hzr_encode.c:521-539)
+    uint32_t sz = 4;
+    const BlkInfo* bi = info + ((size_t)f * s.nb_alloc + k) * s.nblk;
+    for (uint32_t b = 0; b < s.nblk; ++b) sz += 7u + bi[b].payload_len;
+    return sz;
+}
+
+__global__ void k_frame_sizes(const BlkInfo* __restrict__ info, Shape s, const uint8_t* __restrict__ frame_nb,
+                              uint32_t n_frames, uint32_t* __restrict__ sizes)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    uint32_t sz = 1 + s.hdr_bytes;  // method byte + header (signal_packer_base.cpp:83-91)
+    const uint32_t nb = frame_nb[f];
+    for (uint32_t k = 0; k < nb; ++k) sz += 4u + chunk_bytes(info, s, f, k);  // len:u32 + stream (:78)
+    sizes[f] = sz;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_offsets(const uint32_t* __restrict__ sizes, uint32_t n_frames,
+                                                        uint64_t* __restrict__ offsets, Counters* __restrict__ ctr,
+                                                        uint32_t frame_bytes)
+{
+    __shared__ unsigned long long s_w[33];
+    const uint32_t per = (n_frames + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(n_frames, threadIdx.x * per), hi = min(n_frames, lo + per);
+    unsigned long long sum = 0;
+    for (uint32_t f = lo; f < hi; ++f) sum += sizes[f];
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane_id() >= (uint32_t)o) inc += y;
+    }
+    if (lane_id() == 31) s_w[warp_id()] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) {
+            unsigned long long t = s_w[w];
+            s_w[w] = run;
+            run += t;
+        }
+        s_w[32] = run;
+    }
+    __syncthreads();
+    unsigned long long off = s_w[warp_id()] + inc - sum;
+    for (uint32_t f = lo; f < hi; ++f) {
+        offsets[f] = off;
+        off += sizes[f];
+    }
+    if (threadIdx.x == 0) {
+        offsets[n_frames] = s_w[32];
+        atomicAdd(&ctr->frames_compressed, (unsigned long long)n_frames);
+        atomicAdd(&ctr->raw_bytes_in, (unsigned long long)n_frames * frame_bytes);
+        atomicAdd(&ctr->compressed_bytes_out, s_w[32]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 4. encode: one CTA per block.  The block's bytes [7-byte header | payload] are staged in
+// shared memory starting at byte 9 (so the payload is 16-byte aligned at byte 16), the CRC is
+// taken from the staged payload and the whole thing is copied to its final, arbitrarily
+// aligned position in the output stream.
+// ------------------------------------------------------------------------------------------
+constexpr size_t kEncodeSmem = (size_t)(4 + kBlock / 4 + 2) * 4;
+
+struct LenSink {
+    const uint32_t* sc;
+    uint32_t bits;
+    __device__ __forceinline__ void token(uint32_t sym, uint32_t, uint32_t eb) { bits += (sc[sym] >> 27) + eb; }
+};
+
+struct EmitSink {
+    const uint32_t* sc;
+    uint32_t* stg;  // staging words; bit position 0 = payload bit 0
+    unsigned long long acc;
+    uint32_t nacc, wptr;
+    bool first;
+    __device__ __forceinline__ void flush()
+    {
+        if (first) {
+            atomicOr(&stg[wptr], (uint32_t)acc);
+            first = false;
+        } else {
+            stg[wptr] = (uint32_t)acc;
+        }
+        ++wptr;
+        acc >>= 32;
+        nacc -= 32;
+    }
+    __device__ __forceinline__ void append(uint32_t v, uint32_t nbits)
+    {
+        acc |= (unsigned long long)v << nacc;
+        nacc += nbits;
+        if (nacc >= 32) flush();
+    }
+    __device__ __forceinline__ void token(uint32_t sym, uint32_t ev, uint32_t eb)
+    {
+        const uint32_t c = sc[sym];
+        append(c & 0x07FFFFFFu, c >> 27);
+        if (eb) append(ev, eb);
+    }
+    __device__ __forceinline__ void finish()
+    {
+        if (nacc) atomicOr(&stg[wptr], (uint32_t)acc);
+    }
+};
+
+// copy `len` bytes from shared memory (byte offset `soff` into the word array `sw`) to an
+// arbitrarily aligned global address, 4 bytes per thread-step
+__device__ __forceinline__ void copy_smem_to_global(uint8_t* __restrict__ dst, const uint32_t* sw, uint32_t soff, uint32_t len)
+{
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(sw);
+    uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
+    if (head > len) head = len;
+    if (threadIdx.x < head) dst[threadIdx.x] = sb[soff + threadIdx.x];
+    const uint32_t nw = (len - head) >> 2;
+    const uint32_t so = soff + head;
+    const uint32_t sh = (so & 3u) * 8u, wbase = so >> 2;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+    for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x)
+        dw[i] = __funnelshift_r(sw[wbase + i], sw[wbase + i + 1], sh);
+    const uint32_t done = head + (nw << 2);
+    if (threadIdx.x < len - done) dst[done + threadIdx.x] = sb[soff + done + threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024, 1) k_hzr_encode(const uint8_t* __restrict__ planes, Shape s,
+                                                         const uint8_t* __restrict__ frame_nb,
+                                                         const BlkInfo* __restrict__ info,
+                                                         const uint32_t* __restrict__ codes,
+                                                         const uint32_t* __restrict__ tree,
+                                                         const uint64_t* __restrict__ offsets,
+                                                         const uint8_t* __restrict__ headers,
+                                                         const CrcConst* __restrict__ cc, int zt_sel,
+                                                         uint8_t* __restrict__ dst,
+                                                         uint32_t* __restrict__ sc_bit, uint16_t* __restrict__ sc_carry)
+{
+    extern __shared__ __align__(16) uint32_t stg[];  // [4 + 16384 + 2] staging words
+    __shared__ uint32_t s_codes[kSymStride];
+    __shared__ uint32_t s_zt[1024];
+    __shared__ uint32_t s_wtz[32], s_waz[32], s_scan[33], s_red[33];
+    __shared__ unsigned long long s_dst;
+
+    uint32_t f, k, b;
+    const uint32_t blk = blockIdx.x;
+    blk_decode(s, blk, f, k, b);
+    const uint32_t nb = frame_nb[f];
+    if (k >= nb) return;
+    const uint32_t n = blk_len(s, b);
+    const BlkInfo bi = info[blk];
+    const uint32_t tid = threadIdx.x;
+
+    // position of this block inside the output; frame / chunk framing written by the CTA that
+    // owns the first block (signal_packer_base.cpp:78,83-95; hzr_encode.c:521)
+    if (tid == 0) {
+        unsigned long long pos = offsets[f] + 1 + s.hdr_bytes;
+        for (uint32_t kk = 0; kk < k; ++kk) pos += 4u + chunk_bytes(info, s, f, kk);
+        const BlkInfo* row = info + ((size_t)f * s.nb_alloc + k) * s.nblk;
+        if (b == 0) {
+            const uint32_t clen = chunk_bytes(info, s, f, k);
+            uint8_t* q = dst + pos;
+            q[0] = (uint8_t)clen; q[1] = (uint8_t)(clen >> 8); q[2] = (uint8_t)(clen >> 16); q[3] = (uint8_t)(clen >> 24);
+            q[4] = (uint8_t)s.N; q[5] = (uint8_t)(s.N >> 8); q[6] = (uint8_t)(s.N >> 16); q[7] = (uint8_t)(s.N >> 24);
+            if (k == 0) dst[offsets[f]] = (uint8_t)s.method;
+        }
+        pos += 8;
+        for (uint32_t bb = 0; bb < b; ++bb) pos += 7u + row[bb].payload_len;
+        s_dst = pos;
+    }
+    if (k == 0 && b == 0 && s.hdr_bytes) {
+        for (uint32_t i = tid; i < s.hdr_bytes; i += blockDim.x)
+            dst[offsets[f] + 1 + i] = headers[(size_t)f * s.hdr_bytes + i];
+    }
+    for (uint32_t i = tid; i < 1024; i += blockDim.x) s_zt[i] = __ldg(&cc->zt[zt_sel][0][0] + i);
+
+    const uint8_t* src = blk_ptr(planes, s, f, k, b);
+    uint8_t* sbytes = reinterpret_cast<uint8_t*>(stg);
+
+    if (bi.mode == MODE_FILL) {
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t crc = ~(0x00FFFFFFu ^ __ldg(&cc->byte_tab[0xFFu ^ bi.fill]));
+            uint8_t* q = dst + s_dst;
+            q[0] = 0; q[1] = 0;
+            q[2] = (uint8_t)crc; q[3] = (uint8_t)(crc >> 8); q[4] = (uint8_t)(crc >> 16); q[5] = (uint8_t)(crc >> 24);
+            q[6] = MODE_FILL;
+            q[7] = bi.fill;
+        }
+        return;
+    }
+
+    const uint32_t plen = bi.payload_len;
+    uint32_t* pay = stg + 4;  // payload words (byte 16 of the staging area; header at bytes 9..15)
+    if (bi.mode == MODE_COPY) {
+        // raw plane bytes are the payload (PlainCopy); rows are 16-byte aligned
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(pay);
+        for (uint32_t i = tid; i < (n + 15) / 16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+        __syncthreads();
+    } else {
+        for (uint32_t i = tid; i < kSymStride; i += blockDim.x)
+            s_codes[i] = __ldg(codes + (size_t)blk * kSymStride + i);
+        const uint32_t tw = (bi.tree_nbits + 31u) >> 5, pw = (plen + 3u) >> 2;
+        for (uint32_t i = tid; i < pw + 1; i += blockDim.x)
+            pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
+        const uint32_t nstrips = (n + kStrip - 1) / kStrip;
+        uint32_t w[16];
+        const int valid = load_strip(src, n, tid, w);
+        const uint32_t tz = strip_trailing_zeros(w);
+        const uint32_t carry = strip_carry_in(tz, tz == 64, s_wtz, s_waz);  // (syncs: tables + staging ready)
+        const bool last = tid == nstrips - 1;
+        const bool work = valid > 0 && !(tz == 64 && !last);
+        LenSink ls{s_codes, 0};
+        if (work) walk_strip(w, valid, carry, last, ls);
+        const uint32_t off = bi.tree_nbits + block_exclusive_scan(ls.bits, s_scan, nullptr);
+        if (sc_bit && (tid % kSegStrips) == 0 && tid < nstrips) {
+            sc_bit[(size_t)blk * kMaxSegs + tid / kSegStrips] = off;
+            sc_carry[(size_t)blk * kMaxSegs + tid / kSegStrips] = (uint16_t)carry;
+        }
+        if (work && ls.bits) {
+            EmitSink es{s_codes, pay, 0ull, off & 31u, off >> 5, true};
+            walk_strip(w, valid, carry, last, es);
+            es.finish();
+        }
+        __syncthreads();
+    }
+    const uint32_t crc = block_crc32c(pay, plen, s_zt, cc, s_red);
+    if (tid == 0) {
+        sbytes[9] = (uint8_t)(plen - 1); sbytes[10] = (uint8_t)((plen - 1) >> 8);
+        sbytes[11] = (uint8_t)crc; sbytes[12] = (uint8_t)(crc >> 8); sbytes[13] = (uint8_t)(crc >> 16); sbytes[14] = (uint8_t)(crc >> 24);
+        sbytes[15] = (uint8_t)bi.mode;
+    }
+    __syncthreads();
+    copy_smem_to_global(dst + s_dst, stg, 9, 7u + plen);
+}
+
+// stand-alone CRC-32C of a global buffer of <= 65536 bytes (tests / rspt_gpu_crc32c)
+__global__ void __launch_bounds__(1024) k_crc32c(const uint8_t* __restrict__ data, uint32_t n,
+                                                  const CrcConst* __restrict__ cc, int zt_sel, uint32_t* out)
+{
+    extern __shared__ __align__(16) uint32_t stg[];
+    __shared__ uint32_t s_zt[1024];
+    __shared__ uint32_t s_red[33];
+    uint8_t* sb = reinterpret_cast<uint8_t*>(stg);
+    for (uint32_t i = threadIdx.x; i < ((n + 3) >> 2) + 1; i += blockDim.x) stg[i] = 0;
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_zt[i] = __ldg(&cc->zt[zt_sel][0][0] + i);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sb[i] = data[i];
+    __syncthreads();
+    const uint32_t crc = block_crc32c(stg, n, s_zt, cc, s_red);
+    if (threadIdx.x == 0) *out = crc;
+}
+
+}  // namespace rspt

@@ -1,0 +1,85 @@
+// Host-side state behind an rspt_gpu_packer handle (one per reference packer instance).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "hzr_encode.cuh"
+
+struct rspt_gpu_packer {
+    rspt::Shape s;
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    size_t max_batch;
+    uint32_t enc_threads;  // CTA width of the strip kernels (128/256/512/1024)
+    int zt_sel;
+    bool can_escalate;     // xdelta_hzr with nb < bps
+
+    // compress scratch
+    uint8_t* d_planes;
+    uint32_t* d_hist;
+    uint32_t* d_codes;
+    uint32_t* d_tree;
+    uint32_t* d_children;
+    rspt::BlkInfo* d_info;
+    uint8_t* d_frame_nb;
+    uint32_t* d_need;
+    uint32_t* d_nb_state;
+    uint32_t* d_sizes;
+    uint8_t* d_headers;
+    int32_t* d_words;      // hadamard / dct: de-interleaved samples, then coefficients
+    long long* d_sums;     // hadamard / dct: per (frame, channel) sample sums
+    rspt::Counters* d_ctr;
+    const rspt::CrcConst* d_crc;
+    // decompress scratch
+    void* d_dec;           // block descriptors
+    uint8_t* d_dec_nb;     // per-frame plane count used by the last decompress
+    int32_t* d_status_tmp;
+    // transform constants (dct twiddles)
+    double2* d_twiddle;
+    double2* d_post;
+    float* d_cos;          // dct direct path: the reference's float cosine table
+    // single-frame host API staging
+    uint8_t* d_one_src;
+    uint8_t* d_one_dst;
+    uint64_t* d_one_off;
+    uint8_t* h_pin;
+    size_t h_pin_bytes;
+    // host batch API staging (grown on demand)
+    uint8_t* d_hb_src;
+    uint8_t* d_hb_dst;
+    uint64_t* d_hb_off;
+    size_t hb_frames;
+
+    unsigned long long launches;
+    // stage timing
+    bool timing;
+    std::vector<cudaEvent_t>* ev_free;
+    struct Pending { int stage; cudaEvent_t a, b; };
+    std::vector<Pending>* ev_pending;
+    double stage_ms[8];
+    unsigned long long stage_calls[8];
+    char err[256];
+};
+
+namespace rspt {
+
+inline int fail_cuda(rspt_gpu_packer* p, cudaError_t e, const char* what)
+{
+    if (p) snprintf(p->err, sizeof(p->err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return -2;  // RSPT_E_CUDA
+}
+
+inline int fail_arg(rspt_gpu_packer* p, const char* what)
+{
+    if (p) snprintf(p->err, sizeof(p->err), "%s", what);
+    return -1;  // RSPT_E_ARG
+}
+
+}  // namespace rspt

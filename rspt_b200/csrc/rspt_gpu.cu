@@ -1,0 +1,828 @@
+// librspt_gpu.so -- C ABI (include/rspt_gpu.h) over the sm_100a signal-packer kernels.
+// Host code here only validates arguments, owns device scratch and launches kernels; there is
+// no CPU implementation of any stage.
+#include "../../include/rspt_gpu.h"
+#include "../../include/rspt_synth.h"
+
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "packer.cuh"
+#include "transforms.cuh"
+#include "hzr_decode.cuh"
+#include "spectral.cuh"
+
+using namespace rspt;
+
+// ---------------------------------------------------------------------------------------------
+// per-device constants
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kMaxDevices = 64;
+std::mutex g_mu;
+CrcConst* g_crc[kMaxDevices] = {};
+int32_t* g_synth_tab[kMaxDevices] = {};  // beat[1024] | sine[1024]
+
+uint32_t h_multmodp(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+    for (int i = 0; i < 32; ++i) {
+        if ((a >> (31 - i)) & 1u) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ 0x82F63B78u : b >> 1;
+    }
+    return p;
+}
+
+uint32_t h_xpow(uint64_t n)  // x^n mod P, reflected
+{
+    uint32_t sq = 1u << 30, r = 1u << 31;
+    while (n) {
+        if (n & 1) r = h_multmodp(sq, r);
+        sq = h_multmodp(sq, sq);
+        n >>= 1;
+    }
+    return r;
+}
+
+int ensure_device_constants(int dev)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (dev < 0 || dev >= kMaxDevices) return RSPT_E_ARG;
+    if (g_crc[dev]) return RSPT_OK;
+    std::vector<CrcConst> hc(1);
+    CrcConst& c = hc[0];
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t r = i;
+        for (int k = 0; k < 8; ++k) r = (r >> 1) ^ (0x82F63B78u & (0u - (r & 1u)));
+        c.byte_tab[i] = r;
+    }
+    for (uint32_t j = 0; j < 1024; ++j) c.lane_mul[j] = h_xpow(32ull * (j + 1));
+    for (int t = 0; t < 4; ++t) {
+        const uint32_t T = 128u << t;
+        const uint32_t z = h_xpow(32ull * T);
+        for (int b = 0; b < 4; ++b)
+            for (uint32_t v = 0; v < 256; ++v) c.zt[t][b][v] = h_multmodp(z, v << (8 * b));
+    }
+    CrcConst* d = nullptr;
+    if (cudaMalloc(&d, sizeof(CrcConst)) != cudaSuccess) return RSPT_E_CUDA;
+    if (cudaMemcpy(d, &c, sizeof(CrcConst), cudaMemcpyHostToDevice) != cudaSuccess) return RSPT_E_CUDA;
+    std::vector<int32_t> tab(2 * RSPT_SYNTH_TABLE);
+    rspt_synth_build_tables(tab.data(), tab.data() + RSPT_SYNTH_TABLE);
+    int32_t* dt = nullptr;
+    if (cudaMalloc(&dt, tab.size() * sizeof(int32_t)) != cudaSuccess) return RSPT_E_CUDA;
+    if (cudaMemcpy(dt, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) return RSPT_E_CUDA;
+    g_crc[dev] = d;
+    g_synth_tab[dev] = dt;
+    return RSPT_OK;
+}
+
+size_t hzr_max(size_t n) { return 4 + (n ? ((n + kBlock - 1) / kBlock) * 7 + n : 0); }
+
+template <class T>
+cudaError_t dalloc(T*& ptr, size_t count)
+{
+    return cudaMalloc(reinterpret_cast<void**>(&ptr), count * sizeof(T) + 64);
+}
+
+template <class K>
+cudaError_t allow_smem(K kernel, size_t bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+uint32_t total_blocks(const rspt_gpu_packer* p, size_t frames) { return (uint32_t)(frames * p->s.nb_alloc * p->s.nblk); }
+
+// tile height (samples) of k_xdelta_planes and the dynamic shared memory it needs
+bool xdelta_tile(const Shape& s, uint32_t& ts, size_t& smem)
+{
+    const size_t row = (size_t)s.ch * s.bps, per = row + 4 * (size_t)s.ch;
+    const size_t budget = 96 * 1024;
+    size_t t = (budget - 64 - 8 * (size_t)s.ch) / per;
+    t = t > 512 ? 512 : (t & ~(size_t)31);
+    if (t < 32) return false;
+    const size_t need_t = ((size_t)s.ns + 31) & ~(size_t)31;
+    if (t > need_t) t = need_t;
+    ts = (uint32_t)t;
+    smem = ((t * row + 31) & ~(size_t)15) + (size_t)s.ch * (t + 2) * 4;
+    return true;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// stage timing: events around kernel groups, resolved lazily
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+cudaEvent_t ev_get(rspt_gpu_packer* p)
+{
+    if (!p->ev_free->empty()) {
+        cudaEvent_t e = p->ev_free->back();
+        p->ev_free->pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void ev_resolve(rspt_gpu_packer* p)
+{
+    for (auto& q : *p->ev_pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(q.b) == cudaSuccess && cudaEventElapsedTime(&ms, q.a, q.b) == cudaSuccess) {
+            p->stage_ms[q.stage] += ms;
+            p->stage_calls[q.stage] += 1;
+        }
+        p->ev_free->push_back(q.a);
+        p->ev_free->push_back(q.b);
+    }
+    p->ev_pending->clear();
+}
+
+struct StageTimer {
+    rspt_gpu_packer* p;
+    int stage;
+    cudaEvent_t a = nullptr;
+    StageTimer(rspt_gpu_packer* p_, int stage_) : p(p_), stage(stage_)
+    {
+        if (p->timing) {
+            a = ev_get(p);
+            cudaEventRecord(a, p->stream);
+        }
+    }
+    ~StageTimer()
+    {
+        if (a) {
+            cudaEvent_t b = ev_get(p);
+            cudaEventRecord(b, p->stream);
+            p->ev_pending->push_back({stage, a, b});
+            if (p->ev_pending->size() > 4096) ev_resolve(p);
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" int rspt_gpu_set_stage_timing(rspt_gpu_packer* p, int enable)
+{
+    if (!p) return RSPT_E_ARG;
+    p->timing = enable != 0;
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_get_stage_times(rspt_gpu_packer* p, double* ms, uint64_t* calls, int reset)
+{
+    if (!p) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    ev_resolve(p);
+    for (int i = 0; i < RSPT_STAGE_COUNT; ++i) {
+        if (ms) ms[i] = p->stage_ms[i];
+        if (calls) calls[i] = p->stage_calls[i];
+        if (reset) {
+            p->stage_ms[i] = 0;
+            p->stage_calls[i] = 0;
+        }
+    }
+    return RSPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------------------------
+extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_t nb, int device, void* stream,
+                               size_t max_batch_frames, rspt_gpu_packer** out)
+{
+    if (!out) return RSPT_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return RSPT_E_NOGPU;
+    if (device < 0 || device >= ndev) return RSPT_E_ARG;
+    if (kind < 0 || kind > 3 || bps < 1 || bps > 4 || ch < 1 || ns < 1 || max_batch_frames < 1) return RSPT_E_ARG;
+    if (ch > 65535 || (uint64_t)ch * ns > 0x7FFFFFFFull / 4) return RSPT_E_ARG;
+    if (kind == RSPT_XDELTA_HZR && (nb < 1 || nb > 4)) return RSPT_E_ARG;
+    if (kind == RSPT_HADAMARD && ((ns & (ns - 1)) || ns < 2 || ns > kFwhtMaxN)) return RSPT_E_ARG;  // needs 2^k (fwht.c)
+    if (kind == RSPT_DCT && (ns < 2 || ns > kDctMaxN)) return RSPT_E_ARG;
+    DeviceGuard dg(device);
+    int rc = ensure_device_constants(device);
+    if (rc != RSPT_OK) return rc;
+
+    rspt_gpu_packer* p = new (std::nothrow) rspt_gpu_packer();
+    if (!p) return RSPT_E_ARG;
+    memset(p, 0, sizeof(*p));
+    Shape& s = p->s;
+    s.kind = kind; s.bps = (int)bps; s.ch = (int)ch; s.ns = (int)ns;
+    s.N = (uint32_t)(ch * ns);
+    s.nblk = (s.N + kBlock - 1) / kBlock;
+    // planes: xdelta = ctor argument, escalating up to bps (xdelta.cpp:63-69); hzr 4 (hzr.cpp:39);
+    // hadamard 3 (hadamard.cpp:44); dct 2 (dct.cpp:46)
+    s.nb_init = kind == RSPT_XDELTA_HZR ? (uint32_t)nb : kind == RSPT_HZR ? 4u : kind == RSPT_HADAMARD ? 3u : 2u;
+    p->can_escalate = kind == RSPT_XDELTA_HZR && s.nb_init < (uint32_t)bps;
+    s.nb_alloc = p->can_escalate ? (uint32_t)bps : s.nb_init;
+    s.hdr_bytes = (kind == RSPT_HADAMARD || kind == RSPT_DCT) ? 3u * (uint32_t)ch : 0u;
+    s.plane_stride = (s.N + 15u) & ~15u;
+    s.frame_bytes = (uint32_t)(bps * ch * ns);
+    s.method = kind == RSPT_DCT ? 1u : (kind == RSPT_HADAMARD ? 2u : 0u);
+    p->ev_free = new std::vector<cudaEvent_t>();
+    p->ev_pending = new std::vector<rspt_gpu_packer::Pending>();
+    p->device = device;
+    p->max_batch = max_batch_frames;
+    p->d_crc = g_crc[device];
+    const uint32_t maxn = s.N < kBlock ? s.N : kBlock;
+    const uint32_t strips = (maxn + kStrip - 1) / kStrip;
+    p->enc_threads = strips <= 128 ? 128 : strips <= 256 ? 256 : strips <= 512 ? 512 : 1024;
+    p->zt_sel = p->enc_threads == 128 ? 0 : p->enc_threads == 256 ? 1 : p->enc_threads == 512 ? 2 : 3;
+    p->stream = (cudaStream_t)stream;  // NULL = the CUDA default stream
+    p->own_stream = false;
+    const size_t F = max_batch_frames, nblocks = F * s.nb_alloc * s.nblk;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A(dalloc(p->d_planes, F * s.nb_alloc * (size_t)s.plane_stride));
+    A(dalloc(p->d_hist, nblocks * kSymStride));
+    A(dalloc(p->d_codes, nblocks * kSymStride));
+    A(dalloc(p->d_tree, nblocks * kTreeWords));
+    A(dalloc(p->d_children, nblocks * 260));
+    A(dalloc(p->d_info, nblocks));
+    A(dalloc(p->d_frame_nb, F));
+    A(dalloc(p->d_need, F));
+    A(dalloc(p->d_nb_state, 4));
+    A(dalloc(p->d_sizes, F));
+    A(dalloc(p->d_headers, F * (s.hdr_bytes ? s.hdr_bytes : 1)));
+    A(dalloc(p->d_ctr, 1));
+    A(dalloc(p->d_status_tmp, F));
+    A(dalloc(p->d_dec_nb, F));
+    A(cudaMalloc(&p->d_dec, nblocks * sizeof(DecBlk) + 64));
+    if (kind == RSPT_HADAMARD || kind == RSPT_DCT) {
+        A(dalloc(p->d_words, F * (size_t)s.N));
+        A(dalloc(p->d_sums, F * (size_t)s.ch));
+    }
+    if (e == cudaSuccess && kind == RSPT_DCT) e = dct_build_tables(p);
+    const size_t maxc = rspt_gpu_max_compressed_size(p);
+    A(dalloc(p->d_one_src, (size_t)s.frame_bytes));
+    A(dalloc(p->d_one_dst, maxc));
+    A(dalloc(p->d_one_off, 2));
+    p->h_pin_bytes = maxc > s.frame_bytes ? maxc : s.frame_bytes;
+    p->h_pin_bytes += 64;
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&p->h_pin), p->h_pin_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_frame_nb, (int)s.nb_init, F, p->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ctr, 0, sizeof(Counters), p->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_nb_state, &s.nb_init, 4, cudaMemcpyHostToDevice, p->stream);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_tree, kTreeWarps * sizeof(TreeSmem));
+    if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_decode, kDecodeSmem);
+    if (e == cudaSuccess) e = allow_smem(k_crc32c, kEncodeSmem);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "rspt_gpu_create: %s\n", cudaGetErrorString(e));
+        rspt_gpu_destroy(p);
+        return RSPT_E_CUDA;
+    }
+    *out = p;
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
+{
+    if (!p) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    cudaStreamSynchronize(p->stream);
+    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_children, p->d_info, p->d_frame_nb,
+                    p->d_need, p->d_nb_state, p->d_sizes, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
+                    p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
+                    p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    if (p->h_pin) cudaFreeHost(p->h_pin);
+    if (p->ev_pending) {
+        ev_resolve(p);
+        for (cudaEvent_t e : *p->ev_free) cudaEventDestroy(e);
+        delete p->ev_pending;
+        delete p->ev_free;
+    }
+    if (p->own_stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return RSPT_OK;
+}
+
+extern "C" size_t rspt_gpu_frame_bytes(const rspt_gpu_packer* p) { return p ? p->s.frame_bytes : 0; }
+extern "C" size_t rspt_gpu_header_bytes(const rspt_gpu_packer* p) { return p ? p->s.hdr_bytes : 0; }
+
+extern "C" size_t rspt_gpu_max_compressed_size(const rspt_gpu_packer* p)
+{
+    if (!p) return 0;
+    return 1 + p->s.hdr_bytes + (size_t)p->s.nb_alloc * (4 + hzr_max(p->s.N));
+}
+
+extern "C" size_t rspt_gpu_sidecar_bytes(const rspt_gpu_packer* p, size_t n_frames)
+{
+    if (!p) return 0;
+    return (size_t)total_blocks(p, n_frames) * kMaxSegs * 6 + 64;
+}
+
+extern "C" const char* rspt_gpu_last_error(const rspt_gpu_packer* p) { return p ? p->err : "null handle"; }
+
+extern "C" int rspt_gpu_sync(rspt_gpu_packer* p)
+{
+    if (!p) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_nb(rspt_gpu_packer* p, unsigned* nb)
+{
+    if (!p || !nb) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    uint32_t v = 0;
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(&v, p->d_nb_state, 4, cudaMemcpyDeviceToHost, p->stream));
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    *nb = v;
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_get_counters(rspt_gpu_packer* p, rspt_gpu_counters* out)
+{
+    if (!p || !out) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    Counters c;
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(&c, p->d_ctr, sizeof(c), cudaMemcpyDeviceToHost, p->stream));
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    out->frames_compressed = c.frames_compressed;
+    out->frames_decompressed = c.frames_decompressed;
+    out->raw_bytes_in = c.raw_bytes_in;
+    out->compressed_bytes_out = c.compressed_bytes_out;
+    out->blocks_copy = c.blocks_copy;
+    out->blocks_huff = c.blocks_huff;
+    out->blocks_fill = c.blocks_fill;
+    out->escalations = c.escalations;
+    out->kernel_launches = p->launches;
+    return RSPT_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// compress
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// stage 1: samples -> byte planes (+ header, + need flags)
+int launch_forward_transform(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
+{
+    const Shape& s = p->s;
+    if (s.kind == RSPT_XDELTA_HZR || s.kind == RSPT_HZR) {
+        uint32_t ts;
+        size_t smem;
+        if (!xdelta_tile(s, ts, smem)) return fail_arg(p, "too many channels for the tile kernel");
+        const uint32_t tiles = ((uint32_t)s.ns + ts - 1) / ts;
+        uint32_t* need = p->can_escalate ? p->d_need : nullptr;
+        if (need) RSPT_CUDA_CHECK(cudaMemsetAsync(need, 0, F * sizeof(uint32_t), p->stream));
+        const dim3 grid((unsigned)(F * tiles));
+#define LAUNCH_X(B, ST)                                                                              \
+    do {                                                                                             \
+        RSPT_CUDA_CHECK(allow_smem(k_xdelta_planes<B, ST>, smem));                                   \
+        k_xdelta_planes<B, ST><<<grid, 256, smem, p->stream>>>(d_src, s, ts, tiles, p->d_planes, need); \
+    } while (0)
+        const bool st = s.kind == RSPT_XDELTA_HZR;
+        switch (s.bps) {
+        case 1: if (st) LAUNCH_X(1, true); else LAUNCH_X(1, false); break;
+        case 2: if (st) LAUNCH_X(2, true); else LAUNCH_X(2, false); break;
+        case 3: if (st) LAUNCH_X(3, true); else LAUNCH_X(3, false); break;
+        default: if (st) LAUNCH_X(4, true); else LAUNCH_X(4, false); break;
+        }
+#undef LAUNCH_X
+        p->launches += 1;
+        RSPT_CUDA_CHECK(cudaGetLastError());
+        return RSPT_OK;
+    }
+    return spectral_forward(p, d_src, F);
+}
+
+int launch_frame_nb(rspt_gpu_packer* p, size_t F)
+{
+    if (!p->can_escalate) return RSPT_OK;
+    k_frame_nb<<<1, 1024, 0, p->stream>>>(p->d_need, (uint32_t)F, p->d_nb_state, p->d_frame_nb, p->d_ctr);
+    p->launches += 1;
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    return RSPT_OK;
+}
+
+}  // namespace
+
+extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src, size_t n_frames, uint8_t* d_dst,
+                                       size_t dst_capacity, uint64_t* d_offsets, uint8_t* d_frame_nb, void* d_sidecar)
+{
+    if (!p || !d_src || !d_dst || !d_offsets) return RSPT_E_ARG;
+    if (n_frames == 0) return RSPT_OK;
+    if (n_frames > p->max_batch) return fail_arg(p, "n_frames exceeds max_batch_frames"), RSPT_E_CAPACITY;
+    if (dst_capacity < n_frames * rspt_gpu_max_compressed_size(p))
+        return fail_arg(p, "dst_capacity < n_frames * rspt_gpu_max_compressed_size"), RSPT_E_CAPACITY;
+    DeviceGuard dg(p->device);
+    const Shape& s = p->s;
+    const size_t F = n_frames;
+    const uint32_t nblocks = total_blocks(p, F);
+    int rc = 0;
+    {
+        StageTimer t(p, RSPT_STAGE_TRANSFORM);
+        rc = launch_forward_transform(p, d_src, F);
+        if (rc) return rc;
+        rc = launch_frame_nb(p, F);
+        if (rc) return rc;
+    }
+    {
+        StageTimer t(p, RSPT_STAGE_HIST);
+        k_hzr_hist<<<nblocks, p->enc_threads, 0, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist);
+    }
+    {
+        StageTimer t(p, RSPT_STAGE_TREE);
+        k_hzr_tree<<<(nblocks + 32 * kTreeWarps - 1) / (32 * kTreeWarps), 32 * kTreeWarps, kTreeWarps * sizeof(TreeSmem),
+                     p->stream>>>(p->d_hist, s, p->d_frame_nb, nblocks, p->d_codes, p->d_tree, p->d_children, p->d_info,
+                                  p->d_ctr);
+    }
+    {
+        StageTimer t(p, RSPT_STAGE_LAYOUT);
+        k_frame_sizes<<<(unsigned)((F + 255) / 256), 256, 0, p->stream>>>(p->d_info, s, p->d_frame_nb, (uint32_t)F, p->d_sizes);
+        k_scan_offsets<<<1, 1024, 0, p->stream>>>(p->d_sizes, (uint32_t)F, d_offsets, p->d_ctr, s.frame_bytes);
+    }
+    uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar);
+    uint16_t* sc_carry = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
+    {
+        StageTimer t(p, RSPT_STAGE_ENCODE);
+        k_hzr_encode<<<nblocks, p->enc_threads, kEncodeSmem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_codes,
+                                                                           p->d_tree, d_offsets, p->d_headers, p->d_crc,
+                                                                           p->zt_sel, d_dst, sc_bit, sc_carry);
+    }
+    p->launches += 5;
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    if (d_frame_nb) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_frame_nb, p->d_frame_nb, F, cudaMemcpyDeviceToDevice, p->stream));
+    return RSPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decompress
+// ---------------------------------------------------------------------------------------------
+extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets,
+                                         size_t n_frames, const uint8_t* d_frame_nb, const void* d_sidecar,
+                                         uint8_t* d_dst, int32_t* d_status)
+{
+    if (!p || !d_src || !d_offsets || !d_dst) return RSPT_E_ARG;
+    if (n_frames == 0) return RSPT_OK;
+    if (n_frames > p->max_batch) return fail_arg(p, "n_frames exceeds max_batch_frames"), RSPT_E_CAPACITY;
+    DeviceGuard dg(p->device);
+    const Shape& s = p->s;
+    const size_t F = n_frames;
+    const uint32_t nblocks = total_blocks(p, F);
+    int32_t* status = d_status ? d_status : p->d_status_tmp;
+    DecBlk* dec = reinterpret_cast<DecBlk*>(p->d_dec);
+    // Without an explicit per-frame plane count every frame uses the instance's current count,
+    // as the reference's decompress does (signal_packer_xdelta_hzr.cpp:77).
+    {
+        StageTimer t(p, RSPT_STAGE_PARSE);
+        k_frame_parse<<<(unsigned)((F + 127) / 128), 128, 0, p->stream>>>(d_src, d_offsets, s, d_frame_nb, p->d_nb_state,
+                                                                          (uint32_t)F, dec, p->d_headers, p->d_dec_nb, status, p->d_ctr);
+    }
+    const uint32_t* sc_bit = reinterpret_cast<const uint32_t*>(d_sidecar);
+    const uint16_t* sc_carry = d_sidecar ? reinterpret_cast<const uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
+    {
+        StageTimer t(p, RSPT_STAGE_DECODE);
+        k_hzr_decode<<<nblocks, kDecodeThreads, kDecodeSmem, p->stream>>>(d_src, s, dec, sc_bit, sc_carry, p->d_planes, status);
+    }
+    p->launches += 2;
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    {
+        StageTimer t(p, RSPT_STAGE_INVERSE);
+        int rc = launch_inverse_transform(p, d_dst, F);
+        if (rc) return rc;
+    }
+    return RSPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" int rspt_gpu_compress_host(rspt_gpu_packer* p, const uint8_t* h_src, uint8_t* h_dst, size_t dst_max_len,
+                                      size_t* dst_len)
+{
+    if (!p || !h_src || !h_dst || !dst_len) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    const size_t fb = p->s.frame_bytes, maxc = rspt_gpu_max_compressed_size(p);
+    memcpy(p->h_pin, h_src, fb);
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_one_src, p->h_pin, fb, cudaMemcpyHostToDevice, p->stream));
+    int rc = rspt_gpu_compress_batch(p, p->d_one_src, 1, p->d_one_dst, maxc, p->d_one_off, nullptr, nullptr);
+    if (rc) return rc;
+    uint64_t off[2];
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(off, p->d_one_off, sizeof(off), cudaMemcpyDeviceToHost, p->stream));
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    const size_t len = (size_t)off[1];
+    if (len > dst_max_len) return fail_arg(p, "dst_max_len too small"), RSPT_E_CAPACITY;
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->h_pin, p->d_one_dst, len, cudaMemcpyDeviceToHost, p->stream));
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    memcpy(h_dst, p->h_pin, len);
+    *dst_len = len;
+    return RSPT_OK;
+}
+
+namespace {
+// Length of one frame found by walking its chunk length fields on the host
+// (signal_packer_base.cpp:101-121: frames are self-delimiting given the plane count).
+size_t host_frame_len(const rspt_gpu_packer* p, const uint8_t* h, unsigned nb)
+{
+    size_t pos = 1 + p->s.hdr_bytes;
+    for (unsigned k = 0; k < nb; ++k) {
+        const uint32_t len = (uint32_t)h[pos] | ((uint32_t)h[pos + 1] << 8) | ((uint32_t)h[pos + 2] << 16) |
+                             ((uint32_t)h[pos + 3] << 24);
+        pos += 4 + (size_t)len;
+        if (pos > rspt_gpu_max_compressed_size(p)) return 0;
+    }
+    return pos;
+}
+}  // namespace
+
+extern "C" int rspt_gpu_decompress_host(rspt_gpu_packer* p, const uint8_t* h_src, size_t* src_len, uint8_t* h_dst)
+{
+    if (!p || !h_src || !src_len || !h_dst) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    unsigned nb = 0;
+    int rc = rspt_gpu_nb(p, &nb);
+    if (rc) return rc;
+    const size_t len = host_frame_len(p, h_src, nb);
+    if (!len) return fail_arg(p, "malformed frame"), RSPT_E_STREAM;
+    memcpy(p->h_pin, h_src, len);
+    uint64_t off[2] = {0, (uint64_t)len};
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_one_dst, p->h_pin, len, cudaMemcpyHostToDevice, p->stream));
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_one_off, off, sizeof(off), cudaMemcpyHostToDevice, p->stream));
+    rc = rspt_gpu_decompress_batch(p, p->d_one_dst, p->d_one_off, 1, nullptr, nullptr, p->d_one_src, nullptr);
+    if (rc) return rc;
+    int32_t st = 0;
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(&st, p->d_status_tmp, 4, cudaMemcpyDeviceToHost, p->stream));
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->h_pin, p->d_one_src, p->s.frame_bytes, cudaMemcpyDeviceToHost, p->stream));
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    memcpy(h_dst, p->h_pin, p->s.frame_bytes);
+    *src_len = len;
+    return st ? RSPT_E_STREAM : RSPT_OK;
+}
+
+namespace {
+int ensure_host_batch(rspt_gpu_packer* p, size_t F)
+{
+    if (F <= p->hb_frames) return RSPT_OK;
+    if (p->d_hb_src) cudaFree(p->d_hb_src);
+    if (p->d_hb_dst) cudaFree(p->d_hb_dst);
+    if (p->d_hb_off) cudaFree(p->d_hb_off);
+    p->d_hb_src = p->d_hb_dst = nullptr;
+    p->d_hb_off = nullptr;
+    p->hb_frames = 0;
+    RSPT_CUDA_CHECK(dalloc(p->d_hb_src, F * (size_t)p->s.frame_bytes));
+    RSPT_CUDA_CHECK(dalloc(p->d_hb_dst, F * rspt_gpu_max_compressed_size(p)));
+    RSPT_CUDA_CHECK(dalloc(p->d_hb_off, F + 1));
+    p->hb_frames = F;
+    return RSPT_OK;
+}
+}  // namespace
+
+extern "C" int rspt_gpu_compress_batch_host(rspt_gpu_packer* p, const uint8_t* h_src, size_t n_frames, uint8_t* h_dst,
+                                            size_t dst_capacity, uint64_t* h_offsets)
+{
+    if (!p || !h_src || !h_dst || !h_offsets) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    int rc = ensure_host_batch(p, n_frames);
+    if (rc) return rc;
+    const size_t fb = p->s.frame_bytes;
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_hb_src, h_src, n_frames * fb, cudaMemcpyHostToDevice, p->stream));
+    rc = rspt_gpu_compress_batch(p, p->d_hb_src, n_frames, p->d_hb_dst, n_frames * rspt_gpu_max_compressed_size(p),
+                                 p->d_hb_off, nullptr, nullptr);
+    if (rc) return rc;
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(h_offsets, p->d_hb_off, (n_frames + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, p->stream));
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    const size_t total = (size_t)h_offsets[n_frames];
+    if (total > dst_capacity) return fail_arg(p, "dst_capacity too small"), RSPT_E_CAPACITY;
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(h_dst, p->d_hb_dst, total, cudaMemcpyDeviceToHost, p->stream));
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_decompress_batch_host(rspt_gpu_packer* p, const uint8_t* h_src, const uint64_t* h_offsets,
+                                              size_t n_frames, uint8_t* h_dst)
+{
+    if (!p || !h_src || !h_offsets || !h_dst) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    int rc = ensure_host_batch(p, n_frames);
+    if (rc) return rc;
+    const size_t total = (size_t)h_offsets[n_frames];
+    if (total > n_frames * rspt_gpu_max_compressed_size(p)) return fail_arg(p, "offsets exceed the frame bound"), RSPT_E_STREAM;
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_hb_dst, h_src, total, cudaMemcpyHostToDevice, p->stream));
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_hb_off, h_offsets, (n_frames + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
+    rc = rspt_gpu_decompress_batch(p, p->d_hb_dst, p->d_hb_off, n_frames, nullptr, nullptr, p->d_hb_src, nullptr);
+    if (rc) return rc;
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(h_dst, p->d_hb_src, n_frames * (size_t)p->s.frame_bytes, cudaMemcpyDeviceToHost, p->stream));
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return RSPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage-level entry points for the parity tests
+// ---------------------------------------------------------------------------------------------
+extern "C" int rspt_gpu_debug_planes(rspt_gpu_packer* p, const uint8_t* d_src, size_t n_frames, uint8_t* d_planes,
+                                     uint8_t* d_header)
+{
+    if (!p || !d_src || !d_planes || n_frames > p->max_batch) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    int rc = launch_forward_transform(p, d_src, n_frames);
+    if (rc) return rc;
+    const Shape& s = p->s;
+    RSPT_CUDA_CHECK(cudaMemcpy2DAsync(d_planes, s.N, p->d_planes, s.plane_stride, s.N, n_frames * s.nb_alloc,
+                                      cudaMemcpyDeviceToDevice, p->stream));
+    if (d_header && s.hdr_bytes)
+        RSPT_CUDA_CHECK(cudaMemcpyAsync(d_header, p->d_headers, n_frames * s.hdr_bytes, cudaMemcpyDeviceToDevice, p->stream));
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_debug_hzr_tables(rspt_gpu_packer* p, const uint8_t* d_block, size_t n, uint32_t* d_hist,
+                                         uint32_t* d_codes, uint32_t* d_info)
+{
+    if (!p || !d_block || n < 1 || n > kBlock || ((uintptr_t)d_block & 15)) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    Shape s = p->s;
+    s.N = (uint32_t)n; s.nblk = 1; s.nb_alloc = 1; s.plane_stride = (uint32_t)((n + 15) & ~(size_t)15);
+    k_hzr_hist<<<1, 1024, 0, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist);
+    k_hzr_tree<<<1, 32 * kTreeWarps, kTreeWarps * sizeof(TreeSmem), p->stream>>>(p->d_hist, s, p->d_frame_nb, 1, p->d_codes,
+                                                                                  p->d_tree, p->d_children, p->d_info, p->d_ctr);
+    p->launches += 2;
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    if (d_hist) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_hist, p->d_hist, kNumSymbols * 4, cudaMemcpyDeviceToDevice, p->stream));
+    if (d_codes) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_codes, p->d_codes, kNumSymbols * 4, cudaMemcpyDeviceToDevice, p->stream));
+    if (d_info) {
+        RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+        BlkInfo bi;
+        RSPT_CUDA_CHECK(cudaMemcpy(&bi, p->d_info, sizeof(bi), cudaMemcpyDeviceToHost));
+        uint32_t v[4] = {bi.mode, bi.payload_len, bi.tree_nbits, bi.n_used};
+        RSPT_CUDA_CHECK(cudaMemcpy(d_info, v, sizeof(v), cudaMemcpyHostToDevice));
+    }
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_crc32c(const uint8_t* d_data, size_t n, uint32_t* h_crc, void* stream)
+{
+    if (!d_data || !h_crc || n > kBlock) return RSPT_E_ARG;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RSPT_E_NOGPU;
+    int rc = ensure_device_constants(dev);
+    if (rc) return rc;
+    uint32_t* d_out = nullptr;
+    if (cudaMalloc(&d_out, 4) != cudaSuccess) return RSPT_E_CUDA;
+    allow_smem(k_crc32c, kEncodeSmem);
+    k_crc32c<<<1, 1024, kEncodeSmem, (cudaStream_t)stream>>>(d_data, (uint32_t)n, g_crc[dev], 3, d_out);
+    cudaError_t e = cudaMemcpyAsync(h_crc, d_out, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(d_out);
+    return e == cudaSuccess ? RSPT_OK : RSPT_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic workload, PRDN terms, offset rebasing
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+template <int BPS>
+__global__ void __launch_bounds__(256) k_synth(uint8_t* __restrict__ dst, uint64_t first, uint32_t n_frames, int ch, int ns,
+                                               rspt_synth_params prm, const int32_t* __restrict__ tab)
+{
+    // one CTA per (frame, 256-sample tile); threads run along samples, loop over channels
+    const uint32_t tiles = ((uint32_t)ns + 255u) / 256u;
+    const uint32_t f = blockIdx.x / tiles, s = (blockIdx.x % tiles) * 256u + threadIdx.x;
+    if (f >= n_frames || s >= (uint32_t)ns) return;
+    const int32_t* beat = tab;
+    const int32_t* sine = tab + RSPT_SYNTH_TABLE;
+    uint8_t* out = dst + ((size_t)f * ns + s) * ch * BPS;
+    for (int c = 0; c < ch; ++c) {
+        const rspt_synth_chan k = rspt_synth_channel(&prm, first + f, (uint32_t)c);
+        const uint32_t v = (uint32_t)rspt_synth_sample(&prm, &k, beat, sine, first + f, (uint32_t)c, s, BPS);
+#pragma unroll
+        for (int b = 0; b < BPS; ++b) out[c * BPS + b] = (uint8_t)(v >> (8 * b));
+    }
+}
+
+template <int BPS>
+__global__ void __launch_bounds__(256) k_prdn(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t n_frames,
+                                              int ch, int ns, double* __restrict__ out)
+{
+    // one CTA per (frame, channel): mean = average_32 (utils.cpp:30-40), then the two sums of
+    // lib_rspt_test/rspt_test.cpp:98-111
+    __shared__ long long s_sum[8];
+    __shared__ double s_d[2][8];
+    const uint32_t f = blockIdx.x / ch, c = blockIdx.x % ch;
+    const uint8_t* pa = a + (size_t)f * ns * ch * BPS + (size_t)c * BPS;
+    const uint8_t* pb = b + (size_t)f * ns * ch * BPS + (size_t)c * BPS;
+    const size_t step = (size_t)ch * BPS;
+    long long sum = 0;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) sum += load_sample<BPS>(pa + i * step);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane_id() == 0) s_sum[warp_id()] = sum;
+    __syncthreads();
+    long long tot = 0;
+    for (int w = 0; w < 8; ++w) tot += s_sum[w];
+    const int32_t mean = (int32_t)(long long)((unsigned long long)tot / (unsigned long long)ns);
+    double e2 = 0, d2 = 0;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        const double x = load_sample<BPS>(pa + i * step), y = load_sample<BPS>(pb + i * step);
+        e2 += (x - y) * (x - y);
+        d2 += (x - mean) * (x - mean);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        e2 += __shfl_xor_sync(0xFFFFFFFFu, e2, o);
+        d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, o);
+    }
+    if (lane_id() == 0) {
+        s_d[0][warp_id()] = e2;
+        s_d[1][warp_id()] = d2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0, y = 0;
+        for (int w = 0; w < 8; ++w) {
+            x += s_d[0][w];
+            y += s_d[1][w];
+        }
+        atomicAdd(out, x);
+        atomicAdd(out + 1, y);
+    }
+}
+
+__global__ void k_rebase(uint64_t* off, size_t n, const uint64_t* totals, int rank)
+{
+    unsigned long long base = 0;
+    for (int r = 0; r < rank; ++r) base += totals[r];
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off[i] += base;
+}
+
+}  // namespace
+
+extern "C" int rspt_gpu_synth_ecg(uint8_t* d_dst, uint64_t first_frame, size_t n_frames, int bps, int ch, int ns,
+                                  uint64_t seed, int32_t amplitude, int32_t sigma, void* stream)
+{
+    if (!d_dst || bps < 1 || bps > 4 || ch < 1 || ns < 1) return RSPT_E_ARG;
+    if (n_frames == 0) return RSPT_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RSPT_E_NOGPU;
+    int rc = ensure_device_constants(dev);
+    if (rc) return rc;
+    rspt_synth_params prm = {seed, amplitude, sigma};
+    const uint32_t tiles = ((uint32_t)ns + 255u) / 256u;
+    const dim3 grid((unsigned)(n_frames * tiles));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bps) {
+    case 1: k_synth<1><<<grid, 256, 0, st>>>(d_dst, first_frame, (uint32_t)n_frames, ch, ns, prm, g_synth_tab[dev]); break;
+    case 2: k_synth<2><<<grid, 256, 0, st>>>(d_dst, first_frame, (uint32_t)n_frames, ch, ns, prm, g_synth_tab[dev]); break;
+    case 3: k_synth<3><<<grid, 256, 0, st>>>(d_dst, first_frame, (uint32_t)n_frames, ch, ns, prm, g_synth_tab[dev]); break;
+    default: k_synth<4><<<grid, 256, 0, st>>>(d_dst, first_frame, (uint32_t)n_frames, ch, ns, prm, g_synth_tab[dev]); break;
+    }
+    return cudaGetLastError() == cudaSuccess ? RSPT_OK : RSPT_E_CUDA;
+}
+
+extern "C" int rspt_gpu_prdn_terms(const uint8_t* d_orig, const uint8_t* d_dec, size_t n_frames, int bps, int ch, int ns,
+                                   double* h_out, void* stream)
+{
+    if (!d_orig || !d_dec || !h_out || bps < 1 || bps > 4) return RSPT_E_ARG;
+    double* d_out = nullptr;
+    if (cudaMalloc(&d_out, 16) != cudaSuccess) return RSPT_E_CUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(d_out, 0, 16, st);
+    const dim3 grid((unsigned)(n_frames * ch));
+    switch (bps) {
+    case 1: k_prdn<1><<<grid, 256, 0, st>>>(d_orig, d_dec, (uint32_t)n_frames, ch, ns, d_out); break;
+    case 2: k_prdn<2><<<grid, 256, 0, st>>>(d_orig, d_dec, (uint32_t)n_frames, ch, ns, d_out); break;
+    case 3: k_prdn<3><<<grid, 256, 0, st>>>(d_orig, d_dec, (uint32_t)n_frames, ch, ns, d_out); break;
+    default: k_prdn<4><<<grid, 256, 0, st>>>(d_orig, d_dec, (uint32_t)n_frames, ch, ns, d_out); break;
+    }
+    cudaError_t e = cudaMemcpyAsync(h_out, d_out, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_out);
+    return e == cudaSuccess ? RSPT_OK : RSPT_E_CUDA;
+}
+
+extern "C" int rspt_gpu_rebase_offsets(uint64_t* d_offsets, size_t n, const uint64_t* d_all_totals, int rank, void* stream)
+{
+    if (!d_offsets || !d_all_totals || rank < 0) return RSPT_E_ARG;
+    if (n == 0 || rank == 0) return RSPT_OK;
+    k_rebase<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_offsets, n, d_all_totals, rank);
+    return cudaGetLastError() == cudaSuccess ? RSPT_OK : RSPT_E_CUDA;
+}

@@ -1,0 +1,385 @@
+// Lossy packers: integer fast Walsh-Hadamard transform and DCT-II / DCT-III with the reference's
+// uniform quantisation.  Replaces lib_fwht/fwht.c (fwht_transform :4-28, fwht_normalize :30-34),
+// signal_packer_hadamard.cpp:57-104 and signal_packer_dct.cpp:60-153.
+//
+// hadamard is pure integer arithmetic mod 2^32 (butterfly order is irrelevant) and therefore
+// bit-exact.  dct: the reference evaluates the O(n^2) sum with FLOAT products accumulated in
+// double (dct.cpp:83,96).  Two paths are provided:
+//   * fast (default, ns a power of two): FP64 FFT-based DCT (Makhoul reordering through one
+//     n-point complex FFT in shared memory).  Its result is the exactly-rounded-ish value; it
+//     differs from the reference only where a coefficient lies within ~1e-5 of an integer.
+//   * direct (any ns; RSPT_DCT_DIRECT=1 forces it): the same float-product / double-accumulate
+//     sum in the same order over the same float cosine table, built on the host with the
+//     reference's expression -- bit-exact, O(n^2).
+#pragma once
+
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "packer.cuh"
+#include "transforms.cuh"
+
+namespace rspt {
+
+constexpr uint32_t kFwhtMaxN = 32768;  // ns * 4 bytes of shared memory per channel
+constexpr uint32_t kDctMaxN = 8192;    // ns * 16 bytes of shared memory per channel (fast path)
+
+// floor-mean of a channel exactly as average_32 computes it (utils.cpp:30-40): the int64 sum is
+// divided as UNSIGNED 64-bit by the length and narrowed to int32.
+__device__ __forceinline__ int32_t reference_mean(long long sum, uint32_t len)
+{
+    return (int32_t)(long long)((unsigned long long)sum / (unsigned long long)len);
+}
+
+__device__ __forceinline__ void store_mean24(uint8_t* hdr, int32_t m)
+{
+    hdr[0] = (uint8_t)m; hdr[1] = (uint8_t)((uint32_t)m >> 8); hdr[2] = (uint8_t)((uint32_t)m >> 16);
+}
+
+__device__ __forceinline__ int32_t load_mean24(const uint8_t* hdr)
+{
+    const uint32_t v = (uint32_t)hdr[0] | ((uint32_t)hdr[1] << 8) | ((uint32_t)hdr[2] << 16);
+    return (int32_t)(v << 8) >> 8;  // hadamard.cpp:99, dct.cpp:148
+}
+
+// in-place natural-order FWHT of a[0..n) in shared memory, wrap-around int32 (fwht.c:15-25)
+__device__ __forceinline__ void fwht_smem(uint32_t* a, uint32_t n)
+{
+    for (uint32_t h = n >> 1; h > 0; h >>= 1) {
+        for (uint32_t t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+            const uint32_t i = ((t & ~(h - 1)) << 1) | (t & (h - 1));
+            const uint32_t u = a[i], v = a[i + h];
+            a[i] = u + v;
+            a[i + h] = u - v;
+        }
+        __syncthreads();
+    }
+}
+
+// one CTA per (frame, channel): mean removal, FWHT, q = trunc(X / n), three byte planes
+__global__ void __launch_bounds__(256) k_fwht_fwd(const int32_t* __restrict__ words, const long long* __restrict__ sums,
+                                                   Shape s, uint8_t* __restrict__ planes, uint8_t* __restrict__ headers)
+{
+    extern __shared__ __align__(16) uint32_t a[];
+    const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, n = (uint32_t)s.ns;
+    const int32_t mean = reference_mean(sums[(size_t)f * s.ch + c], n);
+    const int32_t* w = words + (size_t)f * s.N + (size_t)c * n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) a[i] = (uint32_t)w[i] - (uint32_t)mean;
+    if (threadIdx.x == 0) store_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c, mean);
+    __syncthreads();
+    fwht_smem(a, n);
+    const int lg = 31 - __clz((int)n);
+    uint8_t* out = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)c * n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int32_t X = (int32_t)a[i];
+        // (int)(X / (double)(n / 1.0)) -- truncation toward zero of an exact power-of-two quotient
+        const int32_t q = (X + ((X >> 31) & (int32_t)(n - 1))) >> lg;
+        for (uint32_t k = 0; k < s.nb_alloc; ++k) out[(size_t)k * s.plane_stride + i] = (uint8_t)((uint32_t)q >> (8 * k));
+    }
+}
+
+// one CTA per (frame, channel): planes -> q (sign-extended from 24 bits) -> FWHT -> + mean24
+__global__ void __launch_bounds__(256) k_fwht_inv(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ headers,
+                                                   const uint8_t* __restrict__ dec_nb, Shape s, int32_t* __restrict__ words)
+{
+    extern __shared__ __align__(16) uint32_t a[];
+    const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, n = (uint32_t)s.ns;
+    const uint32_t nb = dec_nb[f];
+    const int sh = 32 - 8 * (int)nb;
+    const uint8_t* in = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)c * n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint32_t v = 0;
+        for (uint32_t k = 0; k < nb; ++k) v |= (uint32_t)in[(size_t)k * s.plane_stride + i] << (8 * k);
+        a[i] = (uint32_t)((int32_t)(v << sh) >> sh);
+    }
+    __syncthreads();
+    fwht_smem(a, n);
+    const int32_t mean = load_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c);
+    int32_t* w = words + (size_t)f * s.N + (size_t)c * n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) w[i] = (int32_t)(a[i] + (uint32_t)mean);
+}
+
+// ---- FP64 complex FFT in shared memory ------------------------------------------------------
+// x[0..n) complex, n = 2^lg.  Input must already be in bit-reversed order.  tw[j] = e^{-2 pi i j/n}
+// for j < n/2; INVERSE conjugates it.  Radix-2 decimation in time.
+template <bool INVERSE>
+__device__ __forceinline__ void fft_smem(double2* x, uint32_t n, const double2* __restrict__ tw)
+{
+    uint32_t stage_shift = 31 - __clz((int)n);  // twiddle stride = n / (2*half) = n >> s
+    for (uint32_t half = 1; half < n; half <<= 1) {
+        --stage_shift;
+        for (uint32_t t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+            const uint32_t jj = t & (half - 1);
+            const uint32_t i = ((t & ~(half - 1)) << 1) | jj;
+            double2 w = __ldg(tw + ((size_t)jj << stage_shift));
+            if (INVERSE) w.y = -w.y;
+            const double2 u = x[i], v = x[i + half];
+            const double2 m = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+            x[i] = make_double2(u.x + m.x, u.y + m.y);
+            x[i + half] = make_double2(u.x - m.x, u.y - m.y);
+        }
+        __syncthreads();
+    }
+}
+
+// forward DCT of one channel, fast path.  post[k] = e^{-i pi k / (2n)}.
+__global__ void __launch_bounds__(256) k_dct_fwd_fast(int32_t* __restrict__ words, const long long* __restrict__ sums, Shape s,
+                                                       const double2* __restrict__ tw, const double2* __restrict__ post,
+                                                       uint8_t* __restrict__ headers)
+{
+    extern __shared__ __align__(16) double2 xs[];
+    const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, n = (uint32_t)s.ns;
+    const int lg = 31 - __clz((int)n);
+    const int32_t mean = reference_mean(sums[(size_t)f * s.ch + c], n);
+    int32_t* w = words + (size_t)f * s.N + (size_t)c * n;
+    if (threadIdx.x == 0) store_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c, mean);
+    // v[m] = x[2m], v[n-1-m] = x[2m+1]; stored at the bit-reversed index for the DIT FFT
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+        const int32_t xv = (int32_t)((uint32_t)w[j] - (uint32_t)mean);
+        const uint32_t m = (j & 1u) ? n - 1 - (j >> 1) : (j >> 1);
+        xs[__brev(m) >> (32 - lg)] = make_double2((double)xv, 0.0);
+    }
+    __syncthreads();
+    fft_smem<false>(xs, n, tw);
+    const double ratio1 = sqrt(2.0 / (double)(int)n);
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        const double2 V = xs[k], p = __ldg(post + k);
+        double sum = V.x * p.x - V.y * p.y;
+        const float cs = k ? 1.0f : (float)(1 / sqrt(2.0));
+        sum *= (double)cs * ratio1 / 128.0;  // dct.cpp:84 (quality = 128)
+        w[k] = (int32_t)sum;                 // truncation toward zero, dct.cpp:85
+    }
+}
+
+// forward DCT, direct path: dct.cpp:76-87 verbatim arithmetic.  cosT[x][i] is the float table.
+__global__ void __launch_bounds__(256) k_dct_fwd_direct(int32_t* __restrict__ words, const long long* __restrict__ sums, Shape s,
+                                                         const float* __restrict__ cosT, uint8_t* __restrict__ headers)
+{
+    extern __shared__ __align__(16) float xf[];
+    const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, n = (uint32_t)s.ns;
+    const int32_t mean = reference_mean(sums[(size_t)f * s.ch + c], n);
+    int32_t* w = words + (size_t)f * s.N + (size_t)c * n;
+    if (threadIdx.x == 0) store_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c, mean);
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) xf[j] = (float)(int32_t)((uint32_t)w[j] - (uint32_t)mean);
+    __syncthreads();
+    const double ratio1 = sqrt(2.0 / (double)(int)n);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        double sum = 0;
+        for (uint32_t x = 0; x < n; ++x) sum += (double)__fmul_rn(xf[x], __ldg(cosT + (size_t)x * n + i));
+        const float cs = i ? 1.0f : (float)(1 / sqrt(2.0));
+        sum *= (double)cs * ratio1 / 128.0;
+        w[i] = (int32_t)sum;
+    }
+}
+
+// inverse DCT, fast path: U[0] = T[0], U[k] = conj(post[k]) (T[k] - i T[n-k]) / 2, v = n-point
+// inverse FFT, x[2m] = v[m], x[2m+1] = v[n-1-m]; T[k] = Cs[k] * coef[k].
+__global__ void __launch_bounds__(256) k_dct_inv_fast(int32_t* __restrict__ words, const uint8_t* __restrict__ headers, Shape s,
+                                                       const double2* __restrict__ tw, const double2* __restrict__ post)
+{
+    extern __shared__ __align__(16) double2 xs[];
+    const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, n = (uint32_t)s.ns;
+    const int lg = 31 - __clz((int)n);
+    int32_t* w = words + (size_t)f * s.N + (size_t)c * n;
+    const double cs0 = (double)(float)(1 / sqrt(2.0));
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        double2 U;
+        if (k == 0) {
+            U = make_double2(cs0 * (double)w[0], 0.0);
+        } else {
+            const double a = (double)w[k], b = (double)w[n - k];
+            const double2 p = __ldg(post + k);  // conj(p) * (a - i b) / 2
+            U = make_double2(0.5 * (p.x * a - p.y * b), -0.5 * (p.x * b + p.y * a));
+        }
+        xs[__brev(k) >> (32 - lg)] = U;
+    }
+    __syncthreads();
+    fft_smem<true>(xs, n, tw);
+    const int32_t mean = load_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c);
+    const double scale = sqrt(2.0 / (double)(int)n) * 128.0;  // dct.cpp:97
+    for (uint32_t m = threadIdx.x; m < n; m += blockDim.x) {
+        const uint32_t j = m < (n >> 1) ? 2 * m : 2 * (n - 1 - m) + 1;
+        const double sum = xs[m].x * scale;
+        w[j] = (int32_t)((uint32_t)(int32_t)sum + (uint32_t)mean);
+    }
+}
+
+// inverse DCT, direct path: dct.cpp:89-100 verbatim arithmetic (cosT[i][x])
+__global__ void __launch_bounds__(256) k_dct_inv_direct(int32_t* __restrict__ words, const uint8_t* __restrict__ headers, Shape s,
+                                                         const float* __restrict__ cosT)
+{
+    extern __shared__ __align__(16) float tf[];
+    const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, n = (uint32_t)s.ns;
+    int32_t* w = words + (size_t)f * s.N + (size_t)c * n;
+    const float cs0 = (float)(1 / sqrt(2.0));
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) tf[k] = __fmul_rn(k ? 1.0f : cs0, (float)w[k]);
+    __syncthreads();
+    const int32_t mean = load_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c);
+    const double scale = sqrt(2.0 / (double)(int)n) * 128.0;
+    // each thread owns output samples i; the table row i is contiguous in x
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        double sum = 0;
+        const float* rowp = cosT + (size_t)i * n;
+        for (uint32_t x = 0; x < n; ++x) sum += (double)__fmul_rn(tf[x], __ldg(rowp + x));
+        sum *= scale;
+        w[i] = (int32_t)((uint32_t)(int32_t)sum + (uint32_t)mean);
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------
+inline bool dct_use_direct(const rspt_gpu_packer* p)
+{
+    const uint32_t n = (uint32_t)p->s.ns;
+    const char* e = getenv("RSPT_DCT_DIRECT");
+    return (n & (n - 1)) != 0 || (e && e[0] == '1');
+}
+
+inline cudaError_t dct_build_tables(rspt_gpu_packer* p)
+{
+    const uint32_t n = (uint32_t)p->s.ns;
+    const double PI = 3.14159265358979323846;
+    cudaError_t e = cudaSuccess;
+    if ((n & (n - 1)) == 0) {
+        std::vector<double2> tw(n / 2 + 1), post(n);
+        for (uint32_t j = 0; j < n / 2; ++j) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * j / n;
+            tw[j] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+        for (uint32_t k = 0; k < n; ++k) {
+            const long double a = -3.14159265358979323846264338327950288L * k / (2.0L * n);
+            post[k] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+        e = cudaMalloc(&p->d_twiddle, sizeof(double2) * (n / 2 + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_post, sizeof(double2) * n);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_twiddle, tw.data(), sizeof(double2) * (n / 2), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_post, post.data(), sizeof(double2) * n, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && dct_use_direct(p)) {
+        // COSINES[i][j] = (float)cos(((i << 1) * j + j) * PI / (2n))  (dct.cpp:60-68); the same
+        // symmetric-in-role table serves the forward ([x][i]) and inverse ([i][x]) sums
+        std::vector<float> t((size_t)n * n);
+        const double pi_n_2 = PI / (n * 2.0);
+        for (uint32_t i = 0; i < n; ++i)
+            for (uint32_t j = 0; j < n; ++j) t[(size_t)i * n + j] = (float)cos((double)(int)(((int)i << 1) * (int)j + (int)j) * pi_n_2);
+        e = cudaMalloc(&p->d_cos, sizeof(float) * (size_t)n * n);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_cos, t.data(), sizeof(float) * (size_t)n * n, cudaMemcpyHostToDevice);
+    }
+    return e;
+}
+
+#define SPECTRAL_BPS_SWITCH(KERNEL, ...)                     \
+    switch (s.bps) {                                         \
+    case 1: KERNEL<1> __VA_ARGS__; break;                    \
+    case 2: KERNEL<2> __VA_ARGS__; break;                    \
+    case 3: KERNEL<3> __VA_ARGS__; break;                    \
+    default: KERNEL<4> __VA_ARGS__; break;                   \
+    }
+
+// hadamard / dct: samples -> planes + header
+inline int spectral_forward(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
+{
+    const Shape& s = p->s;
+    const uint32_t tiles = ((uint32_t)s.ns + kPiece - 1) / kPiece;
+    const size_t tile_smem = (size_t)kPiece * s.ch * s.bps + 48;
+    if (tile_smem > 200 * 1024) return fail_arg(p, "too many channels");
+    RSPT_CUDA_CHECK(cudaMemsetAsync(p->d_sums, 0, F * s.ch * sizeof(long long), p->stream));
+    const dim3 g1((unsigned)(F * tiles));
+    switch (s.bps) {
+    case 1: cudaFuncSetAttribute(k_raw_to_words<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    case 2: cudaFuncSetAttribute(k_raw_to_words<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    case 3: cudaFuncSetAttribute(k_raw_to_words<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    default: cudaFuncSetAttribute(k_raw_to_words<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    }
+    SPECTRAL_BPS_SWITCH(k_raw_to_words, <<<g1, 256, tile_smem, p->stream>>>(d_src, s, tiles, p->d_words, p->d_sums));
+    const dim3 g2((unsigned)(F * s.ch));
+    if (s.kind == 2 /*RSPT_HADAMARD*/) {
+        const size_t sm = (size_t)s.ns * 4;
+        cudaFuncSetAttribute(k_fwht_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        k_fwht_fwd<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_planes, p->d_headers);
+        p->launches += 2;
+    } else {
+        if (dct_use_direct(p)) {
+            const size_t sm = (size_t)s.ns * 4;
+            cudaFuncSetAttribute(k_dct_fwd_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            k_dct_fwd_direct<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_cos, p->d_headers);
+        } else {
+            const size_t sm = (size_t)s.ns * 16;
+            cudaFuncSetAttribute(k_dct_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            k_dct_fwd_fast<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_twiddle, p->d_post, p->d_headers);
+        }
+        const uint32_t chunks = (s.N + 1023) / 1024;
+        k_words_stencil_planes<<<(unsigned)(F * chunks), 256, 0, p->stream>>>(p->d_words, s, chunks, p->d_planes);
+        p->launches += 3;
+    }
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// planes (decoded) -> samples, all four packers
+inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F)
+{
+    const Shape& s = p->s;
+    const uint32_t ppc = ((uint32_t)s.ns + kPiece - 1) / kPiece, np = ppc * (uint32_t)s.ch;
+    const size_t tile_bytes = (size_t)kPiece * s.ch * s.bps + 48;
+    const size_t sm_inv = (size_t)2 * np * 4 + tile_bytes;
+    if (sm_inv > 200 * 1024 || tile_bytes > 200 * 1024) return fail_arg(p, "frame too large for the inverse kernel");
+    const dim3 gf((unsigned)F);
+#define INV_LAUNCH(B, SC, RAW)                                                                                   \
+    do {                                                                                                         \
+        cudaFuncSetAttribute(k_planes_to_samples<B, SC, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_inv); \
+        k_planes_to_samples<B, SC, RAW><<<gf, 512, sm_inv, p->stream>>>(p->d_planes, s, p->d_dec_nb, d_dst, p->d_words);  \
+    } while (0)
+    if (s.kind == 0 /*xdelta_hzr*/) {
+        switch (s.bps) {
+        case 1: INV_LAUNCH(1, true, true); break;
+        case 2: INV_LAUNCH(2, true, true); break;
+        case 3: INV_LAUNCH(3, true, true); break;
+        default: INV_LAUNCH(4, true, true); break;
+        }
+        p->launches += 1;
+    } else if (s.kind == 1 /*hzr*/) {
+        switch (s.bps) {
+        case 1: INV_LAUNCH(1, false, true); break;
+        case 2: INV_LAUNCH(2, false, true); break;
+        case 3: INV_LAUNCH(3, false, true); break;
+        default: INV_LAUNCH(4, false, true); break;
+        }
+        p->launches += 1;
+    } else {
+        const dim3 g2((unsigned)(F * s.ch));
+        if (s.kind == 2) {
+            const size_t sm = (size_t)s.ns * 4;
+            cudaFuncSetAttribute(k_fwht_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            k_fwht_inv<<<g2, 256, sm, p->stream>>>(p->d_planes, p->d_headers, p->d_dec_nb, s, p->d_words);
+            p->launches += 1;
+        } else {
+            INV_LAUNCH(4, true, false);  // coefficient words (BPS unused for word output)
+            if (dct_use_direct(p)) {
+                const size_t sm = (size_t)s.ns * 4;
+                cudaFuncSetAttribute(k_dct_inv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                k_dct_inv_direct<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_headers, s, p->d_cos);
+            } else {
+                const size_t sm = (size_t)s.ns * 16;
+                cudaFuncSetAttribute(k_dct_inv_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                k_dct_inv_fast<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_headers, s, p->d_twiddle, p->d_post);
+            }
+            p->launches += 2;
+        }
+        const uint32_t tiles = ppc;
+        switch (s.bps) {
+        case 1: cudaFuncSetAttribute(k_words_to_raw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
+        case 2: cudaFuncSetAttribute(k_words_to_raw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
+        case 3: cudaFuncSetAttribute(k_words_to_raw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
+        default: cudaFuncSetAttribute(k_words_to_raw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
+        }
+        SPECTRAL_BPS_SWITCH(k_words_to_raw, <<<(unsigned)(F * tiles), 256, tile_bytes, p->stream>>>(p->d_words, s, tiles, d_dst));
+        p->launches += 1;
+    }
+#undef INV_LAUNCH
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rspt

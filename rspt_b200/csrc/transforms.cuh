@@ -1,0 +1,373 @@
+// Sample-domain kernels: de-interleave / sign-extend, the delta - offset - xor chain, byte-plane
+// split and their inverses.  Replaces lib_signalpacker/utils.cpp (convert_native_to_i32 :123-191,
+// convert_i32_to_native :51-121, delta_encode :193, offset_32 :215, xor_encode_32 :221,
+// xor_decode_32 :232, delta_decode :204) and the plane split / reassembly of
+// signal_packer_base.cpp:40-68 and :122-138.
+#pragma once
+
+#include "common.cuh"
+#include "hzr_encode.cuh"
+
+namespace rspt {
+
+// cooperative copy of the global byte range [g, g + len) into shared memory at sm + (g & 15):
+// 16-byte vector loads for the aligned interior, byte loads for the ragged ends
+__device__ __forceinline__ uint32_t tile_load(uint8_t* sm, const uint8_t* __restrict__ g, uint32_t len)
+{
+    const uint32_t phase = (uint32_t)((uintptr_t)g & 15u);
+    const uint32_t head = phase ? min(len, 16u - phase) : 0u;
+    for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) sm[phase + i] = g[i];
+    const uint32_t nvec = (len - head) >> 4;
+    const uint4* gv = reinterpret_cast<const uint4*>(g + head);
+    uint4* sv = reinterpret_cast<uint4*>(sm + phase + head);
+    for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) sv[i] = __ldg(gv + i);
+    const uint32_t done = head + (nvec << 4);
+    for (uint32_t i = done + threadIdx.x; i < len; i += blockDim.x) sm[phase + i] = g[i];
+    return phase;
+}
+
+template <int BPS>
+__device__ __forceinline__ int32_t load_sample(const uint8_t* p)
+{
+    uint32_t v = p[0];
+    if (BPS > 1) v |= (uint32_t)p[1] << 8;
+    if (BPS > 2) v |= (uint32_t)p[2] << 16;
+    if (BPS > 3) v |= (uint32_t)p[3] << 24;
+    return (int32_t)(v << (32 - 8 * BPS)) >> (32 - 8 * BPS);  // sign extension (utils.cpp:141,158,174,189)
+}
+
+// x at flat (channel-major) index i of a frame, 0 for i < 0: the predecessor convention of
+// delta_encode / xor_encode_32, whose chains run over the flat [ch*ns] array and therefore
+// cross channel rows (signal_packer_xdelta_hzr.cpp:55-57)
+template <int BPS>
+__device__ __forceinline__ int32_t frame_sample_flat(const uint8_t* __restrict__ frame, const Shape& s, int64_t i)
+{
+    if (i < 0) return 0;
+    const uint32_t c = (uint32_t)(i / s.ns), smp = (uint32_t)(i % s.ns);
+    return load_sample<BPS>(frame + ((size_t)smp * s.ch + c) * BPS);
+}
+
+// planes required to represent y losslessly when only 8*bps bits matter: the smallest nb such
+// that bits [8nb-1 .. 8bps-1] of y agree (equivalent to the reference's decode-and-memcmp test,
+// signal_packer_xdelta_hzr.cpp:59-69)
+__device__ __forceinline__ uint32_t planes_needed(uint32_t y, int bps)
+{
+    uint32_t z = (y ^ (y << 1)) & 0xFFFFFF00u;
+    if (bps < 4) z &= (1u << (8 * bps)) - 1u;
+    return z ? (31u - (uint32_t)__clz((int)z)) / 8u + 1u : 1u;
+}
+
+// raw frame tile -> byte planes.  One CTA handles `ts` consecutive samples of every channel of
+// one frame: the tile is contiguous in the interleaved input, so every input byte is read
+// exactly once, coalesced.  STENCIL = xdelta_hzr (y = ((x-x1)-128) ^ ((x1-x2)-128)), else the
+// plain hzr packer (y = x).
+template <int BPS, bool STENCIL>
+__global__ void __launch_bounds__(256) k_xdelta_planes(const uint8_t* __restrict__ src, Shape s, uint32_t ts,
+                                                        uint32_t tiles_per_frame, uint8_t* __restrict__ planes,
+                                                        uint32_t* __restrict__ need)
+{
+    extern __shared__ __align__(16) uint8_t sm[];
+    const uint32_t f = blockIdx.x / tiles_per_frame, tile = blockIdx.x % tiles_per_frame;
+    const uint32_t s0 = tile * ts;
+    const uint32_t tsv = min(ts, (uint32_t)s.ns - s0);
+    const uint8_t* frame = src + (size_t)f * s.frame_bytes;
+    const uint32_t row = (uint32_t)s.ch * BPS;
+    // shared layout: [raw tile (+15 phase) | xw[ch][ts + 2]]
+    int32_t* xw = reinterpret_cast<int32_t*>(sm + ((ts * row + 31u) & ~15u));
+    const uint32_t xs = ts + 2;
+    const uint32_t phase = tile_load(sm, frame + (size_t)s0 * row, tsv * row);
+    __syncthreads();
+    // de-interleave: lanes run along samples so the strided byte reads spread over banks
+    for (uint32_t e = threadIdx.x; e < tsv * s.ch; e += blockDim.x) {
+        const uint32_t c = e / tsv, j = e % tsv;
+        xw[c * xs + 2 + j] = load_sample<BPS>(sm + phase + (j * s.ch + c) * BPS);
+    }
+    if (STENCIL) {
+        // two predecessors of the first sample of every channel row of this tile
+        for (uint32_t e = threadIdx.x; e < 2u * s.ch; e += blockDim.x) {
+            const uint32_t c = e >> 1, back = 2 - (e & 1);  // back = 2 -> slot 0, back = 1 -> slot 1
+            const int64_t flat = (int64_t)c * s.ns + s0 - back;
+            xw[c * xs + (2 - back)] = frame_sample_flat<BPS>(frame, s, flat);
+        }
+    }
+    __syncthreads();
+    uint32_t my_need = 1;
+    for (uint32_t e = threadIdx.x; e < tsv * s.ch; e += blockDim.x) {
+        const uint32_t c = e / tsv, j = e % tsv;
+        const int32_t* px = xw + c * xs + 2 + j;
+        uint32_t y = (uint32_t)px[0];
+        if (STENCIL) {
+            const uint32_t x0 = (uint32_t)px[0], x1 = (uint32_t)px[-1], x2 = (uint32_t)px[-2];
+            uint32_t d0 = x0 - x1 - 128u, d1 = x1 - x2 - 128u;
+            // the very first word of the frame has no predecessor delta: y[0] = x[0] - 128
+            if (c == 0 && s0 + j == 0) d1 = 0;
+            y = d0 ^ d1;
+            if (need) my_need = max(my_need, planes_needed(y, BPS));
+        }
+        uint8_t* out = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)c * s.ns + s0 + j;
+        for (uint32_t k = 0; k < s.nb_alloc; ++k) out[(size_t)k * s.plane_stride] = (uint8_t)(y >> (8 * k));
+    }
+    if (STENCIL && need) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_need = max(my_need, __shfl_xor_sync(0xFFFFFFFFu, my_need, o));
+        if (lane_id() == 0 && my_need > 1) atomicMax(&need[f], my_need);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// planes -> samples.  One CTA per frame.  The decode-side chains are two scans over the flat
+// [ch*ns] order that cross channel rows: d = prefix-xor(y) (xor_decode_32, utils.cpp:232-236),
+// x = prefix-sum(d + 128) (offset_32(+128) and delta_decode, :204-219).  The frame is cut into
+// PIECES of 256 consecutive samples of one channel (one warp, 8 samples per lane); piece totals
+// are scanned in shared memory: pass 1 xor totals, pass 2 sums of d + 128, pass 3 the samples.
+// OUT_RAW: pass 3 walks sample tiles, transposes through shared memory and stores interleaved
+// little-endian samples (convert_i32_to_native, utils.cpp:51-121) with coalesced writes;
+// otherwise the int32 words are stored in flat order (input of the inverse DCT).
+// ------------------------------------------------------------------------------------------
+constexpr int kPiece = 256;
+
+// y[0..7] for flat elements [e0, e0 + cnt) of one frame, sign-extended from 8*nb bits
+// (signal_packer_base.cpp:126-138)
+__device__ __forceinline__ void load_y8(const uint8_t* __restrict__ fplanes, uint32_t stride, uint32_t nb, uint32_t e0,
+                                        uint32_t cnt, uint32_t (&y)[8])
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = 0;
+    const bool vec = cnt == 8 && ((e0 & 7u) == 0);
+    for (uint32_t k = 0; k < nb; ++k) {
+        const uint8_t* row = fplanes + (size_t)k * stride + e0;
+        if (vec) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(row));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                y[i] |= ((v.x >> (8 * i)) & 0xFFu) << (8 * k);
+                y[4 + i] |= ((v.y >> (8 * i)) & 0xFFu) << (8 * k);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if ((uint32_t)i < cnt) y[i] |= (uint32_t)row[i] << (8 * k);
+        }
+    }
+    const int sh = 32 - 8 * (int)nb;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = (uint32_t)((int32_t)(y[i] << sh) >> sh);
+}
+
+// exclusive scan (xor or add) of a shared array by warp 0
+template <bool XOR>
+__device__ __forceinline__ void smem_exclusive_scan(uint32_t* a, uint32_t n)
+{
+    if (warp_id() == 0) {
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane_id();
+            const uint32_t v = i < n ? a[i] : 0u;
+            uint32_t inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane_id() >= (uint32_t)o) inc = XOR ? (inc ^ t) : (inc + t);
+            }
+            if (i < n) a[i] = XOR ? (carry ^ inc ^ v) : (carry + inc - v);
+            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            carry = XOR ? (carry ^ tot) : (carry + tot);
+        }
+    }
+}
+
+template <int BPS, bool SCAN, bool OUT_RAW>
+__global__ void __launch_bounds__(512) k_planes_to_samples(const uint8_t* __restrict__ planes, Shape s,
+                                                            const uint8_t* __restrict__ dec_nb,
+                                                            uint8_t* __restrict__ dst_raw, int32_t* __restrict__ dst_words)
+{
+    extern __shared__ __align__(16) uint32_t sm32[];
+    const uint32_t f = blockIdx.x;
+    const uint32_t nb = dec_nb[f];
+    const uint32_t ns = (uint32_t)s.ns, ch = (uint32_t)s.ch;
+    const uint32_t ppc = (ns + kPiece - 1) / kPiece, np = ppc * ch;
+    uint32_t* pxor = sm32;          // [np]
+    uint32_t* psum = sm32 + np;     // [np]
+    uint32_t* tile = sm32 + 2 * np; // OUT_RAW: [kPiece * ch * BPS bytes] (+4 words slack)
+    const uint8_t* fpl = planes + (size_t)f * s.nb_alloc * s.plane_stride;
+    const uint32_t lane = lane_id(), wid = warp_id(), nwarps = blockDim.x >> 5;
+    uint32_t y[8];
+
+    if (SCAN) {
+        for (uint32_t p = wid; p < np; p += nwarps) {
+            const uint32_t c = p / ppc, j = p % ppc;
+            const uint32_t s0 = j * kPiece + lane * 8;
+            const uint32_t cnt = s0 < ns ? min(8u, ns - s0) : 0u;
+            load_y8(fpl, s.plane_stride, nb, c * ns + s0, cnt, y);
+            uint32_t x = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x ^= (uint32_t)i < cnt ? y[i] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+            if (lane == 0) pxor[p] = x;
+        }
+        __syncthreads();
+        smem_exclusive_scan<true>(pxor, np);
+        __syncthreads();
+        for (uint32_t p = wid; p < np; p += nwarps) {
+            const uint32_t c = p / ppc, j = p % ppc;
+            const uint32_t s0 = j * kPiece + lane * 8;
+            const uint32_t cnt = s0 < ns ? min(8u, ns - s0) : 0u;
+            load_y8(fpl, s.plane_stride, nb, c * ns + s0, cnt, y);
+            // lane-local inclusive xor prefix, then the lanes before me
+            uint32_t run = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                run ^= (uint32_t)i < cnt ? y[i] : 0u;
+                y[i] = run;
+            }
+            uint32_t inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc ^= t;
+            }
+            const uint32_t before = pxor[p] ^ inc ^ run;
+            uint32_t sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if ((uint32_t)i < cnt) sum += (y[i] ^ before) + 128u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+            if (lane == 0) psum[p] = sum;
+        }
+        __syncthreads();
+        smem_exclusive_scan<false>(psum, np);
+        __syncthreads();
+    }
+
+    const uint32_t row = ch * BPS;
+    uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+    // pass 3: tile j = samples [j*256, j*256+256) of every channel
+    for (uint32_t j = 0; j < ppc; ++j) {
+        const uint32_t tsv = min((uint32_t)kPiece, ns - j * kPiece);
+        for (uint32_t c = wid; c < ch; c += nwarps) {
+            const uint32_t p = c * ppc + j;
+            const uint32_t s0 = j * kPiece + lane * 8;
+            const uint32_t cnt = s0 < ns ? min(8u, ns - s0) : 0u;
+            load_y8(fpl, s.plane_stride, nb, c * ns + s0, cnt, y);
+            if (SCAN) {
+                uint32_t run = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    run ^= (uint32_t)i < cnt ? y[i] : 0u;
+                    y[i] = run;
+                }
+                uint32_t inc = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= (uint32_t)o) inc ^= t;
+                }
+                const uint32_t before = pxor[p] ^ inc ^ run;
+                uint32_t acc = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc += (uint32_t)i < cnt ? (y[i] ^ before) + 128u : 0u;
+                    y[i] = acc;
+                }
+                uint32_t sinc = acc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, sinc, o);
+                    if (lane >= (uint32_t)o) sinc += t;
+                }
+                const uint32_t base = psum[p] + sinc - acc;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] += base;
+            }
+            if (OUT_RAW) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if ((uint32_t)i < cnt) {
+                        uint8_t* q = tb + ((lane * 8 + i) * ch + c) * BPS;
+#pragma unroll
+                        for (int bb = 0; bb < BPS; ++bb) q[bb] = (uint8_t)(y[i] >> (8 * bb));
+                    }
+            } else {
+                int32_t* w = dst_words + (size_t)f * s.N + (size_t)c * ns + s0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if ((uint32_t)i < cnt) w[i] = (int32_t)y[i];
+            }
+        }
+        if (OUT_RAW) {
+            __syncthreads();
+            copy_smem_to_global(dst_raw + (size_t)f * s.frame_bytes + (size_t)j * kPiece * row, tile, 0, tsv * row);
+            __syncthreads();
+        }
+    }
+}
+
+// int32 words [ch][ns] -> interleaved little-endian samples; one CTA per (frame, 256-sample tile)
+template <int BPS>
+__global__ void __launch_bounds__(256) k_words_to_raw(const int32_t* __restrict__ words, Shape s, uint32_t tiles,
+                                                       uint8_t* __restrict__ dst)
+{
+    extern __shared__ __align__(16) uint32_t sm32[];
+    uint8_t* tb = reinterpret_cast<uint8_t*>(sm32);
+    const uint32_t f = blockIdx.x / tiles, j = blockIdx.x % tiles;
+    const uint32_t ns = (uint32_t)s.ns, ch = (uint32_t)s.ch, row = ch * BPS;
+    const uint32_t s0 = j * kPiece, tsv = min((uint32_t)kPiece, ns - s0);
+    const int32_t* w = words + (size_t)f * s.N;
+    for (uint32_t e = threadIdx.x; e < tsv * ch; e += blockDim.x) {
+        const uint32_t c = e / tsv, i = e % tsv;
+        const uint32_t v = (uint32_t)w[(size_t)c * ns + s0 + i];
+        uint8_t* q = tb + (i * ch + c) * BPS;
+#pragma unroll
+        for (int bb = 0; bb < BPS; ++bb) q[bb] = (uint8_t)(v >> (8 * bb));
+    }
+    __syncthreads();
+    copy_smem_to_global(dst + (size_t)f * s.frame_bytes + (size_t)s0 * row, sm32, 0, tsv * row);
+}
+
+// interleaved samples -> int32 words [ch][ns] (+ per-channel sums for the mean); one CTA per
+// (frame, sample tile)
+template <int BPS>
+__global__ void __launch_bounds__(256) k_raw_to_words(const uint8_t* __restrict__ src, Shape s, uint32_t tiles,
+                                                       int32_t* __restrict__ words, long long* __restrict__ sums)
+{
+    extern __shared__ __align__(16) uint8_t sm[];
+    const uint32_t f = blockIdx.x / tiles, j = blockIdx.x % tiles;
+    const uint32_t ns = (uint32_t)s.ns, ch = (uint32_t)s.ch, row = ch * BPS;
+    const uint32_t s0 = j * kPiece, tsv = min((uint32_t)kPiece, ns - s0);
+    const uint32_t phase = tile_load(sm, src + (size_t)f * s.frame_bytes + (size_t)s0 * row, tsv * row);
+    __syncthreads();
+    int32_t* w = words + (size_t)f * s.N;
+    // a warp takes one channel at a time so that its partial sum needs one atomic
+    for (uint32_t c = warp_id(); c < ch; c += (blockDim.x >> 5)) {
+        long long acc = 0;
+        for (uint32_t i = lane_id(); i < tsv; i += 32) {
+            const int32_t v = load_sample<BPS>(sm + phase + (i * ch + c) * BPS);
+            w[(size_t)c * ns + s0 + i] = v;
+            acc += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        if (lane_id() == 0) atomicAdd(reinterpret_cast<unsigned long long*>(sums + (size_t)f * ch + c), (unsigned long long)acc);
+    }
+}
+
+// flat int32 words -> byte planes with the delta / offset / xor stencil (dct coefficients,
+// signal_packer_dct.cpp:117-119); one CTA per (frame, 1024-element chunk)
+__global__ void __launch_bounds__(256) k_words_stencil_planes(const int32_t* __restrict__ words, Shape s, uint32_t chunks,
+                                                               uint8_t* __restrict__ planes)
+{
+    const uint32_t f = blockIdx.x / chunks, cidx = blockIdx.x % chunks;
+    const int32_t* w = words + (size_t)f * s.N;
+    uint8_t* out = planes + (size_t)f * s.nb_alloc * s.plane_stride;
+    for (uint32_t i = cidx * 1024u + threadIdx.x; i < min(s.N, (cidx + 1) * 1024u); i += blockDim.x) {
+        const uint32_t x0 = (uint32_t)w[i], x1 = i >= 1 ? (uint32_t)w[i - 1] : 0u, x2 = i >= 2 ? (uint32_t)w[i - 2] : 0u;
+        const uint32_t d0 = x0 - x1 - 128u, d1 = i >= 1 ? x1 - x2 - 128u : 0u;
+        const uint32_t y = d0 ^ d1;
+        for (uint32_t k = 0; k < s.nb_alloc; ++k) out[(size_t)k * s.plane_stride + i] = (uint8_t)(y >> (8 * k));
+    }
+}
+
+}  // namespace rspt

@@ -1,0 +1,364 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, the committed golden vectors
+and -- where oracle/_ref/libref.so travelled with the repo -- the unmodified reference.
+Bit-exact for everything integer; stated tolerances for the dct packer.  Needs a B200."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+torch = pytest.importorskip("torch")
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def R():
+    import rspt_b200
+    from rspt_b200 import packer
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return packer
+
+
+def to_dev(a):
+    return torch.from_numpy(np.array(a, dtype=np.uint8, copy=True).reshape(-1)).cuda()
+
+
+def make_raw(rng, bps, ch, ns, amp=None, kind="walk"):
+    amp = amp or (1 << min(8 * bps - 2, 14))
+    if kind == "walk":
+        x = np.cumsum(rng.integers(-amp // 16 - 1, amp // 16 + 2, (ns, ch)), axis=0)
+    else:
+        x = rng.integers(-amp, amp, (ns, ch))
+    x = np.clip(x, -(1 << (8 * bps - 1)), (1 << (8 * bps - 1)) - 1).astype(np.int32)
+    return x.astype("<i4").view(np.uint8).reshape(ns, ch, 4)[:, :, :bps].copy().reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_synth_generator_matches_cpu(R, oracle):
+    for (first, n, bps, ch, ns) in [(0, 3, 3, 12, 8192), (7, 2, 4, 12, 4096), (1000000, 3, 2, 5, 1000), (3, 2, 1, 1, 77)]:
+        amp = 20000 if bps >= 3 else (100 if bps == 1 else 5000)
+        g = R.synth_ecg(first, n, bps, ch, ns, amplitude=amp).cpu().numpy()
+        c = oracle.synth_ecg(first, n, bps, ch, ns, amplitude=amp).reshape(-1)
+        assert np.array_equal(g, c), (first, n, bps, ch, ns)
+
+
+def test_crc32c_kernel(R, oracle):
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 7, 8, 9, 11, 12, 63, 64, 65, 1000, 4097, 65535, 65536):
+        buf = rng.integers(0, 256, n, dtype=np.uint8)
+        assert R.crc32c(buf) == oracle.crc32c(buf), n
+    assert R.crc32c(np.frombuffer(b"123456789", np.uint8)) == 0xE3069283
+
+
+def _hzr_buffers(rng):
+    out = []
+    for n in (1, 2, 3, 7, 22, 23, 278, 279, 1000, 16662, 16663, 33324, 40000, 65535, 65536):
+        out.append(np.zeros(n, np.uint8))
+        out.append(rng.integers(0, 256, n, dtype=np.uint8))
+        out.append(rng.integers(0, 4, n, dtype=np.uint8))
+        sp = np.zeros(n, np.uint8)
+        k = max(1, n // 50)
+        sp[rng.integers(0, n, k)] = rng.integers(1, 256, k, dtype=np.uint8)
+        out.append(sp)
+        out.append(np.clip(np.rint(rng.laplace(0, 6, n)), -120, 120).astype(np.int8).view(np.uint8))
+        out.append(np.full(n, 255, np.uint8))
+        z = np.zeros(n, np.uint8)
+        z[-1] = 9
+        out.append(z)
+        z = np.zeros(n, np.uint8)
+        z[0] = 9
+        out.append(z)
+    for p in (0.5, 0.9, 0.99):
+        out.append((rng.random(65536) < p).astype(np.uint8) * 3 + 1)
+    out.append(rng.integers(0, 200, 65536, dtype=np.uint8))
+    out.append(np.tile(np.arange(256, dtype=np.uint8), 256))          # every count equal: tie-breaking
+    out.append(np.repeat(np.arange(1, 24, dtype=np.uint8), [2 ** min(i, 11) for i in range(23)])[:65536])
+    return out
+
+
+def test_hzr_histogram_tree_and_plan(R, oracle):
+    """Per-block stages: token histogram, non-canonical Huffman codes, mode + payload size."""
+    p = R.SignalPacker.new_hzr(1, 1, 65536, max_batch_frames=1)
+    rng = np.random.default_rng(7)
+    for buf in _hzr_buffers(rng):
+        hist, codes, info = p.debug_hzr_tables(buf)
+        want_hist = oracle.hzr_histogram(buf)
+        assert np.array_equal(hist, want_hist), buf.size
+        mode, plen = oracle.hzr_block_plan(buf)
+        assert (int(info[0]), int(info[1])) == (mode, plen), (buf.size, info, mode, plen)
+        if mode == 1:
+            n_used, code, ln, tree, tree_nbits = oracle.hzr_build_codes(want_hist)
+            used = want_hist > 0
+            assert np.array_equal(codes[used] & 0x07FFFFFF, code[used])
+            assert np.array_equal(codes[used] >> 27, ln[used])
+            assert int(info[2]) == tree_nbits and int(info[3]) == n_used
+
+
+PLANE_CASES = [
+    ("xdelta_hzr", 3, 12, 8192, 3), ("xdelta_hzr", 4, 12, 4096, 3), ("xdelta_hzr", 2, 5, 1000, 2),
+    ("xdelta_hzr", 1, 3, 700, 1), ("xdelta_hzr", 4, 1, 8192, 4), ("xdelta_hzr", 3, 2, 1, 3),
+    ("xdelta_hzr", 4, 3, 2, 3), ("xdelta_hzr", 3, 7, 33, 3),
+    ("hzr", 3, 12, 8192, 0), ("hzr", 1, 2, 999, 0), ("hzr", 4, 3, 5000, 0),
+    ("hadamard", 4, 12, 4096, 0), ("hadamard", 3, 3, 16384, 0), ("hadamard", 2, 2, 8, 0), ("hadamard", 1, 1, 32768, 0),
+]
+
+
+@pytest.mark.parametrize("kind,bps,ch,ns,nb", PLANE_CASES)
+def test_transform_planes_bit_exact(R, oracle, kind, bps, ch, ns, nb):
+    """Stage 1 (de-interleave, delta/offset/xor or FWHT+quantise, plane split) against the oracle's words."""
+    rng = np.random.default_rng(ns * 7 + ch)
+    nfr = 3
+    raws = [make_raw(rng, bps, ch, ns, kind="walk" if i else "noise") for i in range(nfr)]
+    p = R.SignalPacker(kind, bps, ch, ns, nb or 3, max_batch_frames=nfr)
+    planes, hdr = p.debug_planes(to_dev(np.concatenate(raws)))
+    o = oracle.OraclePacker(kind, bps, ch, ns, nb or 3)
+    for i, raw in enumerate(raws):
+        words, header = o.transform(raw)
+        for k in range(planes.shape[1]):
+            want = ((words.view(np.uint32) >> (8 * k)) & 0xFF).astype(np.uint8)
+            assert np.array_equal(planes[i, k], want), (kind, i, k)
+        if o.header_bytes:
+            assert np.array_equal(hdr[i], header)
+
+
+STREAM_CASES = [
+    ("xdelta_hzr", 3, 12, 8192, 3, 4), ("xdelta_hzr", 4, 12, 4096, 3, 3), ("xdelta_hzr", 4, 1, 8192, 3, 2),
+    ("xdelta_hzr", 2, 5, 1000, 2, 5), ("xdelta_hzr", 1, 3, 700, 1, 3), ("xdelta_hzr", 3, 3, 20000, 3, 2),
+    ("xdelta_hzr", 4, 12, 16384, 3, 2), ("xdelta_hzr", 3, 2, 1, 3, 4), ("xdelta_hzr", 3, 7, 33, 3, 4),
+    ("xdelta_hzr", 4, 2, 70001, 4, 2),
+    ("hzr", 3, 12, 8192, 0, 3), ("hzr", 4, 12, 4096, 0, 2), ("hzr", 1, 2, 999, 0, 3), ("hzr", 2, 1, 140000, 0, 2),
+    ("hadamard", 4, 12, 4096, 0, 3), ("hadamard", 3, 3, 16384, 0, 2), ("hadamard", 2, 2, 8, 0, 3),
+]
+
+
+@pytest.mark.parametrize("kind,bps,ch,ns,nb,nfr", STREAM_CASES)
+def test_stream_bit_exact_and_round_trip(R, oracle, kind, bps, ch, ns, nb, nfr):
+    """Whole path: the concatenated frames equal the oracle's bytes; decode (indexed and serial)
+    restores the oracle's decode, which for the lossless packers is the input."""
+    rng = np.random.default_rng(ns + 13 * ch + bps)
+    fb = bps * ch * ns
+    if bps >= 2 and ns >= 64:
+        raws = oracle.synth_ecg(11, nfr, bps, ch, ns, amplitude=20000 if bps >= 3 else 3000)
+    else:
+        raws = np.stack([make_raw(rng, bps, ch, ns) for _ in range(nfr)])
+    raws[nfr - 1] = 0 if nfr > 2 else raws[nfr - 1]  # an all-zero frame: FILL blocks
+    p = R.SignalPacker(kind, bps, ch, ns, nb or 3, max_batch_frames=nfr)
+    batch = p.compress_batch(to_dev(raws))
+    torch.cuda.synchronize()
+    offs = batch.offsets.cpu().numpy()
+    stream = batch.stream.cpu().numpy()
+    o = oracle.OraclePacker(kind, bps, ch, ns, nb or 3)
+    want_dec = []
+    for i in range(nfr):
+        want = o.compress(raws[i])
+        got = stream[offs[i]:offs[i + 1]].tobytes()
+        assert len(got) == len(want), (kind, i, len(got), len(want))
+        assert got == want, (kind, i)
+        want_dec.append(np.frombuffer(o.decompress(want)[0], np.uint8))
+    assert np.array_equal(batch.frame_nb.cpu().numpy(), np.full(nfr, o.nb, np.uint8))
+    want_dec = np.stack(want_dec)
+    if kind in ("xdelta_hzr", "hzr"):
+        assert np.array_equal(want_dec, raws.reshape(nfr, fb))
+    for use_sc in (True, False):
+        status = torch.full((nfr,), 7, dtype=torch.int32, device="cuda")
+        dec = p.decompress_batch(batch, status=status, use_sidecar=use_sc)
+        torch.cuda.synchronize()
+        assert not status.cpu().numpy().any()
+        assert np.array_equal(dec.cpu().numpy().reshape(nfr, fb), want_dec), (kind, use_sc)
+    c = p.counters()
+    assert c["frames_compressed"] == nfr and c["frames_decompressed"] == 2 * nfr
+    assert c["compressed_bytes_out"] == offs[nfr]
+    assert c["blocks_copy"] + c["blocks_huff"] + c["blocks_fill"] == nfr * o.nb * ((ch * ns + 65535) // 65536)
+
+
+def test_golden_vectors(R, golden, golden_inputs):
+    """The committed vectors produced by the unmodified reference (tests/golden/make_golden.py)."""
+    for case in golden["cases"]:
+        kind, bps, ch, ns = case["kind"], case["bps"], case["ch"], case["ns"]
+        fb = bps * ch * ns
+        data = golden_inputs[case["input"]]
+        nfr = len(case["frames"])
+        if kind == "dct":
+            os.environ["RSPT_DCT_DIRECT"] = "1"  # the bit-exact path; the fast path has its own test
+        try:
+            p = R.SignalPacker(kind, bps, ch, ns, case["nb"] or 3, max_batch_frames=nfr)
+        finally:
+            os.environ.pop("RSPT_DCT_DIRECT", None)
+        batch = p.compress_batch(to_dev(data[: nfr * fb]))
+        torch.cuda.synchronize()
+        offs = batch.offsets.cpu().numpy()
+        stream = batch.stream.cpu().numpy()
+        dec = p.decompress_batch(batch).cpu().numpy().reshape(nfr, fb)
+        for i, want in enumerate(case["frames"]):
+            got = stream[offs[i]:offs[i + 1]]
+            assert len(got) == want["len"], (case["name"], i, len(got), want["len"])
+            assert sha(got) == want["sha256"], (case["name"], i)
+            assert sha(dec[i]) == want["dec_sha256"], (case["name"], i)
+        assert p.nb == case["final_nb"], case["name"]
+
+
+def test_xdelta_plane_escalation(R, oracle):
+    """nb < bps: the plane count is a sticky running max over frames, across batches
+    (signal_packer_xdelta_hzr.cpp:63-69)."""
+    rng = np.random.default_rng(3)
+    bps, ch, ns = 4, 3, 500
+    amps = [20, 20, 3000, 20, 20, 900000, 20, 20]
+    raws = np.stack([make_raw(rng, bps, ch, ns, amp=a, kind="noise") for a in amps])
+    p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 1, max_batch_frames=8)
+    o = oracle.OraclePacker("xdelta_hzr", bps, ch, ns, 1)
+    want_nb = []
+    want = []
+    for r in raws:
+        want.append(o.compress(r))
+        want_nb.append(o.nb)
+    got_nb = []
+    for lo, hi in ((0, 3), (3, 8)):  # two batches: the state must carry over
+        batch = p.compress_batch(to_dev(raws[lo:hi]))
+        torch.cuda.synchronize()
+        offs = batch.offsets.cpu().numpy()
+        stream = batch.stream.cpu().numpy()
+        for i in range(hi - lo):
+            assert stream[offs[i]:offs[i + 1]].tobytes() == want[lo + i], (lo, i)
+        got_nb += batch.frame_nb.cpu().numpy().tolist()
+        dec = p.decompress_batch(batch).cpu().numpy().reshape(hi - lo, -1)
+        assert np.array_equal(dec, raws[lo:hi].reshape(hi - lo, -1))
+    assert got_nb == want_nb and len(set(want_nb)) >= 3
+    assert p.nb == o.nb and p.counters()["escalations"] == o.escalations
+
+
+def test_host_api_single_frame_readme_example(R, oracle):
+    """The README / test_5 call sequence (rspt_test.cpp:225-256) through the host entry points."""
+    import math
+    import zlib
+    sine = np.array([int(math.sin(i / 100.0) * 1000.0) for i in range(8192)], np.int32).view(np.uint8)
+    c = R.SignalPacker.new_xdelta_hzr(4, 1, 8192, 3)
+    comp = c.compress(sine)
+    assert len(comp) == 2028 and "%08x" % zlib.crc32(comp) == "672647f0"
+    dec, used = c.decompress(comp)
+    assert used == 2028 and dec == sine.tobytes()
+
+
+def test_decodes_streams_from_cpu_reference(R, oracle):
+    """Interop: frames written by the CPU side (no decode index) are decoded on the GPU."""
+    from conftest import has_ref
+    impl = "reference" if has_ref() else "port"
+    for kind, bps, ch, ns in (("xdelta_hzr", 3, 12, 8192), ("hzr", 3, 3, 5000), ("hadamard", 4, 4, 4096)):
+        raws = oracle.synth_ecg(0, 3, bps, ch, ns)
+        cpu = oracle.make_packer(kind, bps, ch, ns, 3, impl)
+        frames = [cpu.compress(r) for r in raws]
+        offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+        p = R.SignalPacker(kind, bps, ch, ns, 3, max_batch_frames=3)
+        dec, status = p.decompress_stream(b"".join(frames), offs)
+        assert not status.any()
+        for i, f in enumerate(frames):
+            assert dec[i].tobytes() == cpu.decompress(f)[0]
+
+
+def test_corrupt_stream_is_reported_not_silent(R, oracle):
+    raws = oracle.synth_ecg(0, 2, 3, 4, 2048)
+    cpu = oracle.OraclePacker("xdelta_hzr", 3, 4, 2048, 3)
+    frames = [bytearray(cpu.compress(r)) for r in raws]
+    frames[1][0] = 9            # bad method byte
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+    p = R.SignalPacker.new_xdelta_hzr(3, 4, 2048, 3, max_batch_frames=2)
+    dec, status = p.decompress_stream(b"".join(bytes(f) for f in frames), offs)
+    assert status[0] == 0 and status[1] != 0
+    assert dec[0].tobytes() == raws[0].tobytes()
+
+
+DCT_CASES = [(4, 12, 4096, 4), (3, 3, 4096, 2), (4, 2, 512, 6), (2, 3, 64, 4)]
+
+
+@pytest.mark.parametrize("bps,ch,ns,nfr", DCT_CASES)
+def test_dct_fast_path_tolerance(R, oracle, bps, ch, ns, nfr):
+    """dct, FFT-based FP64 path: quantised coefficients equal the reference's on >= 99.9 % of
+    values and never differ by more than 1 LSB; reconstruction PRDN within 0.01 percentage points."""
+    raws = oracle.synth_ecg(3, nfr, bps, ch, ns, amplitude=20000 if bps >= 3 else 3000)
+    fb = bps * ch * ns
+    p = R.SignalPacker.new_dct(bps, ch, ns, max_batch_frames=nfr)
+    batch = p.compress_batch(to_dev(raws))
+    dec = p.decompress_batch(batch).cpu().numpy().reshape(nfr, fb)
+    torch.cuda.synchronize()
+    offs = batch.offsets.cpu().numpy()
+    stream = batch.stream.cpu().numpy()
+    o = oracle.OraclePacker("dct", bps, ch, ns)
+    o2 = oracle.OraclePacker("dct", bps, ch, ns)
+    n_all = n_bad = 0
+    for i in range(nfr):
+        want = o.compress(raws[i])
+        got = stream[offs[i]:offs[i + 1]].tobytes()
+        # compare the coefficients both decoders reconstruct from the two streams
+        wd, _ = o.decompress(want)
+        gd, _ = o2.decompress(got)
+        # coefficient-level: undo the entropy coding only (oracle planes -> words) via transform()
+        ww, wh = o.transform(raws[i])
+        planes, gh = p.debug_planes(to_dev(raws[i]))
+        gw = (planes[0, 0].astype(np.uint32) | (planes[0, 1].astype(np.uint32) << 8))
+        diff = ((ww.view(np.uint32) & 0xFFFF) != gw)
+        n_all += diff.size
+        n_bad += int(diff.sum())
+        assert np.array_equal(gh[0], wh)                       # the means are integer: exact
+        prd_ref = oracle.prdn(raws[i], wd, bps, ch, ns)
+        prd_gpu = oracle.prdn(raws[i], dec[i], bps, ch, ns)
+        assert abs(prd_ref - prd_gpu) < 0.01, (prd_ref, prd_gpu)
+        d = np.frombuffer(wd, np.uint8).astype(np.int64) - dec[i].astype(np.int64)
+    # a differing coefficient perturbs the xor/delta-coded neighbours too, hence the loose word bound
+    assert n_bad <= max(3, n_all // 1000), (n_bad, n_all)
+
+
+def test_dct_direct_path_bit_exact(R, oracle):
+    """dct, O(n^2) path with the reference's float-product / double-accumulate arithmetic."""
+    os.environ["RSPT_DCT_DIRECT"] = "1"
+    try:
+        for bps, ch, ns in ((4, 3, 512), (3, 2, 300), (4, 2, 4096)):
+            raws = oracle.synth_ecg(1, 2, bps, ch, ns)
+            p = R.SignalPacker.new_dct(bps, ch, ns, max_batch_frames=2)
+            batch = p.compress_batch(to_dev(raws))
+            dec = p.decompress_batch(batch).cpu().numpy().reshape(2, -1)
+            offs = batch.offsets.cpu().numpy()
+            stream = batch.stream.cpu().numpy()
+            o = oracle.OraclePacker("dct", bps, ch, ns)
+            for i in range(2):
+                want = o.compress(raws[i])
+                assert stream[offs[i]:offs[i + 1]].tobytes() == want, (bps, ch, ns, i)
+                assert dec[i].tobytes() == o.decompress(want)[0]
+    finally:
+        os.environ.pop("RSPT_DCT_DIRECT", None)
+
+
+def test_prdn_kernel(R, oracle):
+    raws = oracle.synth_ecg(0, 2, 4, 12, 4096)
+    p = R.SignalPacker.new_hadamard(4, 12, 4096, max_batch_frames=2)
+    d = to_dev(raws)
+    dec = p.decompress_batch(p.compress_batch(d))
+    torch.cuda.synchronize()
+    got = R.prdn(d, dec, 2, 4, 12, 4096)
+    # oracle: same formula over both frames
+    o = oracle.OraclePacker("hadamard", 4, 12, 4096)
+    both = np.concatenate([np.frombuffer(o.decompress(o.compress(r))[0], np.uint8) for r in raws])
+    a = raws.reshape(-1).view("<i4").reshape(2, 4096, 12).astype(np.float64)
+    b = both.view("<i4").reshape(2, 4096, 12).astype(np.float64)
+    mean = np.floor(a.sum(axis=1, keepdims=True) / 4096)
+    want = np.sqrt(((a - b) ** 2).sum() / ((a - mean) ** 2).sum()) * 100
+    assert abs(got - want) < 1e-9 * max(1.0, want)
+
+
+def test_large_batch_round_trip_property(R):
+    """BASELINE config 2 shape at a batch big enough to fill the GPU: size-independent checks --
+    encode -> decode is the identity, offsets are a strictly increasing scan, CR is sane."""
+    bps, ch, ns, nfr = 3, 12, 8192, 2048
+    p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 3, max_batch_frames=nfr)
+    raw = R.synth_ecg(0, nfr, bps, ch, ns)
+    batch = p.compress_batch(raw)
+    dec = p.decompress_batch(batch)
+    torch.cuda.synchronize()
+    assert torch.equal(raw, dec)
+    offs = batch.offsets.cpu().numpy()
+    assert offs[0] == 0 and np.all(np.diff(offs) > 0)
+    cr = raw.numel() / offs[-1]
+    assert 2.5 < cr < 5.0, cr
