@@ -190,6 +190,47 @@ __device__ __forceinline__ void walk_strip(const uint32_t (&w)[16], int valid, u
     if (last_strip && zrun) emit_run(zrun, sink);
 }
 
+// ---- shared-memory staging of a whole block ---------------------------------------------------
+// The block's bytes live in shared memory as 16-word strips; word j of strip t is stored at
+// t*16 + (j ^ ((t >> 1) & 15)) so that the 32 lanes of a warp, each reading word j of its own
+// strip, hit 32 different banks.
+__device__ __forceinline__ uint32_t strip_word_index(uint32_t t, uint32_t j) { return (t << 4) | (j ^ ((t >> 1) & 15u)); }
+
+// Walk of one staged strip.  `valid` bytes are meaningful; the rest of the strip is zero.
+template <class Sink>
+__device__ __forceinline__ void walk_strip_staged(const uint32_t* in_sw, uint32_t t, int valid, uint32_t carry,
+                                                  bool last_strip, Sink& sink)
+{
+    uint32_t zrun = carry;
+    const uint32_t base = t << 4, sw = (t >> 1) & 15u;
+    const int nwords = (valid + 3) >> 2;
+#pragma unroll 1
+    for (int j = 0; j < nwords; ++j) {
+        const uint32_t x = in_sw[base | ((uint32_t)j ^ sw)];
+        const int nbv = valid - 4 * j;
+        if (x == 0) {
+            zrun += nbv >= 4 ? 4u : (uint32_t)nbv;
+            continue;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (b < nbv) {
+                const uint32_t v = (x >> (8 * b)) & 0xFFu;
+                if (v) {
+                    if (zrun) {
+                        emit_run(zrun, sink);
+                        zrun = 0;
+                    }
+                    sink.token(v, 0u, 0u);
+                } else {
+                    ++zrun;
+                }
+            }
+        }
+    }
+    if (last_strip && zrun) emit_run(zrun, sink);
+}
+
 // ---- block-wide exclusive scan of one uint32 per thread (blockDim.x multiple of 32, <= 1024)
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /*[33]*/, uint32_t* total)
 {
@@ -216,6 +257,35 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     __syncthreads();
     if (total) *total = s_warp[32];
     return s_warp[wid] + inc - v;
+}
+
+// Load block [src, src+n) into swizzled shared memory (thread t <-> strip t; blockDim.x must be
+// >= the number of strips), compute every strip's pending zero run and the compact list of
+// strips that own at least one token.  Returns this thread's position-independent facts through
+// s_carry / s_list and the number of active strips.  Ends with a __syncthreads().
+__device__ __forceinline__ uint32_t stage_block(const uint8_t* __restrict__ src, uint32_t n, uint32_t* in_sw,
+                                                uint16_t* s_carry, uint16_t* s_list, uint32_t* s_wtz, uint32_t* s_waz,
+                                                uint32_t* s_scan)
+{
+    const uint32_t t = threadIdx.x;
+    const uint32_t nstrips = (n + kStrip - 1) / kStrip;
+    uint32_t w[16];
+    const int valid = load_strip(src, n, t, w);
+    const uint32_t tz = strip_trailing_zeros(w);
+    if (t < nstrips) {
+        const uint32_t sw = (t >> 1) & 15u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) in_sw[(t << 4) | ((uint32_t)j ^ sw)] = w[j];
+    }
+    const uint32_t carry = strip_carry_in(tz, tz == 64, s_wtz, s_waz);
+    const bool last = t + 1 == nstrips;
+    const bool active = valid > 0 && (tz != 64 || last);
+    uint32_t n_active;
+    const uint32_t pos = block_exclusive_scan(active ? 1u : 0u, s_scan, &n_active);
+    if (active) s_list[pos] = (uint16_t)t;
+    if (t < nstrips) s_carry[t] = (uint16_t)carry;
+    __syncthreads();
+    return n_active;
 }
 
 #define RSPT_CUDA_CHECK(call)                                      \

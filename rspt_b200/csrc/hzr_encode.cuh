@@ -98,12 +98,16 @@ struct HistSink {
     __device__ __forceinline__ void token(uint32_t sym, uint32_t, uint32_t) { atomicAdd(&sh[sym], 1u); }
 };
 
+constexpr size_t kStageSmem = (size_t)kBlock;  // swizzled copy of one block
+
 __global__ void __launch_bounds__(1024) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
                                                     const uint8_t* __restrict__ frame_nb,
                                                     uint32_t* __restrict__ hist)
 {
+    extern __shared__ __align__(16) uint32_t in_sw[];
     __shared__ uint32_t sh[kSymStride];
-    __shared__ uint32_t s_wtz[32], s_waz[32];
+    __shared__ uint16_t s_carry[1024], s_list[1024];
+    __shared__ uint32_t s_wtz[32], s_waz[32], s_scan[33];
     uint32_t f, k, b;
     const uint32_t blk = blockIdx.x;
     blk_decode(s, blk, f, k, b);
@@ -111,17 +115,12 @@ __global__ void __launch_bounds__(1024) k_hzr_hist(const uint8_t* __restrict__ p
     const uint32_t n = blk_len(s, b);
     for (uint32_t i = threadIdx.x; i < kSymStride; i += blockDim.x) sh[i] = 0;
     const uint32_t nstrips = (n + kStrip - 1) / kStrip;
-    uint32_t w[16];
-    const uint8_t* src = blk_ptr(planes, s, f, k, b);
-    for (uint32_t base = 0; base < nstrips; base += blockDim.x) {
-        // (blocks are at most 1024 strips, so with blockDim.x == 1024 this loop runs once;
-        // narrower CTAs are used for small shapes and also run it once)
-        const uint32_t t = base + threadIdx.x;
-        const int valid = load_strip(src, n, t, w);
-        const uint32_t tz = strip_trailing_zeros(w);
-        const uint32_t carry = strip_carry_in(tz, tz == 64, s_wtz, s_waz);
+    const uint32_t n_active = stage_block(blk_ptr(planes, s, f, k, b), n, in_sw, s_carry, s_list, s_wtz, s_waz, s_scan);
+    if (threadIdx.x < n_active) {
+        const uint32_t t = s_list[threadIdx.x];
+        const int valid = (int)min((uint32_t)kStrip, n - t * kStrip);
         HistSink sink{sh};
-        if (valid > 0 && !(tz == 64 && t != nstrips - 1)) walk_strip(w, valid, carry, t == nstrips - 1, sink);
+        walk_strip_staged(in_sw, t, valid, s_carry[t], t + 1 == nstrips, sink);
     }
     __syncthreads();
     uint32_t* out = hist + (size_t)blk * kSymStride;
@@ -401,14 +400,22 @@ __device__ __forceinline__ uint32_t chunk_bytes(const BlkInfo* info, const Shape
     return sz;
 }
 
+// per frame: total size and the byte offset (from the frame start) of every block's 7-byte header
 __global__ void k_frame_sizes(const BlkInfo* __restrict__ info, Shape s, const uint8_t* __restrict__ frame_nb,
-                              uint32_t n_frames, uint32_t* __restrict__ sizes)
+                              uint32_t n_frames, uint32_t* __restrict__ sizes, uint32_t* __restrict__ blk_off)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     uint32_t sz = 1 + s.hdr_bytes;  // method byte + header (signal_packer_base.cpp:83-91)
     const uint32_t nb = frame_nb[f];
-    for (uint32_t k = 0; k < nb; ++k) sz += 4u + chunk_bytes(info, s, f, k);  // len:u32 + stream (:78)
+    for (uint32_t k = 0; k < nb; ++k) {
+        sz += 8;  // chunk len:u32 (:78) + hzr decoded size:u32 (hzr_encode.c:521)
+        const size_t row = ((size_t)f * s.nb_alloc + k) * s.nblk;
+        for (uint32_t b = 0; b < s.nblk; ++b) {
+            blk_off[row + b] = sz;
+            sz += 7u + info[row + b].payload_len;
+        }
+    }
     sizes[f] = sz;
 }
 
@@ -458,8 +465,6 @@ __global__ void __launch_bounds__(1024) k_scan_offsets(const uint32_t* __restric
 // taken from the staged payload and the whole thing is copied to its final, arbitrarily
 // aligned position in the output stream.
 // ------------------------------------------------------------------------------------------
-constexpr size_t kEncodeSmem = (size_t)(4 + kBlock / 4 + 2) * 4;
-
 struct LenSink {
     const uint32_t* sc;
     uint32_t bits;
@@ -520,9 +525,13 @@ __device__ __forceinline__ void copy_smem_to_global(uint8_t* __restrict__ dst, c
     if (threadIdx.x < len - done) dst[done + threadIdx.x] = sb[soff + done + threadIdx.x];
 }
 
+constexpr uint32_t kStgWords = 4 + kBlock / 4 + 2;
+constexpr size_t kEncodeSmem = kStageSmem + (size_t)kStgWords * 4;
+
 __global__ void __launch_bounds__(1024, 1) k_hzr_encode(const uint8_t* __restrict__ planes, Shape s,
                                                          const uint8_t* __restrict__ frame_nb,
                                                          const BlkInfo* __restrict__ info,
+                                                         const uint32_t* __restrict__ blk_off,
                                                          const uint32_t* __restrict__ codes,
                                                          const uint32_t* __restrict__ tree,
                                                          const uint64_t* __restrict__ offsets,
@@ -531,11 +540,14 @@ __global__ void __launch_bounds__(1024, 1) k_hzr_encode(const uint8_t* __restric
                                                          uint8_t* __restrict__ dst,
                                                          uint32_t* __restrict__ sc_bit, uint16_t* __restrict__ sc_carry)
 {
-    extern __shared__ __align__(16) uint32_t stg[];  // [4 + 16384 + 2] staging words
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* in_sw = smem;                      // [16384] staged input block
+    uint32_t* stg = smem + kBlock / 4;           // [kStgWords] output: header at bytes 9..15, payload at 16
     __shared__ uint32_t s_codes[kSymStride];
     __shared__ uint32_t s_zt[1024];
+    __shared__ uint32_t s_bits[1024];
+    __shared__ uint16_t s_carry[1024], s_list[1024];
     __shared__ uint32_t s_wtz[32], s_waz[32], s_scan[33], s_red[33];
-    __shared__ unsigned long long s_dst;
 
     uint32_t f, k, b;
     const uint32_t blk = blockIdx.x;
@@ -545,48 +557,42 @@ __global__ void __launch_bounds__(1024, 1) k_hzr_encode(const uint8_t* __restric
     const uint32_t n = blk_len(s, b);
     const BlkInfo bi = info[blk];
     const uint32_t tid = threadIdx.x;
+    const unsigned long long frame_off = offsets[f];
+    uint8_t* out = dst + frame_off + blk_off[blk];
 
-    // position of this block inside the output; frame / chunk framing written by the CTA that
-    // owns the first block (signal_packer_base.cpp:78,83-95; hzr_encode.c:521)
-    if (tid == 0) {
-        unsigned long long pos = offsets[f] + 1 + s.hdr_bytes;
-        for (uint32_t kk = 0; kk < k; ++kk) pos += 4u + chunk_bytes(info, s, f, kk);
-        const BlkInfo* row = info + ((size_t)f * s.nb_alloc + k) * s.nblk;
-        if (b == 0) {
-            const uint32_t clen = chunk_bytes(info, s, f, k);
-            uint8_t* q = dst + pos;
+    // frame / chunk framing, written by the CTA that owns the chunk's first block
+    // (signal_packer_base.cpp:78,83-95; hzr_encode.c:521)
+    if (b == 0) {
+        if (tid == 0) {
+            uint32_t clen = 4;
+            const size_t row = ((size_t)f * s.nb_alloc + k) * s.nblk;
+            for (uint32_t bb = 0; bb < s.nblk; ++bb) clen += 7u + info[row + bb].payload_len;
+            uint8_t* q = out - 8;
             q[0] = (uint8_t)clen; q[1] = (uint8_t)(clen >> 8); q[2] = (uint8_t)(clen >> 16); q[3] = (uint8_t)(clen >> 24);
             q[4] = (uint8_t)s.N; q[5] = (uint8_t)(s.N >> 8); q[6] = (uint8_t)(s.N >> 16); q[7] = (uint8_t)(s.N >> 24);
-            if (k == 0) dst[offsets[f]] = (uint8_t)s.method;
+            if (k == 0) dst[frame_off] = (uint8_t)s.method;
         }
-        pos += 8;
-        for (uint32_t bb = 0; bb < b; ++bb) pos += 7u + row[bb].payload_len;
-        s_dst = pos;
+        if (k == 0)
+            for (uint32_t i = tid; i < s.hdr_bytes; i += blockDim.x) dst[frame_off + 1 + i] = headers[(size_t)f * s.hdr_bytes + i];
     }
-    if (k == 0 && b == 0 && s.hdr_bytes) {
-        for (uint32_t i = tid; i < s.hdr_bytes; i += blockDim.x)
-            dst[offsets[f] + 1 + i] = headers[(size_t)f * s.hdr_bytes + i];
-    }
-    for (uint32_t i = tid; i < 1024; i += blockDim.x) s_zt[i] = __ldg(&cc->zt[zt_sel][0][0] + i);
-
-    const uint8_t* src = blk_ptr(planes, s, f, k, b);
-    uint8_t* sbytes = reinterpret_cast<uint8_t*>(stg);
 
     if (bi.mode == MODE_FILL) {
-        __syncthreads();
         if (tid == 0) {
             const uint32_t crc = ~(0x00FFFFFFu ^ __ldg(&cc->byte_tab[0xFFu ^ bi.fill]));
-            uint8_t* q = dst + s_dst;
-            q[0] = 0; q[1] = 0;
-            q[2] = (uint8_t)crc; q[3] = (uint8_t)(crc >> 8); q[4] = (uint8_t)(crc >> 16); q[5] = (uint8_t)(crc >> 24);
-            q[6] = MODE_FILL;
-            q[7] = bi.fill;
+            out[0] = 0; out[1] = 0;
+            out[2] = (uint8_t)crc; out[3] = (uint8_t)(crc >> 8); out[4] = (uint8_t)(crc >> 16); out[5] = (uint8_t)(crc >> 24);
+            out[6] = MODE_FILL;
+            out[7] = bi.fill;
         }
         return;
     }
 
+    for (uint32_t i = tid; i < 1024; i += blockDim.x) s_zt[i] = __ldg(&cc->zt[zt_sel][0][0] + i);
+    const uint8_t* src = blk_ptr(planes, s, f, k, b);
+    uint8_t* sbytes = reinterpret_cast<uint8_t*>(stg);
     const uint32_t plen = bi.payload_len;
-    uint32_t* pay = stg + 4;  // payload words (byte 16 of the staging area; header at bytes 9..15)
+    uint32_t* pay = stg + 4;
+
     if (bi.mode == MODE_COPY) {
         // raw plane bytes are the payload (PlainCopy); rows are 16-byte aligned
         const uint4* s4 = reinterpret_cast<const uint4*>(src);
@@ -594,28 +600,35 @@ __global__ void __launch_bounds__(1024, 1) k_hzr_encode(const uint8_t* __restric
         for (uint32_t i = tid; i < (n + 15) / 16; i += blockDim.x) d4[i] = __ldg(s4 + i);
         __syncthreads();
     } else {
-        for (uint32_t i = tid; i < kSymStride; i += blockDim.x)
-            s_codes[i] = __ldg(codes + (size_t)blk * kSymStride + i);
+        for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_codes[i] = __ldg(codes + (size_t)blk * kSymStride + i);
         const uint32_t tw = (bi.tree_nbits + 31u) >> 5, pw = (plen + 3u) >> 2;
-        for (uint32_t i = tid; i < pw + 1; i += blockDim.x)
-            pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
+        for (uint32_t i = tid; i < pw + 1; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
+        s_bits[tid] = 0;
         const uint32_t nstrips = (n + kStrip - 1) / kStrip;
-        uint32_t w[16];
-        const int valid = load_strip(src, n, tid, w);
-        const uint32_t tz = strip_trailing_zeros(w);
-        const uint32_t carry = strip_carry_in(tz, tz == 64, s_wtz, s_waz);  // (syncs: tables + staging ready)
-        const bool last = tid == nstrips - 1;
-        const bool work = valid > 0 && !(tz == 64 && !last);
-        LenSink ls{s_codes, 0};
-        if (work) walk_strip(w, valid, carry, last, ls);
-        const uint32_t off = bi.tree_nbits + block_exclusive_scan(ls.bits, s_scan, nullptr);
+        const uint32_t n_active = stage_block(src, n, in_sw, s_carry, s_list, s_wtz, s_waz, s_scan);
+        uint32_t t = 0, carry = 0;
+        int valid = 0;
+        if (tid < n_active) {
+            t = s_list[tid];
+            carry = s_carry[t];
+            valid = (int)min((uint32_t)kStrip, n - t * kStrip);
+            LenSink ls{s_codes, 0};
+            walk_strip_staged(in_sw, t, valid, carry, t + 1 == nstrips, ls);
+            s_bits[t] = ls.bits;
+        }
+        __syncthreads();
+        const uint32_t mine = s_bits[tid];
+        const uint32_t off = bi.tree_nbits + block_exclusive_scan(mine, s_scan, nullptr);
+        s_bits[tid] = off;  // (each thread rewrites only its own entry; the scan has synchronised)
         if (sc_bit && (tid % kSegStrips) == 0 && tid < nstrips) {
             sc_bit[(size_t)blk * kMaxSegs + tid / kSegStrips] = off;
-            sc_carry[(size_t)blk * kMaxSegs + tid / kSegStrips] = (uint16_t)carry;
+            sc_carry[(size_t)blk * kMaxSegs + tid / kSegStrips] = s_carry[tid];
         }
-        if (work && ls.bits) {
-            EmitSink es{s_codes, pay, 0ull, off & 31u, off >> 5, true};
-            walk_strip(w, valid, carry, last, es);
+        __syncthreads();
+        if (tid < n_active) {
+            const uint32_t o = s_bits[t];
+            EmitSink es{s_codes, pay, 0ull, o & 31u, o >> 5, true};
+            walk_strip_staged(in_sw, t, valid, carry, t + 1 == nstrips, es);
             es.finish();
         }
         __syncthreads();
@@ -627,7 +640,7 @@ __global__ void __launch_bounds__(1024, 1) k_hzr_encode(const uint8_t* __restric
         sbytes[15] = (uint8_t)bi.mode;
     }
     __syncthreads();
-    copy_smem_to_global(dst + s_dst, stg, 9, 7u + plen);
+    copy_smem_to_global(out, stg, 9, 7u + plen);
 }
 
 // stand-alone CRC-32C of a global buffer of <= 65536 bytes (tests / rspt_gpu_crc32c)

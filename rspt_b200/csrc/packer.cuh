@@ -20,6 +20,7 @@ struct rspt_gpu_packer {
     uint32_t enc_threads;  // CTA width of the strip kernels (128/256/512/1024)
     int zt_sel;
     bool can_escalate;     // xdelta_hzr with nb < bps
+    bool dct_direct;       // dct: O(n^2) bit-exact path (fixed at create time)
 
     // compress scratch
     uint8_t* d_planes;
@@ -32,6 +33,7 @@ struct rspt_gpu_packer {
     uint32_t* d_need;
     uint32_t* d_nb_state;
     uint32_t* d_sizes;
+    uint32_t* d_blk_off;   // per block: offset of its header from the frame start
     uint8_t* d_headers;
     int32_t* d_words;      // hadamard / dct: de-interleaved samples, then coefficients
     long long* d_sums;     // hadamard / dct: per (frame, channel) sample sums

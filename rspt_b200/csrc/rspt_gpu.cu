@@ -263,6 +263,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_need, F));
     A(dalloc(p->d_nb_state, 4));
     A(dalloc(p->d_sizes, F));
+    A(dalloc(p->d_blk_off, nblocks));
     A(dalloc(p->d_headers, F * (s.hdr_bytes ? s.hdr_bytes : 1)));
     A(dalloc(p->d_ctr, 1));
     A(dalloc(p->d_status_tmp, F));
@@ -272,6 +273,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
         A(dalloc(p->d_words, F * (size_t)s.N));
         A(dalloc(p->d_sums, F * (size_t)s.ch));
     }
+    p->dct_direct = kind == RSPT_DCT && dct_choose_direct((uint32_t)ns);
     if (e == cudaSuccess && kind == RSPT_DCT) e = dct_build_tables(p);
     const size_t maxc = rspt_gpu_max_compressed_size(p);
     A(dalloc(p->d_one_src, (size_t)s.frame_bytes));
@@ -285,6 +287,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_nb_state, &s.nb_init, 4, cudaMemcpyHostToDevice, p->stream);
     if (e == cudaSuccess) e = allow_smem(k_hzr_tree, kTreeWarps * sizeof(TreeSmem));
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_hist, kStageSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_decode, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_crc32c, kEncodeSmem);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
@@ -303,7 +306,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     DeviceGuard dg(p->device);
     cudaStreamSynchronize(p->stream);
     void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_children, p->d_info, p->d_frame_nb,
-                    p->d_need, p->d_nb_state, p->d_sizes, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
+                    p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
                     p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off};
     for (void* q : ptrs)
@@ -446,7 +449,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     }
     {
         StageTimer t(p, RSPT_STAGE_HIST);
-        k_hzr_hist<<<nblocks, p->enc_threads, 0, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist);
+        k_hzr_hist<<<nblocks, p->enc_threads, kStageSmem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist);
     }
     {
         StageTimer t(p, RSPT_STAGE_TREE);
@@ -456,14 +459,14 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     }
     {
         StageTimer t(p, RSPT_STAGE_LAYOUT);
-        k_frame_sizes<<<(unsigned)((F + 255) / 256), 256, 0, p->stream>>>(p->d_info, s, p->d_frame_nb, (uint32_t)F, p->d_sizes);
+        k_frame_sizes<<<(unsigned)((F + 255) / 256), 256, 0, p->stream>>>(p->d_info, s, p->d_frame_nb, (uint32_t)F, p->d_sizes, p->d_blk_off);
         k_scan_offsets<<<1, 1024, 0, p->stream>>>(p->d_sizes, (uint32_t)F, d_offsets, p->d_ctr, s.frame_bytes);
     }
     uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar);
     uint16_t* sc_carry = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
     {
         StageTimer t(p, RSPT_STAGE_ENCODE);
-        k_hzr_encode<<<nblocks, p->enc_threads, kEncodeSmem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_codes,
+        k_hzr_encode<<<nblocks, p->enc_threads, kEncodeSmem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off, p->d_codes,
                                                                            p->d_tree, d_offsets, p->d_headers, p->d_crc,
                                                                            p->zt_sel, d_dst, sc_bit, sc_carry);
     }
@@ -660,7 +663,7 @@ extern "C" int rspt_gpu_debug_hzr_tables(rspt_gpu_packer* p, const uint8_t* d_bl
     DeviceGuard dg(p->device);
     Shape s = p->s;
     s.N = (uint32_t)n; s.nblk = 1; s.nb_alloc = 1; s.plane_stride = (uint32_t)((n + 15) & ~(size_t)15);
-    k_hzr_hist<<<1, 1024, 0, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist);
+    k_hzr_hist<<<1, 1024, kStageSmem, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist);
     k_hzr_tree<<<1, 32 * kTreeWarps, kTreeWarps * sizeof(TreeSmem), p->stream>>>(p->d_hist, s, p->d_frame_nb, 1, p->d_codes,
                                                                                   p->d_tree, p->d_children, p->d_info, p->d_ctr);
     p->launches += 2;

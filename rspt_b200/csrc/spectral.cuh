@@ -229,9 +229,12 @@ __global__ void __launch_bounds__(256) k_dct_inv_direct(int32_t* __restrict__ wo
 }
 
 // ---- host side ----------------------------------------------------------------------------
-inline bool dct_use_direct(const rspt_gpu_packer* p)
+inline bool dct_use_direct(const rspt_gpu_packer* p) { return p->dct_direct; }
+
+// decided once, when the handle is created: non-power-of-two lengths need the direct path,
+// RSPT_DCT_DIRECT=1 requests it
+inline bool dct_choose_direct(uint32_t n)
 {
-    const uint32_t n = (uint32_t)p->s.ns;
     const char* e = getenv("RSPT_DCT_DIRECT");
     return (n & (n - 1)) != 0 || (e && e[0] == '1');
 }

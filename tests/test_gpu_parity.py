@@ -204,11 +204,20 @@ def test_golden_vectors(R, golden, golden_inputs):
 
 def test_xdelta_plane_escalation(R, oracle):
     """nb < bps: the plane count is a sticky running max over frames, across batches
-    (signal_packer_xdelta_hzr.cpp:63-69)."""
+    (signal_packer_xdelta_hzr.cpp:63-69).  Frames are built so that 1, then 2, 3 and 4 planes
+    are needed: a flat-order ramp with increments in [0, 200] keeps every post-xor word in int8."""
     rng = np.random.default_rng(3)
     bps, ch, ns = 4, 3, 500
-    amps = [20, 20, 3000, 20, 20, 900000, 20, 20]
-    raws = np.stack([make_raw(rng, bps, ch, ns, amp=a, kind="noise") for a in amps])
+
+    def ramp(maxinc, jump_at=None, jump=0):
+        inc = rng.integers(0, maxinc + 1, ch * ns).astype(np.int64)
+        if jump_at is not None:
+            inc[jump_at] += jump
+        x = np.cumsum(inc).reshape(ch, ns).T.astype(np.int32)      # flat (channel-major) order is monotone
+        return np.ascontiguousarray(x).astype("<i4").view(np.uint8).reshape(-1)
+
+    raws = np.stack([ramp(200), ramp(200), ramp(200, 700, 20000), ramp(200), ramp(200, 5, 3000000), ramp(100),
+                     ramp(200, 1499, 1 << 29), ramp(50)])
     p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 1, max_batch_frames=8)
     o = oracle.OraclePacker("xdelta_hzr", bps, ch, ns, 1)
     want_nb = []
@@ -216,6 +225,7 @@ def test_xdelta_plane_escalation(R, oracle):
     for r in raws:
         want.append(o.compress(r))
         want_nb.append(o.nb)
+    assert want_nb == [1, 1, 2, 2, 3, 3, 4, 4], want_nb
     got_nb = []
     for lo, hi in ((0, 3), (3, 8)):  # two batches: the state must carry over
         batch = p.compress_batch(to_dev(raws[lo:hi]))
@@ -227,8 +237,8 @@ def test_xdelta_plane_escalation(R, oracle):
         got_nb += batch.frame_nb.cpu().numpy().tolist()
         dec = p.decompress_batch(batch).cpu().numpy().reshape(hi - lo, -1)
         assert np.array_equal(dec, raws[lo:hi].reshape(hi - lo, -1))
-    assert got_nb == want_nb and len(set(want_nb)) >= 3
-    assert p.nb == o.nb and p.counters()["escalations"] == o.escalations
+    assert got_nb == want_nb
+    assert p.nb == o.nb == 4 and p.counters()["escalations"] == o.escalations == 3
 
 
 def test_host_api_single_frame_readme_example(R, oracle):
