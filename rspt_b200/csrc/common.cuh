@@ -197,6 +197,12 @@ __device__ __forceinline__ void walk_strip(const uint32_t (&w)[16], int valid, u
 __device__ __forceinline__ uint32_t strip_word_index(uint32_t t, uint32_t j) { return (t << 4) | (j ^ ((t >> 1) & 15u)); }
 
 // Walk of one staged strip.  `valid` bytes are meaningful; the rest of the strip is zero.
+// Fast path: a zero byte whose neighbours are non-zero is simply the literal token 0
+// (hzr_encode.c:152-153, run of one), so a word in which every byte is either non-zero or such
+// an isolated zero -- and no run is pending -- emits four tokens with no run bookkeeping.  In
+// dense planes that is ~99 % of the words, which keeps the warp converged; genuine runs
+// (two or more zeros, or a zero in the strip's last byte, whose run may continue in the next
+// strip) take the general path.
 template <class Sink>
 __device__ __forceinline__ void walk_strip_staged(const uint32_t* in_sw, uint32_t t, int valid, uint32_t carry,
                                                   bool last_strip, Sink& sink)
@@ -204,29 +210,40 @@ __device__ __forceinline__ void walk_strip_staged(const uint32_t* in_sw, uint32_
     uint32_t zrun = carry;
     const uint32_t base = t << 4, sw = (t >> 1) & 15u;
     const int nwords = (valid + 3) >> 2;
+    uint32_t x = in_sw[base | sw];  // word 0
 #pragma unroll 1
     for (int j = 0; j < nwords; ++j) {
-        const uint32_t x = in_sw[base | ((uint32_t)j ^ sw)];
+        const uint32_t xn = j + 1 < nwords ? in_sw[base | ((uint32_t)(j + 1) ^ sw)] : 0u;
         const int nbv = valid - 4 * j;
         if (x == 0) {
             zrun += nbv >= 4 ? 4u : (uint32_t)nbv;
-            continue;
-        }
+        } else {
+            const uint32_t nzf = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;  // bit 7 of every non-zero byte
+            const uint32_t nxt = (nzf >> 8) | ((xn & 0xFFu) ? 0x80000000u : 0u);        // ... of every byte's successor
+            if (zrun == 0 && nbv >= 4 && (nzf | nxt) == 0x80808080u) {
+                sink.token(x & 0xFFu, 0u, 0u);
+                sink.token((x >> 8) & 0xFFu, 0u, 0u);
+                sink.token((x >> 16) & 0xFFu, 0u, 0u);
+                sink.token(x >> 24, 0u, 0u);
+            } else {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            if (b < nbv) {
-                const uint32_t v = (x >> (8 * b)) & 0xFFu;
-                if (v) {
-                    if (zrun) {
-                        emit_run(zrun, sink);
-                        zrun = 0;
+                for (int b = 0; b < 4; ++b) {
+                    if (b < nbv) {
+                        const uint32_t v = (x >> (8 * b)) & 0xFFu;
+                        if (v) {
+                            if (zrun) {
+                                emit_run(zrun, sink);
+                                zrun = 0;
+                            }
+                            sink.token(v, 0u, 0u);
+                        } else {
+                            ++zrun;
+                        }
                     }
-                    sink.token(v, 0u, 0u);
-                } else {
-                    ++zrun;
                 }
             }
         }
+        x = xn;
     }
     if (last_strip && zrun) emit_run(zrun, sink);
 }

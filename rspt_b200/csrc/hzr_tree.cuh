@@ -1,0 +1,261 @@
+// hzr tree build for sm_100a: one warp per hzr block.
+//
+// Replaces MakeTree (lib_hzr/hzr_encode.c:222-283), StoreTree (:177-219), OnlySingleCode
+// (:285-305) and the size / mode decision of EncodeSingleBlock (:377-382, :399-405, :466-467).
+// hzr's Huffman code is NOT canonical: code words follow the exact merge order of MakeTree, whose
+// selection loop (:247-261) picks, every round, the two live nodes that are smallest under the key
+// (count ascending, node index descending) -- leaves are indexed in ascending symbol order and
+// internal nodes after them in creation order.  child_a = the smallest, child_b = the second;
+// the code of child_b gets bit `depth` set (LSB-first codes); the tree is serialised pre-order,
+// branch = 0, leaf = 1 + 9-bit symbol.
+//
+// Phases (all 32 lanes unless noted):
+//   A  load the 261 counts, classify (FILL?), compact the used symbols into sort keys
+//      count << 9 | (511 - symbol), sort ascending (register bitonic network for <= 32 symbols,
+//      shared-memory bitonic network otherwise)
+//   B  lane 0: two-queue merge (sorted leaves / internal nodes in creation order).  Internal
+//      nodes win ties against leaves; inside a run of equal-weight internal nodes the most
+//      recently created one is taken first -- exactly MakeTree's tie-break.  Also counts the
+//      leaves below every internal node.
+//   C  lane 0: top-down pass in reverse creation order (a parent is always created after its
+//      children): depth, code and pre-order bit offset of every node.  A subtree with l leaves
+//      serialises to 11*l - 1 bits, which places child_b without walking child_a.
+//   D  leaves in parallel: code table entry, tree bits, payload bit total, maximum code length.
+#pragma once
+
+#include "common.cuh"
+
+namespace rspt {
+
+constexpr int kTreeWarps = 4;
+
+struct TreeWarpSmem {
+    uint32_t key[512];         // sorted leaf keys
+    uint32_t icnt[260];        // B: internal node weight; C: node code
+    uint32_t child[260];       // child_a | child_b << 16; ids < 512 are leaf ranks, 512 + j internal node j
+    uint32_t ninfo[260];       // leaves below (bits 0-8) | depth (9-13) | pre-order bit offset (14-25)
+    uint32_t lcode[264];       // per leaf rank: code
+    uint32_t linfo[264];       // per leaf rank: depth | bit offset << 8
+    uint32_t tree[kTreeWords];
+};
+
+struct Counters {
+    unsigned long long frames_compressed, frames_decompressed, raw_bytes_in, compressed_bytes_out;
+    unsigned long long blocks_copy, blocks_huff, blocks_fill, escalations;
+};
+
+// Block addressing: blk = (f * nb_alloc + k) * nblk + b
+__device__ __forceinline__ void blk_decode(const Shape& s, uint32_t blk, uint32_t& f, uint32_t& k, uint32_t& b)
+{
+    b = blk % s.nblk;
+    uint32_t fk = blk / s.nblk;
+    k = fk % s.nb_alloc;
+    f = fk / s.nb_alloc;
+}
+
+__device__ __forceinline__ const uint8_t* blk_ptr(const uint8_t* planes, const Shape& s, uint32_t f, uint32_t k, uint32_t b)
+{
+    return planes + ((size_t)f * s.nb_alloc + k) * s.plane_stride + (size_t)b * kBlock;
+}
+
+__global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __restrict__ hist, Shape s,
+                                                               const uint8_t* __restrict__ frame_nb,
+                                                               uint32_t total_blocks,
+                                                               uint32_t* __restrict__ codes,
+                                                               uint32_t* __restrict__ tree,
+                                                               BlkInfo* __restrict__ info,
+                                                               Counters* __restrict__ ctr)
+{
+    __shared__ TreeWarpSmem s_all[kTreeWarps];
+    TreeWarpSmem& S = s_all[warp_id()];
+    const uint32_t lane = lane_id();
+    const uint32_t blk = blockIdx.x * kTreeWarps + warp_id();
+    if (blk >= total_blocks) return;
+    uint32_t f, k, b;
+    blk_decode(s, blk, f, k, b);
+    if (k >= frame_nb[f]) return;
+    const uint32_t n = blk_len(s, b);
+    const uint32_t* h = hist + (size_t)blk * kSymStride;
+
+    // ---- phase A: classify and compact
+    uint32_t L = 0, nz = 0, nzsym = 0, zero_class = 0;
+    uint32_t mykey = 0xFFFFFFFFu;  // register copy for the <= 32 symbol network
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const uint32_t sym = r * 32 + lane;
+        const uint32_t c = sym < kNumSymbols ? __ldg(h + sym) : 0u;
+        const bool used = c != 0;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, used);
+        const uint32_t pos = L + __popc(m & ((1u << lane) - 1u));
+        if (used) S.key[pos] = (c << 9) | (511u - sym);
+        L += __popc(m);
+        if (r == 0) {
+            zero_class |= m & 1u;
+            const uint32_t mm = m & ~1u;
+            nz += __popc(mm);
+            if (mm) nzsym = __ffs(mm) - 1;
+        } else if (r < 8) {
+            nz += __popc(m);
+            if (m && !nzsym) nzsym = r * 32 + __ffs(m) - 1;
+        } else {
+            zero_class |= m != 0;
+        }
+    }
+    if (nz + (zero_class ? 1u : 0u) == 1u) {
+        // single value class -> FILL (OnlySingleCode); payload is in[0]
+        if (lane == 0) {
+            BlkInfo bi;
+            bi.payload_len = 1; bi.total_bits = 8; bi.tree_nbits = 0;
+            bi.mode = MODE_FILL; bi.fill = (uint8_t)(nz ? nzsym : 0u); bi.n_used = L;
+            info[blk] = bi;
+            atomicAdd(&ctr->blocks_fill, 1ull);
+        }
+        return;
+    }
+    __syncwarp();
+    if (L <= 32) {
+        // one key per lane, bitonic network over the warp
+        mykey = lane < L ? S.key[lane] : 0xFFFFFFFFu;
+#pragma unroll
+        for (uint32_t kk = 2; kk <= 32; kk <<= 1)
+#pragma unroll
+            for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+                const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, mykey, j);
+                const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+                mykey = (lower == up) ? min(mykey, other) : max(mykey, other);
+            }
+        S.key[lane] = mykey;
+    } else {
+        uint32_t P = 64;
+        while (P < L) P <<= 1;
+        for (uint32_t i = L + lane; i < P; i += 32) S.key[i] = 0xFFFFFFFFu;
+        __syncwarp();
+        for (uint32_t kk = 2; kk <= P; kk <<= 1)
+            for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+                for (uint32_t idx = lane; idx < (P >> 1); idx += 32) {
+                    const uint32_t i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));
+                    const uint32_t ixj = i | j;
+                    const uint32_t a = S.key[i], c2 = S.key[ixj];
+                    const bool up = (i & kk) == 0;
+                    if ((a > c2) == up) {
+                        S.key[i] = c2;
+                        S.key[ixj] = a;
+                    }
+                }
+                __syncwarp();
+            }
+    }
+    for (uint32_t i = lane; i < kTreeWords; i += 32) S.tree[i] = 0;
+    __syncwarp();
+
+    // ---- phase B + C: lane 0
+    if (lane == 0) {
+        uint32_t li = 0, fr = 0, top = 0, run_end = 0, ni = 0;
+        bool started = false;
+        uint32_t lc = S.key[0] >> 9;
+        for (uint32_t round = 0; round + 1 < L; ++round) {
+            uint32_t id[2], wt[2], lv[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint32_t ic = fr < ni ? S.icnt[fr] : 0xFFFFFFFFu;
+                if (ic <= lc) {
+                    if (!started) {
+                        top = fr + 1;
+                        while (top < ni && S.icnt[top] == ic) ++top;
+                        run_end = top;
+                        started = true;
+                    }
+                    --top;
+                    id[q] = 512u + top;
+                    wt[q] = ic;
+                    lv[q] = S.ninfo[top];
+                    if (top == fr) {
+                        fr = run_end;
+                        started = false;
+                    }
+                } else {
+                    id[q] = li;
+                    wt[q] = lc;
+                    lv[q] = 1;
+                    ++li;
+                    lc = li < L ? (S.key[li] >> 9) : 0xFFFFFFFFu;
+                }
+            }
+            S.icnt[ni] = wt[0] + wt[1];
+            S.child[ni] = id[0] | (id[1] << 16);
+            S.ninfo[ni] = lv[0] + lv[1];
+            ++ni;
+        }
+        // top-down: root = last internal node, depth 0, code 0, offset 0
+        S.icnt[L - 2] = 0;
+        S.ninfo[L - 2] &= 511u;
+        for (int j = (int)L - 2; j >= 0; --j) {
+            const uint32_t inf = S.ninfo[j], code = S.icnt[j], ch = S.child[j];
+            const uint32_t depth = (inf >> 9) & 31u, off = inf >> 14;
+            const uint32_t a = ch & 0xFFFFu, bb = ch >> 16;
+            uint32_t bits_a;
+            if (a < 512u) {
+                S.lcode[a] = code;
+                S.linfo[a] = (depth + 1) | ((off + 1) << 8);
+                bits_a = 10;
+            } else {
+                const uint32_t la = S.ninfo[a - 512u] & 511u;
+                S.icnt[a - 512u] = code;
+                S.ninfo[a - 512u] = la | ((depth + 1) << 9) | ((off + 1) << 14);
+                bits_a = 11u * la - 1u;
+            }
+            const uint32_t code_b = code | (1u << depth), off_b = off + 1 + bits_a;
+            if (bb < 512u) {
+                S.lcode[bb] = code_b;
+                S.linfo[bb] = (depth + 1) | (off_b << 8);
+            } else {
+                const uint32_t lb = S.ninfo[bb - 512u] & 511u;
+                S.icnt[bb - 512u] = code_b;
+                S.ninfo[bb - 512u] = lb | ((depth + 1) << 9) | (off_b << 14);
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- phase D: leaves in parallel
+    uint32_t token_bits = 0, maxlen = 0;
+    uint32_t* my_codes = codes + (size_t)blk * kSymStride;
+    for (uint32_t i = lane; i < L; i += 32) {
+        const uint32_t kv = S.key[i];
+        const uint32_t sym = 511u - (kv & 511u), cnt = kv >> 9;
+        const uint32_t li2 = S.linfo[i], code = S.lcode[i];
+        const uint32_t depth = li2 & 255u, off = li2 >> 8;
+        my_codes[sym] = code | (depth << 27);
+        token_bits += cnt * (depth + sym_extra_bits(sym));
+        maxlen = max(maxlen, depth);
+        const unsigned long long bits = (unsigned long long)(1u | (sym << 1)) << (off & 31u);
+        atomicOr(&S.tree[off >> 5], (uint32_t)bits);
+        if (bits >> 32) atomicOr(&S.tree[(off >> 5) + 1], (uint32_t)(bits >> 32));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        token_bits += __shfl_xor_sync(0xFFFFFFFFu, token_bits, o);
+        maxlen = max(maxlen, __shfl_xor_sync(0xFFFFFFFFu, maxlen, o));
+    }
+    __syncwarp();
+    const uint32_t tree_nbits = 11u * L - 1u;
+    uint32_t* my_tree = tree + (size_t)blk * kTreeWords;
+    for (uint32_t i = lane; i < ((tree_nbits + 31u) >> 5); i += 32) my_tree[i] = S.tree[i];
+    if (lane == 0) {
+        BlkInfo bi;
+        bi.tree_nbits = (uint16_t)tree_nbits;
+        bi.total_bits = tree_nbits + token_bits;
+        const uint32_t bytes = (bi.total_bits + 7u) >> 3;
+        // capped block stream (hzr_encode.c:377-382), 16-bit size field (:466-467); codes longer
+        // than 27 bits cannot occur for <= 65536 tokens (Fibonacci bound ~ 23)
+        const bool copy = bytes > n || bytes >= kBlock || maxlen > 27u;
+        bi.mode = copy ? MODE_COPY : MODE_HUFF;
+        bi.payload_len = copy ? n : bytes;
+        bi.fill = (uint8_t)maxlen;  // HUFF: longest code word (selects the encoder's merge width)
+        bi.n_used = L;
+        info[blk] = bi;
+        atomicAdd(copy ? &ctr->blocks_copy : &ctr->blocks_huff, 1ull);
+    }
+}
+
+}  // namespace rspt
