@@ -7,6 +7,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "hzr_tree.cuh"
 
 namespace rspt {
 
@@ -75,22 +76,6 @@ __device__ __forceinline__ uint32_t block_crc32c(const uint32_t* words, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------
-// Block addressing: blk = (f * nb_alloc + k) * nblk + b
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void blk_decode(const Shape& s, uint32_t blk, uint32_t& f, uint32_t& k, uint32_t& b)
-{
-    b = blk % s.nblk;
-    uint32_t fk = blk / s.nblk;
-    k = fk % s.nb_alloc;
-    f = fk / s.nb_alloc;
-}
-
-__device__ __forceinline__ const uint8_t* blk_ptr(const uint8_t* planes, const Shape& s, uint32_t f, uint32_t k, uint32_t b)
-{
-    return planes + ((size_t)f * s.nb_alloc + k) * s.plane_stride + (size_t)b * kBlock;
-}
-
-// ------------------------------------------------------------------------------------------
 // 1. histogram: one CTA per block, one 64-byte strip per thread
 // ------------------------------------------------------------------------------------------
 struct HistSink {
@@ -125,234 +110,6 @@ __global__ void __launch_bounds__(1024) k_hzr_hist(const uint8_t* __restrict__ p
     __syncthreads();
     uint32_t* out = hist + (size_t)blk * kSymStride;
     for (uint32_t i = threadIdx.x; i < kSymStride; i += blockDim.x) out[i] = sh[i];
-}
-
-// ------------------------------------------------------------------------------------------
-// 2. tree build: a warp owns 32 blocks.  Phase A (warp-cooperative, one block at a time):
-// classify, compact and sort the used symbols by (count asc, symbol desc).  Phase B (one lane
-// per block): two-queue merge that reproduces MakeTree's selection order -- internal nodes
-// win ties against leaves and, among equal-weight internal nodes, the most recently created
-// wins (hzr_encode.c:247-261).  Phase C (one lane per block): pre-order walk that assigns the
-// LSB-first codes, serialises the tree (StoreTree) and totals the payload bits.
-// ------------------------------------------------------------------------------------------
-constexpr int kTreeWarps = 3;
-struct TreeSmem {
-    uint32_t leaf[kNumSymbols][32];  // sorted keys: count << 9 | (511 - symbol)
-    uint32_t icnt[260][32];          // internal node weights; reused as the DFS stack
-    uint32_t tmp[512];
-};
-
-struct Counters {
-    unsigned long long frames_compressed, frames_decompressed, raw_bytes_in, compressed_bytes_out;
-    unsigned long long blocks_copy, blocks_huff, blocks_fill, escalations;
-};
-
-__global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __restrict__ hist, Shape s,
-                                                               const uint8_t* __restrict__ frame_nb,
-                                                               uint32_t total_blocks,
-                                                               uint32_t* __restrict__ codes,
-                                                               uint32_t* __restrict__ tree,
-                                                               uint32_t* __restrict__ children,
-                                                               BlkInfo* __restrict__ info,
-                                                               Counters* __restrict__ ctr)
-{
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    TreeSmem& S = reinterpret_cast<TreeSmem*>(smem_raw)[warp_id()];
-    const uint32_t lane = lane_id();
-    const uint32_t base = (blockIdx.x * kTreeWarps + warp_id()) * 32u;
-    if (base >= total_blocks) return;
-
-    int myL = 0;         // leaves of this lane's tree (0 = nothing to build)
-    uint32_t myn = 0;    // block length
-    uint32_t n_copy = 0, n_huff = 0, n_fill = 0;
-
-    // ---- phase A
-    for (uint32_t jj = 0; jj < 32; ++jj) {
-        const uint32_t blk = base + jj;
-        if (blk >= total_blocks) break;
-        uint32_t f, k, b;
-        blk_decode(s, blk, f, k, b);
-        if (k >= frame_nb[f]) continue;
-        const uint32_t n = blk_len(s, b);
-        const uint32_t* h = hist + (size_t)blk * kSymStride;
-        uint32_t key[9];
-        uint32_t L = 0, nz = 0, nzsym = 0, zero_class = 0;
-#pragma unroll
-        for (int r = 0; r < 9; ++r) {
-            const uint32_t sym = r * 32 + lane;
-            const uint32_t c = sym < kNumSymbols ? __ldg(h + sym) : 0u;
-            if (sym < kSymStride) codes[(size_t)blk * kSymStride + sym] = 0;
-            const bool used = c != 0;
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, used);
-            const uint32_t pos = L + __popc(m & ((1u << lane) - 1u));
-            key[r] = (c << 9) | (511u - sym);
-            if (used) S.tmp[pos] = key[r];
-            L += __popc(m);
-            if (r == 0) {
-                zero_class |= m & 1u;
-                const uint32_t mm = m & ~1u;
-                nz += __popc(mm);
-                if (mm) nzsym = __ffs(mm) - 1;
-            } else if (r < 8) {
-                nz += __popc(m);
-                if (m && !nzsym) nzsym = r * 32 + __ffs(m) - 1;
-            } else {
-                zero_class |= m != 0;
-            }
-        }
-        if (nz + (zero_class ? 1u : 0u) == 1u) {
-            // single value class -> FILL (OnlySingleCode); payload is in[0]
-            if (lane == 0) {
-                BlkInfo bi;
-                bi.payload_len = 1; bi.total_bits = 8; bi.tree_nbits = 0;
-                bi.mode = MODE_FILL; bi.fill = (uint8_t)(nz ? nzsym : 0u); bi.n_used = L;
-                info[blk] = bi;
-            }
-            ++n_fill;
-            continue;
-        }
-        // pad to a power of two >= 32 and bitonic-sort ascending in shared memory
-        uint32_t P = 32;
-        while (P < L) P <<= 1;
-        for (uint32_t i = L + lane; i < P; i += 32) S.tmp[i] = 0xFFFFFFFFu;
-        __syncwarp();
-        for (uint32_t kk = 2; kk <= P; kk <<= 1)
-            for (uint32_t jx = kk >> 1; jx > 0; jx >>= 1) {
-                for (uint32_t idx = lane; idx < (P >> 1); idx += 32) {
-                    const uint32_t i = ((idx & ~(jx - 1)) << 1) | (idx & (jx - 1));
-                    const uint32_t ixj = i | jx;
-                    const uint32_t a = S.tmp[i], c2 = S.tmp[ixj];
-                    const bool up = (i & kk) == 0;
-                    if ((a > c2) == up) {
-                        S.tmp[i] = c2;
-                        S.tmp[ixj] = a;
-                    }
-                }
-                __syncwarp();
-            }
-        for (uint32_t i = lane; i < L; i += 32) S.leaf[i][jj] = S.tmp[i];
-        __syncwarp();
-        if (lane == jj) {
-            myL = (int)L;
-            myn = n;
-        }
-    }
-    __syncwarp();
-
-    // ---- phase B: two-queue merge, one lane per tree
-    const uint32_t blk = base + lane;
-    uint32_t* my_children = children + (size_t)blk * 260;
-    {
-        int maxL = myL;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxL = max(maxL, __shfl_xor_sync(0xFFFFFFFFu, maxL, o));
-        uint32_t li = 0, fr = 0, top = 0, run_end = 0, ni = 0;
-        bool started = false;
-        for (int round = 0; round + 1 < maxL; ++round) {
-            if (round + 1 < myL) {
-                uint32_t id[2], wt[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const uint32_t lc = li < (uint32_t)myL ? (S.leaf[li][lane] >> 9) : 0xFFFFFFFFu;
-                    const uint32_t ic = fr < ni ? S.icnt[fr][lane] : 0xFFFFFFFFu;
-                    if (ic <= lc) {
-                        if (!started) {
-                            top = fr + 1;
-                            while (top < ni && S.icnt[top][lane] == ic) ++top;
-                            run_end = top;
-                            started = true;
-                        }
-                        --top;
-                        id[q] = 512u + top;
-                        wt[q] = ic;
-                        if (top == fr) {
-                            fr = run_end;
-                            started = false;
-                        }
-                    } else {
-                        id[q] = li;
-                        wt[q] = lc;
-                        ++li;
-                    }
-                }
-                S.icnt[ni][lane] = wt[0] + wt[1];
-                my_children[ni] = id[0] | (id[1] << 16);
-                ++ni;
-            }
-        }
-    }
-    __syncwarp();
-
-    // ---- phase C: pre-order walk (child_a first), codes + tree bits + payload size
-    {
-        uint32_t sp = 0;
-        if (myL >= 2) {
-            S.icnt[0][lane] = 512u + (uint32_t)(myL - 2);  // root = last internal node, depth 0
-            S.icnt[128][lane] = 0;
-            sp = 1;
-        }
-        unsigned long long acc = 0;
-        uint32_t nacc = 0, wi = 0, token_bits = 0, too_deep = 0;
-        uint32_t* my_tree = tree + (size_t)blk * kTreeWords;
-        uint32_t* my_codes = codes + (size_t)blk * kSymStride;
-        while (__any_sync(0xFFFFFFFFu, sp > 0)) {
-            if (sp > 0) {
-                --sp;
-                const uint32_t e = S.icnt[sp][lane];
-                const uint32_t code = S.icnt[128 + sp][lane];
-                const uint32_t id = e & 0xFFFFu, depth = e >> 16;
-                if (id < 512u) {
-                    const uint32_t kv = S.leaf[id][lane];
-                    const uint32_t sym = 511u - (kv & 511u), cnt = kv >> 9;
-                    acc |= (unsigned long long)(1u | (sym << 1)) << nacc;
-                    nacc += 10;
-                    my_codes[sym] = code | (depth << 27);
-                    token_bits += cnt * (depth + sym_extra_bits(sym));
-                    too_deep |= depth > 27u;
-                } else {
-                    nacc += 1;
-                    const uint32_t ch = my_children[id - 512u];
-                    S.icnt[sp][lane] = (ch >> 16) | ((depth + 1) << 16);  // child_b: bit `depth` = 1
-                    S.icnt[128 + sp][lane] = code | (1u << depth);
-                    ++sp;
-                    S.icnt[sp][lane] = (ch & 0xFFFFu) | ((depth + 1) << 16);  // child_a on top
-                    S.icnt[128 + sp][lane] = code;
-                    ++sp;
-                }
-                if (nacc >= 32) {
-                    my_tree[wi++] = (uint32_t)acc;
-                    acc >>= 32;
-                    nacc -= 32;
-                }
-            }
-        }
-        if (myL >= 2) {
-            if (nacc) my_tree[wi++] = (uint32_t)acc;
-            BlkInfo bi;
-            bi.tree_nbits = (uint16_t)(11 * myL - 1);
-            bi.total_bits = bi.tree_nbits + token_bits;
-            const uint32_t bytes = (bi.total_bits + 7u) >> 3;
-            // capped block stream (hzr_encode.c:377-382) and 16-bit size field (:466-467)
-            const bool copy = bytes > myn || bytes >= kBlock || too_deep;
-            bi.mode = copy ? MODE_COPY : MODE_HUFF;
-            bi.payload_len = copy ? myn : bytes;
-            bi.fill = 0;
-            bi.n_used = (uint32_t)myL;
-            info[blk] = bi;
-            if (copy) ++n_copy; else ++n_huff;
-        }
-    }
-    // counters (n_fill is warp-uniform; n_copy / n_huff are per lane)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_copy += __shfl_xor_sync(0xFFFFFFFFu, n_copy, o);
-        n_huff += __shfl_xor_sync(0xFFFFFFFFu, n_huff, o);
-    }
-    if (lane == 0) {
-        if (n_copy) atomicAdd(&ctr->blocks_copy, (unsigned long long)n_copy);
-        if (n_huff) atomicAdd(&ctr->blocks_huff, (unsigned long long)n_huff);
-        if (n_fill) atomicAdd(&ctr->blocks_fill, (unsigned long long)n_fill);
-    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@
 
 namespace rspt {
 
-constexpr int kTreeWarps = 4;
+constexpr int kTreeWarps = 1;  // one tree per CTA: a finished (sparse) tree frees its shared memory at once
 
 struct TreeWarpSmem {
     uint32_t key[512];         // sorted leaf keys

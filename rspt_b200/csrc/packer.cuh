@@ -27,7 +27,6 @@ struct rspt_gpu_packer {
     uint32_t* d_hist;
     uint32_t* d_codes;
     uint32_t* d_tree;
-    uint32_t* d_children;
     rspt::BlkInfo* d_info;
     uint8_t* d_frame_nb;
     uint32_t* d_need;

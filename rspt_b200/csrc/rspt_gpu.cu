@@ -123,6 +123,21 @@ bool xdelta_tile(const Shape& s, uint32_t& ts, size_t& smem)
     return true;
 }
 
+// quads per tile and dynamic shared memory of k_xdelta_planes_fast; false = shape not eligible
+bool xdelta_fast_tile(const Shape& s, const uint8_t* d_src, uint32_t& tsq, size_t& smem)
+{
+    if ((s.ch & 3) || (s.ns & 3) || s.ns < 4 || ((uintptr_t)d_src & 15)) return false;
+    const size_t row = (size_t)s.ch * s.bps;
+    for (uint32_t t = 128; t >= 32; t >>= 1) {
+        smem = (size_t)(t + 1) * (row + 1) * 4;
+        if (smem <= 56 * 1024) {
+            tsq = t;
+            return true;
+        }
+    }
+    return false;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -257,7 +272,6 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_hist, nblocks * kSymStride));
     A(dalloc(p->d_codes, nblocks * kSymStride));
     A(dalloc(p->d_tree, nblocks * kTreeWords));
-    A(dalloc(p->d_children, nblocks * 260));
     A(dalloc(p->d_info, nblocks));
     A(dalloc(p->d_frame_nb, F));
     A(dalloc(p->d_need, F));
@@ -285,7 +299,6 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_frame_nb, (int)s.nb_init, F, p->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ctr, 0, sizeof(Counters), p->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_nb_state, &s.nb_init, 4, cudaMemcpyHostToDevice, p->stream);
-    if (e == cudaSuccess) e = allow_smem(k_hzr_tree, kTreeWarps * sizeof(TreeSmem));
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_hist, kStageSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_decode, kDecodeSmem);
@@ -305,7 +318,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     if (!p) return RSPT_E_ARG;
     DeviceGuard dg(p->device);
     cudaStreamSynchronize(p->stream);
-    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_children, p->d_info, p->d_frame_nb,
+    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
                     p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off};
@@ -389,19 +402,40 @@ int launch_forward_transform(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
 {
     const Shape& s = p->s;
     if (s.kind == RSPT_XDELTA_HZR || s.kind == RSPT_HZR) {
+        uint32_t* need = p->can_escalate ? p->d_need : nullptr;
+        if (need) RSPT_CUDA_CHECK(cudaMemsetAsync(need, 0, F * sizeof(uint32_t), p->stream));
+        const bool st = s.kind == RSPT_XDELTA_HZR;
+        uint32_t tsq;
+        size_t fsmem;
+        if (xdelta_fast_tile(s, d_src, tsq, fsmem)) {
+            const uint32_t nq = (uint32_t)s.ns >> 2, tiles = (nq + tsq - 1) / tsq;
+            const dim3 grid((unsigned)(F * tiles));
+#define LAUNCH_F(B, ST)                                                                                   \
+    do {                                                                                                  \
+        RSPT_CUDA_CHECK(allow_smem(k_xdelta_planes_fast<B, ST>, fsmem));                                  \
+        k_xdelta_planes_fast<B, ST><<<grid, 128, fsmem, p->stream>>>(d_src, s, tsq, tiles, p->d_planes, need); \
+    } while (0)
+            switch (s.bps) {
+            case 1: if (st) LAUNCH_F(1, true); else LAUNCH_F(1, false); break;
+            case 2: if (st) LAUNCH_F(2, true); else LAUNCH_F(2, false); break;
+            case 3: if (st) LAUNCH_F(3, true); else LAUNCH_F(3, false); break;
+            default: if (st) LAUNCH_F(4, true); else LAUNCH_F(4, false); break;
+            }
+#undef LAUNCH_F
+            p->launches += 1;
+            RSPT_CUDA_CHECK(cudaGetLastError());
+            return RSPT_OK;
+        }
         uint32_t ts;
         size_t smem;
         if (!xdelta_tile(s, ts, smem)) return fail_arg(p, "too many channels for the tile kernel");
         const uint32_t tiles = ((uint32_t)s.ns + ts - 1) / ts;
-        uint32_t* need = p->can_escalate ? p->d_need : nullptr;
-        if (need) RSPT_CUDA_CHECK(cudaMemsetAsync(need, 0, F * sizeof(uint32_t), p->stream));
         const dim3 grid((unsigned)(F * tiles));
 #define LAUNCH_X(B, ST)                                                                              \
     do {                                                                                             \
         RSPT_CUDA_CHECK(allow_smem(k_xdelta_planes<B, ST>, smem));                                   \
         k_xdelta_planes<B, ST><<<grid, 256, smem, p->stream>>>(d_src, s, ts, tiles, p->d_planes, need); \
     } while (0)
-        const bool st = s.kind == RSPT_XDELTA_HZR;
         switch (s.bps) {
         case 1: if (st) LAUNCH_X(1, true); else LAUNCH_X(1, false); break;
         case 2: if (st) LAUNCH_X(2, true); else LAUNCH_X(2, false); break;
@@ -453,9 +487,8 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     }
     {
         StageTimer t(p, RSPT_STAGE_TREE);
-        k_hzr_tree<<<(nblocks + 32 * kTreeWarps - 1) / (32 * kTreeWarps), 32 * kTreeWarps, kTreeWarps * sizeof(TreeSmem),
-                     p->stream>>>(p->d_hist, s, p->d_frame_nb, nblocks, p->d_codes, p->d_tree, p->d_children, p->d_info,
-                                  p->d_ctr);
+        k_hzr_tree<<<(nblocks + kTreeWarps - 1) / kTreeWarps, 32 * kTreeWarps, 0, p->stream>>>(
+            p->d_hist, s, p->d_frame_nb, nblocks, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
     }
     {
         StageTimer t(p, RSPT_STAGE_LAYOUT);
@@ -664,8 +697,7 @@ extern "C" int rspt_gpu_debug_hzr_tables(rspt_gpu_packer* p, const uint8_t* d_bl
     Shape s = p->s;
     s.N = (uint32_t)n; s.nblk = 1; s.nb_alloc = 1; s.plane_stride = (uint32_t)((n + 15) & ~(size_t)15);
     k_hzr_hist<<<1, 1024, kStageSmem, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist);
-    k_hzr_tree<<<1, 32 * kTreeWarps, kTreeWarps * sizeof(TreeSmem), p->stream>>>(p->d_hist, s, p->d_frame_nb, 1, p->d_codes,
-                                                                                  p->d_tree, p->d_children, p->d_info, p->d_ctr);
+    k_hzr_tree<<<1, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, 1, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
     p->launches += 2;
     RSPT_CUDA_CHECK(cudaGetLastError());
     if (d_hist) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_hist, p->d_hist, kNumSymbols * 4, cudaMemcpyDeviceToDevice, p->stream));

@@ -116,6 +116,152 @@ __global__ void __launch_bounds__(256) k_xdelta_planes(const uint8_t* __restrict
 
 
 // ------------------------------------------------------------------------------------------
+// Fast path of the forward sample transform (ch % 4 == 0, ns % 4 == 0): same results as
+// k_xdelta_planes with ~2.5 instructions per raw byte.
+//
+// A CTA owns `tsq` sample QUADS (4 consecutive samples of every channel; 4*row bytes, contiguous
+// and 16-byte aligned in the interleaved input) plus one halo quad in front (the two predecessor
+// samples of the stencil).  Quads are staged in shared memory at a stride of row + 1 words -- an
+// odd stride, so that 32 lanes reading the same word of 32 consecutive quads hit 32 banks.
+// A work item is (channel group g of 4 channels, quad jq): 6 rows x BPS words are read, the
+// 4 x BPS bytes of a row are unpacked with one PRMT per sample (sign replication in the
+// selector), the 3-tap stencil runs in registers, and a 4 x 4 byte transpose (8 PRMT) turns four
+// consecutive y words into one 32-bit word per plane, stored coalesced (lanes run along jq).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// the 4 sign-extended samples packed in BPS consecutive words
+template <int BPS>
+__device__ __forceinline__ void unpack4(const uint32_t* w, uint32_t (&x)[4])
+{
+    if (BPS == 4) {
+        x[0] = w[0]; x[1] = w[1]; x[2] = w[2]; x[3] = w[3];
+    } else if (BPS == 3) {
+        x[0] = prmt(w[0], w[0], 0xA210u);
+        x[1] = prmt(w[0], w[1], 0xD543u);
+        x[2] = prmt(w[1], w[2], 0xC432u);
+        x[3] = prmt(w[2], w[2], 0xB321u);
+    } else if (BPS == 2) {
+        x[0] = prmt(w[0], w[0], 0x9910u);
+        x[1] = prmt(w[0], w[0], 0xBB32u);
+        x[2] = prmt(w[1], w[1], 0x9910u);
+        x[3] = prmt(w[1], w[1], 0xBB32u);
+    } else {
+        x[0] = prmt(w[0], w[0], 0x8880u);
+        x[1] = prmt(w[0], w[0], 0x9991u);
+        x[2] = prmt(w[0], w[0], 0xAAA2u);
+        x[3] = prmt(w[0], w[0], 0xBBB3u);
+    }
+}
+
+template <int BPS, bool STENCIL>
+__global__ void __launch_bounds__(128) k_xdelta_planes_fast(const uint8_t* __restrict__ src, Shape s, uint32_t tsq,
+                                                             uint32_t tiles_per_frame, uint8_t* __restrict__ planes,
+                                                             uint32_t* __restrict__ need)
+{
+    extern __shared__ __align__(16) uint32_t smw[];
+    const uint32_t f = blockIdx.x / tiles_per_frame, tile = blockIdx.x % tiles_per_frame;
+    const uint32_t row = (uint32_t)s.ch * BPS;       // bytes per sample row == words per quad
+    const uint32_t qstride = row + 1;                // words
+    const uint32_t cpq = row >> 2;                   // 16-byte chunks per quad
+    const uint32_t nq = (uint32_t)s.ns >> 2;         // quads per frame
+    const uint32_t q0 = tile * tsq;
+    const uint32_t tq = min(tsq, nq - q0);           // quads of this tile
+    const uint8_t* frame = src + (size_t)f * s.frame_bytes;
+    const uint32_t halo = (STENCIL && q0 > 0) ? 1u : 0u;
+    // stage quads [q0 - halo, q0 + tq) at slots [1 - halo, 1 + tq)
+    {
+        const uint4* g4 = reinterpret_cast<const uint4*>(frame + (size_t)(q0 - halo) * 4u * row);
+        const uint32_t nchunks = (tq + halo) * cpq;
+        uint32_t q = threadIdx.x / cpq, r = threadIdx.x % cpq;
+        const uint32_t dq = blockDim.x / cpq, dr = blockDim.x % cpq;
+        for (uint32_t c = threadIdx.x; c < nchunks; c += blockDim.x) {
+            const uint4 v = __ldg(g4 + c);
+            uint32_t* d = smw + (q + 1 - halo) * qstride + 4u * r;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            q += dq; r += dr;
+            if (r >= cpq) { r -= cpq; ++q; }
+        }
+    }
+    __syncthreads();
+    const uint32_t G = (uint32_t)s.ch >> 2;
+    const uint32_t rw = row >> 2;                    // words per row
+    uint32_t my_need = 1;
+    for (uint32_t item = threadIdx.x; item < G * tq; item += blockDim.x) {
+        const uint32_t g = item / tq, jq = item - g * tq;
+        const uint32_t* base = smw + (jq + 1) * qstride + g * BPS;
+        uint32_t x[6][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t w[4];
+#pragma unroll
+            for (int t = 0; t < BPS; ++t) w[t] = base[i * rw + t];
+            unpack4<BPS>(w, x[i + 2]);
+        }
+        if (STENCIL) {
+            if (q0 + jq > 0) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int t = 0; t < BPS; ++t) w[t] = base[(int)(i + 2) * (int)rw - (int)qstride + t];
+                    unpack4<BPS>(w, x[i]);
+                }
+            } else {
+                // first quad of the frame: the flat chain continues from the end of the previous
+                // channel row (signal_packer_xdelta_hzr.cpp:55-57 run over the flat [ch*ns] array)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int64_t flat = (int64_t)(4 * g + cc) * s.ns;
+                    x[0][cc] = (uint32_t)frame_sample_flat<BPS>(frame, s, flat - 2);
+                    x[1][cc] = (uint32_t)frame_sample_flat<BPS>(frame, s, flat - 1);
+                }
+            }
+        }
+        const uint32_t s_first = (q0 + jq) << 2;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            uint32_t y[4];
+            if (STENCIL) {
+                uint32_t d[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) d[i] = x[i + 1][cc] - x[i][cc] - 128u;
+                // the very first word of the frame has no predecessor delta: y[0] = x[0] - 128
+                if (s_first == 0 && g == 0 && cc == 0) d[0] = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[i] = d[i + 1] ^ d[i];
+                if (need) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) my_need = max(my_need, planes_needed(y[i], BPS));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[i] = x[i + 2][cc];
+            }
+            const uint32_t t01 = prmt(y[0], y[1], 0x5140u), t23 = prmt(y[2], y[3], 0x5140u);
+            const uint32_t u01 = prmt(y[0], y[1], 0x7362u), u23 = prmt(y[2], y[3], 0x7362u);
+            uint32_t* out = reinterpret_cast<uint32_t*>(planes + (size_t)f * s.nb_alloc * s.plane_stride +
+                                                        (size_t)(4 * g + cc) * s.ns + s_first);
+            const uint32_t ps = s.plane_stride >> 2;
+            out[0] = prmt(t01, t23, 0x5410u);
+            if (s.nb_alloc > 1) out[ps] = prmt(t01, t23, 0x7632u);
+            if (s.nb_alloc > 2) out[2 * ps] = prmt(u01, u23, 0x5410u);
+            if (s.nb_alloc > 3) out[3 * ps] = prmt(u01, u23, 0x7632u);
+        }
+    }
+    if (STENCIL && need) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_need = max(my_need, __shfl_xor_sync(0xFFFFFFFFu, my_need, o));
+        if (lane_id() == 0 && my_need > 1) atomicMax(&need[f], my_need);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // planes -> samples.  One CTA per frame.  The decode-side chains are two scans over the flat
 // [ch*ns] order that cross channel rows: d = prefix-xor(y) (xor_decode_32, utils.cpp:232-236),
 // x = prefix-sum(d + 128) (offset_32(+128) and delta_decode, :204-219).  The frame is cut into

@@ -103,6 +103,9 @@ PLANE_CASES = [
     ("xdelta_hzr", 3, 12, 8192, 3), ("xdelta_hzr", 4, 12, 4096, 3), ("xdelta_hzr", 2, 5, 1000, 2),
     ("xdelta_hzr", 1, 3, 700, 1), ("xdelta_hzr", 4, 1, 8192, 4), ("xdelta_hzr", 3, 2, 1, 3),
     ("xdelta_hzr", 4, 3, 2, 3), ("xdelta_hzr", 3, 7, 33, 3),
+    # shapes of the quad-tiled fast transform (ch % 4 == 0, ns % 4 == 0): partial tiles, planes > bps
+    ("xdelta_hzr", 2, 4, 1000, 2), ("xdelta_hzr", 1, 8, 700, 1), ("xdelta_hzr", 3, 4, 4, 3),
+    ("xdelta_hzr", 3, 8, 516, 4), ("xdelta_hzr", 4, 16, 2052, 2), ("hzr", 2, 8, 2052, 0), ("hzr", 1, 4, 8, 0),
     ("hzr", 3, 12, 8192, 0), ("hzr", 1, 2, 999, 0), ("hzr", 4, 3, 5000, 0),
     ("hadamard", 4, 12, 4096, 0), ("hadamard", 3, 3, 16384, 0), ("hadamard", 2, 2, 8, 0), ("hadamard", 1, 1, 32768, 0),
 ]
