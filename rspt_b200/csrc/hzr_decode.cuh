@@ -5,8 +5,9 @@
 //
 // Parallelism: frames and hzr blocks are located by a cheap header walk (one thread per frame);
 // each block is decoded by one CTA.  Inside a block the token stream has no sync points, so the
-// decoder is seeded from the encoder's out-of-band index (one bit offset + pending zero run per
-// 256 output bytes, rspt_gpu_compress_batch's d_sidecar) and every thread decodes one segment
+// decoder is seeded from the encoder's out-of-band index (per 256 output bytes: the bit offset of
+// the first token that starts there + the leading bytes covered by a zero run that started
+// earlier; rspt_gpu_compress_batch's d_sidecar) and every thread decodes one segment
 // through a 10-bit lookup table.  Streams without an index (produced by the CPU reference) are
 // decoded by a single thread per block.
 #pragma once
@@ -153,7 +154,7 @@ __device__ __forceinline__ uint32_t dec_swizzle(uint32_t w) { return w ^ ((w >> 
 __global__ void __launch_bounds__(kDecodeThreads) k_hzr_decode(const uint8_t* __restrict__ src, Shape s,
                                                                 const DecBlk* __restrict__ dec,
                                                                 const uint32_t* __restrict__ sc_bit,
-                                                                const uint16_t* __restrict__ sc_carry,
+                                                                const uint16_t* __restrict__ sc_skip,
                                                                 uint8_t* __restrict__ planes, int32_t* __restrict__ status)
 {
     extern __shared__ __align__(16) uint32_t stg[];  // decoded block, word-swizzled per 256-byte segment
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kDecodeThreads) k_hzr_decode(const uint8_t* __
         uint32_t bitpos, outpos, end_bit;
         if (indexed) {
             bitpos = sc_bit[(size_t)blk * kMaxSegs + tid];
-            outpos = tid * kSegBytes - sc_carry[(size_t)blk * kMaxSegs + tid];
+            outpos = tid * kSegBytes + sc_skip[(size_t)blk * kMaxSegs + tid];
             end_bit = tid + 1 < nseg ? sc_bit[(size_t)blk * kMaxSegs + tid + 1] : 0xFFFFFFFFu;
         } else {
             bitpos = s_meta[1];

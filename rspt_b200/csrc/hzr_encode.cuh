@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "hzr_tree.cuh"
+#include "hzr_hist.cuh"
 
 namespace rspt {
 
@@ -73,43 +74,6 @@ __device__ __forceinline__ uint32_t block_crc32c(const uint32_t* words, uint32_t
     }
     __syncthreads();
     return s_red[32];
-}
-
-// ------------------------------------------------------------------------------------------
-// 1. histogram: one CTA per block, one 64-byte strip per thread
-// ------------------------------------------------------------------------------------------
-struct HistSink {
-    uint32_t* sh;
-    __device__ __forceinline__ void token(uint32_t sym, uint32_t, uint32_t) { atomicAdd(&sh[sym], 1u); }
-};
-
-constexpr size_t kStageSmem = (size_t)kBlock;  // swizzled copy of one block
-
-__global__ void __launch_bounds__(1024) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
-                                                    const uint8_t* __restrict__ frame_nb,
-                                                    uint32_t* __restrict__ hist)
-{
-    extern __shared__ __align__(16) uint32_t in_sw[];
-    __shared__ uint32_t sh[kSymStride];
-    __shared__ uint16_t s_carry[1024], s_list[1024];
-    __shared__ uint32_t s_wtz[32], s_waz[32], s_scan[33];
-    uint32_t f, k, b;
-    const uint32_t blk = blockIdx.x;
-    blk_decode(s, blk, f, k, b);
-    if (k >= frame_nb[f]) return;
-    const uint32_t n = blk_len(s, b);
-    for (uint32_t i = threadIdx.x; i < kSymStride; i += blockDim.x) sh[i] = 0;
-    const uint32_t nstrips = (n + kStrip - 1) / kStrip;
-    const uint32_t n_active = stage_block(blk_ptr(planes, s, f, k, b), n, in_sw, s_carry, s_list, s_wtz, s_waz, s_scan);
-    if (threadIdx.x < n_active) {
-        const uint32_t t = s_list[threadIdx.x];
-        const int valid = (int)min((uint32_t)kStrip, n - t * kStrip);
-        HistSink sink{sh};
-        walk_strip_staged(in_sw, t, valid, s_carry[t], t + 1 == nstrips, sink);
-    }
-    __syncthreads();
-    uint32_t* out = hist + (size_t)blk * kSymStride;
-    for (uint32_t i = threadIdx.x; i < kSymStride; i += blockDim.x) out[i] = sh[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -217,11 +181,26 @@ __global__ void __launch_bounds__(1024) k_scan_offsets(const uint32_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------
-// 4. encode: one CTA per block.  The block's bytes [7-byte header | payload] are staged in
-// shared memory starting at byte 9 (so the payload is 16-byte aligned at byte 16), the CRC is
-// taken from the staged payload and the whole thing is copied to its final, arbitrarily
-// aligned position in the output stream.
+// 4. encode: one CTA of 16 warps per block.  The block is walked in GROUPS of 16 warp-steps
+// (8 KiB); in a group every lane owns 16 consecutive bytes and the tokens that START in them:
+// its literals and the zero runs whose first zero lies in the chunk (a run that continues into
+// later chunks is measured with the lane's forward zero count: stop bits of the following lanes,
+// then the per-step leading-zero counts left by k_hzr_hist).  Per group:
+//   1. lane bit length (dense chunks -- 16 tokens, one per byte -- keep their 16 table entries
+//      in registers; other chunks walk their tokens)
+//   2. warp scan + one __syncthreads: exclusive bit offset of every lane in the block's payload
+//   3. the lane appends its code words into the shared-memory staging buffer: 64-bit
+//      accumulator, 32-bit flushes; the first and the last (partial) word are OR-ed atomically
+//      because they are shared with the neighbouring lanes.
+// The block's bytes [7-byte header | payload] are staged in shared memory starting at byte 9
+// (payload 16-byte aligned at byte 16); the CRC-32C is taken from the staged payload and the
+// whole thing is copied to its final, arbitrarily aligned position in the output stream
+// (hzr_encode.c:410-484, WriteBits :94-113).
 // ------------------------------------------------------------------------------------------
+constexpr int kEncThreads = 512;
+constexpr int kEncWarps = kEncThreads / 32;
+constexpr int kEncZtSel = 2;  // log2(kEncThreads / 128)
+
 struct LenSink {
     const uint32_t* sc;
     uint32_t bits;
@@ -264,6 +243,25 @@ struct EmitSink {
     }
 };
 
+// tokens that start in one chunk, in stream order
+template <class Sink>
+__device__ __forceinline__ void walk_chunk(const Chunk& c, uint32_t starts, uint32_t fwd, Sink& sink)
+{
+    const uint32_t w[4] = {c.v.x, c.v.y, c.v.z, c.v.w};
+    uint32_t m = c.nz | starts;
+    while (m) {
+        const uint32_t p = __ffs(m) - 1u;
+        m &= m - 1u;
+        if ((c.nz >> p) & 1u) {
+            const uint32_t x = p < 8 ? (p < 4 ? w[0] : w[1]) : (p < 12 ? w[2] : w[3]);
+            sink.token((x >> (8u * (p & 3u))) & 0xFFu, 0u, 0u);
+        } else {
+            const uint32_t sb = c.stop >> p;
+            emit_run(sb ? (uint32_t)__ffs(sb) - 1u : 16u - p + fwd, sink);
+        }
+    }
+}
+
 // copy `len` bytes from shared memory (byte offset `soff` into the word array `sw`) to an
 // arbitrarily aligned global address, 4 bytes per thread-step
 __device__ __forceinline__ void copy_smem_to_global(uint8_t* __restrict__ dst, const uint32_t* sw, uint32_t soff, uint32_t len)
@@ -282,29 +280,28 @@ __device__ __forceinline__ void copy_smem_to_global(uint8_t* __restrict__ dst, c
     if (threadIdx.x < len - done) dst[done + threadIdx.x] = sb[soff + done + threadIdx.x];
 }
 
-constexpr uint32_t kStgWords = 4 + kBlock / 4 + 2;
-constexpr size_t kEncodeSmem = kStageSmem + (size_t)kStgWords * 4;
+constexpr uint32_t kStgWords = 4 + kBlock / 4 + 4;
+constexpr size_t kEncodeSmem = (size_t)kStgWords * 4;
 
-__global__ void __launch_bounds__(1024, 1) k_hzr_encode(const uint8_t* __restrict__ planes, Shape s,
-                                                         const uint8_t* __restrict__ frame_nb,
-                                                         const BlkInfo* __restrict__ info,
-                                                         const uint32_t* __restrict__ blk_off,
-                                                         const uint32_t* __restrict__ codes,
-                                                         const uint32_t* __restrict__ tree,
-                                                         const uint64_t* __restrict__ offsets,
-                                                         const uint8_t* __restrict__ headers,
-                                                         const CrcConst* __restrict__ cc, int zt_sel,
-                                                         uint8_t* __restrict__ dst,
-                                                         uint32_t* __restrict__ sc_bit, uint16_t* __restrict__ sc_carry)
+__global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __restrict__ planes, Shape s,
+                                                                const uint8_t* __restrict__ frame_nb,
+                                                                const BlkInfo* __restrict__ info,
+                                                                const uint32_t* __restrict__ blk_off,
+                                                                const uint32_t* __restrict__ codes,
+                                                                const uint32_t* __restrict__ tree,
+                                                                const uint16_t* __restrict__ step_lz,
+                                                                const uint64_t* __restrict__ offsets,
+                                                                const uint8_t* __restrict__ headers,
+                                                                const CrcConst* __restrict__ cc,
+                                                                uint8_t* __restrict__ dst,
+                                                                uint32_t* __restrict__ sc_bit, uint16_t* __restrict__ sc_skip)
 {
-    extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t* in_sw = smem;                      // [16384] staged input block
-    uint32_t* stg = smem + kBlock / 4;           // [kStgWords] output: header at bytes 9..15, payload at 16
+    extern __shared__ __align__(16) uint32_t stg[];  // header at bytes 9..15, payload from byte 16
     __shared__ uint32_t s_codes[kSymStride];
     __shared__ uint32_t s_zt[1024];
-    __shared__ uint32_t s_bits[1024];
-    __shared__ uint16_t s_carry[1024], s_list[1024];
-    __shared__ uint32_t s_wtz[32], s_waz[32], s_scan[33], s_red[33];
+    __shared__ uint32_t s_after[kMaxSteps];          // zeros that follow the end of every step
+    __shared__ uint32_t s_tot[2][kEncWarps];
+    __shared__ uint32_t s_red[33];
 
     uint32_t f, k, b;
     const uint32_t blk = blockIdx.x;
@@ -313,7 +310,7 @@ __global__ void __launch_bounds__(1024, 1) k_hzr_encode(const uint8_t* __restric
     if (k >= nb) return;
     const uint32_t n = blk_len(s, b);
     const BlkInfo bi = info[blk];
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     const unsigned long long frame_off = offsets[f];
     uint8_t* out = dst + frame_off + blk_off[blk];
 
@@ -344,7 +341,7 @@ __global__ void __launch_bounds__(1024, 1) k_hzr_encode(const uint8_t* __restric
         return;
     }
 
-    for (uint32_t i = tid; i < 1024; i += blockDim.x) s_zt[i] = __ldg(&cc->zt[zt_sel][0][0] + i);
+    for (uint32_t i = tid; i < 1024; i += blockDim.x) s_zt[i] = __ldg(&cc->zt[kEncZtSel][0][0] + i);
     const uint8_t* src = blk_ptr(planes, s, f, k, b);
     uint8_t* sbytes = reinterpret_cast<uint8_t*>(stg);
     const uint32_t plen = bi.payload_len;
@@ -357,36 +354,119 @@ __global__ void __launch_bounds__(1024, 1) k_hzr_encode(const uint8_t* __restric
         for (uint32_t i = tid; i < (n + 15) / 16; i += blockDim.x) d4[i] = __ldg(s4 + i);
         __syncthreads();
     } else {
+        const uint32_t nsteps = (n + kStepBytes - 1) / kStepBytes;
         for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_codes[i] = __ldg(codes + (size_t)blk * kSymStride + i);
         const uint32_t tw = (bi.tree_nbits + 31u) >> 5, pw = (plen + 3u) >> 2;
-        for (uint32_t i = tid; i < pw + 1; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
-        s_bits[tid] = 0;
-        const uint32_t nstrips = (n + kStrip - 1) / kStrip;
-        const uint32_t n_active = stage_block(src, n, in_sw, s_carry, s_list, s_wtz, s_waz, s_scan);
-        uint32_t t = 0, carry = 0;
-        int valid = 0;
-        if (tid < n_active) {
-            t = s_list[tid];
-            carry = s_carry[t];
-            valid = (int)min((uint32_t)kStrip, n - t * kStrip);
-            LenSink ls{s_codes, 0};
-            walk_strip_staged(in_sw, t, valid, carry, t + 1 == nstrips, ls);
-            s_bits[t] = ls.bits;
+        for (uint32_t i = tid; i < pw + 2; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
+        if (wid == kEncWarps - 1) {
+            // s_after[st] = zeros between the end of step st and the next stop byte (or the block
+            // end): suffix chain over the per-step leading-zero counts, 4 steps per lane
+            const uint16_t* lzp = step_lz + (size_t)blk * kMaxSteps;
+            uint32_t lz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t st = 4u * lane + j;
+                lz[j] = st < nsteps ? (uint32_t)lzp[st] : 0u;  // beyond the block: a stop at once
+            }
+            // leading zeros counted from the start of my 4 steps, and whether all 4 are zero
+            uint32_t mine = 0;
+            bool open = true;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (open) {
+                    mine += lz[j];
+                    open = lz[j] == kStepAllZero;
+                }
+            const uint32_t openm = __ballot_sync(0xFFFFFFFFu, open);
+            const uint32_t above = lane < 31 ? ~openm & ~((2u << lane) - 1u) : 0u;  // closed lanes after me
+            const uint32_t q = above ? (uint32_t)__ffs(above) - 1u : 31u;
+            const uint32_t mq = __shfl_sync(0xFFFFFFFFu, mine, q);
+            // zeros that follow the end of my 4 steps
+            uint32_t carry = above ? 4u * kStepBytes * (q - lane - 1u) + mq : 4u * kStepBytes * (31u - lane);
+#pragma unroll
+            for (int j = 3; j >= 0; --j) {
+                const uint32_t st = 4u * lane + j;
+                if (st < kMaxSteps) s_after[st] = carry;
+                carry = lz[j] == kStepAllZero ? carry + kStepBytes : lz[j];
+            }
         }
         __syncthreads();
-        const uint32_t mine = s_bits[tid];
-        const uint32_t off = bi.tree_nbits + block_exclusive_scan(mine, s_scan, nullptr);
-        s_bits[tid] = off;  // (each thread rewrites only its own entry; the scan has synchronised)
-        if (sc_bit && (tid % kSegStrips) == 0 && tid < nstrips) {
-            sc_bit[(size_t)blk * kMaxSegs + tid / kSegStrips] = off;
-            sc_carry[(size_t)blk * kMaxSegs + tid / kSegStrips] = s_carry[tid];
-        }
-        __syncthreads();
-        if (tid < n_active) {
-            const uint32_t o = s_bits[t];
-            EmitSink es{s_codes, pay, 0ull, o & 31u, o >> 5, true};
-            walk_strip_staged(in_sw, t, valid, carry, t + 1 == nstrips, es);
-            es.finish();
+
+        uint32_t base = bi.tree_nbits;  // bit offset of the group (same in every thread)
+        const uint32_t ngroups = (nsteps + kEncWarps - 1) / kEncWarps;
+        for (uint32_t g = 0; g < ngroups; ++g) {
+            const uint32_t st = g * kEncWarps + wid;
+            const uint32_t off = st * kStepBytes + lane * 16u;
+            const Chunk c = load_chunk(src, n, off);
+            uint32_t prevz, nextz;
+            neighbour_zero(c.z, prevz, nextz);
+            if (lane == 0) prevz = (off > 0 && off <= n) ? (src[off - 1] == 0 ? 1u : 0u) : 0u;
+            const uint32_t anyt = __ballot_sync(0xFFFFFFFFu, c.stop != 0u);
+            const uint32_t first_stop = c.stop ? (uint32_t)__ffs(c.stop) - 1u : 16u;
+            const uint32_t above = lane < 31 ? anyt & ~((2u << lane) - 1u) : 0u;
+            const uint32_t q = above ? (uint32_t)__ffs(above) - 1u : 0u;
+            const uint32_t fq = __shfl_sync(0xFFFFFFFFu, first_stop, q);
+            // zeros between the end of my chunk and the next stop byte of the block
+            const uint32_t fwd = above ? 16u * (q - lane - 1u) + fq
+                                       : 16u * (31u - lane) + (st < nsteps ? s_after[st] : 0u);
+            const uint32_t starts = c.z & ~((c.z << 1) | prevz);
+            const uint32_t cont = (c.z >> 1) | ((fwd > 0u ? 1u : 0u) << 15);  // the byte after is a zero too
+            // dense chunk: 16 valid bytes, every zero byte is a run of exactly one
+            const bool dense = c.valid == 16 && c.z == (starts & ~cont);
+            uint32_t cw[16];
+            uint32_t bits = 0;
+            if (dense) {
+                const uint32_t w[4] = {c.v.x, c.v.y, c.v.z, c.v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    cw[4 * j + 0] = s_codes[w[j] & 0xFFu];
+                    cw[4 * j + 1] = s_codes[(w[j] >> 8) & 0xFFu];
+                    cw[4 * j + 2] = s_codes[(w[j] >> 16) & 0xFFu];
+                    cw[4 * j + 3] = s_codes[w[j] >> 24];
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) bits += cw[j] >> 27;
+            } else if (c.nz | starts) {
+                LenSink ls{s_codes, 0};
+                walk_chunk(c, starts, fwd, ls);
+                bits = ls.bits;
+            }
+            // exclusive bit offset of the lane
+            uint32_t inc = bits;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
+            }
+            if (lane == 31) s_tot[g & 1][wid] = inc;
+            __syncthreads();
+            uint32_t t = lane < kEncWarps ? s_tot[g & 1][lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < kEncWarps; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, t, o);
+                if (lane >= (uint32_t)o) t += y;
+            }
+            const uint32_t wbase = wid ? __shfl_sync(0xFFFFFFFFu, t, wid - 1) : 0u;
+            const uint32_t gtot = __shfl_sync(0xFFFFFFFFu, t, kEncWarps - 1);
+            const uint32_t o = base + wbase + inc - bits;
+            base += gtot;
+            if (sc_bit && (lane & 15u) == 0 && off < n) {
+                // decode index: first token that starts in this 256-byte segment, and the bytes at
+                // its head that belong to a run started earlier
+                const uint32_t seg = off >> 8;
+                sc_bit[(size_t)blk * kMaxSegs + seg] = o;
+                sc_skip[(size_t)blk * kMaxSegs + seg] = (uint16_t)(prevz ? (c.stop ? first_stop : 16u + fwd) : 0u);
+            }
+            if (bits) {
+                EmitSink es{s_codes, pay, 0ull, o & 31u, o >> 5, true};
+                if (dense) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) es.append(cw[j] & 0x07FFFFFFu, cw[j] >> 27);
+                } else {
+                    walk_chunk(c, starts, fwd, es);
+                }
+                es.finish();
+            }
         }
         __syncthreads();
     }

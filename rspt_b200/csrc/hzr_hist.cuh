@@ -1,0 +1,202 @@
+// hzr token histogram for sm_100a: one CTA per hzr block, 16 bytes per lane, 512 bytes per
+// warp-step.  Replaces Histogram (lib_hzr/hzr_encode.c:133-173).
+//
+// Tokens (hzr_encode.c:140-170): every non-zero byte is a literal; every maximal zero run inside
+// the block is cut greedily into chunks of <= 16662 and each chunk becomes one of the symbols
+// 0 (run of 1), 256 (run of 2), 257..260 (longer runs, with extra bits).  The literal counts are
+// order-free; only the zero runs need structure:
+//   * a warp owns a CONTIGUOUS range of steps and walks it in order, so the zeros pending at the
+//     end of one step are simply carried in a (warp-uniform) register to the next;
+//   * inside a step every lane turns its 16 bytes into a 16-bit "stop" mask (non-zero or beyond
+//     the block end).  Isolated zeros (both neighbours non-zero) are symbol 0 and are counted
+//     with one popc; runs of >= 2 that start in a lane are measured against the lane's own stop
+//     bits or, through one ballot + shuffle, against the next lane that has a stop bit;
+//   * runs that touch the step start / end are not counted locally: the step reports its leading
+//     and trailing zero counts, the warp chains them across its steps, and thread 0 chains the
+//     (at most 8) warp ranges at the end.
+// The per-step leading-zero counts are also written out (step_lz): k_hzr_encode uses them to
+// measure runs that leave a step without re-reading the block.
+#pragma once
+
+#include "common.cuh"
+#include "hzr_tree.cuh"
+
+namespace rspt {
+
+constexpr int kHistThreads = 256;
+constexpr int kStepBytes = 512;                     // one warp-step: 32 lanes x 16 bytes
+constexpr int kMaxSteps = kBlock / kStepBytes;      // 128 per block
+constexpr uint32_t kStepAllZero = kStepBytes;       // step_lz value of a step without any stop byte
+
+// 4-bit mask of the non-zero bytes of a word
+__device__ __forceinline__ uint32_t nz_nibble(uint32_t x)
+{
+    const uint32_t t = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+    return (t * 0x00204081u) >> 28;  // bits 7,15,23,31 -> bits 28..31
+}
+
+__device__ __forceinline__ uint32_t nz_mask16(const uint4& v)
+{
+    return nz_nibble(v.x) | (nz_nibble(v.y) << 4) | (nz_nibble(v.z) << 8) | (nz_nibble(v.w) << 12);
+}
+
+// One lane's view of a warp-step.
+struct Chunk {
+    uint4 v;         // the 16 bytes (garbage beyond `valid`)
+    int valid;       // bytes of the block in this chunk, 0..16
+    uint32_t nz;     // non-zero valid bytes
+    uint32_t stop;   // nz | bytes beyond the block end: everything that terminates a zero run
+    uint32_t z;      // valid zero bytes
+};
+
+__device__ __forceinline__ Chunk load_chunk(const uint8_t* __restrict__ blk, uint32_t n, uint32_t off)
+{
+    Chunk c;
+    const int valid = (int)n - (int)off;
+    c.valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
+    c.v = make_uint4(0, 0, 0, 0);
+    if (c.valid > 0) c.v = __ldg(reinterpret_cast<const uint4*>(blk + off));
+    const uint32_t vm = (1u << c.valid) - 1u;
+    c.nz = ((c.v.x | c.v.y | c.v.z | c.v.w) == 0u) ? 0u : (nz_mask16(c.v) & vm);
+    c.stop = c.nz | (0xFFFFu & ~vm);
+    c.z = ~c.stop & 0xFFFFu;
+    return c;
+}
+
+// zero flags of the neighbouring bytes inside the step; bytes outside the step count as zero so
+// that runs touching the step boundary are never treated as closed
+__device__ __forceinline__ void neighbour_zero(uint32_t z, uint32_t& prevz, uint32_t& nextz)
+{
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, z, 1), dn = __shfl_down_sync(0xFFFFFFFFu, z, 1);
+    prevz = lane_id() > 0 ? (up >> 15) & 1u : 1u;
+    nextz = lane_id() < 31 ? dn & 1u : 1u;
+}
+
+struct HistSink {
+    uint32_t* run;  // [0] symbol 0, [1..5] symbols 256..260
+    __device__ __forceinline__ void token(uint32_t sym, uint32_t, uint32_t) { atomicAdd(&run[sym ? sym - 255u : 0u], 1u); }
+};
+
+__global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
+                                                            const uint8_t* __restrict__ frame_nb,
+                                                            uint32_t* __restrict__ hist,
+                                                            uint16_t* __restrict__ step_lz)
+{
+    __shared__ uint32_t s_lit[256];  // raw byte counts; [0] is scratch (zeros are tokenised as runs)
+    __shared__ uint32_t s_run[8];
+    __shared__ uint32_t s_wsum[kHistThreads / 32][3];  // per warp range: seen, lead, trail
+    uint32_t f, k, b;
+    const uint32_t blk = blockIdx.x;
+    blk_decode(s, blk, f, k, b);
+    if (k >= frame_nb[f]) return;
+    const uint32_t n = blk_len(s, b);
+    const uint8_t* src = blk_ptr(planes, s, f, k, b);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = 0;
+    if (threadIdx.x < 8) s_run[threadIdx.x] = 0;
+    __syncthreads();
+
+    const uint32_t lane = lane_id(), wid = warp_id(), nwarps = blockDim.x >> 5;
+    const uint32_t nsteps = (n + kStepBytes - 1) / kStepBytes;
+    const uint32_t spw = (nsteps + nwarps - 1) / nwarps;
+    const uint32_t s_lo = min(nsteps, wid * spw), s_hi = min(nsteps, s_lo + spw);
+    uint16_t* my_lz = step_lz + (size_t)blk * kMaxSteps;
+    HistSink sink{s_run};
+    uint32_t pending = 0, lead = 0, cnt0 = 0;
+    bool seen = false;
+    for (uint32_t st = s_lo; st < s_hi; ++st) {
+        const Chunk c = load_chunk(src, n, st * kStepBytes + lane * 16u);
+        const uint32_t anyt = __ballot_sync(0xFFFFFFFFu, c.stop != 0u);
+        if (anyt == 0u) {
+            if (lane == 0) my_lz[st] = (uint16_t)kStepAllZero;
+            pending += kStepBytes;
+            continue;
+        }
+        // literals
+        if (c.nz) {
+            if (c.valid == 16 && __popc(c.nz) >= 8) {
+                const uint32_t w[4] = {c.v.x, c.v.y, c.v.z, c.v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    atomicAdd(&s_lit[w[j] & 0xFFu], 1u);
+                    atomicAdd(&s_lit[(w[j] >> 8) & 0xFFu], 1u);
+                    atomicAdd(&s_lit[(w[j] >> 16) & 0xFFu], 1u);
+                    atomicAdd(&s_lit[w[j] >> 24], 1u);
+                }
+            } else {
+                const uint32_t w[4] = {c.v.x, c.v.y, c.v.z, c.v.w};
+                uint32_t m = c.nz;
+                while (m) {
+                    const uint32_t p = __ffs(m) - 1u;
+                    m &= m - 1u;
+                    const uint32_t x = p < 8 ? (p < 4 ? w[0] : w[1]) : (p < 12 ? w[2] : w[3]);
+                    atomicAdd(&s_lit[(x >> (8u * (p & 3u))) & 0xFFu], 1u);
+                }
+            }
+        }
+        // zero runs closed inside the step
+        uint32_t prevz, nextz;
+        neighbour_zero(c.z, prevz, nextz);
+        const uint32_t starts = c.z & ~((c.z << 1) | prevz);
+        const uint32_t cont = (c.z >> 1) | (nextz << 15);  // the byte after is a zero too
+        cnt0 += __popc(starts & ~cont);
+        uint32_t rs2 = starts & cont;
+        // position of the first / last stop bit of every lane, for the neighbours
+        const uint32_t first_stop = c.stop ? (uint32_t)__ffs(c.stop) - 1u : 16u;
+        if (__any_sync(0xFFFFFFFFu, rs2 != 0u)) {
+            const uint32_t above = lane < 31 ? anyt & ~((2u << lane) - 1u) : 0u;
+            const uint32_t q = above ? (uint32_t)__ffs(above) - 1u : 0u;
+            const uint32_t fq = __shfl_sync(0xFFFFFFFFu, first_stop, q);
+            const uint32_t fwd = 16u * (q - lane - 1u) + fq;  // zeros after my chunk (valid iff above != 0)
+            while (rs2) {
+                const uint32_t p = __ffs(rs2) - 1u;
+                rs2 &= rs2 - 1u;
+                const uint32_t sb = c.stop >> p;
+                if (sb) emit_run((uint32_t)__ffs(sb) - 1u, sink);
+                else if (above) emit_run(16u - p + fwd, sink);
+                // else: the run leaves the step; it is part of the step's trailing zeros
+            }
+        }
+        // chain the step's leading / trailing zeros along the warp's range
+        const uint32_t qf = (uint32_t)__ffs(anyt) - 1u, ql = 31u - (uint32_t)__clz((int)anyt);
+        const uint32_t lz = 16u * qf + __shfl_sync(0xFFFFFFFFu, first_stop, qf);
+        const uint32_t last_stop = c.stop ? 31u - (uint32_t)__clz((int)c.stop) : 0u;
+        const uint32_t tz = 16u * (31u - ql) + 15u - __shfl_sync(0xFFFFFFFFu, last_stop, ql);
+        if (lane == 0) my_lz[st] = (uint16_t)lz;
+        const uint32_t run = pending + lz;
+        if (!seen) {
+            lead = run;
+            seen = true;
+        } else if (run && lane == 0) {
+            emit_run(run, sink);
+        }
+        pending = tz;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt0 += __shfl_xor_sync(0xFFFFFFFFu, cnt0, o);
+    if (lane == 0) {
+        if (cnt0) atomicAdd(&s_run[0], cnt0);
+        s_wsum[wid][0] = seen;
+        s_wsum[wid][1] = lead;
+        s_wsum[wid][2] = pending;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t pend = 0;
+        for (uint32_t w = 0; w < nwarps; ++w) {
+            if (!s_wsum[w][0]) {
+                pend += s_wsum[w][2];
+            } else {
+                const uint32_t run = pend + s_wsum[w][1];
+                if (run) emit_run(run, sink);
+                pend = s_wsum[w][2];
+            }
+        }
+        if (pend) emit_run(pend, sink);
+    }
+    __syncthreads();
+    uint32_t* out = hist + (size_t)blk * kSymStride;
+    for (uint32_t i = threadIdx.x; i < kSymStride; i += blockDim.x)
+        out[i] = i == 0 ? s_run[0] : (i < 256 ? s_lit[i] : (i < (uint32_t)kNumSymbols ? s_run[i - 255] : 0u));
+}
+
+}  // namespace rspt

@@ -17,8 +17,7 @@ struct rspt_gpu_packer {
     cudaStream_t stream;
     bool own_stream;
     size_t max_batch;
-    uint32_t enc_threads;  // CTA width of the strip kernels (128/256/512/1024)
-    int zt_sel;
+    size_t enc_smem;       // dynamic shared memory of k_hzr_encode (staging of the largest block)
     bool can_escalate;     // xdelta_hzr with nb < bps
     bool dct_direct;       // dct: O(n^2) bit-exact path (fixed at create time)
 
@@ -27,6 +26,7 @@ struct rspt_gpu_packer {
     uint32_t* d_hist;
     uint32_t* d_codes;
     uint32_t* d_tree;
+    uint16_t* d_step_lz;   // per 512-byte step of every block: leading zero count (512 = all zero)
     rspt::BlkInfo* d_info;
     uint8_t* d_frame_nb;
     uint32_t* d_need;

@@ -260,9 +260,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     p->max_batch = max_batch_frames;
     p->d_crc = g_crc[device];
     const uint32_t maxn = s.N < kBlock ? s.N : kBlock;
-    const uint32_t strips = (maxn + kStrip - 1) / kStrip;
-    p->enc_threads = strips <= 128 ? 128 : strips <= 256 ? 256 : strips <= 512 ? 512 : 1024;
-    p->zt_sel = p->enc_threads == 128 ? 0 : p->enc_threads == 256 ? 1 : p->enc_threads == 512 ? 2 : 3;
+    p->enc_smem = (size_t)(4 + (maxn + 3) / 4 + 4) * 4;  // staging of the largest block: header words + payload + slack
     p->stream = (cudaStream_t)stream;  // NULL = the CUDA default stream
     p->own_stream = false;
     const size_t F = max_batch_frames, nblocks = F * s.nb_alloc * s.nblk;
@@ -272,6 +270,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_hist, nblocks * kSymStride));
     A(dalloc(p->d_codes, nblocks * kSymStride));
     A(dalloc(p->d_tree, nblocks * kTreeWords));
+    A(dalloc(p->d_step_lz, nblocks * kMaxSteps));
     A(dalloc(p->d_info, nblocks));
     A(dalloc(p->d_frame_nb, F));
     A(dalloc(p->d_need, F));
@@ -300,7 +299,6 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ctr, 0, sizeof(Counters), p->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_nb_state, &s.nb_init, 4, cudaMemcpyHostToDevice, p->stream);
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
-    if (e == cudaSuccess) e = allow_smem(k_hzr_hist, kStageSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_decode, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_crc32c, kEncodeSmem);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
@@ -318,7 +316,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     if (!p) return RSPT_E_ARG;
     DeviceGuard dg(p->device);
     cudaStreamSynchronize(p->stream);
-    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_info, p->d_frame_nb,
+    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
                     p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off};
@@ -483,7 +481,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     }
     {
         StageTimer t(p, RSPT_STAGE_HIST);
-        k_hzr_hist<<<nblocks, p->enc_threads, kStageSmem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist);
+        k_hzr_hist<<<nblocks, kHistThreads, 0, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz);
     }
     {
         StageTimer t(p, RSPT_STAGE_TREE);
@@ -496,12 +494,12 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         k_scan_offsets<<<1, 1024, 0, p->stream>>>(p->d_sizes, (uint32_t)F, d_offsets, p->d_ctr, s.frame_bytes);
     }
     uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar);
-    uint16_t* sc_carry = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
+    uint16_t* sc_skip = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
     {
         StageTimer t(p, RSPT_STAGE_ENCODE);
-        k_hzr_encode<<<nblocks, p->enc_threads, kEncodeSmem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off, p->d_codes,
-                                                                           p->d_tree, d_offsets, p->d_headers, p->d_crc,
-                                                                           p->zt_sel, d_dst, sc_bit, sc_carry);
+        k_hzr_encode<<<nblocks, kEncThreads, p->enc_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
+                                                                        p->d_codes, p->d_tree, p->d_step_lz, d_offsets,
+                                                                        p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip);
     }
     p->launches += 5;
     RSPT_CUDA_CHECK(cudaGetLastError());
@@ -533,10 +531,10 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
                                                                           (uint32_t)F, dec, p->d_headers, p->d_dec_nb, status, p->d_ctr);
     }
     const uint32_t* sc_bit = reinterpret_cast<const uint32_t*>(d_sidecar);
-    const uint16_t* sc_carry = d_sidecar ? reinterpret_cast<const uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
+    const uint16_t* sc_skip = d_sidecar ? reinterpret_cast<const uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
     {
         StageTimer t(p, RSPT_STAGE_DECODE);
-        k_hzr_decode<<<nblocks, kDecodeThreads, kDecodeSmem, p->stream>>>(d_src, s, dec, sc_bit, sc_carry, p->d_planes, status);
+        k_hzr_decode<<<nblocks, kDecodeThreads, kDecodeSmem, p->stream>>>(d_src, s, dec, sc_bit, sc_skip, p->d_planes, status);
     }
     p->launches += 2;
     RSPT_CUDA_CHECK(cudaGetLastError());
@@ -696,7 +694,7 @@ extern "C" int rspt_gpu_debug_hzr_tables(rspt_gpu_packer* p, const uint8_t* d_bl
     DeviceGuard dg(p->device);
     Shape s = p->s;
     s.N = (uint32_t)n; s.nblk = 1; s.nb_alloc = 1; s.plane_stride = (uint32_t)((n + 15) & ~(size_t)15);
-    k_hzr_hist<<<1, 1024, kStageSmem, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist);
+    k_hzr_hist<<<1, kHistThreads, 0, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz);
     k_hzr_tree<<<1, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, 1, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
     p->launches += 2;
     RSPT_CUDA_CHECK(cudaGetLastError());
