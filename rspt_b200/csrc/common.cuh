@@ -31,7 +31,8 @@ struct BlkInfo {
     uint16_t tree_nbits;
     uint8_t mode;
     uint8_t fill;
-    uint32_t n_used;       // symbols with a non-zero count
+    uint16_t n_used;       // symbols with a non-zero count
+    uint16_t n_tokens;     // tokens of the block, saturated at 65535 (selects the encoder path)
 };
 
 struct Shape {

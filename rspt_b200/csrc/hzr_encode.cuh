@@ -262,6 +262,14 @@ __device__ __forceinline__ void walk_word(uint32_t x, uint32_t nz, uint32_t star
 // its code word; a run's extra bits fill the next slot.
 __device__ __forceinline__ uint32_t slot_bits(uint32_t cw) { return cw >> 27; }
 
+// bit length of the tokens of one zero run of z >= 1 bytes (hzr_encode.c:146-166)
+__device__ __forceinline__ uint32_t run_bits(uint32_t z, const uint32_t* sc)
+{
+    LenSink ls{sc, 0};
+    emit_run(z, ls);
+    return ls.bits;
+}
+
 // copy `len` bytes from shared memory (byte offset `soff` into the word array `sw`) to an
 // arbitrarily aligned global address, 4 bytes per thread-step
 __device__ __forceinline__ void copy_smem_to_global(uint8_t* __restrict__ dst, const uint32_t* sw, uint32_t soff, uint32_t len)
@@ -394,6 +402,100 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
 
         uint32_t base = bi.tree_nbits;  // bit offset of the group (same in every thread)
         const uint32_t ngroups = (nsteps + kEncWarps - 1) / kEncWarps;
+        // ---- sparse blocks (few tokens): compact the non-zero bytes into a sorted list
+        // (position | value << 16) behind the payload in the staging buffer, then give every list
+        // entry to one thread: the zero run in front of the byte (gap to the previous entry) and
+        // the literal.  One extra pseudo entry closes the run that reaches the block end.
+        const uint32_t cap_words = (min(s.N, kBlock) + 3u) / 4u + 4u;  // words behind `pay` (see enc_smem)
+        const bool sparse = (uint32_t)bi.n_tokens * 4u <= n && pw + 2u + (uint32_t)bi.n_tokens + 2u <= cap_words;
+        if (sparse) {
+            uint32_t* list = pay + pw + 2u;
+            uint32_t m = 0;  // entries so far (same in every thread)
+            for (uint32_t g = 0; g < ngroups; ++g) {
+                const uint32_t st = g * kEncWarps + wid;
+                const uint32_t off = st * kStepBytes + lane * 16u;
+                const Chunk c = load_chunk(src, n, off);
+                const uint32_t cnt = __popc(c.nz);
+                uint32_t inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= (uint32_t)o) inc += y;
+                }
+                if (lane == 31) s_tot[g & 1][wid] = inc;
+                __syncthreads();
+                uint32_t tw2 = lane < kEncWarps ? s_tot[g & 1][lane] : 0u;
+#pragma unroll
+                for (int o = 1; o < kEncWarps; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tw2, o);
+                    if (lane >= (uint32_t)o) tw2 += y;
+                }
+                uint32_t at = m + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u) + inc - cnt;
+                m += __shfl_sync(0xFFFFFFFFu, tw2, kEncWarps - 1);
+                const uint32_t w[4] = {c.v.x, c.v.y, c.v.z, c.v.w};
+                uint32_t mk = c.nz;
+                while (mk) {
+                    const uint32_t p = __ffs(mk) - 1u;
+                    mk &= mk - 1u;
+                    const uint32_t x = p < 8 ? (p < 4 ? w[0] : w[1]) : (p < 12 ? w[2] : w[3]);
+                    list[at++] = (off + p) | (((x >> (8u * (p & 3u))) & 0xFFu) << 16);
+                }
+            }
+            __syncthreads();
+            // entry i < m: zeros (prev, cur) then the literal at cur; entry m: zeros (prev, n)
+            const uint32_t rounds = (m + 1u + kEncThreads - 1u) / kEncThreads;
+            for (uint32_t r = 0; r < rounds; ++r) {
+                const uint32_t i = r * kEncThreads + tid;
+                uint32_t bits = 0, gap = 0, cur = 0, val = 0, rs = 0;
+                const bool live = i <= m;
+                if (live) {
+                    const uint32_t e = i < m ? list[i] : n;
+                    cur = e & 0xFFFFu;
+                    if (i == m) cur = n;
+                    val = e >> 16;
+                    rs = i ? (list[i - 1] & 0xFFFFu) + 1u : 0u;
+                    gap = cur - rs;
+                    if (gap) bits = run_bits(gap, s_codes);
+                    if (i < m) bits += s_codes[val] >> 27;
+                }
+                uint32_t inc = bits;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= (uint32_t)o) inc += y;
+                }
+                const uint32_t par = (ngroups + r) & 1u;
+                if (lane == 31) s_tot[par][wid] = inc;
+                __syncthreads();
+                uint32_t tw2 = lane < kEncWarps ? s_tot[par][lane] : 0u;
+#pragma unroll
+                for (int o = 1; o < kEncWarps; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tw2, o);
+                    if (lane >= (uint32_t)o) tw2 += y;
+                }
+                const uint32_t o0 = base + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u) + inc - bits;
+                base += __shfl_sync(0xFFFFFFFFu, tw2, kEncWarps - 1);
+                if (live) {
+                    const uint32_t o_lit = o0 + bits - (i < m ? s_codes[val] >> 27 : 0u);
+                    if (bits) {
+                        EmitSink es{s_codes, pay, 0ull, o0 & 31u, o0 >> 5, true};
+                        if (gap) emit_run(gap, es);
+                        if (i < m) es.token(val, 0u, 0u);
+                        es.finish();
+                    }
+                    if (sc_bit) {
+                        // decode index entries of the 256-byte boundaries B in [rs, cur], B < n: at
+                        // B == rs the entry's first token starts; later boundaries lie inside the
+                        // zero run and resume at the literal
+                        for (uint32_t B = (rs + 255u) & ~255u; B <= cur && B < n; B += 256u) {
+                            sc_bit[(size_t)blk * kMaxSegs + (B >> 8)] = B == rs ? o0 : o_lit;
+                            sc_skip[(size_t)blk * kMaxSegs + (B >> 8)] = (uint16_t)(B == rs ? 0u : cur - B);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        } else
         for (uint32_t g = 0; g < ngroups; ++g) {
             const uint32_t st = g * kEncWarps + wid;
             const uint32_t sbase = st * kStepBytes;

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
         if (lane == 0) {
             BlkInfo bi;
             bi.payload_len = 1; bi.total_bits = 8; bi.tree_nbits = 0;
-            bi.mode = MODE_FILL; bi.fill = (uint8_t)(nz ? nzsym : 0u); bi.n_used = L;
+            bi.mode = MODE_FILL; bi.fill = (uint8_t)(nz ? nzsym : 0u); bi.n_used = (uint16_t)L; bi.n_tokens = 0;
             info[blk] = bi;
             atomicAdd(&ctr->blocks_fill, 1ull);
         }
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
     __syncwarp();
 
     // ---- phase D: leaves in parallel
-    uint32_t token_bits = 0, maxlen = 0;
+    uint32_t token_bits = 0, maxlen = 0, ntok = 0;
     uint32_t* my_codes = codes + (size_t)blk * kSymStride;
     for (uint32_t i = lane; i < L; i += 32) {
         const uint32_t kv = S.key[i];
@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
         const uint32_t depth = li2 & 255u, off = li2 >> 8;
         my_codes[sym] = code | (depth << 27);
         token_bits += cnt * (depth + sym_extra_bits(sym));
+        ntok += cnt;
         maxlen = max(maxlen, depth);
         const unsigned long long bits = (unsigned long long)(1u | (sym << 1)) << (off & 31u);
         atomicOr(&S.tree[off >> 5], (uint32_t)bits);
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         token_bits += __shfl_xor_sync(0xFFFFFFFFu, token_bits, o);
+        ntok += __shfl_xor_sync(0xFFFFFFFFu, ntok, o);
         maxlen = max(maxlen, __shfl_xor_sync(0xFFFFFFFFu, maxlen, o));
     }
     __syncwarp();
@@ -252,7 +254,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
         bi.mode = copy ? MODE_COPY : MODE_HUFF;
         bi.payload_len = copy ? n : bytes;
         bi.fill = (uint8_t)maxlen;  // HUFF: longest code word (selects the encoder's merge width)
-        bi.n_used = L;
+        bi.n_used = (uint16_t)L;
+        bi.n_tokens = (uint16_t)min(ntok, 65535u);
         info[blk] = bi;
         atomicAdd(copy ? &ctr->blocks_copy : &ctr->blocks_huff, 1ull);
     }

@@ -4,6 +4,7 @@ import csv, subprocess, sys, io, collections
 csv.field_size_limit(10**9)
 rep, kre = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+sortkey = sys.argv[4] if len(sys.argv) > 4 else "samples"
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kre],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
@@ -39,6 +40,6 @@ print(f"total warp-inst {tot['inst']:.3g} thread-inst/warp-inst {tot['tinst']/ma
 stalls = {n: v for n, v in tot.items() if n.startswith("stall_")}
 print("stall mix:", ", ".join(f"{n[6:]} {100*v/max(sum(stalls.values()),1):.0f}%" for n, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:7]))
 print(f"{'file:line':28s} {'%inst':>6s} {'%smp':>6s} {'lanes':>5s} {'bankx':>8s}  top-stall  source")
-for key, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
+for key, a in sorted(agg.items(), key=lambda kv: -kv[1][sortkey])[:top]:
     st = max(((n, v) for n, v in a.items() if n.startswith("stall_")), key=lambda kv: kv[1], default=("", 0))
     print(f"{key[0]+':'+str(key[1]):28s} {100*a['inst']/max(tot['inst'],1):6.1f} {100*a['samples']/max(tot['samples'],1):6.1f} {a['tinst']/max(a['inst'],1):5.1f} {a['bankx']:8.0f}  {st[0][6:]:10s} {src.get(key,'')[:90]}")
