@@ -496,77 +496,56 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             }
             __syncthreads();
         } else
+        // ---- dense blocks: a lane owns 16 consecutive bytes (4 words) of its warp's 512-byte step
         for (uint32_t g = 0; g < ngroups; ++g) {
             const uint32_t st = g * kEncWarps + wid;
-            const uint32_t sbase = st * kStepBytes;
-            // ---- load: round r of the step = bytes [128r, 128r + 128), one word per lane.  Masks
-            // of the 4 rounds are packed nibble-wise into 16-bit words.
-            uint32_t x[4];
-            uint32_t NZ = 0, INV = 0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const uint32_t off = sbase + 128u * r + 4u * lane;
-                const int valid = (int)n - (int)off;
-                x[r] = valid > 0 ? __ldg(reinterpret_cast<const uint32_t*>(src + off)) : 0u;
-                const uint32_t vm = valid >= 4 ? 0xFu : (valid > 0 ? (1u << valid) - 1u : 0u);
-                NZ |= (nz_nibble(x[r]) & vm) << (4 * r);
-                INV |= (0xFu & ~vm) << (4 * r);
+            const uint32_t sbase = st * kStepBytes, off = sbase + lane * 16u;
+            uint32_t x[4], NZ, INV = 0;
+            // zero flag of the byte before the step (lane 0 only; issued with the main load)
+            uint32_t pstep = 1;
+            if (lane == 0 && sbase > 0 && sbase <= n) pstep = src[sbase - 1];
+            if (sbase + kStepBytes <= n) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + off));
+                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+                NZ = nz_mask16(v);
+            } else {
+                const Chunk c = load_chunk(src, n, off);
+                x[0] = c.v.x; x[1] = c.v.y; x[2] = c.v.z; x[3] = c.v.w;
+                NZ = c.nz;
+                INV = c.stop & ~c.nz;
             }
             const uint32_t STOP = NZ | INV, Z = ~STOP & 0xFFFFu;
             const uint32_t after = st < nsteps ? s_after[st] : 0u;  // zeros that follow the step
-            // ---- zero flags of the neighbouring bytes: previous byte at bit 4r, next at 4r + 3
             const uint32_t z_up = __shfl_up_sync(0xFFFFFFFFu, Z, 1), z_dn = __shfl_down_sync(0xFFFFFFFFu, Z, 1);
-            const uint32_t z_31 = __shfl_sync(0xFFFFFFFFu, Z, 31), z_0 = __shfl_sync(0xFFFFFFFFu, Z, 0);
-            uint32_t PZ, NX;
-            if (lane > 0) {
-                PZ = (z_up >> 3) & 0x1111u;
-            } else {
-                const uint32_t pstep = (sbase > 0 && sbase <= n) ? (src[sbase - 1] == 0 ? 1u : 0u) : 0u;
-                PZ = (((z_31 >> 3) << 4) & 0x1110u) | pstep;
-            }
-            if (lane < 31) NX = (z_dn << 3) & 0x8888u;
-            else NX = (((z_0 >> 4) << 3) & 0x0888u) | (after ? 0x8000u : 0u);
-            const uint32_t prevm = ((Z << 1) & 0xEEEEu) | PZ;   // the byte before is a zero
-            const uint32_t nextm = ((Z >> 1) & 0x7777u) | NX;   // the byte after is a zero
+            const uint32_t pz = lane > 0 ? z_up >> 15 : (pstep == 0u ? 1u : 0u);          // the byte before my chunk is a zero
+            const uint32_t nzx = lane < 31 ? z_dn & 1u : (after ? 1u : 0u);              // the byte after my chunk is a zero
+            const uint32_t prevm = (Z << 1) | pz;
+            const uint32_t nextm = (Z >> 1) | (nzx << 15);
             const uint32_t starts = Z & ~prevm;                  // first zero of a run
             const uint32_t run2 = starts & nextm;                // ... of a run of >= 2
-            const uint32_t special = (Z & ~(starts & ~nextm)) | INV;  // every position that is not "one byte, one code"
-            const uint32_t TOK = NZ | starts;
-            // ---- zeros between the end of my word and the next stop byte, per round; only when a
-            // run leaves its word (or the decode index needs a skip count)
-            uint32_t t = STOP;
-            t |= (t >> 1) & 0x7777u;
-            t |= (t >> 2) & 0x3333u;                             // a stop at or above this position in the word
-            const bool want_chain = __any_sync(0xFFFFFFFFu, (run2 & ~t) != 0u || (sc_bit && lane == 0 && (PZ & 0x0101u)));
-            uint32_t fwd[4] = {0, 0, 0, 0}, lead[5];
-            lead[4] = after;
-            if (want_chain) {
-#pragma unroll
-                for (int r = 3; r >= 0; --r) {
-                    const uint32_t sr = (STOP >> (4 * r)) & 0xFu;
-                    const uint32_t sm = __ballot_sync(0xFFFFFFFFu, sr != 0u);
-                    const uint32_t fs = sr ? (uint32_t)__ffs(sr) - 1u : 4u;
-                    const uint32_t qf = sm ? (uint32_t)__ffs(sm) - 1u : 0u;
-                    lead[r] = sm ? 4u * qf + __shfl_sync(0xFFFFFFFFu, fs, qf) : 128u + lead[r + 1];
-                    const uint32_t above = lane < 31 ? sm & ~((2u << lane) - 1u) : 0u;
-                    const uint32_t q = above ? (uint32_t)__ffs(above) - 1u : 0u;
-                    const uint32_t fq = __shfl_sync(0xFFFFFFFFu, fs, q);
-                    fwd[r] = above ? 4u * (q - lane - 1u) + fq : 4u * (31u - lane) + lead[r + 1];
-                }
+            const uint32_t special = (Z & ~(starts & ~nextm)) | INV;  // positions that are not "one byte, one code"
+            // zeros between the end of my chunk and the next stop byte: only when a run leaves its
+            // chunk (nzx on a zero last byte) or the decode index needs a skip count
+            const bool leaves = (Z >> 15) & nzx;
+            const bool idx_lane = sc_bit && (lane & 15u) == 0u;
+            uint32_t fwd = 0;
+            if (__any_sync(0xFFFFFFFFu, leaves || (idx_lane && pz))) {
+                const uint32_t sm = __ballot_sync(0xFFFFFFFFu, STOP != 0u);
+                const uint32_t fs = STOP ? (uint32_t)__ffs(STOP) - 1u : 16u;
+                const uint32_t above = lane < 31 ? sm & ~((2u << lane) - 1u) : 0u;
+                const uint32_t q = above ? (uint32_t)__ffs(above) - 1u : 0u;
+                const uint32_t fq = __shfl_sync(0xFFFFFFFFu, fs, q);
+                fwd = above ? 16u * (q - lane - 1u) + fq : 16u * (31u - lane) + after;
             }
-            // ---- slots and lane bit lengths
+            // ---- slots and bit lengths, word by word
             uint32_t cw[4][4], xs[4], bits[4], slow = 0;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                bits[r] = 0;
-                xs[r] = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) cw[r][j] = 0;
-                if (!__any_sync(0xFFFFFFFFu, ((TOK >> (4 * r)) & 0xFu) != 0u)) continue;
                 cw[r][0] = s_codes[x[r] & 0xFFu];
                 cw[r][1] = s_codes[(x[r] >> 8) & 0xFFu];
                 cw[r][2] = s_codes[(x[r] >> 16) & 0xFFu];
                 cw[r][3] = s_codes[x[r] >> 24];
+                xs[r] = 0;
                 const uint32_t sp = (special >> (4 * r)) & 0xFu;
                 if (sp) {
                     // zeros inside runs and bytes beyond the block end carry no token
@@ -574,12 +553,11 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                     for (int j = 0; j < 4; ++j)
                         if ((sp >> j) & 1u) cw[r][j] = 0;
                     uint32_t rs = (run2 >> (4 * r)) & 0xFu;
-                    const uint32_t stop_r = (STOP >> (4 * r)) & 0xFu;
                     while (rs) {
                         const uint32_t j = __ffs(rs) - 1u;
                         rs &= rs - 1u;
-                        const uint32_t sb = stop_r >> j;
-                        const uint32_t len = sb ? (uint32_t)__ffs(sb) - 1u : 4u - j + fwd[r];
+                        const uint32_t sb = STOP >> (4 * r + j);
+                        const uint32_t len = sb ? (uint32_t)__ffs(sb) - 1u : 16u - (4u * r + j) + fwd;
                         if (len > kRunCap) {
                             slow |= 1u << r;  // several tokens: general path
                         } else {
@@ -598,26 +576,23 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                 bits[r] = slot_bits(cw[r][0]) + slot_bits(cw[r][1]) + slot_bits(cw[r][2]) + slot_bits(cw[r][3]) + slot_bits(xs[r]);
                 if (bits[r] > 64u) slow |= 1u << r;
                 if ((slow >> r) & 1u) {
+                    // zeros after word r: my later words, then the chunks that follow
+                    const uint32_t sb = r < 3 ? STOP >> (4 * r + 4) : 0u;
+                    const uint32_t fw = sb ? (uint32_t)__ffs(sb) - 1u : 12u - 4u * r + fwd;
                     LenSink ls{s_codes, 0};
-                    walk_word(x[r], (NZ >> (4 * r)) & 0xFu, (starts >> (4 * r)) & 0xFu, (STOP >> (4 * r)) & 0xFu, fwd[r], ls);
+                    walk_word(x[r], (NZ >> (4 * r)) & 0xFu, (starts >> (4 * r)) & 0xFu, (STOP >> (4 * r)) & 0xFu, fw, ls);
                     bits[r] = ls.bits;
                 }
             }
-            // ---- bit offsets: two packed warp scans (16-bit fields: a lane-round has <= 4 * 41 bits
-            // unless it owns a long zero run, whose tokens are < 200 bits)
-            uint32_t pa = bits[0] | (bits[1] << 16), pb = bits[2] | (bits[3] << 16);
-            const uint32_t pa0 = pa, pb0 = pb;
+            // ---- bit offsets
+            const uint32_t lbits = bits[0] + bits[1] + bits[2] + bits[3];
+            uint32_t inc = lbits;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t ya = __shfl_up_sync(0xFFFFFFFFu, pa, o), yb = __shfl_up_sync(0xFFFFFFFFu, pb, o);
-                if (lane >= (uint32_t)o) {
-                    pa += ya;
-                    pb += yb;
-                }
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
             }
-            const uint32_t ta = __shfl_sync(0xFFFFFFFFu, pa, 31), tb = __shfl_sync(0xFFFFFFFFu, pb, 31);
-            const uint32_t rt0 = ta & 0xFFFFu, rt1 = ta >> 16, rt2 = tb & 0xFFFFu, rt3 = tb >> 16;  // round totals
-            if (lane == 31) s_tot[g & 1][wid] = rt0 + rt1 + rt2 + rt3;
+            if (lane == 31) s_tot[g & 1][wid] = inc;
             __syncthreads();
             uint32_t tw2 = lane < kEncWarps ? s_tot[g & 1][lane] : 0u;
 #pragma unroll
@@ -625,53 +600,42 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                 const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tw2, o);
                 if (lane >= (uint32_t)o) tw2 += y;
             }
-            const uint32_t wbase = base + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u);
+            uint32_t o = base + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u) + inc - lbits;
             base += __shfl_sync(0xFFFFFFFFu, tw2, kEncWarps - 1);
-            pa -= pa0;
-            pb -= pb0;  // exclusive
-            uint32_t ofs[4];
-            ofs[0] = wbase + (pa & 0xFFFFu);
-            ofs[1] = wbase + rt0 + (pa >> 16);
-            ofs[2] = wbase + rt0 + rt1 + (pb & 0xFFFFu);
-            ofs[3] = wbase + rt0 + rt1 + rt2 + (pb >> 16);
-            // ---- decode index: one entry per 256 output bytes (rounds 0 and 2, lane 0)
-            if (sc_bit && lane == 0) {
-#pragma unroll
-                for (int r = 0; r < 4; r += 2) {
-                    const uint32_t off = sbase + 128u * r;
-                    if (off < n) {
-                        sc_bit[(size_t)blk * kMaxSegs + (off >> 8)] = ofs[r];
-                        sc_skip[(size_t)blk * kMaxSegs + (off >> 8)] = (uint16_t)(((PZ >> (4 * r)) & 1u) ? lead[r] : 0u);
-                    }
-                }
+            // ---- decode index: one entry per 256 output bytes (lanes 0 and 16)
+            if (idx_lane && off < n) {
+                sc_bit[(size_t)blk * kMaxSegs + (off >> 8)] = o;
+                sc_skip[(size_t)blk * kMaxSegs + (off >> 8)] = (uint16_t)(pz ? (STOP ? (uint32_t)__ffs(STOP) - 1u : 16u + fwd) : 0u);
             }
             // ---- emit
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                if (bits[r] == 0u) continue;
-                const uint32_t o = ofs[r];
-                if ((slow >> r) & 1u) {
-                    EmitSink es{s_codes, pay, 0ull, o & 31u, o >> 5, true};
-                    walk_word(x[r], (NZ >> (4 * r)) & 0xFu, (starts >> (4 * r)) & 0xFu, (STOP >> (4 * r)) & 0xFu, fwd[r], es);
-                    es.finish();
-                } else {
-                    // <= 64 bits: concatenate the slots, shift to the bit offset, OR into <= 3 words
-                    unsigned long long acc = cw[r][0] & 0x07FFFFFFu;
-                    uint32_t nacc = slot_bits(cw[r][0]);
-                    acc |= (unsigned long long)(cw[r][1] & 0x07FFFFFFu) << nacc;
-                    nacc += slot_bits(cw[r][1]);
-                    acc |= (unsigned long long)(cw[r][2] & 0x07FFFFFFu) << nacc;
-                    nacc += slot_bits(cw[r][2]);
-                    acc |= (unsigned long long)(cw[r][3] & 0x07FFFFFFu) << nacc;
-                    nacc += slot_bits(cw[r][3]);
-                    if (xs[r]) acc |= (unsigned long long)(xs[r] & 0x07FFFFFFu) << nacc;
-                    const uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32), sh = o & 31u;
-                    uint32_t* w = pay + (o >> 5);
-                    const uint32_t v0 = lo << sh, v1 = __funnelshift_l(lo, hi, sh), v2 = __funnelshift_l(hi, 0u, sh);
-                    atomicOr(w, v0);
-                    if (v1) atomicOr(w + 1, v1);
-                    if (v2) atomicOr(w + 2, v2);
+                if (bits[r]) {
+                    if ((slow >> r) & 1u) {
+                        const uint32_t sb = r < 3 ? STOP >> (4 * r + 4) : 0u;
+                        const uint32_t fw = sb ? (uint32_t)__ffs(sb) - 1u : 12u - 4u * r + fwd;
+                        EmitSink es{s_codes, pay, 0ull, o & 31u, o >> 5, true};
+                        walk_word(x[r], (NZ >> (4 * r)) & 0xFu, (starts >> (4 * r)) & 0xFu, (STOP >> (4 * r)) & 0xFu, fw, es);
+                        es.finish();
+                    } else {
+                        // <= 64 bits: concatenate the slots (last first), shift to the bit offset,
+                        // OR into <= 3 staging words
+                        uint32_t lo = xs[r] & 0x07FFFFFFu, hi = 0;
+#pragma unroll
+                        for (int j = 3; j >= 0; --j) {
+                            const uint32_t l = slot_bits(cw[r][j]);
+                            hi = __funnelshift_l(lo, hi, l);
+                            lo = (lo << l) | (cw[r][j] & 0x07FFFFFFu);
+                        }
+                        const uint32_t sh = o & 31u;
+                        uint32_t* w = pay + (o >> 5);
+                        const uint32_t v0 = lo << sh, v1 = __funnelshift_l(lo, hi, sh), v2 = __funnelshift_l(hi, 0u, sh);
+                        atomicOr(w, v0);
+                        if (v1) atomicOr(w + 1, v1);
+                        if (v2) atomicOr(w + 2, v2);
+                    }
                 }
+                o += bits[r];
             }
         }
         __syncthreads();
