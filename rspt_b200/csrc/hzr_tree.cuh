@@ -17,9 +17,9 @@
 //      nodes win ties against leaves; inside a run of equal-weight internal nodes the most
 //      recently created one is taken first -- exactly MakeTree's tie-break.  Also counts the
 //      leaves below every internal node.
-//   C  lane 0: top-down pass in reverse creation order (a parent is always created after its
-//      children): depth, code and pre-order bit offset of every node.  A subtree with l leaves
-//      serialises to 11*l - 1 bits, which places child_b without walking child_a.
+//   C  breadth-first top-down pass, one frontier node per lane: depth, code and pre-order bit
+//      offset of every node.  A subtree with l leaves serialises to 11*l - 1 bits, which places
+//      child_b without walking child_a.
 //   D  leaves in parallel: code table entry, tree bits, payload bit total, maximum code length.
 #pragma once
 
@@ -31,12 +31,13 @@ constexpr int kTreeWarps = 1;  // one tree per CTA: a finished (sparse) tree fre
 
 struct TreeWarpSmem {
     uint32_t key[512];         // sorted leaf keys
-    uint32_t icnt[260];        // B: internal node weight; C: node code
-    uint32_t child[260];       // child_a | child_b << 16; ids < 512 are leaf ranks, 512 + j internal node j
-    uint32_t ninfo[260];       // leaves below (bits 0-8) | depth (9-13) | pre-order bit offset (14-25)
+    uint32_t icnt[260];        // B: internal node weight (| bit 31: next node has equal weight); C: node code
+    uint32_t child[260];       // child_a | child_b << 10 | leaves below << 20; ids < 512 are leaf ranks, 512 + j internal node j
+    uint32_t ninfo[260];       // C: depth | pre-order bit offset << 8
     uint32_t lcode[264];       // per leaf rank: code
     uint32_t linfo[264];       // per leaf rank: depth | bit offset << 8
     uint32_t tree[kTreeWords];
+    uint16_t front[2][264];    // C: breadth-first frontiers (internal node indices)
 };
 
 struct Counters {
@@ -148,74 +149,131 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
     for (uint32_t i = lane; i < kTreeWords; i += 32) S.tree[i] = 0;
     __syncwarp();
 
-    // ---- phase B + C: lane 0
+    // ---- phase B: lane 0, two-queue merge.  Registers hold both queue heads; an internal node's
+    // weight word carries a flag "the node created right after me has the same weight", so the
+    // common pick (a run of one) needs no look-ahead load.
+    constexpr uint32_t kInf = 0x7FFFFFFFu, kEqNext = 0x80000000u;
     if (lane == 0) {
-        uint32_t li = 0, fr = 0, top = 0, run_end = 0, ni = 0;
-        bool started = false;
-        uint32_t lc = S.key[0] >> 9;
+        uint32_t li = 0, lc = S.key[0] >> 9;          // leaf queue head
+        uint32_t fr = 0, ni = 0, ic = kInf;           // internal queue: head index, count, head weight
+        bool icf = false;                             // head has an equal-weight successor
+        uint32_t top = 0, run_end = 0, last_w = kInf;
+        bool in_run = false;
         for (uint32_t round = 0; round + 1 < L; ++round) {
             uint32_t id[2], wt[2], lv[2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const uint32_t ic = fr < ni ? S.icnt[fr] : 0xFFFFFFFFu;
                 if (ic <= lc) {
-                    if (!started) {
-                        top = fr + 1;
-                        while (top < ni && S.icnt[top] == ic) ++top;
-                        run_end = top;
-                        started = true;
+                    uint32_t pick;
+                    bool advance;
+                    if (!in_run) {
+                        if (!icf) {
+                            pick = fr;
+                            advance = true;
+                            run_end = fr + 1;
+                        } else {
+                            top = fr + 1;
+                            while (top < ni && (S.icnt[top] & kInf) == ic) ++top;
+                            run_end = top;
+                            in_run = true;
+                            pick = --top;
+                            advance = false;  // a flagged run has >= 2 nodes
+                        }
+                    } else {
+                        pick = --top;
+                        advance = top == fr;
                     }
-                    --top;
-                    id[q] = 512u + top;
+                    id[q] = 512u + pick;
                     wt[q] = ic;
-                    lv[q] = S.ninfo[top];
-                    if (top == fr) {
+                    lv[q] = S.child[pick] >> 20;
+                    if (advance) {
+                        in_run = false;
                         fr = run_end;
-                        started = false;
+                        if (fr < ni) {
+                            const uint32_t raw = S.icnt[fr];
+                            ic = raw & kInf;
+                            icf = (raw & kEqNext) != 0u;
+                        } else {
+                            ic = kInf;
+                            icf = false;
+                        }
                     }
                 } else {
                     id[q] = li;
                     wt[q] = lc;
                     lv[q] = 1;
                     ++li;
-                    lc = li < L ? (S.key[li] >> 9) : 0xFFFFFFFFu;
+                    lc = li < L ? (S.key[li] >> 9) : kInf;
                 }
             }
-            S.icnt[ni] = wt[0] + wt[1];
-            S.child[ni] = id[0] | (id[1] << 16);
-            S.ninfo[ni] = lv[0] + lv[1];
+            const uint32_t w = wt[0] + wt[1];
+            if (w == last_w) {
+                S.icnt[ni - 1] = w | kEqNext;
+                if (ni - 1 == fr) icf = true;
+            }
+            if (fr == ni) {
+                ic = w;
+                icf = false;
+            }
+            S.icnt[ni] = w;
+            S.child[ni] = id[0] | (id[1] << 10) | ((lv[0] + lv[1]) << 20);
+            last_w = w;
             ++ni;
         }
-        // top-down: root = last internal node, depth 0, code 0, offset 0
+        // root = last internal node: depth 0, code 0, pre-order offset 0
         S.icnt[L - 2] = 0;
-        S.ninfo[L - 2] &= 511u;
-        for (int j = (int)L - 2; j >= 0; --j) {
-            const uint32_t inf = S.ninfo[j], code = S.icnt[j], ch = S.child[j];
-            const uint32_t depth = (inf >> 9) & 31u, off = inf >> 14;
-            const uint32_t a = ch & 0xFFFFu, bb = ch >> 16;
-            uint32_t bits_a;
-            if (a < 512u) {
-                S.lcode[a] = code;
-                S.linfo[a] = (depth + 1) | ((off + 1) << 8);
-                bits_a = 10;
-            } else {
-                const uint32_t la = S.ninfo[a - 512u] & 511u;
-                S.icnt[a - 512u] = code;
-                S.ninfo[a - 512u] = la | ((depth + 1) << 9) | ((off + 1) << 14);
-                bits_a = 11u * la - 1u;
-            }
-            const uint32_t code_b = code | (1u << depth), off_b = off + 1 + bits_a;
-            if (bb < 512u) {
-                S.lcode[bb] = code_b;
-                S.linfo[bb] = (depth + 1) | (off_b << 8);
-            } else {
-                const uint32_t lb = S.ninfo[bb - 512u] & 511u;
-                S.icnt[bb - 512u] = code_b;
-                S.ninfo[bb - 512u] = lb | ((depth + 1) << 9) | (off_b << 14);
-            }
-        }
+        S.ninfo[L - 2] = 0;
+        S.front[0][0] = (uint16_t)(L - 2);
     }
     __syncwarp();
+
+    // ---- phase C: breadth-first top-down pass, one frontier node per lane
+    {
+        uint32_t nf = 1, cur = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+        while (nf) {
+            uint32_t nn = 0;
+            for (uint32_t fb = 0; fb < nf; fb += 32) {
+                const uint32_t i = fb + lane;
+                const bool act = i < nf;
+                uint32_t a = 0, bb = 0;
+                if (act) {
+                    const uint32_t j = S.front[cur][i];
+                    const uint32_t ch = S.child[j], code = S.icnt[j], inf = S.ninfo[j];
+                    const uint32_t depth = inf & 255u, off = inf >> 8;
+                    a = ch & 1023u;
+                    bb = (ch >> 10) & 1023u;
+                    const uint32_t st_a = (depth + 1) | ((off + 1) << 8);
+                    uint32_t bits_a = 10;
+                    if (a < 512u) {
+                        S.lcode[a] = code;
+                        S.linfo[a] = st_a;
+                    } else {
+                        bits_a = 11u * (S.child[a - 512u] >> 20) - 1u;
+                        S.icnt[a - 512u] = code;
+                        S.ninfo[a - 512u] = st_a;
+                    }
+                    const uint32_t code_b = code | (1u << depth), st_b = (depth + 1) | ((off + 1 + bits_a) << 8);
+                    if (bb < 512u) {
+                        S.lcode[bb] = code_b;
+                        S.linfo[bb] = st_b;
+                    } else {
+                        S.icnt[bb - 512u] = code_b;
+                        S.ninfo[bb - 512u] = st_b;
+                    }
+                }
+                const bool ia = act && a >= 512u, ib = act && bb >= 512u;
+                const uint32_t ma = __ballot_sync(0xFFFFFFFFu, ia), mb = __ballot_sync(0xFFFFFFFFu, ib);
+                if (ia) S.front[cur ^ 1][nn + __popc(ma & lt)] = (uint16_t)(a - 512u);
+                nn += __popc(ma);
+                if (ib) S.front[cur ^ 1][nn + __popc(mb & lt)] = (uint16_t)(bb - 512u);
+                nn += __popc(mb);
+            }
+            __syncwarp();
+            cur ^= 1;
+            nf = nn;
+        }
+    }
 
     // ---- phase D: leaves in parallel
     uint32_t token_bits = 0, maxlen = 0, ntok = 0;
