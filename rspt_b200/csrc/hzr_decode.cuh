@@ -18,7 +18,7 @@
 namespace rspt {
 
 constexpr int kDecodeThreads = 256;
-constexpr int kLutBits = 10;
+constexpr int kLutBits = 12;
 constexpr uint32_t kModeZero = 3;      // frame failed to parse: emit zeros
 constexpr uint32_t kModeInactive = 255;
 
@@ -101,34 +101,28 @@ __global__ void __launch_bounds__(128) k_frame_parse(const uint8_t* __restrict__
     status[f] = err ? -4 : 0;
 }
 
-// sequential bit reader over global memory, LSB-first, 32-bit aligned refills
+// sequential bit reader over the payload staged in shared memory (word 0 = payload bytes 0..3),
+// LSB-first, 32-bit refills into a 64-bit window
 struct BitReader {
-    const uint32_t* words;   // aligned base
-    uint32_t nwords;         // aligned words that overlap the payload
+    const uint32_t* words;
     uint32_t widx;
     unsigned long long buf;
     uint32_t cnt;
-    __device__ __forceinline__ void init(const uint8_t* payload, uint32_t plen, uint32_t bitpos)
+    __device__ __forceinline__ void init(const uint32_t* pay_words, uint32_t bitpos)
     {
-        const uintptr_t a = (uintptr_t)payload;
-        words = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        const uint32_t lead = (uint32_t)(a & 3u);
-        nwords = (lead + plen + 3u) >> 2;
-        const uint32_t abs_bit = lead * 8u + bitpos;
-        widx = abs_bit >> 5;
-        buf = 0;
-        cnt = 0;
-        refill();
-        const uint32_t drop = abs_bit & 31u;
+        words = pay_words;
+        widx = bitpos >> 5;
+        buf = (unsigned long long)words[widx] | ((unsigned long long)words[widx + 1] << 32);
+        widx += 2;
+        const uint32_t drop = bitpos & 31u;
         buf >>= drop;
-        cnt -= drop;
+        cnt = 64u - drop;
     }
     __device__ __forceinline__ void refill()
     {
-        while (cnt <= 32) {
-            const uint32_t w = widx < nwords ? __ldg(words + widx) : 0u;
-            buf |= (unsigned long long)w << cnt;
-            cnt += 32;
+        if (cnt <= 32u) {
+            buf |= (unsigned long long)words[widx] << cnt;
+            cnt += 32u;
             ++widx;
         }
     }
@@ -146,50 +140,108 @@ struct BitReader {
     }
 };
 
-constexpr uint32_t kDecStageWords = kBlock / 4;
-constexpr size_t kDecodeSmem = (size_t)kDecStageWords * 4;
+// Writes one thread's output range [0, len) of a 16-byte aligned destination in order: bytes are
+// gathered into a word, words into a 16-byte window, windows go out with one 128-bit store.
+// Every byte of the range is written exactly once (zero runs as zeros), so the destination needs
+// no clearing; the last window may run up to 15 bytes past `len` (plane rows are padded to 16).
+struct SegWriter {
+    uint8_t* dst;
+    uint32_t len, pos, w, v0, v1, v2;
+    __device__ __forceinline__ void init(uint8_t* d, uint32_t l)
+    {
+        dst = d; len = l; pos = 0; w = 0; v0 = v1 = v2 = 0;
+    }
+    __device__ __forceinline__ void push_word()
+    {
+        const uint32_t k = ((pos - 1u) >> 2) & 3u;
+        if (k == 0) v0 = w;
+        else if (k == 1) v1 = w;
+        else if (k == 2) v2 = w;
+        else *reinterpret_cast<uint4*>(dst + ((pos - 1u) & ~15u)) = make_uint4(v0, v1, v2, w);
+        w = 0;
+    }
+    __device__ __forceinline__ void put(uint32_t byte)
+    {
+        w |= byte << (8u * (pos & 3u));
+        ++pos;
+        if ((pos & 3u) == 0u) push_word();
+    }
+    // z zero bytes, clipped to the range
+    __device__ __forceinline__ void zeros(uint32_t z)
+    {
+        z = min(z, len - pos);
+        while (z) {
+            if ((pos & 15u) == 0u && z >= 16u) {
+                *reinterpret_cast<uint4*>(dst + pos) = make_uint4(0, 0, 0, 0);
+                pos += 16u;
+                z -= 16u;
+            } else if ((pos & 3u) == 0u && z >= 4u) {
+                pos += 4u;
+                z -= 4u;
+                push_word();
+            } else {
+                put(0u);
+                --z;
+            }
+        }
+    }
+    // pad the open window with zeros and store it
+    __device__ __forceinline__ void finish()
+    {
+        zeros(len - pos);
+        while (pos & 15u) put(0u);
+    }
+};
 
-__device__ __forceinline__ uint32_t dec_swizzle(uint32_t w) { return w ^ ((w >> 6) & 31u); }
+constexpr uint32_t kDecPayWords = kBlock / 4 + 4;
+constexpr size_t kDecodeSmem = (size_t)kDecPayWords * 4;
+constexpr uint32_t kLongFlag = 0x8000u;
 
-__global__ void __launch_bounds__(kDecodeThreads) k_hzr_decode(const uint8_t* __restrict__ src, Shape s,
-                                                                const DecBlk* __restrict__ dec,
-                                                                const uint32_t* __restrict__ sc_bit,
-                                                                const uint16_t* __restrict__ sc_skip,
-                                                                uint8_t* __restrict__ planes, int32_t* __restrict__ status)
+// One CTA per hzr block.  The payload is staged in shared memory (coalesced, re-aligned); the
+// code table comes from the decode index (sc_codes) or, for streams without one, from RecoverTree
+// run by one thread; a 12-bit look-up table maps the next bits to (symbol, length), longer codes
+// are matched against the short list of long code words.  With the index every thread decodes the
+// tokens that start in its 256-byte segment and writes exactly that segment; without it thread 0
+// decodes the whole block.
+__global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t* __restrict__ src, Shape s,
+                                                                   const DecBlk* __restrict__ dec,
+                                                                   const uint32_t* __restrict__ sc_bit,
+                                                                   const uint16_t* __restrict__ sc_skip,
+                                                                   const uint32_t* __restrict__ sc_codes,
+                                                                   uint8_t* __restrict__ planes, int32_t* __restrict__ status)
 {
-    extern __shared__ __align__(16) uint32_t stg[];  // decoded block, word-swizzled per 256-byte segment
-    __shared__ uint16_t s_lut[1 << kLutBits];        // <0x8000: sym | len << 9 ; >=0x8000: node index
-    __shared__ uint16_t s_child[2 * kNumSymbols][2];
-    __shared__ int16_t s_nsym[2 * kNumSymbols];      // >= 0 leaf symbol, -1 branch
-    __shared__ uint32_t s_leaf_code[kNumSymbols];
-    __shared__ uint16_t s_leaf_info[kNumSymbols];    // sym | len << 9
-    __shared__ uint32_t s_meta[4];                   // n_leaves, tree_end_bit, error, single-leaf flag
+    extern __shared__ __align__(16) uint32_t payw[];  // payload words (+ zero slack)
+    __shared__ __align__(16) uint16_t s_lut[1 << kLutBits];  // sym | len << 9, or kLongFlag; serial path: tree scratch first
+    __shared__ uint32_t s_cw[kSymStride];            // code | len << 27 per symbol, 0 = unused
+    __shared__ uint16_t s_long[kSymStride];          // symbols whose code is longer than the table
+    __shared__ uint32_t s_meta[4];                   // tree_end_bit, error, long count
 
-    const uint32_t blk = blockIdx.x, tid = threadIdx.x;
+    const uint32_t blk = blockIdx.x, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     const DecBlk d = dec[blk];
     if (d.mode == kModeInactive) return;
     uint32_t f, k, b;
     blk_decode(s, blk, f, k, b);
     uint8_t* out = planes + ((size_t)f * s.nb_alloc + k) * s.plane_stride + (size_t)b * kBlock;
-    uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
-    const uint32_t n = d.out_n, nw = (n + 3u) >> 2;
+    uint4* out4 = reinterpret_cast<uint4*>(out);
+    const uint32_t n = d.out_n, nq = (n + 15u) >> 4;
     const uint8_t* pay = src + d.payload_off;
 
     if (d.mode == MODE_FILL || d.mode == kModeZero) {
         const uint32_t v = d.mode == MODE_FILL ? pay[0] * 0x01010101u : 0u;  // memset (dec:362-370)
-        for (uint32_t i = tid; i < nw; i += blockDim.x) out32[i] = v;
+        for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(v, v, v, v);
         return;
     }
+    const uintptr_t pa = (uintptr_t)pay;
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3);
+    const uint32_t lead = (uint32_t)(pa & 3u), sh = lead * 8u;
     if (d.mode == MODE_COPY) {
         if (d.payload_len != n) {  // "Encoded / decoded size mismatch (COPY)" dec:351-355
             if (tid == 0) status[f] = -4;
-            for (uint32_t i = tid; i < nw; i += blockDim.x) out32[i] = 0;
+            for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
             return;
         }
-        const uintptr_t a = (uintptr_t)pay;
-        const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        const uint32_t lead = (uint32_t)(a & 3u), sh = lead * 8u;
-        const uint32_t naw = (lead + n + 3u) >> 2;
+        const uint32_t naw = (lead + n + 3u) >> 2, nw = (n + 3u) >> 2;
+        uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
         for (uint32_t i = tid; i < nw; i += blockDim.x) {
             const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
             out32[i] = __funnelshift_r(lo, hi, sh);
@@ -197,114 +249,129 @@ __global__ void __launch_bounds__(kDecodeThreads) k_hzr_decode(const uint8_t* __
         return;
     }
 
-    // ---- MODE_HUFF
-    for (uint32_t i = tid; i < kDecStageWords; i += blockDim.x) stg[i] = 0;
-    for (uint32_t i = tid; i < (1u << kLutBits); i += blockDim.x) s_lut[i] = 0;
-    if (tid == 0) {
-        // RecoverTree (dec:263-333), iteratively: pre-order, 0 = branch, 1 + 9-bit symbol = leaf
-        BitReader r;
-        r.init(pay, d.payload_len, 0);
-        uint32_t nodes = 0, leaves = 0, err = 0, bits_used = 0;
-        uint32_t st_parent[40], st_code[40], st_depth[40];
-        int sp = 0;
-        uint32_t parent = 0xFFFFu, which = 0, code = 0, depth = 0;
-        for (;;) {
-            if (nodes >= 2 * kNumSymbols - 1 || depth > 31) { err = 1; break; }
-            const uint32_t me = nodes++;
-            if (parent != 0xFFFFu) s_child[parent][which] = (uint16_t)me;
-            r.refill();
-            const uint32_t leaf = r.take(1);
-            ++bits_used;
-            if (leaf) {
-                const uint32_t sym = r.take(9);
-                bits_used += 9;
-                if (sym >= kNumSymbols || leaves >= kNumSymbols) { err = 1; break; }
-                s_nsym[me] = (int16_t)sym;
-                s_leaf_code[leaves] = code;
-                s_leaf_info[leaves] = (uint16_t)(sym | (depth << 9));
-                ++leaves;
-                if (sp == 0) break;
-                --sp;
-                parent = st_parent[sp]; which = 1; code = st_code[sp]; depth = st_depth[sp];
-            } else {
-                s_nsym[me] = -1;
-                if (depth == kLutBits) s_lut[code] = (uint16_t)(0x8000u | me);
-                if (sp >= 40) { err = 1; break; }
-                st_parent[sp] = me; st_code[sp] = code | (1u << depth); st_depth[sp] = depth + 1; ++sp;
-                parent = me; which = 0; depth = depth + 1;
-            }
+    // ---- MODE_HUFF: stage the payload
+    const uint32_t plen = d.payload_len, pwords = (plen + 3u) >> 2, naw = (lead + plen + 3u) >> 2;
+    for (uint32_t i = tid; i < pwords + 4u; i += blockDim.x) {
+        uint32_t v = 0;
+        if (i < pwords) {
+            const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
+            v = __funnelshift_r(lo, hi, sh);
         }
-        if (bits_used > d.payload_len * 8u) err = 1;
-        s_meta[0] = leaves;
-        s_meta[1] = bits_used;
-        s_meta[2] = err;
-        s_meta[3] = (nodes == 1);
+        payw[i] = v;
     }
-    __syncthreads();
-    if (s_meta[2]) {
+    for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_lut)[i] = kLongFlag | (kLongFlag << 16);
+    const bool indexed = sc_bit != nullptr;
+    if (indexed) {
+        for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = i < (uint32_t)kNumSymbols ? sc_codes[(size_t)blk * kSymStride + i] : 0u;
+        if (tid == 0) { s_meta[0] = 0; s_meta[1] = 0; s_meta[2] = 0; }
+        __syncthreads();
+    } else {
+        for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            // RecoverTree (dec:263-333), iteratively: pre-order, 0 = branch, 1 + 9-bit symbol = leaf.
+            // Only the code word of every leaf is needed: a stack of (code, depth) of pending
+            // right children.
+            BitReader r;
+            r.init(payw, 0);
+            uint32_t nodes = 0, leaves = 0, err = 0, bits_used = 0;
+            uint32_t st_code[40], st_depth[40];
+            int sp = 0;
+            uint32_t code = 0, depth = 0;
+            for (;;) {
+                if (nodes >= 2 * kNumSymbols - 1 || depth > 27u) { err = 1; break; }
+                ++nodes;
+                r.refill();
+                const uint32_t leaf = r.take(1);
+                ++bits_used;
+                if (leaf) {
+                    const uint32_t sym = r.take(9);
+                    bits_used += 9;
+                    if (sym >= (uint32_t)kNumSymbols || leaves >= (uint32_t)kNumSymbols || s_cw[sym] != 0u) { err = 1; break; }
+                    // lone leaf: 1-bit code (dec:306 `hzr_max(bits, 1)`)
+                    s_cw[sym] = code | (max(depth, 1u) << 27);
+                    ++leaves;
+                    if (sp == 0) break;
+                    --sp;
+                    code = st_code[sp]; depth = st_depth[sp];
+                } else {
+                    if (sp >= 40) { err = 1; break; }
+                    st_code[sp] = code | (1u << depth); st_depth[sp] = depth + 1; ++sp;
+                    depth = depth + 1;
+                }
+            }
+            if (bits_used > plen * 8u) err = 1;
+            s_meta[0] = bits_used;
+            s_meta[1] = err;
+            s_meta[2] = 0;
+        }
+        __syncthreads();
+    }
+    if (s_meta[1]) {
         if (tid == 0) status[f] = -4;
-        for (uint32_t i = tid; i < nw; i += blockDim.x) out32[i] = 0;
+        for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
         return;
     }
-    const bool single = s_meta[3] != 0;
-    for (uint32_t l = tid; l < s_meta[0]; l += blockDim.x) {
-        const uint32_t info = s_leaf_info[l];
-        uint32_t len = info >> 9;
-        const uint32_t code = s_leaf_code[l];
-        if (single) len = 1;  // lone leaf: 1-bit code (dec:306 `hzr_max(bits, 1)`)
+    // look-up table: a warp per symbol, lanes over the 2^(12 - len) entries that end in its code
+    for (uint32_t sym = wid; sym < (uint32_t)kNumSymbols; sym += (blockDim.x >> 5)) {
+        const uint32_t cw = s_cw[sym];
+        if (cw == 0u) continue;
+        const uint32_t len = cw >> 27, code = cw & 0x07FFFFFFu;
         if (len <= (uint32_t)kLutBits) {
-            const uint16_t e = (uint16_t)((info & 511u) | (len << 9));
-            for (uint32_t i = 0; i < (1u << (kLutBits - len)); ++i) s_lut[(i << len) | code] = e;
+            const uint16_t e = (uint16_t)(sym | (len << 9));
+            for (uint32_t i = lane; i < (1u << (kLutBits - len)); i += 32) s_lut[(i << len) | code] = e;
+        } else if (lane == 0) {
+            s_long[atomicAdd(&s_meta[2], 1u)] = (uint16_t)sym;
         }
     }
     __syncthreads();
 
     const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
     uint32_t my_err = 0;
-    const bool indexed = sc_bit != nullptr;
     if (indexed ? tid < nseg : tid == 0) {
-        uint32_t bitpos, outpos, end_bit;
+        uint32_t bitpos, seg0, seg_len, skip, end_bit;
         if (indexed) {
             bitpos = sc_bit[(size_t)blk * kMaxSegs + tid];
-            outpos = tid * kSegBytes + sc_skip[(size_t)blk * kMaxSegs + tid];
+            skip = sc_skip[(size_t)blk * kMaxSegs + tid];
             end_bit = tid + 1 < nseg ? sc_bit[(size_t)blk * kMaxSegs + tid + 1] : 0xFFFFFFFFu;
+            seg0 = tid * kSegBytes;
+            seg_len = min((uint32_t)kSegBytes, n - seg0);
         } else {
-            bitpos = s_meta[1];
-            outpos = 0;
+            bitpos = s_meta[0];
+            skip = 0;
             end_bit = 0xFFFFFFFFu;
+            seg0 = 0;
+            seg_len = n;
         }
-        const uint32_t limit_bits = d.payload_len * 8u;
-        if (bitpos > limit_bits || outpos > n) my_err = 1;
+        const uint32_t limit_bits = plen * 8u, nlong = s_meta[2];
+        if (bitpos > limit_bits) { my_err = 1; bitpos = 0; }
+        SegWriter wr;
+        wr.init(out + seg0, seg_len);
+        wr.zeros(skip);  // bytes covered by a zero run that started in an earlier segment
         BitReader r;
-        r.init(pay, d.payload_len, my_err ? 0 : bitpos);
-        uint8_t* sb = reinterpret_cast<uint8_t*>(stg);
-        while (!my_err && bitpos < end_bit && outpos < n) {
+        r.init(payw, bitpos);
+        while (!my_err && bitpos < end_bit && wr.pos < seg_len) {
             r.refill();
-            const uint32_t e = s_lut[r.peek(kLutBits)];
-            uint32_t sym;
-            if (!(e & 0x8000u)) {
-                const uint32_t len = (e >> 9) & 15u;
-                if (len == 0) { my_err = 1; break; }
-                sym = e & 511u;
-                r.skip(len);
-                bitpos += len;
-            } else {
-                uint32_t node = e & 0x3FFu;
-                r.skip(kLutBits);
-                bitpos += kLutBits;
-                while (s_nsym[node] < 0) {  // codes longer than the table: walk the tree (dec:418-431)
-                    if (r.cnt == 0) r.refill();
-                    node = s_child[node][r.take(1)];
-                    ++bitpos;
+            uint32_t e = s_lut[r.peek(kLutBits)];
+            if (e & kLongFlag) {
+                // code longer than the table: match the few long code words (dec:418-431 walks the tree)
+                e = 0;
+                for (uint32_t j = 0; j < nlong; ++j) {
+                    const uint32_t sym = s_long[j], cw = s_cw[sym], len = cw >> 27;
+                    if (((uint32_t)r.buf & ((1u << len) - 1u)) == (cw & 0x07FFFFFFu)) {
+                        e = sym | (len << 9);
+                        break;
+                    }
                 }
-                sym = (uint32_t)s_nsym[node];
+                if (e == 0u) { my_err = 1; break; }
             }
-            if (sym < 256u) {
-                const uint32_t w = outpos >> 2;
-                sb[(dec_swizzle(w) << 2) | (outpos & 3u)] = (uint8_t)sym;
-                ++outpos;
+            const uint32_t len = e >> 9, sym = e & 511u;
+            r.skip(len);
+            bitpos += len;
+            if (sym < 256u && sym != 0u) {
+                wr.put(sym);
             } else {
-                uint32_t z = 2;
+                uint32_t z = sym == 0u ? 1u : 2u;
                 if (sym > 256u) {
                     const uint32_t eb = sym_extra_bits(sym);
                     r.refill();
@@ -312,15 +379,14 @@ __global__ void __launch_bounds__(kDecodeThreads) k_hzr_decode(const uint8_t* __
                     bitpos += eb;
                     z = ev + (sym == 257u ? 3u : sym == 258u ? 7u : sym == 259u ? 23u : 279u);
                 }
-                if (outpos + z > n) { my_err = 1; break; }  // "Output buffer full" dec:473-476
-                outpos += z;
+                if (seg0 + wr.pos + z > n) { my_err = 1; break; }  // "Output buffer full" dec:473-476
+                wr.zeros(z);
             }
             if (bitpos > limit_bits) my_err = 1;
         }
+        wr.finish();
     }
     if (my_err) status[f] = -4;
-    __syncthreads();
-    for (uint32_t i = tid; i < nw; i += blockDim.x) out32[i] = stg[dec_swizzle(i)];
 }
 
 }  // namespace rspt

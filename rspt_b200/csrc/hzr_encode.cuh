@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                                                                 const uint8_t* __restrict__ headers,
                                                                 const CrcConst* __restrict__ cc,
                                                                 uint8_t* __restrict__ dst,
-                                                                uint32_t* __restrict__ sc_bit, uint16_t* __restrict__ sc_skip)
+                                                                uint32_t* __restrict__ sc_bit, uint16_t* __restrict__ sc_skip,
+                                                                uint32_t* __restrict__ sc_codes)
 {
     extern __shared__ __align__(16) uint32_t stg[];  // header at bytes 9..15, payload from byte 16
     __shared__ uint32_t s_codes[kSymStride];
@@ -363,7 +364,11 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
         __syncthreads();
     } else {
         const uint32_t nsteps = (n + kStepBytes - 1) / kStepBytes;
-        for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_codes[i] = __ldg(codes + (size_t)blk * kSymStride + i);
+        for (uint32_t i = tid; i < kSymStride; i += blockDim.x) {
+            const uint32_t cw = __ldg(codes + (size_t)blk * kSymStride + i);
+            s_codes[i] = cw;
+            if (sc_codes) sc_codes[(size_t)blk * kSymStride + i] = cw;  // decode index: the block's code table
+        }
         const uint32_t tw = (bi.tree_nbits + 31u) >> 5, pw = (plen + 3u) >> 2;
         for (uint32_t i = tid; i < pw + 2; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
         if (wid == kEncWarps - 1) {

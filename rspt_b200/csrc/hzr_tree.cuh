@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, used);
         const uint32_t pos = L + __popc(m & ((1u << lane) - 1u));
         if (used) S.key[pos] = (c << 9) | (511u - sym);
+        else if (sym < (uint32_t)kSymStride) codes[(size_t)blk * kSymStride + sym] = 0;  // 0 = symbol has no code
         L += __popc(m);
         if (r == 0) {
             zero_class |= m & 1u;

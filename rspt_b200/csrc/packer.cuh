@@ -18,6 +18,7 @@ struct rspt_gpu_packer {
     bool own_stream;
     size_t max_batch;
     size_t enc_smem;       // dynamic shared memory of k_hzr_encode (staging of the largest block)
+    size_t dec_smem;       // dynamic shared memory of k_hzr_decode (payload of the largest block)
     bool can_escalate;     // xdelta_hzr with nb < bps
     bool dct_direct;       // dct: O(n^2) bit-exact path (fixed at create time)
 

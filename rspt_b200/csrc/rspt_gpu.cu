@@ -261,6 +261,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     p->d_crc = g_crc[device];
     const uint32_t maxn = s.N < kBlock ? s.N : kBlock;
     p->enc_smem = (size_t)(4 + (maxn + 3) / 4 + 4) * 4;  // staging of the largest block: header words + payload + slack
+    p->dec_smem = (size_t)((maxn + 3) / 4 + 4) * 4;      // payload of the largest block + zero slack
     p->stream = (cudaStream_t)stream;  // NULL = the CUDA default stream
     p->own_stream = false;
     const size_t F = max_batch_frames, nblocks = F * s.nb_alloc * s.nblk;
@@ -346,7 +347,7 @@ extern "C" size_t rspt_gpu_max_compressed_size(const rspt_gpu_packer* p)
 extern "C" size_t rspt_gpu_sidecar_bytes(const rspt_gpu_packer* p, size_t n_frames)
 {
     if (!p) return 0;
-    return (size_t)total_blocks(p, n_frames) * kMaxSegs * 6 + 64;
+    return (size_t)total_blocks(p, n_frames) * (kMaxSegs * 6 + kSymStride * 4) + 64;
 }
 
 extern "C" const char* rspt_gpu_last_error(const rspt_gpu_packer* p) { return p ? p->err : "null handle"; }
@@ -495,11 +496,12 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     }
     uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar);
     uint16_t* sc_skip = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
+    uint32_t* sc_codes = d_sidecar ? reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
     {
         StageTimer t(p, RSPT_STAGE_ENCODE);
         k_hzr_encode<<<nblocks, kEncThreads, p->enc_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
                                                                         p->d_codes, p->d_tree, p->d_step_lz, d_offsets,
-                                                                        p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip);
+                                                                        p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip, sc_codes);
     }
     p->launches += 5;
     RSPT_CUDA_CHECK(cudaGetLastError());
@@ -532,9 +534,10 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
     }
     const uint32_t* sc_bit = reinterpret_cast<const uint32_t*>(d_sidecar);
     const uint16_t* sc_skip = d_sidecar ? reinterpret_cast<const uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
+    const uint32_t* sc_codes = d_sidecar ? reinterpret_cast<const uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
     {
         StageTimer t(p, RSPT_STAGE_DECODE);
-        k_hzr_decode<<<nblocks, kDecodeThreads, kDecodeSmem, p->stream>>>(d_src, s, dec, sc_bit, sc_skip, p->d_planes, status);
+        k_hzr_decode<<<nblocks, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec, sc_bit, sc_skip, sc_codes, p->d_planes, status);
     }
     p->launches += 2;
     RSPT_CUDA_CHECK(cudaGetLastError());
