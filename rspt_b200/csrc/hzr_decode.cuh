@@ -146,36 +146,35 @@ struct BitReader {
 // no clearing; the last window may run up to 15 bytes past `len` (plane rows are padded to 16).
 struct SegWriter {
     uint8_t* dst;
-    uint32_t len, pos, w, v0, v1, v2;
+    uint32_t len, pos, w, sh, v0, v1, v2;
     __device__ __forceinline__ void init(uint8_t* d, uint32_t l)
     {
-        dst = d; len = l; pos = 0; w = 0; v0 = v1 = v2 = 0;
+        dst = d; len = l; pos = 0; w = 0; sh = 0; v0 = v1 = v2 = 0;
     }
+    // the word `w` that ends at byte `pos` is complete
     __device__ __forceinline__ void push_word()
     {
         const uint32_t k = ((pos - 1u) >> 2) & 3u;
-        if (k == 0) v0 = w;
-        else if (k == 1) v1 = w;
-        else if (k == 2) v2 = w;
-        else *reinterpret_cast<uint4*>(dst + ((pos - 1u) & ~15u)) = make_uint4(v0, v1, v2, w);
+        if (k == 3u) *reinterpret_cast<uint4*>(dst + ((pos - 1u) & ~15u)) = make_uint4(v0, v1, v2, w);
+        v0 = k == 0u ? w : v0;
+        v1 = k == 1u ? w : v1;
+        v2 = k == 2u ? w : v2;
         w = 0;
+        sh = 0;
     }
     __device__ __forceinline__ void put(uint32_t byte)
     {
-        w |= byte << (8u * (pos & 3u));
+        w |= byte << sh;
+        sh += 8u;
         ++pos;
-        if ((pos & 3u) == 0u) push_word();
+        if (sh == 32u) push_word();
     }
     // z zero bytes, clipped to the range
     __device__ __forceinline__ void zeros(uint32_t z)
     {
         z = min(z, len - pos);
-        while (z) {
-            if ((pos & 15u) == 0u && z >= 16u) {
-                *reinterpret_cast<uint4*>(dst + pos) = make_uint4(0, 0, 0, 0);
-                pos += 16u;
-                z -= 16u;
-            } else if ((pos & 3u) == 0u && z >= 4u) {
+        while (z && (pos & 15u)) {  // close the open 16-byte window
+            if (sh == 0u && z >= 4u) {
                 pos += 4u;
                 z -= 4u;
                 push_word();
@@ -184,6 +183,12 @@ struct SegWriter {
                 --z;
             }
         }
+        for (; z >= 16u; z -= 16u, pos += 16u) *reinterpret_cast<uint4*>(dst + pos) = make_uint4(0, 0, 0, 0);
+        for (; z >= 4u; z -= 4u) {
+            pos += 4u;
+            push_word();
+        }
+        for (; z; --z) put(0u);
     }
     // pad the open window with zeros and store it
     __device__ __forceinline__ void finish()
@@ -328,23 +333,45 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
 
     const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
     uint32_t my_err = 0;
-    if (indexed ? tid < nseg : tid == 0) {
-        uint32_t bitpos, seg0, seg_len, skip, end_bit;
-        if (indexed) {
+    uint32_t bitpos = 0, seg0 = 0, seg_len = 0, skip = 0, end_bit = 0;
+    bool mine = false;
+    if (indexed) {
+        if (tid < nseg) {
             bitpos = sc_bit[(size_t)blk * kMaxSegs + tid];
             skip = sc_skip[(size_t)blk * kMaxSegs + tid];
             end_bit = tid + 1 < nseg ? sc_bit[(size_t)blk * kMaxSegs + tid + 1] : 0xFFFFFFFFu;
             seg0 = tid * kSegBytes;
             seg_len = min((uint32_t)kSegBytes, n - seg0);
-        } else {
-            bitpos = s_meta[0];
-            skip = 0;
-            end_bit = 0xFFFFFFFFu;
-            seg0 = 0;
-            seg_len = n;
+            mine = true;
         }
+        // segments that lie entirely inside a zero run: cleared by the warp, two per store
+        const bool all_zero = mine && skip >= seg_len;
+        uint32_t zm = __ballot_sync(0xFFFFFFFFu, all_zero);
+        while (zm) {
+            const uint32_t la = __ffs(zm) - 1u;
+            zm &= zm - 1u;
+            uint32_t lb = 32u;
+            if (zm) {
+                lb = __ffs(zm) - 1u;
+                zm &= zm - 1u;
+            }
+            const uint32_t sl = lane < 16 ? la : lb;
+            if (sl < 32u) {
+                const uint32_t sg = (tid & ~31u) + sl, q = sg * (kSegBytes / 16) + (lane & 15u);
+                if (q < nq) out4[q] = make_uint4(0, 0, 0, 0);
+            }
+        }
+        if (all_zero) mine = false;
+    } else if (tid == 0) {
+        bitpos = s_meta[0];
+        end_bit = 0xFFFFFFFFu;
+        seg_len = n;
+        mine = true;
+    }
+    if (mine) {
         const uint32_t limit_bits = plen * 8u, nlong = s_meta[2];
         if (bitpos > limit_bits) { my_err = 1; bitpos = 0; }
+        end_bit = min(end_bit, limit_bits);
         SegWriter wr;
         wr.init(out + seg0, seg_len);
         wr.zeros(skip);  // bytes covered by a zero run that started in an earlier segment
@@ -368,10 +395,10 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
             const uint32_t len = e >> 9, sym = e & 511u;
             r.skip(len);
             bitpos += len;
-            if (sym < 256u && sym != 0u) {
-                wr.put(sym);
+            if (sym < 256u) {
+                wr.put(sym);  // literal; symbol 0 is a zero run of one
             } else {
-                uint32_t z = sym == 0u ? 1u : 2u;
+                uint32_t z = 2u;
                 if (sym > 256u) {
                     const uint32_t eb = sym_extra_bits(sym);
                     r.refill();
@@ -382,8 +409,8 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                 if (seg0 + wr.pos + z > n) { my_err = 1; break; }  // "Output buffer full" dec:473-476
                 wr.zeros(z);
             }
-            if (bitpos > limit_bits) my_err = 1;
         }
+        if (bitpos > limit_bits) my_err = 1;
         wr.finish();
     }
     if (my_err) status[f] = -4;
