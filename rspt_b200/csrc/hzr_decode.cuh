@@ -141,60 +141,44 @@ struct BitReader {
 };
 
 // Writes one thread's output range [0, len) of a 16-byte aligned destination in order: bytes are
-// gathered into a word, words into a 16-byte window, windows go out with one 128-bit store.
-// Every byte of the range is written exactly once (zero runs as zeros), so the destination needs
-// no clearing; the last window may run up to 15 bytes past `len` (plane rows are padded to 16).
+// gathered into a word and every completed word goes out with one 32-bit store (lanes drift out
+// of phase after zero runs, so a wider per-lane window would only add divergent bookkeeping;
+// the L2 merges the partial sectors).  Zero runs use 128-bit stores where they are aligned.
+// Every byte of the range is written exactly once, so the destination needs no clearing; the
+// last word may run up to 3 bytes past `len` (plane rows are padded to 16).
 struct SegWriter {
     uint8_t* dst;
-    uint32_t len, pos, w, sh, v0, v1, v2;
+    uint32_t len, pos, w, sh;
     __device__ __forceinline__ void init(uint8_t* d, uint32_t l)
     {
-        dst = d; len = l; pos = 0; w = 0; sh = 0; v0 = v1 = v2 = 0;
-    }
-    // the word `w` that ends at byte `pos` is complete
-    __device__ __forceinline__ void push_word()
-    {
-        const uint32_t k = ((pos - 1u) >> 2) & 3u;
-        if (k == 3u) *reinterpret_cast<uint4*>(dst + ((pos - 1u) & ~15u)) = make_uint4(v0, v1, v2, w);
-        v0 = k == 0u ? w : v0;
-        v1 = k == 1u ? w : v1;
-        v2 = k == 2u ? w : v2;
-        w = 0;
-        sh = 0;
+        dst = d; len = l; pos = 0; w = 0; sh = 0;
     }
     __device__ __forceinline__ void put(uint32_t byte)
     {
         w |= byte << sh;
         sh += 8u;
         ++pos;
-        if (sh == 32u) push_word();
+        if (sh == 32u) {
+            *reinterpret_cast<uint32_t*>(dst + pos - 4u) = w;
+            w = 0;
+            sh = 0;
+        }
     }
     // z zero bytes, clipped to the range
     __device__ __forceinline__ void zeros(uint32_t z)
     {
         z = min(z, len - pos);
-        while (z && (pos & 15u)) {  // close the open 16-byte window
-            if (sh == 0u && z >= 4u) {
-                pos += 4u;
-                z -= 4u;
-                push_word();
-            } else {
-                put(0u);
-                --z;
-            }
-        }
+        for (; z && sh; --z) put(0u);                    // close the open word
+        for (; z >= 4u && (pos & 15u); z -= 4u, pos += 4u) *reinterpret_cast<uint32_t*>(dst + pos) = 0u;
         for (; z >= 16u; z -= 16u, pos += 16u) *reinterpret_cast<uint4*>(dst + pos) = make_uint4(0, 0, 0, 0);
-        for (; z >= 4u; z -= 4u) {
-            pos += 4u;
-            push_word();
-        }
+        for (; z >= 4u; z -= 4u, pos += 4u) *reinterpret_cast<uint32_t*>(dst + pos) = 0u;
         for (; z; --z) put(0u);
     }
-    // pad the open window with zeros and store it
+    // pad the open word with zeros and store it
     __device__ __forceinline__ void finish()
     {
         zeros(len - pos);
-        while (pos & 15u) put(0u);
+        while (sh) put(0u);
     }
 };
 

@@ -329,6 +329,35 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
     const size_t sm_inv = (size_t)2 * np * 4 + tile_bytes;
     if (sm_inv > 200 * 1024 || tile_bytes > 200 * 1024) return fail_arg(p, "frame too large for the inverse kernel");
     const dim3 gf((unsigned)F);
+    // fast path: 4-channel groups, 128-sample pieces, PRMT packing (transforms.cuh)
+    if ((s.kind == 0 || s.kind == 1) && (s.ch & 3) == 0 && (s.ns % (int)kInvPiece) == 0 && ((uintptr_t)d_dst & 15) == 0) {
+        const size_t row = (size_t)s.ch * s.bps;
+        const size_t npf = (size_t)((uint32_t)s.ns / kInvPiece) * s.ch;  // 128-element pieces per frame
+        uint32_t tpg = 8;  // sample tiles per output group, sized to keep 4 CTAs per SM
+        size_t smf = 0;
+        for (; tpg >= 1; tpg >>= 1) {
+            smf = 2 * npf * 4 + (size_t)tpg * 32 * (row + 1) * 4;
+            if (smf <= 54 * 1024) break;
+        }
+        if (tpg >= 1) {
+#define INVF_LAUNCH(B, SC)                                                                                            \
+    do {                                                                                                              \
+        cudaFuncSetAttribute(k_planes_to_samples_fast<B, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf); \
+        k_planes_to_samples_fast<B, SC><<<gf, kInvThreads, smf, p->stream>>>(p->d_planes, s, p->d_dec_nb, tpg, d_dst);   \
+    } while (0)
+            const bool sc = s.kind == 0;
+            switch (s.bps) {
+            case 1: if (sc) INVF_LAUNCH(1, true); else INVF_LAUNCH(1, false); break;
+            case 2: if (sc) INVF_LAUNCH(2, true); else INVF_LAUNCH(2, false); break;
+            case 3: if (sc) INVF_LAUNCH(3, true); else INVF_LAUNCH(3, false); break;
+            default: if (sc) INVF_LAUNCH(4, true); else INVF_LAUNCH(4, false); break;
+            }
+#undef INVF_LAUNCH
+            p->launches += 1;
+            RSPT_CUDA_CHECK(cudaGetLastError());
+            return 0;
+        }
+    }
 #define INV_LAUNCH(B, SC, RAW)                                                                                   \
     do {                                                                                                         \
         cudaFuncSetAttribute(k_planes_to_samples<B, SC, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_inv); \

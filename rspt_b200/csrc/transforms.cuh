@@ -451,6 +451,172 @@ __global__ void __launch_bounds__(512) k_planes_to_samples(const uint8_t* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fast path of planes -> samples (ch % 4 == 0, ns % 128 == 0): one CTA of 8 warps per frame.
+// A PIECE is 128 consecutive flat elements (one warp, 4 per lane, one 32-bit word per plane).
+//   pass 1  xor of every piece (plane words folded byte-wise; no transpose needed)
+//   pass 2  sum of (prefix-xor + 128) of every piece
+//   pass 3  a warp takes (4 channels x 128 samples): per channel the 4 x 4 byte transpose back to
+//           sign-extended words, lane-local + warp xor scan, +128, lane-local + warp add scan;
+//           the four channels' samples are packed row-wise with PRMT into a shared-memory tile
+//           (quad stride row + 1 words, conflict-free) that the CTA then copies out coalesced.
+// SCAN = false is the plain hzr packer (no chain).
+// ------------------------------------------------------------------------------------------
+constexpr int kInvThreads = 256;
+constexpr uint32_t kInvPiece = 128;
+
+// plane words (4 consecutive elements each) -> the 4 sign-extended 32-bit words
+__device__ __forceinline__ void planes_to_words(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, uint32_t nb, uint32_t (&y)[4])
+{
+    // missing planes = sign bytes of the highest stored plane (signal_packer_base.cpp:126-138)
+    if (nb == 1) q1 = prmt(q0, q0, 0xBA98u);
+    if (nb <= 2) q2 = prmt(q1, q1, 0xBA98u);
+    if (nb <= 3) q3 = prmt(q2, q2, 0xBA98u);
+    const uint32_t t01 = prmt(q0, q1, 0x5140u), t23 = prmt(q2, q3, 0x5140u);
+    const uint32_t u01 = prmt(q0, q1, 0x7362u), u23 = prmt(q2, q3, 0x7362u);
+    y[0] = prmt(t01, t23, 0x5410u);
+    y[1] = prmt(t01, t23, 0x7632u);
+    y[2] = prmt(u01, u23, 0x5410u);
+    y[3] = prmt(u01, u23, 0x7632u);
+}
+
+__device__ __forceinline__ uint32_t warp_xor_inclusive(uint32_t v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane_id() >= (uint32_t)o) v ^= t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t warp_add_inclusive(uint32_t v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane_id() >= (uint32_t)o) v += t;
+    }
+    return v;
+}
+
+template <int BPS, bool SCAN>
+__global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const uint8_t* __restrict__ planes, Shape s,
+                                                                            const uint8_t* __restrict__ dec_nb,
+                                                                            uint32_t tiles_per_group,
+                                                                            uint8_t* __restrict__ dst_raw)
+{
+    extern __shared__ __align__(16) uint32_t sm32[];
+    const uint32_t f = blockIdx.x;
+    const uint32_t nb = dec_nb[f];
+    const uint32_t ns = (uint32_t)s.ns, ch = (uint32_t)s.ch;
+    const uint32_t ppc = ns / kInvPiece, np = ppc * ch;      // pieces per channel row / per frame
+    uint32_t* pxor = sm32;           // [np] exclusive xor carry of every piece
+    uint32_t* psum = sm32 + np;      // [np] exclusive sum carry
+    uint32_t* tile = sm32 + 2 * np;  // output tile: quads of 4 sample rows at a stride of row + 1 words
+    const uint32_t* fpl = reinterpret_cast<const uint32_t*>(planes + (size_t)f * s.nb_alloc * s.plane_stride);
+    const uint32_t pstride = s.plane_stride >> 2;
+    const uint32_t lane = lane_id(), wid = warp_id(), nwarps = blockDim.x >> 5;
+    const int sext = 32 - 8 * (int)nb;
+
+    if (SCAN) {
+        // pass 1: xor of all words of a piece = byte-wise fold of the plane words
+        for (uint32_t p = wid; p < np; p += nwarps) {
+            uint32_t x = 0;
+            for (uint32_t k = 0; k < nb; ++k) {
+                uint32_t w = __ldg(fpl + k * pstride + p * 32u + lane);
+                w ^= w >> 16;
+                w ^= w >> 8;
+                x |= (w & 0xFFu) << (8 * k);
+            }
+            x = (uint32_t)((int32_t)(x << sext) >> sext);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+            if (lane == 0) pxor[p] = x;
+        }
+        __syncthreads();
+        smem_exclusive_scan<true>(pxor, np);
+        __syncthreads();
+        // pass 2: sum of (prefix-xor + 128) over every piece
+        for (uint32_t p = wid; p < np; p += nwarps) {
+            uint32_t q[4] = {0, 0, 0, 0};
+            for (uint32_t k = 0; k < nb; ++k) q[k] = __ldg(fpl + k * pstride + p * 32u + lane);
+            uint32_t y[4];
+            planes_to_words(q[0], q[1], q[2], q[3], nb, y);
+            y[1] ^= y[0]; y[2] ^= y[1]; y[3] ^= y[2];
+            const uint32_t before = pxor[p] ^ warp_xor_inclusive(y[3]) ^ y[3];
+            uint32_t sum = (y[0] ^ before) + (y[1] ^ before) + (y[2] ^ before) + (y[3] ^ before) + 512u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+            if (lane == 0) psum[p] = sum;
+        }
+        __syncthreads();
+        smem_exclusive_scan<false>(psum, np);
+        __syncthreads();
+    }
+
+    // pass 3: groups of `tiles_per_group` sample tiles (128 samples each); work item = (tile, channel group)
+    const uint32_t row = ch * BPS, rw = row >> 2, qstride = row + 1, G = ch >> 2, cpq = row >> 2;
+    for (uint32_t t0 = 0; t0 < ppc; t0 += tiles_per_group) {
+        const uint32_t nt = min(tiles_per_group, ppc - t0);
+        for (uint32_t item = wid; item < nt * G; item += nwarps) {
+            const uint32_t tl = item / G, g = item - tl * G, t = t0 + tl;
+            uint32_t x[4][4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const uint32_t c = 4 * g + cc, p = c * ppc + t;
+                uint32_t q[4] = {0, 0, 0, 0};
+                for (uint32_t k = 0; k < nb; ++k) q[k] = __ldg(fpl + k * pstride + p * 32u + lane);
+                planes_to_words(q[0], q[1], q[2], q[3], nb, x[cc]);
+                if (SCAN) {
+                    uint32_t* y = x[cc];
+                    y[1] ^= y[0]; y[2] ^= y[1]; y[3] ^= y[2];
+                    const uint32_t before = pxor[p] ^ warp_xor_inclusive(y[3]) ^ y[3];
+                    y[0] = (y[0] ^ before) + 128u;
+                    y[1] = (y[1] ^ before) + 128u + y[0];
+                    y[2] = (y[2] ^ before) + 128u + y[1];
+                    y[3] = (y[3] ^ before) + 128u + y[2];
+                    const uint32_t base = psum[p] + warp_add_inclusive(y[3]) - y[3];
+                    y[0] += base; y[1] += base; y[2] += base; y[3] += base;
+                }
+            }
+            // pack the 4 channels of every sample row into BPS words (convert_i32_to_native, utils.cpp:51-121)
+            uint32_t* out = tile + (tl * 32u + lane) * qstride + g * BPS;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t a = x[0][i], b = x[1][i], c2 = x[2][i], d = x[3][i];
+                if (BPS == 4) {
+                    out[i * rw + 0] = a; out[i * rw + 1] = b; out[i * rw + 2] = c2; out[i * rw + 3] = d;
+                } else if (BPS == 3) {
+                    out[i * rw + 0] = prmt(a, b, 0x4210u);
+                    out[i * rw + 1] = prmt(b, c2, 0x5421u);
+                    out[i * rw + 2] = prmt(c2, d, 0x6542u);
+                } else if (BPS == 2) {
+                    out[i * rw + 0] = prmt(a, b, 0x5410u);
+                    out[i * rw + 1] = prmt(c2, d, 0x5410u);
+                } else {
+                    out[i * rw + 0] = prmt(prmt(a, b, 0x0040u), prmt(c2, d, 0x0040u), 0x5410u);
+                }
+            }
+        }
+        __syncthreads();
+        // coalesced copy of the group's rows (contiguous in the interleaved output); drops the pad word
+        {
+            uint4* g4 = reinterpret_cast<uint4*>(dst_raw + (size_t)f * s.frame_bytes + (size_t)t0 * kInvPiece * row);
+            const uint32_t nchunks = nt * 32u * cpq;
+            uint32_t q = threadIdx.x / cpq, r = threadIdx.x % cpq;
+            const uint32_t dq = blockDim.x / cpq, dr = blockDim.x % cpq;
+            for (uint32_t c = threadIdx.x; c < nchunks; c += blockDim.x) {
+                const uint32_t* sp = tile + q * qstride + 4u * r;
+                g4[c] = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                q += dq; r += dr;
+                if (r >= cpq) { r -= cpq; ++q; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // int32 words [ch][ns] -> interleaved little-endian samples; one CTA per (frame, 256-sample tile)
 template <int BPS>
 __global__ void __launch_bounds__(256) k_words_to_raw(const int32_t* __restrict__ words, Shape s, uint32_t tiles,
