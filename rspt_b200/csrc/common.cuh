@@ -18,9 +18,9 @@ constexpr int kTreeWords = 92;         // >= ceil((11*261-1)/32)
 constexpr uint32_t kBlock = 65536;     // HZR_MAX_BLOCK_SIZE, hzr_internal.h:109
 constexpr uint32_t kRunCap = 16662;    // hzr_encode.c:149
 constexpr int kStrip = 64;             // bytes per thread-strip
-constexpr int kSegStrips = 4;          // strips per decode segment (sidecar granularity: 256 B)
+constexpr int kSegStrips = 2;          // strips per decode segment (decode index granularity: 128 B)
 constexpr int kSegBytes = kStrip * kSegStrips;
-constexpr int kMaxSegs = kBlock / kSegBytes;  // 256 per block
+constexpr int kMaxSegs = kBlock / kSegBytes;  // 512 per block
 
 enum : uint32_t { MODE_COPY = 0, MODE_HUFF = 1, MODE_FILL = 2 };  // hzr_internal.h:98-101
 

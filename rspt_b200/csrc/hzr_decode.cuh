@@ -17,7 +17,7 @@
 
 namespace rspt {
 
-constexpr int kDecodeThreads = 256;
+constexpr int kDecodeThreads = kMaxSegs;  // one thread per decode segment
 constexpr int kLutBits = 12;
 constexpr uint32_t kModeZero = 3;      // frame failed to parse: emit zeros
 constexpr uint32_t kModeInactive = 255;
@@ -190,7 +190,7 @@ constexpr uint32_t kLongFlag = 0x8000u;
 // code table comes from the decode index (sc_codes) or, for streams without one, from RecoverTree
 // run by one thread; a 12-bit look-up table maps the next bits to (symbol, length), longer codes
 // are matched against the short list of long code words.  With the index every thread decodes the
-// tokens that start in its 256-byte segment and writes exactly that segment; without it thread 0
+// tokens that start in its 128-byte segment and writes exactly that segment; without it thread 0
 // decodes the whole block.
 __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t* __restrict__ src, Shape s,
                                                                    const DecBlk* __restrict__ dec,
@@ -328,20 +328,22 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
             seg_len = min((uint32_t)kSegBytes, n - seg0);
             mine = true;
         }
-        // segments that lie entirely inside a zero run: cleared by the warp, two per store
+        // segments that lie entirely inside a zero run: cleared by the warp, several per store
+        constexpr uint32_t kQ = kSegBytes / 16, kPer = 32 / kQ;  // 16-byte chunks per segment, segments per store
         const bool all_zero = mine && skip >= seg_len;
         uint32_t zm = __ballot_sync(0xFFFFFFFFu, all_zero);
         while (zm) {
-            const uint32_t la = __ffs(zm) - 1u;
-            zm &= zm - 1u;
-            uint32_t lb = 32u;
-            if (zm) {
-                lb = __ffs(zm) - 1u;
-                zm &= zm - 1u;
+            uint32_t sl = 32u;
+#pragma unroll
+            for (uint32_t j = 0; j < kPer; ++j) {
+                if (zm) {
+                    const uint32_t l = __ffs(zm) - 1u;
+                    zm &= zm - 1u;
+                    if (lane / kQ == j) sl = l;
+                }
             }
-            const uint32_t sl = lane < 16 ? la : lb;
             if (sl < 32u) {
-                const uint32_t sg = (tid & ~31u) + sl, q = sg * (kSegBytes / 16) + (lane & 15u);
+                const uint32_t sg = (tid & ~31u) + sl, q = sg * kQ + (lane % kQ);
                 if (q < nq) out4[q] = make_uint4(0, 0, 0, 0);
             }
         }

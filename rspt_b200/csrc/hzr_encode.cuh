@@ -489,12 +489,12 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                         es.finish();
                     }
                     if (sc_bit) {
-                        // decode index entries of the 256-byte boundaries B in [rs, cur], B < n: at
+                        // decode index entries of the segment boundaries B in [rs, cur], B < n: at
                         // B == rs the entry's first token starts; later boundaries lie inside the
                         // zero run and resume at the literal
-                        for (uint32_t B = (rs + 255u) & ~255u; B <= cur && B < n; B += 256u) {
-                            sc_bit[(size_t)blk * kMaxSegs + (B >> 8)] = B == rs ? o0 : o_lit;
-                            sc_skip[(size_t)blk * kMaxSegs + (B >> 8)] = (uint16_t)(B == rs ? 0u : cur - B);
+                        for (uint32_t B = (rs + kSegBytes - 1u) & ~(uint32_t)(kSegBytes - 1); B <= cur && B < n; B += kSegBytes) {
+                            sc_bit[(size_t)blk * kMaxSegs + B / kSegBytes] = B == rs ? o0 : o_lit;
+                            sc_skip[(size_t)blk * kMaxSegs + B / kSegBytes] = (uint16_t)(B == rs ? 0u : cur - B);
                         }
                     }
                 }
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             // zeros between the end of my chunk and the next stop byte: only when a run leaves its
             // chunk (nzx on a zero last byte) or the decode index needs a skip count
             const bool leaves = (Z >> 15) & nzx;
-            const bool idx_lane = sc_bit && (lane & 15u) == 0u;
+            const bool idx_lane = sc_bit && (lane & (kSegBytes / 16 - 1)) == 0u;
             uint32_t fwd = 0;
             if (__any_sync(0xFFFFFFFFu, leaves || (idx_lane && pz))) {
                 const uint32_t sm = __ballot_sync(0xFFFFFFFFu, STOP != 0u);
@@ -607,10 +607,10 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             }
             uint32_t o = base + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u) + inc - lbits;
             base += __shfl_sync(0xFFFFFFFFu, tw2, kEncWarps - 1);
-            // ---- decode index: one entry per 256 output bytes (lanes 0 and 16)
+            // ---- decode index: one entry per segment of kSegBytes output bytes
             if (idx_lane && off < n) {
-                sc_bit[(size_t)blk * kMaxSegs + (off >> 8)] = o;
-                sc_skip[(size_t)blk * kMaxSegs + (off >> 8)] = (uint16_t)(pz ? (STOP ? (uint32_t)__ffs(STOP) - 1u : 16u + fwd) : 0u);
+                sc_bit[(size_t)blk * kMaxSegs + off / kSegBytes] = o;
+                sc_skip[(size_t)blk * kMaxSegs + off / kSegBytes] = (uint16_t)(pz ? (STOP ? (uint32_t)__ffs(STOP) - 1u : 16u + fwd) : 0u);
             }
             // ---- emit
 #pragma unroll

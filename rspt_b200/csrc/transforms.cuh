@@ -519,36 +519,62 @@ __global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const
     const uint32_t lane = lane_id(), wid = warp_id(), nwarps = blockDim.x >> 5;
     const int sext = 32 - 8 * (int)nb;
 
+    // plane words of piece p for this lane; planes >= nb are replaced by sign bytes later, so
+    // every allocated plane is simply loaded (independent loads, all in flight together)
+    const uint32_t nba = s.nb_alloc;
+    auto load_piece = [&](uint32_t p, uint32_t (&q)[4]) {
+        const uint32_t* a = fpl + p * 32u + lane;
+        q[0] = __ldg(a);
+        q[1] = nba > 1 ? __ldg(a + pstride) : 0u;
+        q[2] = nba > 2 ? __ldg(a + 2 * pstride) : 0u;
+        q[3] = nba > 3 ? __ldg(a + 3 * pstride) : 0u;
+    };
+    constexpr int U = 4;  // pieces in flight per warp
     if (SCAN) {
         // pass 1: xor of all words of a piece = byte-wise fold of the plane words
-        for (uint32_t p = wid; p < np; p += nwarps) {
-            uint32_t x = 0;
-            for (uint32_t k = 0; k < nb; ++k) {
-                uint32_t w = __ldg(fpl + k * pstride + p * 32u + lane);
-                w ^= w >> 16;
-                w ^= w >> 8;
-                x |= (w & 0xFFu) << (8 * k);
-            }
-            x = (uint32_t)((int32_t)(x << sext) >> sext);
+        for (uint32_t p0 = wid * U; p0 < np; p0 += nwarps * U) {
+            uint32_t q[U][4];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
-            if (lane == 0) pxor[p] = x;
+            for (int u = 0; u < U; ++u)
+                if (p0 + u < np) load_piece(p0 + u, q[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (p0 + u >= np) break;
+                uint32_t x = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t w = (uint32_t)k < nb ? q[u][k] : 0u;
+                    w ^= w >> 16;
+                    w ^= w >> 8;
+                    x |= (w & 0xFFu) << (8 * k);
+                }
+                x = (uint32_t)((int32_t)(x << sext) >> sext);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+                if (lane == 0) pxor[p0 + u] = x;
+            }
         }
         __syncthreads();
         smem_exclusive_scan<true>(pxor, np);
         __syncthreads();
         // pass 2: sum of (prefix-xor + 128) over every piece
-        for (uint32_t p = wid; p < np; p += nwarps) {
-            uint32_t q[4] = {0, 0, 0, 0};
-            for (uint32_t k = 0; k < nb; ++k) q[k] = __ldg(fpl + k * pstride + p * 32u + lane);
-            uint32_t y[4];
-            planes_to_words(q[0], q[1], q[2], q[3], nb, y);
-            y[1] ^= y[0]; y[2] ^= y[1]; y[3] ^= y[2];
-            const uint32_t before = pxor[p] ^ warp_xor_inclusive(y[3]) ^ y[3];
-            uint32_t sum = (y[0] ^ before) + (y[1] ^ before) + (y[2] ^ before) + (y[3] ^ before) + 512u;
+        for (uint32_t p0 = wid * U; p0 < np; p0 += nwarps * U) {
+            uint32_t q[U][4];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-            if (lane == 0) psum[p] = sum;
+            for (int u = 0; u < U; ++u)
+                if (p0 + u < np) load_piece(p0 + u, q[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (p0 + u >= np) break;
+                uint32_t y[4];
+                planes_to_words(q[u][0], q[u][1], q[u][2], q[u][3], nb, y);
+                y[1] ^= y[0]; y[2] ^= y[1]; y[3] ^= y[2];
+                const uint32_t before = pxor[p0 + u] ^ warp_xor_inclusive(y[3]) ^ y[3];
+                uint32_t sum = (y[0] ^ before) + (y[1] ^ before) + (y[2] ^ before) + (y[3] ^ before) + 512u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+                if (lane == 0) psum[p0 + u] = sum;
+            }
         }
         __syncthreads();
         smem_exclusive_scan<false>(psum, np);
@@ -563,11 +589,11 @@ __global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const
             const uint32_t tl = item / G, g = item - tl * G, t = t0 + tl;
             uint32_t x[4][4];
 #pragma unroll
+            for (int cc = 0; cc < 4; ++cc) load_piece((4 * g + cc) * ppc + t, x[cc]);
+#pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 const uint32_t c = 4 * g + cc, p = c * ppc + t;
-                uint32_t q[4] = {0, 0, 0, 0};
-                for (uint32_t k = 0; k < nb; ++k) q[k] = __ldg(fpl + k * pstride + p * 32u + lane);
-                planes_to_words(q[0], q[1], q[2], q[3], nb, x[cc]);
+                planes_to_words(x[cc][0], x[cc][1], x[cc][2], x[cc][3], nb, x[cc]);
                 if (SCAN) {
                     uint32_t* y = x[cc];
                     y[1] ^= y[0]; y[2] ^= y[1]; y[3] ^= y[2];
