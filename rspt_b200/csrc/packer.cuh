@@ -11,6 +11,17 @@
 #include "common.cuh"
 #include "hzr_encode.cuh"
 
+// streams, events and double buffers of the pipelined host-buffer compress (rspt_gpu_compress_batch_host)
+struct HostPipe {
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev_in[2], ev_comp[2], ev_off[2], ev_out[2];
+    uint8_t* d_src[2];
+    uint8_t* d_dst[2];
+    uint64_t* d_off[2];
+    uint64_t* h_off[2];
+    size_t chunk;  // frames per chunk; 0 = not set up yet
+};
+
 struct rspt_gpu_packer {
     rspt::Shape s;
     int device;
@@ -58,6 +69,7 @@ struct rspt_gpu_packer {
     uint8_t* d_hb_dst;
     uint64_t* d_hb_off;
     size_t hb_frames;
+    HostPipe pipe;
 
     unsigned long long launches;
     // stage timing

@@ -4,6 +4,8 @@
 #include "../../include/rspt_gpu.h"
 #include "../../include/rspt_synth.h"
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <new>
 #include <vector>
@@ -105,6 +107,8 @@ struct DeviceGuard {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+void destroy_host_pipe(rspt_gpu_packer* p);
 
 uint32_t total_blocks(const rspt_gpu_packer* p, size_t frames) { return (uint32_t)(frames * p->s.nb_alloc * p->s.nblk); }
 
@@ -324,6 +328,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p->h_pin) cudaFreeHost(p->h_pin);
+    destroy_host_pipe(p);
     if (p->ev_pending) {
         ev_resolve(p);
         for (cudaEvent_t e : *p->ev_free) cudaEventDestroy(e);
@@ -631,6 +636,55 @@ int ensure_host_batch(rspt_gpu_packer* p, size_t F)
     p->hb_frames = F;
     return RSPT_OK;
 }
+
+// Host-buffer compress runs as a three-stage pipeline over chunks of frames: H2D of chunk i+1,
+// the kernels of chunk i and D2H of chunk i-1 overlap on three streams with two device buffers.
+// The payload D2H of a chunk needs its byte total on the host, so the host waits for the (tiny)
+// offsets copy of the previous chunk while the next chunk is already queued.
+int ensure_host_pipe(rspt_gpu_packer* p)
+{
+    HostPipe& hp = p->pipe;
+    if (hp.chunk) return RSPT_OK;
+    size_t c = (size_t)(32u << 20) / p->s.frame_bytes;  // ~32 MB of raw input per chunk
+    if (const char* e = getenv("RSPT_HOST_CHUNK_FRAMES")) c = (size_t)atol(e);
+    if (c < 1) c = 1;
+    if (c > p->max_batch) c = p->max_batch;
+    RSPT_CUDA_CHECK(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+    RSPT_CUDA_CHECK(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        RSPT_CUDA_CHECK(cudaEventCreateWithFlags(&hp.ev_in[b], cudaEventDisableTiming));
+        RSPT_CUDA_CHECK(cudaEventCreateWithFlags(&hp.ev_comp[b], cudaEventDisableTiming));
+        RSPT_CUDA_CHECK(cudaEventCreateWithFlags(&hp.ev_off[b], cudaEventDisableTiming));
+        RSPT_CUDA_CHECK(cudaEventCreateWithFlags(&hp.ev_out[b], cudaEventDisableTiming));
+        RSPT_CUDA_CHECK(dalloc(hp.d_src[b], c * (size_t)p->s.frame_bytes));
+        RSPT_CUDA_CHECK(dalloc(hp.d_dst[b], c * rspt_gpu_max_compressed_size(p)));
+        RSPT_CUDA_CHECK(dalloc(hp.d_off[b], c + 1));
+        RSPT_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&hp.h_off[b]), (c + 1) * sizeof(uint64_t)));
+    }
+    hp.chunk = c;
+    return RSPT_OK;
+}
+
+void destroy_host_pipe(rspt_gpu_packer* p)
+{
+    HostPipe& hp = p->pipe;
+    if (!hp.s_in && !hp.s_out) return;
+    if (hp.s_in) cudaStreamSynchronize(hp.s_in);
+    if (hp.s_out) cudaStreamSynchronize(hp.s_out);
+    for (int b = 0; b < 2; ++b) {
+        if (hp.ev_in[b]) cudaEventDestroy(hp.ev_in[b]);
+        if (hp.ev_comp[b]) cudaEventDestroy(hp.ev_comp[b]);
+        if (hp.ev_off[b]) cudaEventDestroy(hp.ev_off[b]);
+        if (hp.ev_out[b]) cudaEventDestroy(hp.ev_out[b]);
+        if (hp.d_src[b]) cudaFree(hp.d_src[b]);
+        if (hp.d_dst[b]) cudaFree(hp.d_dst[b]);
+        if (hp.d_off[b]) cudaFree(hp.d_off[b]);
+        if (hp.h_off[b]) cudaFreeHost(hp.h_off[b]);
+    }
+    if (hp.s_in) cudaStreamDestroy(hp.s_in);
+    if (hp.s_out) cudaStreamDestroy(hp.s_out);
+    memset(&hp, 0, sizeof(hp));
+}
 }  // namespace
 
 extern "C" int rspt_gpu_compress_batch_host(rspt_gpu_packer* p, const uint8_t* h_src, size_t n_frames, uint8_t* h_dst,
@@ -638,20 +692,50 @@ extern "C" int rspt_gpu_compress_batch_host(rspt_gpu_packer* p, const uint8_t* h
 {
     if (!p || !h_src || !h_dst || !h_offsets) return RSPT_E_ARG;
     DeviceGuard dg(p->device);
-    int rc = ensure_host_batch(p, n_frames);
+    int rc = ensure_host_pipe(p);
     if (rc) return rc;
-    const size_t fb = p->s.frame_bytes;
-    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_hb_src, h_src, n_frames * fb, cudaMemcpyHostToDevice, p->stream));
-    rc = rspt_gpu_compress_batch(p, p->d_hb_src, n_frames, p->d_hb_dst, n_frames * rspt_gpu_max_compressed_size(p),
-                                 p->d_hb_off, nullptr, nullptr);
-    if (rc) return rc;
-    RSPT_CUDA_CHECK(cudaMemcpyAsync(h_offsets, p->d_hb_off, (n_frames + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, p->stream));
+    HostPipe& hp = p->pipe;
+    const size_t fb = p->s.frame_bytes, maxc = rspt_gpu_max_compressed_size(p), C = hp.chunk;
+    const size_t nchunks = (n_frames + C - 1) / C;
+    uint64_t running = 0;  // bytes of the chunks whose offsets have reached the host
+    h_offsets[0] = 0;
+    int status = RSPT_OK;
+    // stage 3 of chunk j: wait for its offsets, rebase them, start the payload copy
+    auto drain = [&](size_t j) -> int {
+        const int b = (int)(j & 1);
+        const size_t f0 = j * C, nf = (n_frames - f0 < C) ? n_frames - f0 : C;
+        RSPT_CUDA_CHECK(cudaEventSynchronize(hp.ev_off[b]));
+        for (size_t i = 1; i <= nf; ++i) h_offsets[f0 + i] = running + hp.h_off[b][i];
+        const uint64_t total = hp.h_off[b][nf];
+        if (running + total > dst_capacity) return fail_arg(p, "dst_capacity too small"), RSPT_E_CAPACITY;
+        RSPT_CUDA_CHECK(cudaMemcpyAsync(h_dst + running, hp.d_dst[b], (size_t)total, cudaMemcpyDeviceToHost, hp.s_out));
+        RSPT_CUDA_CHECK(cudaEventRecord(hp.ev_out[b], hp.s_out));
+        running += total;
+        return RSPT_OK;
+    };
+    for (size_t j = 0; j < nchunks && status == RSPT_OK; ++j) {
+        const int b = (int)(j & 1);
+        const size_t f0 = j * C, nf = (n_frames - f0 < C) ? n_frames - f0 : C;
+        // stage 1: H2D once the kernels of chunk j-2 have released the input buffer
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(hp.s_in, hp.ev_comp[b], 0));
+        RSPT_CUDA_CHECK(cudaMemcpyAsync(hp.d_src[b], h_src + f0 * fb, nf * fb, cudaMemcpyHostToDevice, hp.s_in));
+        RSPT_CUDA_CHECK(cudaEventRecord(hp.ev_in[b], hp.s_in));
+        // stage 2: kernels, once the input is there and the payload of chunk j-2 has left the output buffer
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, hp.ev_in[b], 0));
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, hp.ev_out[b], 0));
+        status = rspt_gpu_compress_batch(p, hp.d_src[b], nf, hp.d_dst[b], nf * maxc, hp.d_off[b], nullptr, nullptr);
+        if (status != RSPT_OK) break;
+        RSPT_CUDA_CHECK(cudaEventRecord(hp.ev_comp[b], p->stream));
+        // stage 3 of the previous chunk, then queue this chunk's offsets copy behind it
+        if (j > 0) status = drain(j - 1);
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(hp.s_out, hp.ev_comp[b], 0));
+        RSPT_CUDA_CHECK(cudaMemcpyAsync(hp.h_off[b], hp.d_off[b], (nf + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, hp.s_out));
+        RSPT_CUDA_CHECK(cudaEventRecord(hp.ev_off[b], hp.s_out));
+    }
+    if (status == RSPT_OK && nchunks > 0) status = drain(nchunks - 1);
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(hp.s_out));
     RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
-    const size_t total = (size_t)h_offsets[n_frames];
-    if (total > dst_capacity) return fail_arg(p, "dst_capacity too small"), RSPT_E_CAPACITY;
-    RSPT_CUDA_CHECK(cudaMemcpyAsync(h_dst, p->d_hb_dst, total, cudaMemcpyDeviceToHost, p->stream));
-    RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
-    return RSPT_OK;
+    return status;
 }
 
 extern "C" int rspt_gpu_decompress_batch_host(rspt_gpu_packer* p, const uint8_t* h_src, const uint64_t* h_offsets,

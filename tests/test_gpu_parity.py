@@ -375,3 +375,28 @@ def test_large_batch_round_trip_property(R):
     assert offs[0] == 0 and np.all(np.diff(offs) > 0)
     cr = raw.numel() / offs[-1]
     assert 2.5 < cr < 5.0, cr
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 64])
+def test_host_batch_pipeline_matches_device_batch(R, oracle, chunk, monkeypatch):
+    """rspt_gpu_compress_batch_host (chunked H2D / kernels / D2H pipeline) returns the same bytes and
+    offsets as the device-resident batch call, for ragged chunk counts; and the host decompress
+    call restores the input."""
+    monkeypatch.setenv("RSPT_HOST_CHUNK_FRAMES", str(chunk))
+    bps, ch, ns, nfr = 3, 12, 2048, 10
+    raws = oracle.synth_ecg(5, nfr, bps, ch, ns)
+    p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 3, max_batch_frames=nfr)
+    batch = p.compress_batch(to_dev(raws))
+    torch.cuda.synchronize()
+    offs = batch.offsets.cpu().numpy().astype(np.uint64)
+    stream = batch.stream.cpu().numpy()[: int(offs[nfr])]
+    src = torch.from_numpy(raws.reshape(-1).copy()).pin_memory()
+    dst = torch.empty(nfr * p.max_compressed_size, dtype=torch.uint8).pin_memory()
+    hoff = np.zeros(nfr + 1, np.uint64)
+    total = p.compress_batch_host(src.numpy(), dst.numpy(), hoff)
+    assert total == int(offs[nfr])
+    assert np.array_equal(hoff, offs)
+    assert np.array_equal(dst.numpy()[:total], stream)
+    out = np.empty(nfr * bps * ch * ns, np.uint8)
+    p.decompress_batch_host(dst.numpy()[: total + 16], hoff, out)
+    assert np.array_equal(out, raws.reshape(-1))
