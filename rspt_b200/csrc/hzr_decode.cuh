@@ -149,9 +149,10 @@ struct BitReader {
 struct SegWriter {
     uint8_t* dst;
     uint32_t len, pos, w, sh;
-    __device__ __forceinline__ void init(uint8_t* d, uint32_t l)
+    bool cleared;  // the destination already holds zeros: zero runs are skipped, not written
+    __device__ __forceinline__ void init(uint8_t* d, uint32_t l, bool pre_cleared)
     {
-        dst = d; len = l; pos = 0; w = 0; sh = 0;
+        dst = d; len = l; pos = 0; w = 0; sh = 0; cleared = pre_cleared;
     }
     __device__ __forceinline__ void put(uint32_t byte)
     {
@@ -168,6 +169,20 @@ struct SegWriter {
     __device__ __forceinline__ void zeros(uint32_t z)
     {
         z = min(z, len - pos);
+        if (cleared) {
+            const uint32_t np = pos + z;
+            if ((np >> 2) != (pos >> 2)) {  // the run leaves the open word
+                if (sh) *reinterpret_cast<uint32_t*>(dst + (pos & ~3u)) = w;
+                w = 0;
+            }
+            pos = np;
+            sh = (pos & 3u) * 8u;
+            return;
+        }
+        if (z < 8u) {  // short runs (dense planes): byte by byte, no alignment bookkeeping
+            for (; z; --z) put(0u);
+            return;
+        }
         for (; z && sh; --z) put(0u);                    // close the open word
         for (; z >= 4u && (pos & 15u); z -= 4u, pos += 4u) *reinterpret_cast<uint32_t*>(dst + pos) = 0u;
         for (; z >= 16u; z -= 16u, pos += 16u) *reinterpret_cast<uint4*>(dst + pos) = make_uint4(0, 0, 0, 0);
@@ -316,6 +331,13 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     __syncthreads();
 
     const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
+    // blocks that are mostly zeros (payload < 1/4 of the output): clear the whole output once,
+    // coalesced; zero runs then cost nothing.  Dense blocks write their zeros in place instead.
+    const bool pre_clear = plen * 4u < n;
+    if (pre_clear) {
+        for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+    }
     uint32_t my_err = 0;
     uint32_t bitpos = 0, seg0 = 0, seg_len = 0, skip = 0, end_bit = 0;
     bool mine = false;
@@ -331,7 +353,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         // segments that lie entirely inside a zero run: cleared by the warp, several per store
         constexpr uint32_t kQ = kSegBytes / 16, kPer = 32 / kQ;  // 16-byte chunks per segment, segments per store
         const bool all_zero = mine && skip >= seg_len;
-        uint32_t zm = __ballot_sync(0xFFFFFFFFu, all_zero);
+        uint32_t zm = pre_clear ? 0u : __ballot_sync(0xFFFFFFFFu, all_zero);
         while (zm) {
             uint32_t sl = 32u;
 #pragma unroll
@@ -359,7 +381,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         if (bitpos > limit_bits) { my_err = 1; bitpos = 0; }
         end_bit = min(end_bit, limit_bits);
         SegWriter wr;
-        wr.init(out + seg0, seg_len);
+        wr.init(out + seg0, seg_len, pre_clear);
         wr.zeros(skip);  // bytes covered by a zero run that started in an earlier segment
         BitReader r;
         r.init(payw, bitpos);

@@ -157,67 +157,70 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
     if (lane == 0) {
         uint32_t li = 0, lc = S.key[0] >> 9;          // leaf queue head
         uint32_t fr = 0, ni = 0, ic = kInf;           // internal queue: head index, count, head weight
-        bool icf = false;                             // head has an equal-weight successor
-        uint32_t top = 0, run_end = 0, last_w = kInf;
+        uint32_t icf = 0;                             // head has an equal-weight successor (flag bit)
+        uint32_t last_w = kInf;
+        // one pick: the lighter head; ties go to the internal node.  Branch-free unless the
+        // internal head starts a run of equal weights (then the latest of the run goes first).
+        uint32_t top = 0, run_end = 0;
         bool in_run = false;
-        for (uint32_t round = 0; round + 1 < L; ++round) {
-            uint32_t id[2], wt[2], lv[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (ic <= lc) {
-                    uint32_t pick;
-                    bool advance;
-                    if (!in_run) {
-                        if (!icf) {
-                            pick = fr;
-                            advance = true;
-                            run_end = fr + 1;
-                        } else {
-                            top = fr + 1;
-                            while (top < ni && (S.icnt[top] & kInf) == ic) ++top;
-                            run_end = top;
-                            in_run = true;
-                            pick = --top;
-                            advance = false;  // a flagged run has >= 2 nodes
-                        }
-                    } else {
-                        pick = --top;
-                        advance = top == fr;
-                    }
-                    id[q] = 512u + pick;
-                    wt[q] = ic;
-                    lv[q] = S.child[pick] >> 20;
-                    if (advance) {
-                        in_run = false;
-                        fr = run_end;
-                        if (fr < ni) {
-                            const uint32_t raw = S.icnt[fr];
-                            ic = raw & kInf;
-                            icf = (raw & kEqNext) != 0u;
-                        } else {
-                            ic = kInf;
-                            icf = false;
-                        }
-                    }
+        auto pick = [&](uint32_t& id, uint32_t& wt, uint32_t& lv) {
+            const bool take_int = ic <= lc;
+            if (take_int && (in_run || icf)) {
+                uint32_t pk;
+                bool advance;
+                if (!in_run) {
+                    top = fr + 1;
+                    while (top < ni && (S.icnt[top] & kInf) == ic) ++top;
+                    run_end = top;
+                    in_run = true;
+                    pk = --top;
+                    advance = false;  // a flagged run has >= 2 nodes
                 } else {
-                    id[q] = li;
-                    wt[q] = lc;
-                    lv[q] = 1;
-                    ++li;
-                    lc = li < L ? (S.key[li] >> 9) : kInf;
+                    pk = --top;
+                    advance = top == fr;
                 }
+                id = 512u + pk;
+                wt = ic;
+                lv = S.child[pk] >> 20;
+                if (advance) {
+                    in_run = false;
+                    fr = run_end;
+                    const uint32_t raw = fr < ni ? S.icnt[fr] : kInf;
+                    ic = raw & kInf;
+                    icf = raw & kEqNext;
+                }
+                return;
             }
-            const uint32_t w = wt[0] + wt[1];
+            // heads after this pick, loaded unconditionally (indices stay inside the arrays)
+            const uint32_t nfr = fr + (take_int ? 1u : 0u), nli = li + (take_int ? 0u : 1u);
+            const uint32_t raw = S.icnt[nfr], nk = S.key[nli], ch = S.child[fr];
+            id = take_int ? 512u + fr : li;
+            wt = take_int ? ic : lc;
+            lv = take_int ? ch >> 20 : 1u;
+            if (take_int) {
+                ic = nfr < ni ? raw & kInf : kInf;
+                icf = nfr < ni ? raw & kEqNext : 0u;
+            } else {
+                lc = nli < L ? nk >> 9 : kInf;
+            }
+            fr = nfr;
+            li = nli;
+        };
+        for (uint32_t round = 0; round + 1 < L; ++round) {
+            uint32_t id0, id1, w0, w1, lv0, lv1;
+            pick(id0, w0, lv0);
+            pick(id1, w1, lv1);
+            const uint32_t w = w0 + w1;
             if (w == last_w) {
                 S.icnt[ni - 1] = w | kEqNext;
-                if (ni - 1 == fr) icf = true;
+                if (ni - 1 == fr) icf = kEqNext;
             }
             if (fr == ni) {
                 ic = w;
-                icf = false;
+                icf = 0;
             }
             S.icnt[ni] = w;
-            S.child[ni] = id[0] | (id[1] << 10) | ((lv[0] + lv[1]) << 20);
+            S.child[ni] = id0 | (id1 << 10) | ((lv0 + lv1) << 20);
             last_w = w;
             ++ni;
         }
