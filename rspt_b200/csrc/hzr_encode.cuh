@@ -288,7 +288,7 @@ __device__ __forceinline__ void copy_smem_to_global(uint8_t* __restrict__ dst, c
     if (threadIdx.x < len - done) dst[done + threadIdx.x] = sb[soff + done + threadIdx.x];
 }
 
-constexpr uint32_t kStgWords = 4 + kBlock / 4 + 4;
+constexpr uint32_t kStgWords = 4 + kBlock / 4 + 8;
 constexpr size_t kEncodeSmem = (size_t)kStgWords * 4;
 
 __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __restrict__ planes, Shape s,
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
 {
     extern __shared__ __align__(16) uint32_t stg[];  // header at bytes 9..15, payload from byte 16
     __shared__ uint32_t s_codes[kSymStride];
-    __shared__ uint32_t s_zt[1024];
+    __shared__ __align__(16) uint32_t s_zt[1024];
     __shared__ uint32_t s_after[kMaxSteps];          // zeros that follow the end of every step
     __shared__ uint32_t s_tot[2][kEncWarps];
     __shared__ uint32_t s_red[33];
@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
         return;
     }
 
-    for (uint32_t i = tid; i < 1024; i += blockDim.x) s_zt[i] = __ldg(&cc->zt[kEncZtSel][0][0] + i);
+    for (uint32_t i = tid; i < 256; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_zt)[i] = __ldg(reinterpret_cast<const uint4*>(&cc->zt[kEncZtSel][0][0]) + i);
     const uint8_t* src = blk_ptr(planes, s, f, k, b);
     uint8_t* sbytes = reinterpret_cast<uint8_t*>(stg);
     const uint32_t plen = bi.payload_len;
@@ -370,7 +371,10 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             if (sc_codes) sc_codes[(size_t)blk * kSymStride + i] = cw;  // decode index: the block's code table
         }
         const uint32_t tw = (bi.tree_nbits + 31u) >> 5, pw = (plen + 3u) >> 2;
-        for (uint32_t i = tid; i < pw + 2; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
+        // staging: tree words, then zeros (the code words are OR-ed in)
+        const uint32_t tw4 = (tw + 3u) & ~3u;
+        for (uint32_t i = tid; i < tw4; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
+        for (uint32_t i = (tw4 >> 2) + tid; i < ((pw + 2u + 3u) >> 2); i += blockDim.x) reinterpret_cast<uint4*>(pay)[i] = make_uint4(0, 0, 0, 0);
         if (wid == kEncWarps - 1) {
             // s_after[st] = zeros between the end of step st and the next stop byte (or the block
             // end): suffix chain over the per-step leading-zero counts, 4 steps per lane
@@ -451,17 +455,26 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             const uint32_t rounds = (m + 1u + kEncThreads - 1u) / kEncThreads;
             for (uint32_t r = 0; r < rounds; ++r) {
                 const uint32_t i = r * kEncThreads + tid;
-                uint32_t bits = 0, gap = 0, cur = 0, val = 0, rs = 0;
+                uint32_t bits = 0, gap = 0, cur = 0, rs = 0;
+                // slots of the common case (one run token at most): run code, run extra bits, literal
+                uint32_t c_run = 0, c_ext = 0, c_lit = 0;
                 const bool live = i <= m;
                 if (live) {
                     const uint32_t e = i < m ? list[i] : n;
-                    cur = e & 0xFFFFu;
-                    if (i == m) cur = n;
-                    val = e >> 16;
+                    cur = i < m ? e & 0xFFFFu : n;
                     rs = i ? (list[i - 1] & 0xFFFFu) + 1u : 0u;
                     gap = cur - rs;
-                    if (gap) bits = run_bits(gap, s_codes);
-                    if (i < m) bits += s_codes[val] >> 27;
+                    if (i < m) c_lit = s_codes[e >> 16];
+                    if (gap > kRunCap) {
+                        bits = run_bits(gap, s_codes);
+                    } else if (gap) {
+                        uint32_t sym, ev, eb;
+                        run_token(gap, sym, ev, eb);
+                        c_run = s_codes[sym];
+                        c_ext = ev | (eb << 27);
+                        bits = slot_bits(c_run) + eb;
+                    }
+                    bits += slot_bits(c_lit);
                 }
                 uint32_t inc = bits;
 #pragma unroll
@@ -481,12 +494,26 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                 const uint32_t o0 = base + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u) + inc - bits;
                 base += __shfl_sync(0xFFFFFFFFu, tw2, kEncWarps - 1);
                 if (live) {
-                    const uint32_t o_lit = o0 + bits - (i < m ? s_codes[val] >> 27 : 0u);
-                    if (bits) {
+                    const uint32_t o_lit = o0 + bits - slot_bits(c_lit);
+                    if (bits > 64u || gap > kRunCap) {
                         EmitSink es{s_codes, pay, 0ull, o0 & 31u, o0 >> 5, true};
                         if (gap) emit_run(gap, es);
-                        if (i < m) es.token(val, 0u, 0u);
+                        if (i < m) es.append(c_lit & 0x07FFFFFFu, slot_bits(c_lit));
                         es.finish();
+                    } else if (bits) {
+                        // concatenate the slots last-first, shift to the bit offset, OR into <= 3 words
+                        uint32_t lo = c_lit & 0x07FFFFFFu, hi = 0, l = slot_bits(c_ext);
+                        hi = __funnelshift_l(lo, hi, l);
+                        lo = (lo << l) | (c_ext & 0x07FFFFFFu);
+                        l = slot_bits(c_run);
+                        hi = __funnelshift_l(lo, hi, l);
+                        lo = (lo << l) | (c_run & 0x07FFFFFFu);
+                        const uint32_t sh = o0 & 31u;
+                        uint32_t* w = pay + (o0 >> 5);
+                        const uint32_t v0 = lo << sh, v1 = __funnelshift_l(lo, hi, sh), v2 = __funnelshift_l(hi, 0u, sh);
+                        atomicOr(w, v0);
+                        if (v1) atomicOr(w + 1, v1);
+                        if (v2) atomicOr(w + 2, v2);
                     }
                     if (sc_bit) {
                         // decode index entries of the segment boundaries B in [rs, cur], B < n: at
