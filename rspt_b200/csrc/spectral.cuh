@@ -101,6 +101,124 @@ __global__ void __launch_bounds__(256) k_fwht_inv(const uint8_t* __restrict__ pl
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) w[i] = (int32_t)(a[i] + (uint32_t)mean);
 }
 
+// ---- n = 4096 fast path: three radix-16 passes in registers ---------------------------------
+// 256 threads x 16 elements.  Pass 1 takes index bits 8..11 (elements t + 256 j, read straight
+// from global memory), pass 2 bits 4..7, pass 3 bits 0..3 (elements 16 t + j, so a thread ends
+// up with 16 consecutive coefficients and writes one 128-bit word per plane).  Between passes
+// the data sits in shared memory at i + (i >> 5) (one pad word per 32), which keeps the stride-16
+// accesses of pass 3 conflict-free.  Butterfly order is irrelevant mod 2^32, so the result is the
+// reference's natural-order transform (fwht.c:15-25).
+constexpr uint32_t kFwhtFastN = 4096;
+__device__ __forceinline__ uint32_t fwht_phys(uint32_t i) { return i + (i >> 5); }
+
+__device__ __forceinline__ void radix16(uint32_t (&r)[16])
+{
+#pragma unroll
+    for (int h = 1; h < 16; h <<= 1)
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if ((j & h) == 0) {
+                const uint32_t u = r[j], v = r[j + h];
+                r[j] = u + v;
+                r[j + h] = u - v;
+            }
+}
+
+__global__ void __launch_bounds__(256) k_fwht4096_fwd(const int32_t* __restrict__ words, const long long* __restrict__ sums,
+                                                       Shape s, uint8_t* __restrict__ planes, uint8_t* __restrict__ headers)
+{
+    __shared__ uint32_t a[kFwhtFastN + kFwhtFastN / 32];
+    const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, t = threadIdx.x;
+    const int32_t mean = reference_mean(sums[(size_t)f * s.ch + c], kFwhtFastN);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(words) + (size_t)f * s.N + (size_t)c * kFwhtFastN;
+    if (t == 0) store_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c, mean);
+    uint32_t r[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = __ldg(w + t + 256 * j);
+    radix16(r);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[fwht_phys(t + 256 * j)] = r[j];
+    __syncthreads();
+    const uint32_t b2 = (t >> 4) * 256 + (t & 15);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(b2 + 16 * j)];
+    radix16(r);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[fwht_phys(b2 + 16 * j)] = r[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(16 * t + j)];
+    radix16(r);
+    // the per-channel mean is removed before the transform (hadamard.cpp:60-65); by linearity mod
+    // 2^32 that only changes the DC coefficient
+    if (t == 0) r[0] -= kFwhtFastN * (uint32_t)mean;
+    uint32_t pl[4][4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t q[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int32_t X = (int32_t)r[4 * g + i];
+            // (int)(X / (double)n): truncation toward zero of an exact power-of-two quotient (fwht.c:33)
+            q[i] = (uint32_t)((X + ((X >> 31) & (int32_t)(kFwhtFastN - 1))) >> 12);
+        }
+        const uint32_t t01 = prmt(q[0], q[1], 0x5140u), t23 = prmt(q[2], q[3], 0x5140u);
+        const uint32_t u01 = prmt(q[0], q[1], 0x7362u), u23 = prmt(q[2], q[3], 0x7362u);
+        pl[0][g] = prmt(t01, t23, 0x5410u);
+        pl[1][g] = prmt(t01, t23, 0x7632u);
+        pl[2][g] = prmt(u01, u23, 0x5410u);
+        pl[3][g] = prmt(u01, u23, 0x7632u);
+    }
+    uint8_t* out = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)c * kFwhtFastN + 16 * t;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if ((uint32_t)k < s.nb_alloc)
+            *reinterpret_cast<uint4*>(out + (size_t)k * s.plane_stride) = make_uint4(pl[k][0], pl[k][1], pl[k][2], pl[k][3]);
+}
+
+__global__ void __launch_bounds__(256) k_fwht4096_inv(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ headers,
+                                                       const uint8_t* __restrict__ dec_nb, Shape s, int32_t* __restrict__ words)
+{
+    __shared__ uint32_t a[kFwhtFastN + kFwhtFastN / 32];
+    const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, t = threadIdx.x;
+    const uint32_t nb = dec_nb[f];
+    const uint8_t* in = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)c * kFwhtFastN + 16 * t;
+    uint4 pv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        pv[k] = (uint32_t)k < s.nb_alloc ? __ldg(reinterpret_cast<const uint4*>(in + (size_t)k * s.plane_stride)) : make_uint4(0, 0, 0, 0);
+    uint32_t r[16];
+    {
+        uint32_t y[4];
+        planes_to_words(pv[0].x, pv[1].x, pv[2].x, pv[3].x, nb, y);
+        r[0] = y[0]; r[1] = y[1]; r[2] = y[2]; r[3] = y[3];
+        planes_to_words(pv[0].y, pv[1].y, pv[2].y, pv[3].y, nb, y);
+        r[4] = y[0]; r[5] = y[1]; r[6] = y[2]; r[7] = y[3];
+        planes_to_words(pv[0].z, pv[1].z, pv[2].z, pv[3].z, nb, y);
+        r[8] = y[0]; r[9] = y[1]; r[10] = y[2]; r[11] = y[3];
+        planes_to_words(pv[0].w, pv[1].w, pv[2].w, pv[3].w, nb, y);
+        r[12] = y[0]; r[13] = y[1]; r[14] = y[2]; r[15] = y[3];
+    }
+    radix16(r);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[fwht_phys(16 * t + j)] = r[j];
+    __syncthreads();
+    const uint32_t b2 = (t >> 4) * 256 + (t & 15);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(b2 + 16 * j)];
+    radix16(r);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[fwht_phys(b2 + 16 * j)] = r[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(t + 256 * j)];
+    radix16(r);
+    const uint32_t mean = (uint32_t)load_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c);
+    uint32_t* w = reinterpret_cast<uint32_t*>(words) + (size_t)f * s.N + (size_t)c * kFwhtFastN;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[t + 256 * j] = r[j] + mean;
+}
+
 // ---- FP64 complex FFT in shared memory ------------------------------------------------------
 // x[0..n) complex, n = 2^lg.  Input must already be in bit-reversed order.  tw[j] = e^{-2 pi i j/n}
 // for j < n/2; INVERSE conjugates it.  Radix-2 decimation in time.
@@ -299,8 +417,12 @@ inline int spectral_forward(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
     const dim3 g2((unsigned)(F * s.ch));
     if (s.kind == 2 /*RSPT_HADAMARD*/) {
         const size_t sm = (size_t)s.ns * 4;
-        cudaFuncSetAttribute(k_fwht_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        k_fwht_fwd<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_planes, p->d_headers);
+        if ((uint32_t)s.ns == kFwhtFastN) {
+            k_fwht4096_fwd<<<g2, 256, 0, p->stream>>>(p->d_words, p->d_sums, s, p->d_planes, p->d_headers);
+        } else {
+            cudaFuncSetAttribute(k_fwht_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            k_fwht_fwd<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_planes, p->d_headers);
+        }
         p->launches += 2;
     } else {
         if (dct_use_direct(p)) {
@@ -383,8 +505,12 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
         const dim3 g2((unsigned)(F * s.ch));
         if (s.kind == 2) {
             const size_t sm = (size_t)s.ns * 4;
-            cudaFuncSetAttribute(k_fwht_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            k_fwht_inv<<<g2, 256, sm, p->stream>>>(p->d_planes, p->d_headers, p->d_dec_nb, s, p->d_words);
+            if ((uint32_t)s.ns == kFwhtFastN) {
+                k_fwht4096_inv<<<g2, 256, 0, p->stream>>>(p->d_planes, p->d_headers, p->d_dec_nb, s, p->d_words);
+            } else {
+                cudaFuncSetAttribute(k_fwht_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                k_fwht_inv<<<g2, 256, sm, p->stream>>>(p->d_planes, p->d_headers, p->d_dec_nb, s, p->d_words);
+            }
             p->launches += 1;
         } else {
             INV_LAUNCH(4, true, false);  // coefficient words (BPS unused for word output)

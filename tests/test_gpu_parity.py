@@ -108,6 +108,7 @@ PLANE_CASES = [
     ("xdelta_hzr", 3, 8, 516, 4), ("xdelta_hzr", 4, 16, 2052, 2), ("hzr", 2, 8, 2052, 0), ("hzr", 1, 4, 8, 0),
     ("hzr", 3, 12, 8192, 0), ("hzr", 1, 2, 999, 0), ("hzr", 4, 3, 5000, 0),
     ("hadamard", 4, 12, 4096, 0), ("hadamard", 3, 3, 16384, 0), ("hadamard", 2, 2, 8, 0), ("hadamard", 1, 1, 32768, 0),
+    ("hadamard", 3, 5, 4096, 0), ("hadamard", 2, 1, 4096, 0),   # radix-16 register path (ns = 4096), odd channel counts
 ]
 
 
@@ -135,7 +136,7 @@ STREAM_CASES = [
     ("xdelta_hzr", 4, 12, 16384, 3, 2), ("xdelta_hzr", 3, 2, 1, 3, 4), ("xdelta_hzr", 3, 7, 33, 3, 4),
     ("xdelta_hzr", 4, 2, 70001, 4, 2),
     ("hzr", 3, 12, 8192, 0, 3), ("hzr", 4, 12, 4096, 0, 2), ("hzr", 1, 2, 999, 0, 3), ("hzr", 2, 1, 140000, 0, 2),
-    ("hadamard", 4, 12, 4096, 0, 3), ("hadamard", 3, 3, 16384, 0, 2), ("hadamard", 2, 2, 8, 0, 3),
+    ("hadamard", 4, 12, 4096, 0, 3), ("hadamard", 3, 3, 16384, 0, 2), ("hadamard", 2, 2, 8, 0, 3), ("hadamard", 2, 3, 4096, 0, 2),
 ]
 
 
