@@ -64,14 +64,15 @@ __device__ __forceinline__ uint32_t sym_extra_bits(uint32_t sym)
     return sym < 257 ? 0u : (sym == 257 ? 2u : (sym == 258 ? 4u : (sym == 259 ? 8u : 14u)));
 }
 
-// Classify a zero-run chunk z in [1, 16662] -> (symbol, extra value); hzr_encode.c:152-166.
+// Classify a zero-run chunk z in [1, 16662] -> (symbol, extra value, extra bits); hzr_encode.c:152-166.
+// Branch-free: class index 0..5 for 1 | 2 | 3-6 | 7-22 | 23-278 | 279-16662.
 __device__ __forceinline__ void run_token(uint32_t z, uint32_t& sym, uint32_t& ev, uint32_t& eb)
 {
-    if (z <= 2) { sym = z == 1 ? 0u : 256u; ev = 0; eb = 0; }
-    else if (z <= 6) { sym = 257; ev = z - 3; eb = 2; }
-    else if (z <= 22) { sym = 258; ev = z - 7; eb = 4; }
-    else if (z <= 278) { sym = 259; ev = z - 23; eb = 8; }
-    else { sym = 260; ev = z - 279; eb = 14; }
+    const uint32_t idx = (z >= 2u) + (z >= 3u) + (z >= 7u) + (z >= 23u) + (z >= 279u);
+    sym = idx ? 255u + idx : 0u;
+    eb = (0xE84200u >> (4u * idx)) & 0xFu;                      // 0 0 2 4 8 14
+    const uint32_t base = idx == 5u ? 279u : (0x17070300u >> (8u * (idx < 2u ? 0u : idx - 1u))) & 0xFFu;  // 3 7 23
+    ev = idx < 2u ? 0u : z - base;
 }
 
 // ---- strip loading -----------------------------------------------------------------------

@@ -72,10 +72,17 @@ __device__ __forceinline__ void neighbour_zero(uint32_t z, uint32_t& prevz, uint
     nextz = lane_id() < 31 ? dn & 1u : 1u;
 }
 
-struct HistSink {
-    uint32_t* run;  // [0] symbol 0, [1..5] symbols 256..260
-    __device__ __forceinline__ void token(uint32_t sym, uint32_t, uint32_t) { atomicAdd(&run[sym ? sym - 255u : 0u], 1u); }
-};
+// count the tokens of one zero run of z >= 1 bytes; run[0] = symbol 0, run[1..5] = symbols 256..260
+// (branch-free class: 1 | 2 | 3-6 | 7-22 | 23-278 | 279-16662, hzr_encode.c:152-166)
+__device__ __forceinline__ void hist_run(uint32_t z, uint32_t* run)
+{
+    while (z > kRunCap) {
+        atomicAdd(&run[5], 1u);
+        z -= kRunCap;
+    }
+    const uint32_t idx = (z >= 2u) + (z >= 3u) + (z >= 7u) + (z >= 23u) + (z >= 279u);
+    atomicAdd(&run[idx], 1u);
+}
 
 __global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
                                                             const uint8_t* __restrict__ frame_nb,
@@ -100,7 +107,6 @@ __global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __rest
     const uint32_t spw = (nsteps + nwarps - 1) / nwarps;
     const uint32_t s_lo = min(nsteps, wid * spw), s_hi = min(nsteps, s_lo + spw);
     uint16_t* my_lz = step_lz + (size_t)blk * kMaxSteps;
-    HistSink sink{s_run};
     uint32_t pending = 0, lead = 0, cnt0 = 0;
     bool seen = false;
     for (uint32_t st = s_lo; st < s_hi; ++st) {
@@ -147,8 +153,8 @@ __global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __rest
                 const uint32_t p = __ffs(rs2) - 1u;
                 rs2 &= rs2 - 1u;
                 const uint32_t sb = c.stop >> p;
-                if (sb) emit_run((uint32_t)__ffs(sb) - 1u, sink);
-                else if (above) emit_run(16u - p + fwd, sink);
+                if (sb) hist_run((uint32_t)__ffs(sb) - 1u, s_run);
+                else if (above) hist_run(16u - p + fwd, s_run);
                 // else: the run leaves the step; it is part of the step's trailing zeros
             }
         }
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __rest
             lead = run;
             seen = true;
         } else if (run && lane == 0) {
-            emit_run(run, sink);
+            hist_run(run, s_run);
         }
         pending = tz;
     }
@@ -183,11 +189,11 @@ __global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __rest
                 pend += s_wsum[w][2];
             } else {
                 const uint32_t run = pend + s_wsum[w][1];
-                if (run) emit_run(run, sink);
+                if (run) hist_run(run, s_run);
                 pend = s_wsum[w][2];
             }
         }
-        if (pend) emit_run(pend, sink);
+        if (pend) hist_run(pend, s_run);
     }
     __syncthreads();
     uint32_t* out = hist + (size_t)blk * kSymStride;
