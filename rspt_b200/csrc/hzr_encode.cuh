@@ -112,15 +112,6 @@ __global__ void __launch_bounds__(1024) k_frame_nb(const uint32_t* __restrict__ 
     }
 }
 
-__device__ __forceinline__ uint32_t chunk_bytes(const BlkInfo* info, const Shape& s, uint32_t f, uint32_t k)
-{
-    // hzr stream of one plane: 4-byte decoded size + blocks of 7 + payload (hzr_encode.c:521-539)
-    uint32_t sz = 4;
-    const BlkInfo* bi = info + ((size_t)f * s.nb_alloc + k) * s.nblk;
-    for (uint32_t b = 0; b < s.nblk; ++b) sz += 7u + bi[b].payload_len;
-    return sz;
-}
-
 // per frame: total size and the byte offset (from the frame start) of every block's 7-byte header
 __global__ void k_frame_sizes(const BlkInfo* __restrict__ info, Shape s, const uint8_t* __restrict__ frame_nb,
                               uint32_t n_frames, uint32_t* __restrict__ sizes, uint32_t* __restrict__ blk_off)

@@ -1,0 +1,66 @@
+"""BASELINE.json configs at their full sizes on one B200, through size-independent properties:
+encode -> decode is the identity on EVERY frame, frame offsets are a strictly increasing scan, and
+the streams of a sample of frames (first and last of every batch) are byte-identical to the oracle.
+Frames are generated on the device batch by batch (1 M frames of config 2 are 295 GB)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1200)]
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def R():
+    from rspt_b200 import packer
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return packer
+
+
+def _run_config(R, oracle, kind, bps, ch, ns, total_frames, batch, lossless, check_every=1):
+    fb = bps * ch * ns
+    p = R.SignalPacker(kind, bps, ch, ns, 3, max_batch_frames=batch)
+    o = oracle.OraclePacker(kind, bps, ch, ns, 3)
+    out = p.alloc_output(batch)
+    raw = torch.empty(batch * fb, dtype=torch.uint8, device="cuda")
+    dec = torch.empty_like(raw)
+    comp_total = 0
+    nb = (total_frames + batch - 1) // batch
+    for bi in range(nb):
+        first = bi * batch
+        n = min(batch, total_frames - first)
+        R.synth_ecg(first, n, bps, ch, ns, out=raw)
+        b = p.compress_batch(raw[: n * fb], out=out)
+        p.decompress_batch(b, out=dec)
+        offs = b.offsets[: n + 1]
+        assert bool((offs[1:] > offs[:-1]).all()) and int(offs[0].item()) == 0
+        comp_total += int(offs[n].item())
+        if lossless:
+            assert torch.equal(raw[: n * fb], dec[: n * fb]), (kind, bi)
+        if bi % check_every == 0:
+            for i in (0, n - 1):
+                lo, hi = int(offs[i].item()), int(offs[i + 1].item())
+                got = bytes(b.stream[lo:hi].cpu().numpy())
+                host = raw[i * fb:(i + 1) * fb].cpu().numpy()
+                want = o.compress(host)
+                assert got == want, (kind, first + i)
+                if not lossless:
+                    assert dec[i * fb:(i + 1) * fb].cpu().numpy().tobytes() == o.decompress(want)[0], (kind, first + i)
+    p.close()
+    return total_frames * fb / comp_total
+
+
+def test_config2_xdelta_hzr_one_million_frames(R, oracle):
+    """configs[1]: xdelta_hzr, 12 ch x 3 B x 8192 samples, 1 M frames (64 batches of 15 625)."""
+    frames = int(os.environ.get("RSPT_SCALE_FRAMES", "1000000"))
+    cr = _run_config(R, oracle, "xdelta_hzr", 3, 12, 8192, frames, 15625, lossless=True, check_every=4)
+    assert 3.0 < cr < 4.5, cr
+
+
+def test_config3_hadamard_full_size_sample(R, oracle):
+    """configs[2]: hadamard, 12 ch x 4 B x 4096 samples; integer transform, so the stream is bit-exact
+    and the decode equals the reference's decode.  131 072 frames (25.8 GB) keep the run short."""
+    cr = _run_config(R, oracle, "hadamard", 4, 12, 4096, 131072, 16384, lossless=False)
+    assert 3.5 < cr < 6.0, cr
