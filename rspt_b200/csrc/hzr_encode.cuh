@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                                                                 const uint32_t* __restrict__ codes,
                                                                 const uint32_t* __restrict__ tree,
                                                                 const uint16_t* __restrict__ step_lz,
+                                                                const uint32_t* __restrict__ lists,
+                                                                const uint32_t* __restrict__ list_n,
                                                                 const uint64_t* __restrict__ offsets,
                                                                 const uint8_t* __restrict__ headers,
                                                                 const CrcConst* __restrict__ cc,
@@ -347,6 +349,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
     uint8_t* sbytes = reinterpret_cast<uint8_t*>(stg);
     const uint32_t plen = bi.payload_len;
     uint32_t* pay = stg + 4;
+    const uint32_t stg_words = 4u + (min(s.N, kBlock) + 3u) / 4u + 8u;  // staging words; the sparse list follows
 
     if (bi.mode == MODE_COPY) {
         // raw plane bytes are the payload (PlainCopy); rows are 16-byte aligned
@@ -366,7 +369,9 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
         const uint32_t tw4 = (tw + 3u) & ~3u;
         for (uint32_t i = tid; i < tw4; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
         for (uint32_t i = (tw4 >> 2) + tid; i < ((pw + 2u + 3u) >> 2); i += blockDim.x) reinterpret_cast<uint4*>(pay)[i] = make_uint4(0, 0, 0, 0);
-        if (wid == kEncWarps - 1) {
+        const uint32_t m = list_n[blk];
+        const bool sparse = m != kNoList;
+        if (!sparse && wid == kEncWarps - 1) {
             // s_after[st] = zeros between the end of step st and the next stop byte (or the block
             // end): suffix chain over the per-step leading-zero counts, 4 steps per lane
             const uint16_t* lzp = step_lz + (size_t)blk * kMaxSteps;
@@ -402,45 +407,13 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
 
         uint32_t base = bi.tree_nbits;  // bit offset of the group (same in every thread)
         const uint32_t ngroups = (nsteps + kEncWarps - 1) / kEncWarps;
-        // ---- sparse blocks (few tokens): compact the non-zero bytes into a sorted list
-        // (position | value << 16) behind the payload in the staging buffer, then give every list
-        // entry to one thread: the zero run in front of the byte (gap to the previous entry) and
-        // the literal.  One extra pseudo entry closes the run that reaches the block end.
-        const uint32_t cap_words = (min(s.N, kBlock) + 3u) / 4u + 4u;  // words behind `pay` (see enc_smem)
-        const bool sparse = (uint32_t)bi.n_tokens * 4u <= n && pw + 2u + (uint32_t)bi.n_tokens + 2u <= cap_words;
+        // ---- sparse blocks: k_hzr_hist left the sorted list of their non-zero bytes
+        // (position | value << 16).  It is copied behind the staging buffer and every entry goes to
+        // one thread: the zero run in front of the byte (gap to the previous entry) and the
+        // literal.  One extra pseudo entry closes the run that reaches the block end.
         if (sparse) {
-            uint32_t* list = pay + pw + 2u;
-            uint32_t m = 0;  // entries so far (same in every thread)
-            for (uint32_t g = 0; g < ngroups; ++g) {
-                const uint32_t st = g * kEncWarps + wid;
-                const uint32_t off = st * kStepBytes + lane * 16u;
-                const Chunk c = load_chunk(src, n, off);
-                const uint32_t cnt = __popc(c.nz);
-                uint32_t inc = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                    if (lane >= (uint32_t)o) inc += y;
-                }
-                if (lane == 31) s_tot[g & 1][wid] = inc;
-                __syncthreads();
-                uint32_t tw2 = lane < kEncWarps ? s_tot[g & 1][lane] : 0u;
-#pragma unroll
-                for (int o = 1; o < kEncWarps; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tw2, o);
-                    if (lane >= (uint32_t)o) tw2 += y;
-                }
-                uint32_t at = m + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u) + inc - cnt;
-                m += __shfl_sync(0xFFFFFFFFu, tw2, kEncWarps - 1);
-                const uint32_t w[4] = {c.v.x, c.v.y, c.v.z, c.v.w};
-                uint32_t mk = c.nz;
-                while (mk) {
-                    const uint32_t p = __ffs(mk) - 1u;
-                    mk &= mk - 1u;
-                    const uint32_t x = p < 8 ? (p < 4 ? w[0] : w[1]) : (p < 12 ? w[2] : w[3]);
-                    list[at++] = (off + p) | (((x >> (8u * (p & 3u))) & 0xFFu) << 16);
-                }
-            }
+            uint32_t* list = stg + stg_words;
+            for (uint32_t i = tid; i < m; i += blockDim.x) list[i] = __ldg(lists + (size_t)blk * kListCap + i);
             __syncthreads();
             // entry i < m: zeros (prev, cur) then the literal at cur; entry m: zeros (prev, n)
             const uint32_t rounds = (m + 1u + kEncThreads - 1u) / kEncThreads;

@@ -27,6 +27,11 @@ constexpr int kHistThreads = 256;
 constexpr int kStepBytes = 512;                     // one warp-step: 32 lanes x 16 bytes
 constexpr int kMaxSteps = kBlock / kStepBytes;      // 128 per block
 constexpr uint32_t kStepAllZero = kStepBytes;       // step_lz value of a step without any stop byte
+constexpr uint32_t kListCap = 8192;                 // entries of a block's sparse list (position | value << 16)
+constexpr uint32_t kNoList = 0xFFFFFFFFu;           // list_n value of a block that has no sparse list
+
+// entries the sparse list of an n-byte block may hold: at most a quarter of the bytes non-zero
+__host__ __device__ __forceinline__ uint32_t list_cap(uint32_t n) { return n / 4u < kListCap ? n / 4u : kListCap; }
 
 // 4-bit mask of the non-zero bytes of a word
 __device__ __forceinline__ uint32_t nz_nibble(uint32_t x)
@@ -87,8 +92,11 @@ __device__ __forceinline__ void hist_run(uint32_t z, uint32_t* run)
 __global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
                                                             const uint8_t* __restrict__ frame_nb,
                                                             uint32_t* __restrict__ hist,
-                                                            uint16_t* __restrict__ step_lz)
+                                                            uint16_t* __restrict__ step_lz,
+                                                            uint32_t* __restrict__ lists, uint32_t* __restrict__ list_n)
 {
+    extern __shared__ __align__(16) uint32_t s_list[];  // sparse list under construction
+    __shared__ uint32_t s_tot[2][kHistThreads / 32];
     __shared__ uint32_t s_lit[256];  // raw byte counts; [0] is scratch (zeros are tokenised as runs)
     __shared__ uint32_t s_run[8];
     __shared__ uint32_t s_wsum[kHistThreads / 32][3];  // per warp range: seen, lead, trail
@@ -104,6 +112,88 @@ __global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __rest
 
     const uint32_t lane = lane_id(), wid = warp_id(), nwarps = blockDim.x >> 5;
     const uint32_t nsteps = (n + kStepBytes - 1) / kStepBytes;
+
+    // ---- sparse blocks: compact the non-zero bytes into a sorted list (position | value << 16),
+    // optimistically, giving up as soon as it outgrows its capacity (then the block is dense and
+    // takes the scan below).  Every token of a sparse block follows from the list: a literal per
+    // entry, a zero run per gap between neighbouring entries (and before the block end).  The
+    // list is kept for k_hzr_encode, which then never re-reads a sparse block.
+    {
+        // a group = two consecutive steps per warp (32 bytes per lane); counts of the two steps ride
+        // in one packed warp scan
+        const uint32_t cap = list_cap(n), ngroups = (nsteps + 2 * nwarps - 1) / (2 * nwarps);
+        uint32_t m = 0;  // entries so far (same in every thread)
+        bool fits = cap > 0;
+        for (uint32_t g = 0; g < ngroups && fits; ++g) {
+            const uint32_t off0 = (g * nwarps + wid) * 2u * kStepBytes + lane * 16u, off1 = off0 + kStepBytes;
+            const Chunk c0 = load_chunk(src, n, off0), c1 = load_chunk(src, n, off1);
+            const uint32_t cnt = __popc(c0.nz) | (__popc(c1.nz) << 16);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
+            }
+            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            const uint32_t tot0 = tot & 0xFFFFu, tot1 = tot >> 16;
+            if (lane == 31) s_tot[g & 1][wid] = tot0 + tot1;
+            __syncthreads();
+            uint32_t tw2 = lane < nwarps ? s_tot[g & 1][lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < kHistThreads / 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tw2, o);
+                if (lane >= (uint32_t)o) tw2 += y;
+            }
+            const uint32_t wbase = m + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u);
+            m += __shfl_sync(0xFFFFFFFFu, tw2, nwarps - 1);
+            // give up when the list is full -- or at once when the first group is already denser
+            // than a sparse block may be on average (a wrong guess only costs the dense scan)
+            fits = m <= cap && !(g == 0 && m * 4u > min(n, 2u * nwarps * kStepBytes));
+            if (fits) {
+                const uint32_t exc = inc - cnt;
+                uint32_t at0 = wbase + (exc & 0xFFFFu), at1 = wbase + tot0 + (exc >> 16);
+                const uint32_t w0[4] = {c0.v.x, c0.v.y, c0.v.z, c0.v.w}, w1[4] = {c1.v.x, c1.v.y, c1.v.z, c1.v.w};
+                uint32_t mk = c0.nz;
+                while (mk) {
+                    const uint32_t p = __ffs(mk) - 1u;
+                    mk &= mk - 1u;
+                    const uint32_t x = p < 8 ? (p < 4 ? w0[0] : w0[1]) : (p < 12 ? w0[2] : w0[3]);
+                    s_list[at0++] = (off0 + p) | (((x >> (8u * (p & 3u))) & 0xFFu) << 16);
+                }
+                mk = c1.nz;
+                while (mk) {
+                    const uint32_t p = __ffs(mk) - 1u;
+                    mk &= mk - 1u;
+                    const uint32_t x = p < 8 ? (p < 4 ? w1[0] : w1[1]) : (p < 12 ? w1[2] : w1[3]);
+                    s_list[at1++] = (off1 + p) | (((x >> (8u * (p & 3u))) & 0xFFu) << 16);
+                }
+            }
+        }
+        __syncthreads();
+        if (fits) {
+            uint32_t* glist = lists + (size_t)blk * kListCap;
+            for (uint32_t i = threadIdx.x; i <= m; i += blockDim.x) {
+                const uint32_t rs = i ? (s_list[i - 1] & 0xFFFFu) + 1u : 0u;
+                uint32_t cur = n;
+                if (i < m) {
+                    const uint32_t e = s_list[i];
+                    glist[i] = e;
+                    cur = e & 0xFFFFu;
+                    atomicAdd(&s_lit[e >> 16], 1u);
+                }
+                if (cur > rs) hist_run(cur - rs, s_run);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) list_n[blk] = m;
+            uint32_t* out = hist + (size_t)blk * kSymStride;
+            for (uint32_t i = threadIdx.x; i < kSymStride; i += blockDim.x)
+                out[i] = i == 0 ? s_run[0] : (i < 256 ? s_lit[i] : (i < (uint32_t)kNumSymbols ? s_run[i - 255] : 0u));
+            return;
+        }
+        if (threadIdx.x == 0) list_n[blk] = kNoList;
+    }
+
+    // ---- dense blocks
     const uint32_t spw = (nsteps + nwarps - 1) / nwarps;
     const uint32_t s_lo = min(nsteps, wid * spw), s_hi = min(nsteps, s_lo + spw);
     uint16_t* my_lz = step_lz + (size_t)blk * kMaxSteps;

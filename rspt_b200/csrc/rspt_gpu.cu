@@ -266,6 +266,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     const uint32_t maxn = s.N < kBlock ? s.N : kBlock;
     p->enc_smem = (size_t)(4 + (maxn + 3) / 4 + 8) * 4;  // staging of the largest block: header words + payload + slack
     p->dec_smem = (size_t)((maxn + 3) / 4 + 4) * 4;      // payload of the largest block + zero slack
+    p->list_smem = (size_t)list_cap(maxn) * 4;           // sparse list of the largest block
     p->stream = (cudaStream_t)stream;  // NULL = the CUDA default stream
     p->own_stream = false;
     const size_t F = max_batch_frames, nblocks = F * s.nb_alloc * s.nblk;
@@ -276,6 +277,8 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_codes, nblocks * kSymStride));
     A(dalloc(p->d_tree, nblocks * kTreeWords));
     A(dalloc(p->d_step_lz, nblocks * kMaxSteps));
+    A(dalloc(p->d_lists, nblocks * (size_t)kListCap));
+    A(dalloc(p->d_list_n, nblocks));
     A(dalloc(p->d_info, nblocks));
     A(dalloc(p->d_frame_nb, F));
     A(dalloc(p->d_need, F));
@@ -303,7 +306,8 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_frame_nb, (int)s.nb_init, F, p->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ctr, 0, sizeof(Counters), p->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_nb_state, &s.nb_init, 4, cudaMemcpyHostToDevice, p->stream);
-    if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem + (size_t)kListCap * 4);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_hist, (size_t)kListCap * 4);
     if (e == cudaSuccess) e = allow_smem(k_hzr_decode, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_crc32c, kEncodeSmem);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
@@ -321,7 +325,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     if (!p) return RSPT_E_ARG;
     DeviceGuard dg(p->device);
     cudaStreamSynchronize(p->stream);
-    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_info, p->d_frame_nb,
+    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
                     p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off};
@@ -487,7 +491,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     }
     {
         StageTimer t(p, RSPT_STAGE_HIST);
-        k_hzr_hist<<<nblocks, kHistThreads, 0, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz);
+        k_hzr_hist<<<nblocks, kHistThreads, p->list_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
     }
     {
         StageTimer t(p, RSPT_STAGE_TREE);
@@ -504,8 +508,8 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     uint32_t* sc_codes = d_sidecar ? reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
     {
         StageTimer t(p, RSPT_STAGE_ENCODE);
-        k_hzr_encode<<<nblocks, kEncThreads, p->enc_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
-                                                                        p->d_codes, p->d_tree, p->d_step_lz, d_offsets,
+        k_hzr_encode<<<nblocks, kEncThreads, p->enc_smem + p->list_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
+                                                                        p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, d_offsets,
                                                                         p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip, sc_codes);
     }
     p->launches += 5;
@@ -781,7 +785,7 @@ extern "C" int rspt_gpu_debug_hzr_tables(rspt_gpu_packer* p, const uint8_t* d_bl
     DeviceGuard dg(p->device);
     Shape s = p->s;
     s.N = (uint32_t)n; s.nblk = 1; s.nb_alloc = 1; s.plane_stride = (uint32_t)((n + 15) & ~(size_t)15);
-    k_hzr_hist<<<1, kHistThreads, 0, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz);
+    k_hzr_hist<<<1, kHistThreads, 4 * (size_t)list_cap((uint32_t)n), p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
     k_hzr_tree<<<1, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, 1, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
     p->launches += 2;
     RSPT_CUDA_CHECK(cudaGetLastError());
