@@ -491,17 +491,31 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                 }
             }
             __syncthreads();
-        } else
+        } else {
         // ---- dense blocks: a lane owns 16 consecutive bytes (4 words) of its warp's 512-byte step
+        // (the chunk of the next group and the byte before its step are fetched one group ahead, so
+        // their latency hides behind the current group's work)
+        uint4 v_next = make_uint4(0, 0, 0, 0);
+        uint32_t pstep_next = 1;
+        {
+            const uint32_t sb0 = wid * kStepBytes;
+            if (lane == 0 && sb0 > 0 && sb0 <= n) pstep_next = src[sb0 - 1];
+            if (sb0 + kStepBytes <= n) v_next = __ldg(reinterpret_cast<const uint4*>(src + sb0 + lane * 16u));
+        }
         for (uint32_t g = 0; g < ngroups; ++g) {
             const uint32_t st = g * kEncWarps + wid;
             const uint32_t sbase = st * kStepBytes, off = sbase + lane * 16u;
             uint32_t x[4], NZ, INV = 0;
-            // zero flag of the byte before the step (lane 0 only; issued with the main load)
-            uint32_t pstep = 1;
-            if (lane == 0 && sbase > 0 && sbase <= n) pstep = src[sbase - 1];
+            // zero flag of the byte before the step (lane 0 only)
+            const uint32_t pstep = pstep_next;
+            const uint4 v = v_next;
+            {
+                const uint32_t sbn = sbase + kEncWarps * kStepBytes;
+                pstep_next = 1;
+                if (lane == 0 && sbn <= n) pstep_next = src[sbn - 1];
+                if (sbn + kStepBytes <= n) v_next = __ldg(reinterpret_cast<const uint4*>(src + sbn + lane * 16u));
+            }
             if (sbase + kStepBytes <= n) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + off));
                 x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
                 NZ = nz_mask16(v);
             } else {
@@ -633,6 +647,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                 }
                 o += bits[r];
             }
+        }
         }
         __syncthreads();
     }
