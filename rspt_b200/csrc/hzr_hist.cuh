@@ -89,6 +89,32 @@ __device__ __forceinline__ void hist_run(uint32_t z, uint32_t* run)
     atomicAdd(&run[idx], 1u);
 }
 
+// Append the non-zero bytes of every lane's chunk to the list, lane by lane in position order
+// (`at` = list index of the lane's first entry).  Non-zero bytes come in bursts, so instead of
+// every lane looping over its own bytes, the chunks that have any are served two at a time by
+// half a warp each: lane p of the half writes byte p.
+__device__ __forceinline__ void scatter_chunks(const Chunk& c, uint32_t off, uint32_t at, uint32_t* list)
+{
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, c.nz != 0u);
+    const uint32_t lane = lane_id(), p = lane & 15u;
+    while (todo) {
+        const uint32_t la = __ffs(todo) - 1u;
+        todo &= todo - 1u;
+        uint32_t lb = la;  // odd count: the upper half repeats the same chunk, harmlessly
+        if (todo) {
+            lb = __ffs(todo) - 1u;
+            todo &= todo - 1u;
+        }
+        const uint32_t sl = lane < 16 ? la : lb;
+        const uint32_t nz = __shfl_sync(0xFFFFFFFFu, c.nz, sl), a0 = __shfl_sync(0xFFFFFFFFu, at, sl);
+        const uint32_t o0 = __shfl_sync(0xFFFFFFFFu, off, sl);
+        const uint32_t x0 = __shfl_sync(0xFFFFFFFFu, c.v.x, sl), x1 = __shfl_sync(0xFFFFFFFFu, c.v.y, sl);
+        const uint32_t x2 = __shfl_sync(0xFFFFFFFFu, c.v.z, sl), x3 = __shfl_sync(0xFFFFFFFFu, c.v.w, sl);
+        const uint32_t x = p < 8 ? (p < 4 ? x0 : x1) : (p < 12 ? x2 : x3);
+        if ((nz >> p) & 1u) list[a0 + __popc(nz & ((1u << p) - 1u))] = (o0 + p) | (((x >> (8u * (p & 3u))) & 0xFFu) << 16);
+    }
+}
+
 __global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
                                                             const uint8_t* __restrict__ frame_nb,
                                                             uint32_t* __restrict__ hist,
@@ -151,22 +177,9 @@ __global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __rest
             fits = m <= cap && !(g == 0 && m * 4u > min(n, 2u * nwarps * kStepBytes));
             if (fits) {
                 const uint32_t exc = inc - cnt;
-                uint32_t at0 = wbase + (exc & 0xFFFFu), at1 = wbase + tot0 + (exc >> 16);
-                const uint32_t w0[4] = {c0.v.x, c0.v.y, c0.v.z, c0.v.w}, w1[4] = {c1.v.x, c1.v.y, c1.v.z, c1.v.w};
-                uint32_t mk = c0.nz;
-                while (mk) {
-                    const uint32_t p = __ffs(mk) - 1u;
-                    mk &= mk - 1u;
-                    const uint32_t x = p < 8 ? (p < 4 ? w0[0] : w0[1]) : (p < 12 ? w0[2] : w0[3]);
-                    s_list[at0++] = (off0 + p) | (((x >> (8u * (p & 3u))) & 0xFFu) << 16);
-                }
-                mk = c1.nz;
-                while (mk) {
-                    const uint32_t p = __ffs(mk) - 1u;
-                    mk &= mk - 1u;
-                    const uint32_t x = p < 8 ? (p < 4 ? w1[0] : w1[1]) : (p < 12 ? w1[2] : w1[3]);
-                    s_list[at1++] = (off1 + p) | (((x >> (8u * (p & 3u))) & 0xFFu) << 16);
-                }
+                const uint32_t at0 = wbase + (exc & 0xFFFFu), at1 = wbase + tot0 + (exc >> 16);
+                scatter_chunks(c0, off0, at0, s_list);
+                scatter_chunks(c1, off1, at1, s_list);
             }
         }
         __syncthreads();
