@@ -9,72 +9,10 @@
 #include "common.cuh"
 #include "hzr_tree.cuh"
 #include "hzr_hist.cuh"
+#include "hzr_pack.cuh"
+#include "hzr_sparse.cuh"
 
 namespace rspt {
-
-// CRC-32C constants, built on the host at library load (crc_tables.cpp) and kept in global
-// memory: byte table, the per-lane multipliers x^(32(j+1)) and, for every supported CTA width
-// T, the 4x256 table of Z^(4T) (advance the register by 4T zero bytes).
-struct CrcConst {
-    uint32_t byte_tab[256];
-    uint32_t lane_mul[1024];
-    uint32_t zt[4][4][256];  // [log2(T/128)][byte][value]
-};
-
-__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b)
-{
-    // product of two polynomials mod P in the reflected representation (bit 31 = x^0)
-    uint32_t p = 0;
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-        p ^= b & (0u - ((a >> (31 - i)) & 1u));
-        b = (b >> 1) ^ (0x82F63B78u & (0u - (b & 1u)));
-    }
-    return p;
-}
-
-// CRC-32C of `len` bytes that start at the WORD-ALIGNED shared-memory address `words`
-// (hzr_crc32c.c:77-84 semantics: init ~0, final ~).  All threads of the CTA must call it;
-// the result is returned to every thread.  s_zt is the CTA's copy of zt[log2(T/128)],
-// s_red holds 33 words.  blockDim.x must be 128, 256, 512 or 1024.
-__device__ __forceinline__ uint32_t block_crc32c(const uint32_t* words, uint32_t len, const uint32_t* s_zt,
-                                                 const CrcConst* __restrict__ cc, uint32_t* s_red)
-{
-    const uint32_t T = blockDim.x, j = threadIdx.x;
-    uint32_t part = 0;
-    if (len >= 8) {
-        const uint32_t W = len >> 2;
-        if (j < W) {
-            uint32_t S = 0;
-            for (uint32_t i = (W - 1 - j) % T; i < W; i += T) {
-                uint32_t w = words[i];
-                if (i == 0) w = ~w;  // init 0xFFFFFFFF == complement of the first four bytes
-                S = s_zt[S & 255u] ^ s_zt[256 + ((S >> 8) & 255u)] ^ s_zt[512 + ((S >> 16) & 255u)] ^
-                    s_zt[768 + (S >> 24)] ^ w;
-            }
-            part = crc_mulmod(__ldg(&cc->lane_mul[j]), S);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xFFFFFFFFu, part, o);
-    __syncthreads();
-    if (lane_id() == 0) s_red[warp_id()] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t s = 0;
-        for (uint32_t w = 0; w < (T >> 5); ++w) s ^= s_red[w];
-        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
-        uint32_t q = len & ~3u;
-        if (len < 8) {
-            s = 0xFFFFFFFFu;
-            q = 0;
-        }
-        for (; q < len; ++q) s = (s >> 8) ^ __ldg(&cc->byte_tab[(s ^ bytes[q]) & 255u]);
-        s_red[32] = ~s;
-    }
-    __syncthreads();
-    return s_red[32];
-}
 
 // ------------------------------------------------------------------------------------------
 // 3. layout: per-frame plane count (prefix max of `need`, the reference's sticky
@@ -192,48 +130,6 @@ constexpr int kEncThreads = 512;
 constexpr int kEncWarps = kEncThreads / 32;
 constexpr int kEncZtSel = 2;  // log2(kEncThreads / 128)
 
-struct LenSink {
-    const uint32_t* sc;
-    uint32_t bits;
-    __device__ __forceinline__ void token(uint32_t sym, uint32_t, uint32_t eb) { bits += (sc[sym] >> 27) + eb; }
-};
-
-struct EmitSink {
-    const uint32_t* sc;
-    uint32_t* stg;  // staging words; bit position 0 = payload bit 0
-    unsigned long long acc;
-    uint32_t nacc, wptr;
-    bool first;
-    __device__ __forceinline__ void flush()
-    {
-        if (first) {
-            atomicOr(&stg[wptr], (uint32_t)acc);
-            first = false;
-        } else {
-            stg[wptr] = (uint32_t)acc;
-        }
-        ++wptr;
-        acc >>= 32;
-        nacc -= 32;
-    }
-    __device__ __forceinline__ void append(uint32_t v, uint32_t nbits)
-    {
-        acc |= (unsigned long long)v << nacc;
-        nacc += nbits;
-        if (nacc >= 32) flush();
-    }
-    __device__ __forceinline__ void token(uint32_t sym, uint32_t ev, uint32_t eb)
-    {
-        const uint32_t c = sc[sym];
-        append(c & 0x07FFFFFFu, c >> 27);
-        if (eb) append(ev, eb);
-    }
-    __device__ __forceinline__ void finish()
-    {
-        if (nacc) atomicOr(&stg[wptr], (uint32_t)acc);
-    }
-};
-
 // tokens that start in one 4-byte word, in stream order (general path: any run length)
 template <class Sink>
 __device__ __forceinline__ void walk_word(uint32_t x, uint32_t nz, uint32_t starts, uint32_t stop, uint32_t fwd, Sink& sink)
@@ -249,36 +145,6 @@ __device__ __forceinline__ void walk_word(uint32_t x, uint32_t nz, uint32_t star
     }
 }
 
-// A token slot: value | nbits << 27.  A literal or single-token run symbol fills one slot with
-// its code word; a run's extra bits fill the next slot.
-__device__ __forceinline__ uint32_t slot_bits(uint32_t cw) { return cw >> 27; }
-
-// bit length of the tokens of one zero run of z >= 1 bytes (hzr_encode.c:146-166)
-__device__ __forceinline__ uint32_t run_bits(uint32_t z, const uint32_t* sc)
-{
-    LenSink ls{sc, 0};
-    emit_run(z, ls);
-    return ls.bits;
-}
-
-// copy `len` bytes from shared memory (byte offset `soff` into the word array `sw`) to an
-// arbitrarily aligned global address, 4 bytes per thread-step
-__device__ __forceinline__ void copy_smem_to_global(uint8_t* __restrict__ dst, const uint32_t* sw, uint32_t soff, uint32_t len)
-{
-    const uint8_t* sb = reinterpret_cast<const uint8_t*>(sw);
-    uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
-    if (head > len) head = len;
-    if (threadIdx.x < head) dst[threadIdx.x] = sb[soff + threadIdx.x];
-    const uint32_t nw = (len - head) >> 2;
-    const uint32_t so = soff + head;
-    const uint32_t sh = (so & 3u) * 8u, wbase = so >> 2;
-    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-    for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x)
-        dw[i] = __funnelshift_r(sw[wbase + i], sw[wbase + i + 1], sh);
-    const uint32_t done = head + (nw << 2);
-    if (threadIdx.x < len - done) dst[done + threadIdx.x] = sb[soff + done + threadIdx.x];
-}
-
 constexpr uint32_t kStgWords = 4 + kBlock / 4 + 8;
 constexpr size_t kEncodeSmem = (size_t)kStgWords * 4;
 
@@ -289,8 +155,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                                                                 const uint32_t* __restrict__ codes,
                                                                 const uint32_t* __restrict__ tree,
                                                                 const uint16_t* __restrict__ step_lz,
-                                                                const uint32_t* __restrict__ lists,
-                                                                const uint32_t* __restrict__ list_n,
+                                                                const uint32_t* __restrict__ fused,
                                                                 const uint64_t* __restrict__ offsets,
                                                                 const uint8_t* __restrict__ headers,
                                                                 const CrcConst* __restrict__ cc,
@@ -332,6 +197,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             for (uint32_t i = tid; i < s.hdr_bytes; i += blockDim.x) dst[frame_off + 1 + i] = headers[(size_t)f * s.hdr_bytes + i];
     }
 
+    if (fused[blk]) return;  // k_hzr_encode_sparse wrote this block
     if (bi.mode == MODE_FILL) {
         if (tid == 0) {
             const uint32_t crc = ~(0x00FFFFFFu ^ __ldg(&cc->byte_tab[0xFFu ^ bi.fill]));
@@ -343,13 +209,12 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
         return;
     }
 
-    for (uint32_t i = tid; i < 256; i += blockDim.x)
-        reinterpret_cast<uint4*>(s_zt)[i] = __ldg(reinterpret_cast<const uint4*>(&cc->zt[kEncZtSel][0][0]) + i);
-    const uint8_t* src = blk_ptr(planes, s, f, k, b);
     uint8_t* sbytes = reinterpret_cast<uint8_t*>(stg);
     const uint32_t plen = bi.payload_len;
     uint32_t* pay = stg + 4;
-    const uint32_t stg_words = 4u + (min(s.N, kBlock) + 3u) / 4u + 8u;  // staging words; the sparse list follows
+    for (uint32_t i = tid; i < 256; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_zt)[i] = __ldg(reinterpret_cast<const uint4*>(&cc->zt[kEncZtSel][0][0]) + i);
+    const uint8_t* src = blk_ptr(planes, s, f, k, b);
 
     if (bi.mode == MODE_COPY) {
         // raw plane bytes are the payload (PlainCopy); rows are 16-byte aligned
@@ -369,9 +234,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
         const uint32_t tw4 = (tw + 3u) & ~3u;
         for (uint32_t i = tid; i < tw4; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
         for (uint32_t i = (tw4 >> 2) + tid; i < ((pw + 2u + 3u) >> 2); i += blockDim.x) reinterpret_cast<uint4*>(pay)[i] = make_uint4(0, 0, 0, 0);
-        const uint32_t m = list_n[blk];
-        const bool sparse = m != kNoList;
-        if (!sparse && wid == kEncWarps - 1) {
+        if (wid == kEncWarps - 1) {
             // s_after[st] = zeros between the end of step st and the next stop byte (or the block
             // end): suffix chain over the per-step leading-zero counts, 4 steps per lane
             const uint16_t* lzp = step_lz + (size_t)blk * kMaxSteps;
@@ -407,91 +270,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
 
         uint32_t base = bi.tree_nbits;  // bit offset of the group (same in every thread)
         const uint32_t ngroups = (nsteps + kEncWarps - 1) / kEncWarps;
-        // ---- sparse blocks: k_hzr_hist left the sorted list of their non-zero bytes
-        // (position | value << 16).  It is copied behind the staging buffer and every entry goes to
-        // one thread: the zero run in front of the byte (gap to the previous entry) and the
-        // literal.  One extra pseudo entry closes the run that reaches the block end.
-        if (sparse) {
-            uint32_t* list = stg + stg_words;
-            for (uint32_t i = tid; i < m; i += blockDim.x) list[i] = __ldg(lists + (size_t)blk * kListCap + i);
-            __syncthreads();
-            // entry i < m: zeros (prev, cur) then the literal at cur; entry m: zeros (prev, n)
-            const uint32_t rounds = (m + 1u + kEncThreads - 1u) / kEncThreads;
-            for (uint32_t r = 0; r < rounds; ++r) {
-                const uint32_t i = r * kEncThreads + tid;
-                uint32_t bits = 0, gap = 0, cur = 0, rs = 0;
-                // slots of the common case (one run token at most): run code, run extra bits, literal
-                uint32_t c_run = 0, c_ext = 0, c_lit = 0;
-                const bool live = i <= m;
-                if (live) {
-                    const uint32_t e = i < m ? list[i] : n;
-                    cur = i < m ? e & 0xFFFFu : n;
-                    rs = i ? (list[i - 1] & 0xFFFFu) + 1u : 0u;
-                    gap = cur - rs;
-                    if (i < m) c_lit = s_codes[e >> 16];
-                    if (gap > kRunCap) {
-                        bits = run_bits(gap, s_codes);
-                    } else if (gap) {
-                        uint32_t sym, ev, eb;
-                        run_token(gap, sym, ev, eb);
-                        c_run = s_codes[sym];
-                        c_ext = ev | (eb << 27);
-                        bits = slot_bits(c_run) + eb;
-                    }
-                    bits += slot_bits(c_lit);
-                }
-                uint32_t inc = bits;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                    if (lane >= (uint32_t)o) inc += y;
-                }
-                const uint32_t par = (ngroups + r) & 1u;
-                if (lane == 31) s_tot[par][wid] = inc;
-                __syncthreads();
-                uint32_t tw2 = lane < kEncWarps ? s_tot[par][lane] : 0u;
-#pragma unroll
-                for (int o = 1; o < kEncWarps; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tw2, o);
-                    if (lane >= (uint32_t)o) tw2 += y;
-                }
-                const uint32_t o0 = base + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u) + inc - bits;
-                base += __shfl_sync(0xFFFFFFFFu, tw2, kEncWarps - 1);
-                if (live) {
-                    const uint32_t o_lit = o0 + bits - slot_bits(c_lit);
-                    if (bits > 64u || gap > kRunCap) {
-                        EmitSink es{s_codes, pay, 0ull, o0 & 31u, o0 >> 5, true};
-                        if (gap) emit_run(gap, es);
-                        if (i < m) es.append(c_lit & 0x07FFFFFFu, slot_bits(c_lit));
-                        es.finish();
-                    } else if (bits) {
-                        // concatenate the slots last-first, shift to the bit offset, OR into <= 3 words
-                        uint32_t lo = c_lit & 0x07FFFFFFu, hi = 0, l = slot_bits(c_ext);
-                        hi = __funnelshift_l(lo, hi, l);
-                        lo = (lo << l) | (c_ext & 0x07FFFFFFu);
-                        l = slot_bits(c_run);
-                        hi = __funnelshift_l(lo, hi, l);
-                        lo = (lo << l) | (c_run & 0x07FFFFFFu);
-                        const uint32_t sh = o0 & 31u;
-                        uint32_t* w = pay + (o0 >> 5);
-                        const uint32_t v0 = lo << sh, v1 = __funnelshift_l(lo, hi, sh), v2 = __funnelshift_l(hi, 0u, sh);
-                        atomicOr(w, v0);
-                        if (v1) atomicOr(w + 1, v1);
-                        if (v2) atomicOr(w + 2, v2);
-                    }
-                    if (sc_bit) {
-                        // decode index entries of the segment boundaries B in [rs, cur], B < n: at
-                        // B == rs the entry's first token starts; later boundaries lie inside the
-                        // zero run and resume at the literal
-                        for (uint32_t B = (rs + kSegBytes - 1u) & ~(uint32_t)(kSegBytes - 1); B <= cur && B < n; B += kSegBytes) {
-                            sc_bit[(size_t)blk * kMaxSegs + B / kSegBytes] = B == rs ? o0 : o_lit;
-                            sc_skip[(size_t)blk * kMaxSegs + B / kSegBytes] = (uint16_t)(B == rs ? 0u : cur - B);
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-        } else {
+        {
         // ---- dense blocks: a lane owns 16 consecutive bytes (4 words) of its warp's 512-byte step
         // (the chunk of the next group and the byte before its step are fetched one group ahead, so
         // their latency hides behind the current group's work)

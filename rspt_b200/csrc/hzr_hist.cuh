@@ -27,11 +27,6 @@ constexpr int kHistThreads = 256;
 constexpr int kStepBytes = 512;                     // one warp-step: 32 lanes x 16 bytes
 constexpr int kMaxSteps = kBlock / kStepBytes;      // 128 per block
 constexpr uint32_t kStepAllZero = kStepBytes;       // step_lz value of a step without any stop byte
-constexpr uint32_t kListCap = 8192;                 // entries of a block's sparse list (position | value << 16)
-constexpr uint32_t kNoList = 0xFFFFFFFFu;           // list_n value of a block that has no sparse list
-
-// entries the sparse list of an n-byte block may hold: at most a quarter of the bytes non-zero
-__host__ __device__ __forceinline__ uint32_t list_cap(uint32_t n) { return n / 4u < kListCap ? n / 4u : kListCap; }
 
 // 4-bit mask of the non-zero bytes of a word
 __device__ __forceinline__ uint32_t nz_nibble(uint32_t x)
@@ -115,17 +110,34 @@ __device__ __forceinline__ void scatter_chunks(const Chunk& c, uint32_t off, uin
     }
 }
 
-__global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
-                                                            const uint8_t* __restrict__ frame_nb,
-                                                            uint32_t* __restrict__ hist,
-                                                            uint16_t* __restrict__ step_lz,
-                                                            uint32_t* __restrict__ lists, uint32_t* __restrict__ list_n)
+// ---- sparse blocks ---------------------------------------------------------------------------
+// A block with few non-zero bytes (<= kListCap, i.e. mostly long zero runs: the upper byte planes
+// of a delta-coded signal) is tokenised from a sorted list of its non-zero bytes:
+//   1. every warp scans a contiguous range of <= 16 steps, keeping per step and lane the 16-bit
+//      non-zero mask and the exclusive count of non-zero bytes before the chunk (no barrier; the
+//      loads of a batch of steps are in flight together);
+//   2. one block scan of the warp totals, then the non-zero bytes are scattered into the list
+//      (position | value << 16) in shared memory;
+//   3. token histogram from the list: a literal per entry, a zero run per gap.
+// The list goes to global memory for k_hzr_encode_sparse, which packs the block's payload without
+// reading the plane again.  Blocks that are too dense for the list take the dense scan below.
+constexpr uint32_t kListCap = 5120;                 // entries of a block's sparse list
+constexpr uint32_t kNoList = 0xFFFFFFFFu;           // list_n value of a block that has no sparse list
+constexpr size_t kHistSmem = (size_t)kListCap * 4;
+constexpr int kHistSteps = kMaxSteps / (kHistThreads / 32);      // steps per warp: 16
+
+__global__ void __launch_bounds__(kHistThreads, 4) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
+                                                               const uint8_t* __restrict__ frame_nb,
+                                                               uint32_t* __restrict__ hist,
+                                                               uint16_t* __restrict__ step_lz,
+                                                               uint32_t* __restrict__ lists, uint32_t* __restrict__ list_n,
+                                                               int allow_list)
 {
     extern __shared__ __align__(16) uint32_t s_list[];  // sparse list under construction
-    __shared__ uint32_t s_tot[2][kHistThreads / 32];
     __shared__ uint32_t s_lit[256];  // raw byte counts; [0] is scratch (zeros are tokenised as runs)
     __shared__ uint32_t s_run[8];
     __shared__ uint32_t s_wsum[kHistThreads / 32][3];  // per warp range: seen, lead, trail
+    __shared__ uint32_t s_wtot[kHistThreads / 32];
     uint32_t f, k, b;
     const uint32_t blk = blockIdx.x;
     blk_decode(s, blk, f, k, b);
@@ -134,81 +146,108 @@ __global__ void __launch_bounds__(kHistThreads) k_hzr_hist(const uint8_t* __rest
     const uint8_t* src = blk_ptr(planes, s, f, k, b);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = 0;
     if (threadIdx.x < 8) s_run[threadIdx.x] = 0;
-    __syncthreads();
 
-    const uint32_t lane = lane_id(), wid = warp_id(), nwarps = blockDim.x >> 5;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id(), nwarps = blockDim.x >> 5;
     const uint32_t nsteps = (n + kStepBytes - 1) / kStepBytes;
+    const uint32_t spw = (nsteps + nwarps - 1) / nwarps;
+    const uint32_t s_lo = min(nsteps, wid * spw), s_hi = min(nsteps, s_lo + spw);
 
-    // ---- sparse blocks: compact the non-zero bytes into a sorted list (position | value << 16),
-    // optimistically, giving up as soon as it outgrows its capacity (then the block is dense and
-    // takes the scan below).  Every token of a sparse block follows from the list: a literal per
-    // entry, a zero run per gap between neighbouring entries (and before the block end).  The
-    // list is kept for k_hzr_encode, which then never re-reads a sparse block.
-    {
-        // a group = two consecutive steps per warp (32 bytes per lane); counts of the two steps ride
-        // in one packed warp scan
-        const uint32_t cap = list_cap(n), ngroups = (nsteps + 2 * nwarps - 1) / (2 * nwarps);
-        uint32_t m = 0;  // entries so far (same in every thread)
-        bool fits = cap > 0;
-        for (uint32_t g = 0; g < ngroups && fits; ++g) {
-            const uint32_t off0 = (g * nwarps + wid) * 2u * kStepBytes + lane * 16u, off1 = off0 + kStepBytes;
-            const Chunk c0 = load_chunk(src, n, off0), c1 = load_chunk(src, n, off1);
-            const uint32_t cnt = __popc(c0.nz) | (__popc(c1.nz) << 16);
-            uint32_t inc = cnt;
+    // ---- sparse path
+    do {
+        if (!allow_list) break;
+        // density probe: the first chunk of every warp range (spread over the block)
+        const Chunk probe = load_chunk(src, n, s_lo * kStepBytes + lane * 16u);
+        const int dense_chunks = __syncthreads_count(__popc(probe.nz) >= 2);
+        const int probed = __syncthreads_count(probe.valid > 0);
+        if (dense_chunks * 4 > probed) break;
+
+        // 1. masks and in-warp prefix counts of every step of my warp's range
+        uint32_t pk[kHistSteps];  // nz mask | entries of my warp before this chunk << 16
+        uint32_t wrun = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                if (lane >= (uint32_t)o) inc += y;
-            }
-            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            const uint32_t tot0 = tot & 0xFFFFu, tot1 = tot >> 16;
-            if (lane == 31) s_tot[g & 1][wid] = tot0 + tot1;
-            __syncthreads();
-            uint32_t tw2 = lane < nwarps ? s_tot[g & 1][lane] : 0u;
+        for (int j0 = 0; j0 < kHistSteps; j0 += 4) {
+            uint4 v[4];
 #pragma unroll
-            for (int o = 1; o < kHistThreads / 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tw2, o);
-                if (lane >= (uint32_t)o) tw2 += y;
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t st = s_lo + j0 + j, off = st * kStepBytes + lane * 16u;
+                v[j] = make_uint4(0, 0, 0, 0);
+                if (st < s_hi && off < n) v[j] = __ldg(reinterpret_cast<const uint4*>(src + off));
             }
-            const uint32_t wbase = m + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u);
-            m += __shfl_sync(0xFFFFFFFFu, tw2, nwarps - 1);
-            // give up when the list is full -- or at once when the first group is already denser
-            // than a sparse block may be on average (a wrong guess only costs the dense scan)
-            fits = m <= cap && !(g == 0 && m * 4u > min(n, 2u * nwarps * kStepBytes));
-            if (fits) {
-                const uint32_t exc = inc - cnt;
-                const uint32_t at0 = wbase + (exc & 0xFFFFu), at1 = wbase + tot0 + (exc >> 16);
-                scatter_chunks(c0, off0, at0, s_list);
-                scatter_chunks(c1, off1, at1, s_list);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t st = s_lo + j0 + j, off = st * kStepBytes + lane * 16u;
+                uint32_t nz = 0;
+                if ((v[j].x | v[j].y | v[j].z | v[j].w) != 0u) {
+                    const int valid = (int)n - (int)off;  // > 0 here; rows are zero-padded only up to 16
+                    nz = nz_mask16(v[j]) & (valid >= 16 ? 0xFFFFu : (1u << valid) - 1u);
+                }
+                uint32_t inc = 0;
+                if (__any_sync(0xFFFFFFFFu, nz != 0u)) {
+                    const uint32_t cnt = __popc(nz);
+                    inc = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                        if (lane >= (uint32_t)o) inc += y;
+                    }
+                    const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                    inc = wrun + inc - cnt;
+                    wrun += tot;
+                }
+                pk[j0 + j] = nz | (inc << 16);
+                (void)st;
+            }
+        }
+        if (lane == 0) s_wtot[wid] = wrun;
+        __syncthreads();
+        uint32_t wbase = 0, m = 0;
+        for (uint32_t w = 0; w < nwarps; ++w) {
+            const uint32_t t = s_wtot[w];
+            if (w < wid) wbase += t;
+            m += t;
+        }
+        if (m > kListCap || m > n / 4u) break;
+
+        // 2. scatter the non-zero bytes into the list
+        uint32_t* list = s_list;
+#pragma unroll
+        for (int j = 0; j < kHistSteps; ++j) {
+            const uint32_t nz = pk[j] & 0xFFFFu;
+            if (__any_sync(0xFFFFFFFFu, nz != 0u)) {
+                const uint32_t off = (s_lo + j) * kStepBytes + lane * 16u;
+                Chunk c;
+                c.nz = nz;
+                c.v = make_uint4(0, 0, 0, 0);
+                if (nz) c.v = __ldg(reinterpret_cast<const uint4*>(src + off));
+                scatter_chunks(c, off, wbase + (pk[j] >> 16), list);
             }
         }
         __syncthreads();
-        if (fits) {
-            uint32_t* glist = lists + (size_t)blk * kListCap;
-            for (uint32_t i = threadIdx.x; i <= m; i += blockDim.x) {
-                const uint32_t rs = i ? (s_list[i - 1] & 0xFFFFu) + 1u : 0u;
-                uint32_t cur = n;
-                if (i < m) {
-                    const uint32_t e = s_list[i];
-                    glist[i] = e;
-                    cur = e & 0xFFFFu;
-                    atomicAdd(&s_lit[e >> 16], 1u);
-                }
-                if (cur > rs) hist_run(cur - rs, s_run);
+
+        // 3. token histogram: entry i < m = zeros (prev, cur) + the literal at cur; entry m = zeros up to n
+        for (uint32_t i = tid; i <= m; i += blockDim.x) {
+            const uint32_t rs = i ? (list[i - 1] & 0xFFFFu) + 1u : 0u;
+            uint32_t cur = n;
+            if (i < m) {
+                const uint32_t e = list[i];
+                cur = e & 0xFFFFu;
+                atomicAdd(&s_lit[e >> 16], 1u);
             }
-            __syncthreads();
-            if (threadIdx.x == 0) list_n[blk] = m;
-            uint32_t* out = hist + (size_t)blk * kSymStride;
-            for (uint32_t i = threadIdx.x; i < kSymStride; i += blockDim.x)
-                out[i] = i == 0 ? s_run[0] : (i < 256 ? s_lit[i] : (i < (uint32_t)kNumSymbols ? s_run[i - 255] : 0u));
-            return;
+            if (cur > rs) hist_run(cur - rs, s_run);
         }
-        if (threadIdx.x == 0) list_n[blk] = kNoList;
-    }
+        __syncthreads();
+        uint32_t* glist = lists + (size_t)blk * kListCap;
+        for (uint32_t i = tid; i < m; i += blockDim.x) glist[i] = list[i];
+        if (tid == 0) list_n[blk] = m;
+        uint32_t* out = hist + (size_t)blk * kSymStride;
+        for (uint32_t i = tid; i < kSymStride; i += blockDim.x)
+            out[i] = i == 0 ? s_run[0] : (i < 256 ? s_lit[i] : (i < (uint32_t)kNumSymbols ? s_run[i - 255] : 0u));
+        return;
+    } while (0);
+    if (tid == 0) list_n[blk] = kNoList;
+    __syncthreads();
 
     // ---- dense blocks
-    const uint32_t spw = (nsteps + nwarps - 1) / nwarps;
-    const uint32_t s_lo = min(nsteps, wid * spw), s_hi = min(nsteps, s_lo + spw);
     uint16_t* my_lz = step_lz + (size_t)blk * kMaxSteps;
     uint32_t pending = 0, lead = 0, cnt0 = 0;
     bool seen = false;

@@ -1,0 +1,201 @@
+// Sparse hzr blocks for sm_100a, packed from the sorted list of non-zero bytes that k_hzr_hist
+// left (position | value << 16): one CTA per block, the plane is not read again.  Replaces, for
+// these blocks, the encode loop and WriteBits of lib_hzr/hzr_encode.c:410-457, :94-113 and the
+// block header + CRC of :463-484.  Runs after the layout kernels, so the block (7-byte header +
+// payload) goes straight to its place in the output stream; k_hzr_encode skips it.  The decode
+// index of such a block is written here too.
+#pragma once
+
+#include "common.cuh"
+#include "hzr_tree.cuh"
+#include "hzr_hist.cuh"
+#include "hzr_pack.cuh"
+
+namespace rspt {
+
+constexpr int kSpThreads = 256;
+constexpr int kSpZtSel = 1;                              // log2(kSpThreads / 128)
+constexpr uint32_t kSpStageBytes = 10240;                // largest payload packed here
+constexpr uint32_t kSpStageWords = kSpStageBytes / 4 + 8;
+constexpr size_t kSparseSmem = (size_t)(kListCap + 4 + kSpStageWords) * 4;
+
+struct SparseOut {
+    uint32_t* fused;      // [blocks] 1 = block written here, 0 = k_hzr_encode packs the block
+    uint8_t* dst;         // output stream
+    const uint64_t* offsets;   // byte offset of every frame in dst
+    const uint32_t* blk_off;   // per block: offset of its header from the frame start
+    uint32_t* sc_bit;     // decode index (may be null)
+    uint16_t* sc_skip;
+    uint32_t* sc_codes;
+};
+
+__global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, const uint8_t* __restrict__ frame_nb,
+                                                                     const BlkInfo* __restrict__ info,
+                                                                     const uint32_t* __restrict__ codes,
+                                                                     const uint32_t* __restrict__ tree,
+                                                                     const uint32_t* __restrict__ lists,
+                                                                     const uint32_t* __restrict__ list_n,
+                                                                     uint16_t* __restrict__ step_lz,
+                                                                     const CrcConst* __restrict__ cc, SparseOut so)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];  // the list, then the payload staging
+    __shared__ uint32_t s_codes[kSymStride];
+    __shared__ __align__(16) uint32_t s_zt[1024];
+    __shared__ uint32_t s_red[33];
+    __shared__ uint32_t s_wtot[kSpThreads / 32];
+    uint32_t f, k, b;
+    const uint32_t blk = blockIdx.x;
+    blk_decode(s, blk, f, k, b);
+    if (k >= frame_nb[f]) return;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    const uint32_t n = blk_len(s, b);
+    const uint32_t m = list_n[blk];
+    const BlkInfo bi = info[blk];
+    if (m == kNoList || bi.mode != MODE_HUFF) {
+        if (tid == 0) so.fused[blk] = 0u;
+        return;
+    }
+    const uint32_t* glist = lists + (size_t)blk * kListCap;
+    if (bi.payload_len > kSpStageBytes) {
+        // too large for the staging here (rare): k_hzr_encode packs the block from the plane; it
+        // needs the leading zero count of every 512-byte step, which the list gives directly
+        const uint32_t nsteps = (n + kStepBytes - 1) / kStepBytes;
+        for (uint32_t st = tid; st < nsteps; st += blockDim.x) {
+            uint32_t lo = 0, hi = m;  // first entry at or after the step start
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if ((__ldg(glist + mid) & 0xFFFFu) < st * kStepBytes) lo = mid + 1u;
+                else hi = mid;
+            }
+            const uint32_t pos = lo < m ? __ldg(glist + lo) & 0xFFFFu : n;
+            step_lz[(size_t)blk * kMaxSteps + st] = (uint16_t)min(min(pos, n) - st * kStepBytes, (uint32_t)kStepBytes);
+        }
+        if (tid == 0) so.fused[blk] = 0u;
+        return;
+    }
+    uint32_t* list = s_dyn;
+    uint32_t* stg = s_dyn + kListCap;  // block header at bytes 9..15, payload from byte 16
+    uint32_t* pay = stg + 4;
+    const uint32_t plen = bi.payload_len, tw = (bi.tree_nbits + 31u) >> 5, pw = (plen + 3u) >> 2;
+    for (uint32_t i = tid; i < m; i += blockDim.x) list[i] = __ldg(glist + i);
+    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) {
+        const uint32_t cw = __ldg(codes + (size_t)blk * kSymStride + i);
+        s_codes[i] = cw;
+        if (so.sc_codes) so.sc_codes[(size_t)blk * kSymStride + i] = cw;  // decode index: the block's code table
+    }
+    for (uint32_t i = tid; i < 256; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_zt)[i] = __ldg(reinterpret_cast<const uint4*>(&cc->zt[kSpZtSel][0][0]) + i);
+    // staging: tree words, then zeros (the code words are OR-ed in)
+    for (uint32_t i = tid; i < pw + 2u; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
+    __syncthreads();
+
+    // bit packing: warp w owns the entries [w * R, (w + 1) * R), one entry per lane and pass;
+    // pass A adds up the warp's bits, one block scan, pass B places every entry's <= 3 slots
+    // (run code, run extra bits, literal) with a warp scan of the entry bit lengths
+    const uint32_t R = ((m + 1u + blockDim.x - 1u) / blockDim.x) * 32u;
+    const uint32_t e_lo = min(m + 1u, wid * R), e_hi = min(m + 1u, e_lo + R);
+    uint32_t wbits = 0;
+    for (uint32_t i = e_lo + lane; i < e_hi; i += 32) {
+        const uint32_t e = i < m ? list[i] : n;
+        const uint32_t cur = i < m ? e & 0xFFFFu : n;
+        const uint32_t rs = i ? (list[i - 1] & 0xFFFFu) + 1u : 0u;
+        if (cur > rs) wbits += run_bits(cur - rs, s_codes);
+        if (i < m) wbits += s_codes[e >> 16] >> 27;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wbits += __shfl_xor_sync(0xFFFFFFFFu, wbits, o);
+    if (lane == 0) s_wtot[wid] = wbits;
+    __syncthreads();  // also: staging initialised
+    uint32_t base = bi.tree_nbits;
+    for (uint32_t w = 0; w < wid; ++w) base += s_wtot[w];
+    for (uint32_t i0 = e_lo; i0 < e_hi; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool live = i < e_hi;
+        uint32_t bits = 0, gap = 0, cur = 0, rs = 0, c_run = 0, c_ext = 0, c_lit = 0;
+        if (live) {
+            const uint32_t e = i < m ? list[i] : n;
+            cur = i < m ? e & 0xFFFFu : n;
+            rs = i ? (list[i - 1] & 0xFFFFu) + 1u : 0u;
+            gap = cur - rs;
+            if (i < m) c_lit = s_codes[e >> 16];
+            if (gap > kRunCap) {
+                bits = run_bits(gap, s_codes);
+            } else if (gap) {
+                uint32_t sym, ev, eb;
+                run_token(gap, sym, ev, eb);
+                c_run = s_codes[sym];
+                c_ext = ev | (eb << 27);
+                bits = slot_bits(c_run) + eb;
+            }
+            bits += slot_bits(c_lit);
+        }
+        uint32_t inc = bits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+        }
+        const uint32_t o0 = base + inc - bits, o_lit = o0 + bits - slot_bits(c_lit);
+        base += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        if (live) {
+            if (bits > 64u || gap > kRunCap) {
+                EmitSink es{s_codes, pay, 0ull, o0 & 31u, o0 >> 5, true};
+                if (gap) emit_run(gap, es);
+                if (i < m) es.append(c_lit & 0x07FFFFFFu, slot_bits(c_lit));
+                es.finish();
+            } else if (bits) {
+                // concatenate the slots last-first, shift to the bit offset, OR into <= 3 words
+                uint32_t lo = c_lit & 0x07FFFFFFu, hi = 0, l = slot_bits(c_ext);
+                hi = __funnelshift_l(lo, hi, l);
+                lo = (lo << l) | (c_ext & 0x07FFFFFFu);
+                l = slot_bits(c_run);
+                hi = __funnelshift_l(lo, hi, l);
+                lo = (lo << l) | (c_run & 0x07FFFFFFu);
+                const uint32_t sh = o0 & 31u;
+                uint32_t* w = pay + (o0 >> 5);
+                const uint32_t v0 = lo << sh, v1 = __funnelshift_l(lo, hi, sh), v2 = __funnelshift_l(hi, 0u, sh);
+                atomicOr(w, v0);
+                if (v1) atomicOr(w + 1, v1);
+                if (v2) atomicOr(w + 2, v2);
+            }
+        }
+        if (so.sc_bit) {
+            // decode index entries of the segment boundaries B in [rs, cur], B < n: at B == rs
+            // the entry's first token starts; later boundaries lie inside the zero run and
+            // resume at the literal.  The first boundary is written by the entry's own lane,
+            // the rest of a long run by the whole warp.
+            const uint32_t B0 = (rs + kSegBytes - 1u) & ~(uint32_t)(kSegBytes - 1);
+            const bool has = live && B0 <= cur && B0 < n;
+            if (has) {
+                so.sc_bit[(size_t)blk * kMaxSegs + B0 / kSegBytes] = B0 == rs ? o0 : o_lit;
+                so.sc_skip[(size_t)blk * kMaxSegs + B0 / kSegBytes] = (uint16_t)(B0 == rs ? 0u : cur - B0);
+            }
+            const uint32_t lim = min(cur, n - 1u);  // last position a boundary may take
+            uint32_t more = __ballot_sync(0xFFFFFFFFu, has && B0 + kSegBytes <= lim);
+            while (more) {
+                const uint32_t q = __ffs(more) - 1u;
+                more &= more - 1u;
+                const uint32_t qB = __shfl_sync(0xFFFFFFFFu, B0, q) + kSegBytes, qcur = __shfl_sync(0xFFFFFFFFu, cur, q);
+                const uint32_t qlim = __shfl_sync(0xFFFFFFFFu, lim, q), qo = __shfl_sync(0xFFFFFFFFu, o_lit, q);
+                for (uint32_t B = qB + lane * kSegBytes; B <= qlim; B += 32u * kSegBytes) {
+                    so.sc_bit[(size_t)blk * kMaxSegs + B / kSegBytes] = qo;
+                    so.sc_skip[(size_t)blk * kMaxSegs + B / kSegBytes] = (uint16_t)(qcur - B);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const uint32_t crc = block_crc32c(pay, plen, s_zt, cc, s_red);
+    if (tid == 0) {
+        uint8_t* sbytes = reinterpret_cast<uint8_t*>(stg);
+        sbytes[9] = (uint8_t)(plen - 1); sbytes[10] = (uint8_t)((plen - 1) >> 8);
+        sbytes[11] = (uint8_t)crc; sbytes[12] = (uint8_t)(crc >> 8); sbytes[13] = (uint8_t)(crc >> 16); sbytes[14] = (uint8_t)(crc >> 24);
+        sbytes[15] = (uint8_t)MODE_HUFF;
+        so.fused[blk] = 1u;
+    }
+    __syncthreads();
+    copy_smem_to_global(so.dst + so.offsets[f] + so.blk_off[blk], stg, 9, 7u + plen);
+}
+
+}  // namespace rspt

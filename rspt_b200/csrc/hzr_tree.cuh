@@ -52,6 +52,7 @@ __device__ __forceinline__ void blk_decode(const Shape& s, uint32_t blk, uint32_
     uint32_t fk = blk / s.nblk;
     k = fk % s.nb_alloc;
     f = fk / s.nb_alloc;
+    if (s.dbg_skip && ((s.dbg_skip & 1u) ? k == 0u : k != 0u)) k = 0xFFu;
 }
 
 __device__ __forceinline__ const uint8_t* blk_ptr(const uint8_t* planes, const Shape& s, uint32_t f, uint32_t k, uint32_t b)
@@ -59,24 +60,15 @@ __device__ __forceinline__ const uint8_t* blk_ptr(const uint8_t* planes, const S
     return planes + ((size_t)f * s.nb_alloc + k) * s.plane_stride + (size_t)b * kBlock;
 }
 
-__global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __restrict__ hist, Shape s,
-                                                               const uint8_t* __restrict__ frame_nb,
-                                                               uint32_t total_blocks,
-                                                               uint32_t* __restrict__ codes,
-                                                               uint32_t* __restrict__ tree,
-                                                               BlkInfo* __restrict__ info,
-                                                               Counters* __restrict__ ctr)
+// Build the tree of one block with one warp.  h = the block's 261 token counts (global or shared
+// memory), n = block length.  Writes the code table (code | length << 27, 0 = unused symbol) to
+// codes_out[0..263] and the serialised tree to tree_out (global or shared memory).  Returns the
+// block's plan in every lane.  Touches no counters.
+__device__ __forceinline__ BlkInfo warp_build_tree(TreeWarpSmem& S, const uint32_t* h, uint32_t n,
+                                                   uint32_t* codes_out, uint32_t* tree_out)
 {
-    __shared__ TreeWarpSmem s_all[kTreeWarps];
-    TreeWarpSmem& S = s_all[warp_id()];
     const uint32_t lane = lane_id();
-    const uint32_t blk = blockIdx.x * kTreeWarps + warp_id();
-    if (blk >= total_blocks) return;
-    uint32_t f, k, b;
-    blk_decode(s, blk, f, k, b);
-    if (k >= frame_nb[f]) return;
-    const uint32_t n = blk_len(s, b);
-    const uint32_t* h = hist + (size_t)blk * kSymStride;
+    BlkInfo bi;
 
     // ---- phase A: classify and compact
     uint32_t L = 0, nz = 0, nzsym = 0, zero_class = 0;
@@ -84,12 +76,12 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
         const uint32_t sym = r * 32 + lane;
-        const uint32_t c = sym < kNumSymbols ? __ldg(h + sym) : 0u;
+        const uint32_t c = sym < kNumSymbols ? h[sym] : 0u;
         const bool used = c != 0;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, used);
         const uint32_t pos = L + __popc(m & ((1u << lane) - 1u));
         if (used) S.key[pos] = (c << 9) | (511u - sym);
-        else if (sym < (uint32_t)kSymStride) codes[(size_t)blk * kSymStride + sym] = 0;  // 0 = symbol has no code
+        else if (sym < (uint32_t)kSymStride) codes_out[sym] = 0;  // 0 = symbol has no code
         L += __popc(m);
         if (r == 0) {
             zero_class |= m & 1u;
@@ -105,14 +97,9 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
     }
     if (nz + (zero_class ? 1u : 0u) == 1u) {
         // single value class -> FILL (OnlySingleCode); payload is in[0]
-        if (lane == 0) {
-            BlkInfo bi;
-            bi.payload_len = 1; bi.total_bits = 8; bi.tree_nbits = 0;
-            bi.mode = MODE_FILL; bi.fill = (uint8_t)(nz ? nzsym : 0u); bi.n_used = (uint16_t)L; bi.n_tokens = 0;
-            info[blk] = bi;
-            atomicAdd(&ctr->blocks_fill, 1ull);
-        }
-        return;
+        bi.payload_len = 1; bi.total_bits = 8; bi.tree_nbits = 0;
+        bi.mode = MODE_FILL; bi.fill = (uint8_t)(nz ? nzsym : 0u); bi.n_used = (uint16_t)L; bi.n_tokens = 0;
+        return bi;
     }
     __syncwarp();
     if (L <= 32) {
@@ -281,7 +268,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
 
     // ---- phase D: leaves in parallel
     uint32_t token_bits = 0, maxlen = 0, ntok = 0;
-    uint32_t* my_codes = codes + (size_t)blk * kSymStride;
+    uint32_t* my_codes = codes_out;
     for (uint32_t i = lane; i < L; i += 32) {
         const uint32_t kv = S.key[i];
         const uint32_t sym = 511u - (kv & 511u), cnt = kv >> 9;
@@ -303,23 +290,47 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
     }
     __syncwarp();
     const uint32_t tree_nbits = 11u * L - 1u;
-    uint32_t* my_tree = tree + (size_t)blk * kTreeWords;
-    for (uint32_t i = lane; i < ((tree_nbits + 31u) >> 5); i += 32) my_tree[i] = S.tree[i];
-    if (lane == 0) {
-        BlkInfo bi;
-        bi.tree_nbits = (uint16_t)tree_nbits;
-        bi.total_bits = tree_nbits + token_bits;
-        const uint32_t bytes = (bi.total_bits + 7u) >> 3;
-        // capped block stream (hzr_encode.c:377-382), 16-bit size field (:466-467); codes longer
-        // than 27 bits cannot occur for <= 65536 tokens (Fibonacci bound ~ 23)
-        const bool copy = bytes > n || bytes >= kBlock || maxlen > 27u;
-        bi.mode = copy ? MODE_COPY : MODE_HUFF;
-        bi.payload_len = copy ? n : bytes;
-        bi.fill = (uint8_t)maxlen;  // HUFF: longest code word (selects the encoder's merge width)
-        bi.n_used = (uint16_t)L;
-        bi.n_tokens = (uint16_t)min(ntok, 65535u);
+    for (uint32_t i = lane; i < ((tree_nbits + 31u) >> 5); i += 32) tree_out[i] = S.tree[i];
+    bi.tree_nbits = (uint16_t)tree_nbits;
+    bi.total_bits = tree_nbits + token_bits;
+    const uint32_t bytes = (bi.total_bits + 7u) >> 3;
+    // capped block stream (hzr_encode.c:377-382), 16-bit size field (:466-467); codes longer
+    // than 27 bits cannot occur for <= 65536 tokens (Fibonacci bound ~ 23)
+    const bool copy = bytes > n || bytes >= kBlock || maxlen > 27u;
+    bi.mode = copy ? MODE_COPY : MODE_HUFF;
+    bi.payload_len = copy ? n : bytes;
+    bi.fill = (uint8_t)maxlen;  // HUFF: longest code word (selects the encoder's merge width)
+    bi.n_used = (uint16_t)L;
+    bi.n_tokens = (uint16_t)min(ntok, 65535u);
+    return bi;
+}
+
+__device__ __forceinline__ void count_block_mode(Counters* ctr, uint32_t mode)
+{
+    atomicAdd(mode == MODE_FILL ? &ctr->blocks_fill : (mode == MODE_COPY ? &ctr->blocks_copy : &ctr->blocks_huff), 1ull);
+}
+
+// One CTA (one warp) per block.
+__global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __restrict__ hist, Shape s,
+                                                               const uint8_t* __restrict__ frame_nb,
+                                                               uint32_t total_blocks,
+                                                               uint32_t* __restrict__ codes,
+                                                               uint32_t* __restrict__ tree,
+                                                               BlkInfo* __restrict__ info,
+                                                               Counters* __restrict__ ctr)
+{
+    __shared__ TreeWarpSmem s_all[kTreeWarps];
+    TreeWarpSmem& S = s_all[warp_id()];
+    const uint32_t blk = blockIdx.x * kTreeWarps + warp_id();
+    if (blk >= total_blocks) return;
+    uint32_t f, k, b;
+    blk_decode(s, blk, f, k, b);
+    if (k >= frame_nb[f]) return;
+    const BlkInfo bi = warp_build_tree(S, hist + (size_t)blk * kSymStride, blk_len(s, b),
+                                       codes + (size_t)blk * kSymStride, tree + (size_t)blk * kTreeWords);
+    if (lane_id() == 0) {
         info[blk] = bi;
-        atomicAdd(copy ? &ctr->blocks_copy : &ctr->blocks_huff, 1ull);
+        count_block_mode(ctr, bi.mode);
     }
 }
 

@@ -30,7 +30,6 @@ struct rspt_gpu_packer {
     size_t max_batch;
     size_t enc_smem;       // dynamic shared memory of k_hzr_encode (staging of the largest block)
     size_t dec_smem;       // dynamic shared memory of k_hzr_decode (payload of the largest block)
-    size_t list_smem;      // bytes of the sparse list of the largest block (k_hzr_hist, k_hzr_encode)
     bool can_escalate;     // xdelta_hzr with nb < bps
     bool dct_direct;       // dct: O(n^2) bit-exact path (fixed at create time)
 
@@ -41,6 +40,10 @@ struct rspt_gpu_packer {
     uint32_t* d_tree;
     uint32_t* d_lists;     // per block: sorted non-zero bytes (position | value << 16) of sparse blocks, kListCap entries
     uint32_t* d_list_n;    // per block: entries in d_lists, kNoList = dense block
+    uint32_t* d_fused;     // per block: 1 = written by k_hzr_encode_sparse, 0 = k_hzr_encode packs the block
+    cudaStream_t side;     // runs k_hzr_encode_sparse beside k_hzr_encode
+    cudaEvent_t ev_fork, ev_join;
+    bool overlap;          // false: everything on `stream` (RSPT_NO_OVERLAP=1)
     uint16_t* d_step_lz;   // per 512-byte step of every block: leading zero count (512 = all zero)
     rspt::BlkInfo* d_info;
     uint8_t* d_frame_nb;

@@ -258,6 +258,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     s.plane_stride = (s.N + 15u) & ~15u;
     s.frame_bytes = (uint32_t)(bps * ch * ns);
     s.method = kind == RSPT_DCT ? 1u : (kind == RSPT_HADAMARD ? 2u : 0u);
+    s.dbg_skip = getenv("RSPT_DBG_SKIP") ? (uint32_t)atoi(getenv("RSPT_DBG_SKIP")) : 0u;
     p->ev_free = new std::vector<cudaEvent_t>();
     p->ev_pending = new std::vector<rspt_gpu_packer::Pending>();
     p->device = device;
@@ -266,7 +267,6 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     const uint32_t maxn = s.N < kBlock ? s.N : kBlock;
     p->enc_smem = (size_t)(4 + (maxn + 3) / 4 + 8) * 4;  // staging of the largest block: header words + payload + slack
     p->dec_smem = (size_t)((maxn + 3) / 4 + 4) * 4;      // payload of the largest block + zero slack
-    p->list_smem = (size_t)list_cap(maxn) * 4;           // sparse list of the largest block
     p->stream = (cudaStream_t)stream;  // NULL = the CUDA default stream
     p->own_stream = false;
     const size_t F = max_batch_frames, nblocks = F * s.nb_alloc * s.nblk;
@@ -279,6 +279,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_step_lz, nblocks * kMaxSteps));
     A(dalloc(p->d_lists, nblocks * (size_t)kListCap));
     A(dalloc(p->d_list_n, nblocks));
+    A(dalloc(p->d_fused, nblocks));
     A(dalloc(p->d_info, nblocks));
     A(dalloc(p->d_frame_nb, F));
     A(dalloc(p->d_need, F));
@@ -306,8 +307,13 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_frame_nb, (int)s.nb_init, F, p->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ctr, 0, sizeof(Counters), p->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_nb_state, &s.nb_init, 4, cudaMemcpyHostToDevice, p->stream);
-    if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem + (size_t)kListCap * 4);
-    if (e == cudaSuccess) e = allow_smem(k_hzr_hist, (size_t)kListCap * 4);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_hist, kHistSmem);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_encode_sparse, kSparseSmem);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
+    p->overlap = !(getenv("RSPT_NO_OVERLAP") && atoi(getenv("RSPT_NO_OVERLAP")));
     if (e == cudaSuccess) e = allow_smem(k_hzr_decode, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_crc32c, kEncodeSmem);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
@@ -325,7 +331,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     if (!p) return RSPT_E_ARG;
     DeviceGuard dg(p->device);
     cudaStreamSynchronize(p->stream);
-    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_info, p->d_frame_nb,
+    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_fused, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
                     p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off};
@@ -339,6 +345,9 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
         delete p->ev_pending;
         delete p->ev_free;
     }
+    if (p->side) cudaStreamDestroy(p->side);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
     return RSPT_OK;
@@ -489,9 +498,12 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         rc = launch_frame_nb(p, F);
         if (rc) return rc;
     }
+    uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar);
+    uint16_t* sc_skip = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
+    uint32_t* sc_codes = d_sidecar ? reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
     {
         StageTimer t(p, RSPT_STAGE_HIST);
-        k_hzr_hist<<<nblocks, kHistThreads, p->list_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
+        k_hzr_hist<<<nblocks, kHistThreads, kHistSmem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n, 1);
     }
     {
         StageTimer t(p, RSPT_STAGE_TREE);
@@ -503,16 +515,17 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         k_frame_sizes<<<(unsigned)((F + 255) / 256), 256, 0, p->stream>>>(p->d_info, s, p->d_frame_nb, (uint32_t)F, p->d_sizes, p->d_blk_off);
         k_scan_offsets<<<1, 1024, 0, p->stream>>>(p->d_sizes, (uint32_t)F, d_offsets, p->d_ctr, s.frame_bytes);
     }
-    uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar);
-    uint16_t* sc_skip = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
-    uint32_t* sc_codes = d_sidecar ? reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
     {
+        // sparse blocks from their lists, then everything else from the planes
         StageTimer t(p, RSPT_STAGE_ENCODE);
-        k_hzr_encode<<<nblocks, kEncThreads, p->enc_smem + p->list_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
-                                                                        p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, d_offsets,
+        const SparseOut so{p->d_fused, d_dst, d_offsets, p->d_blk_off, sc_bit, sc_skip, sc_codes};
+        k_hzr_encode_sparse<<<nblocks, kSpThreads, kSparseSmem, p->stream>>>(s, p->d_frame_nb, p->d_info, p->d_codes, p->d_tree, p->d_lists,
+                                                                             p->d_list_n, p->d_step_lz, p->d_crc, so);
+        k_hzr_encode<<<nblocks, kEncThreads, p->enc_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
+                                                                        p->d_codes, p->d_tree, p->d_step_lz, p->d_fused, d_offsets,
                                                                         p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip, sc_codes);
     }
-    p->launches += 5;
+    p->launches += 6;
     RSPT_CUDA_CHECK(cudaGetLastError());
     if (d_frame_nb) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_frame_nb, p->d_frame_nb, F, cudaMemcpyDeviceToDevice, p->stream));
     return RSPT_OK;
@@ -785,7 +798,7 @@ extern "C" int rspt_gpu_debug_hzr_tables(rspt_gpu_packer* p, const uint8_t* d_bl
     DeviceGuard dg(p->device);
     Shape s = p->s;
     s.N = (uint32_t)n; s.nblk = 1; s.nb_alloc = 1; s.plane_stride = (uint32_t)((n + 15) & ~(size_t)15);
-    k_hzr_hist<<<1, kHistThreads, 4 * (size_t)list_cap((uint32_t)n), p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
+    k_hzr_hist<<<1, kHistThreads, kHistSmem, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n, 1);
     k_hzr_tree<<<1, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, 1, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
     p->launches += 2;
     RSPT_CUDA_CHECK(cudaGetLastError());
