@@ -14,6 +14,7 @@ struct CrcConst {
     uint32_t byte_tab[256];
     uint32_t lane_mul[1024];
     uint32_t zt[4][4][256];  // [log2(T/128)][byte][value]
+    uint32_t zt32[4][256];   // the same table for T = 32 (warp_crc32c)
 };
 
 __device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b)
@@ -69,6 +70,39 @@ __device__ __forceinline__ uint32_t block_crc32c(const uint32_t* words, uint32_t
     }
     __syncthreads();
     return s_red[32];
+}
+
+// CRC-32C of `len` bytes at the WORD-ALIGNED shared-memory address `words`, computed by ONE warp
+// (all 32 lanes must call it; every lane gets the result).  Same scheme as block_crc32c with
+// T = 32; the advance table is read through the read-only cache instead of shared memory.
+__device__ __forceinline__ uint32_t warp_crc32c(const uint32_t* words, uint32_t len, const CrcConst* __restrict__ cc)
+{
+    const uint32_t j = lane_id();
+    const uint32_t* zt = &cc->zt32[0][0];
+    uint32_t part = 0;
+    if (len >= 8) {
+        const uint32_t W = len >> 2;
+        if (j < W) {
+            uint32_t S = 0;
+            for (uint32_t i = (W - 1 - j) & 31u; i < W; i += 32) {
+                uint32_t w = words[i];
+                if (i == 0) w = ~w;  // init 0xFFFFFFFF == complement of the first four bytes
+                S = __ldg(zt + (S & 255u)) ^ __ldg(zt + 256 + ((S >> 8) & 255u)) ^ __ldg(zt + 512 + ((S >> 16) & 255u)) ^
+                    __ldg(zt + 768 + (S >> 24)) ^ w;
+            }
+            part = crc_mulmod(__ldg(&cc->lane_mul[j]), S);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xFFFFFFFFu, part, o);
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
+    uint32_t s = part, q = len & ~3u;
+    if (len < 8) {
+        s = 0xFFFFFFFFu;
+        q = 0;
+    }
+    for (; q < len; ++q) s = (s >> 8) ^ __ldg(&cc->byte_tab[(s ^ bytes[q]) & 255u]);
+    return ~s;
 }
 
 struct LenSink {

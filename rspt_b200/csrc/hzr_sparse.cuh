@@ -14,8 +14,7 @@
 namespace rspt {
 
 constexpr int kSpThreads = 256;
-constexpr int kSpZtSel = 1;                              // log2(kSpThreads / 128)
-constexpr uint32_t kSpStageBytes = 10240;                // largest payload packed here
+constexpr uint32_t kSpStageBytes = 12288;                // largest payload packed here
 constexpr uint32_t kSpStageWords = kSpStageBytes / 4 + 8;
 constexpr size_t kSparseSmem = (size_t)(kListCap + 4 + kSpStageWords) * 4;
 
@@ -40,8 +39,6 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];  // the list, then the payload staging
     __shared__ uint32_t s_codes[kSymStride];
-    __shared__ __align__(16) uint32_t s_zt[1024];
-    __shared__ uint32_t s_red[33];
     __shared__ uint32_t s_wtot[kSpThreads / 32];
     uint32_t f, k, b;
     const uint32_t blk = blockIdx.x;
@@ -83,8 +80,6 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
         s_codes[i] = cw;
         if (so.sc_codes) so.sc_codes[(size_t)blk * kSymStride + i] = cw;  // decode index: the block's code table
     }
-    for (uint32_t i = tid; i < 256; i += blockDim.x)
-        reinterpret_cast<uint4*>(s_zt)[i] = __ldg(reinterpret_cast<const uint4*>(&cc->zt[kSpZtSel][0][0]) + i);
     // staging: tree words, then zeros (the code words are OR-ed in)
     for (uint32_t i = tid; i < pw + 2u; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
     __syncthreads();
@@ -99,7 +94,14 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
         const uint32_t e = i < m ? list[i] : n;
         const uint32_t cur = i < m ? e & 0xFFFFu : n;
         const uint32_t rs = i ? (list[i - 1] & 0xFFFFu) + 1u : 0u;
-        if (cur > rs) wbits += run_bits(cur - rs, s_codes);
+        const uint32_t gap = cur - rs;
+        if (gap > kRunCap) {
+            wbits += run_bits(gap, s_codes);
+        } else {
+            uint32_t sym, ev, eb;
+            run_token(gap, sym, ev, eb);  // gap 0 classifies as a run of 1; masked out below
+            wbits += gap ? (s_codes[sym] >> 27) + eb : 0u;
+        }
         if (i < m) wbits += s_codes[e >> 16] >> 27;
     }
 #pragma unroll
@@ -186,16 +188,16 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
     }
     __syncthreads();
 
-    const uint32_t crc = block_crc32c(pay, plen, s_zt, cc, s_red);
-    if (tid == 0) {
-        uint8_t* sbytes = reinterpret_cast<uint8_t*>(stg);
-        sbytes[9] = (uint8_t)(plen - 1); sbytes[10] = (uint8_t)((plen - 1) >> 8);
-        sbytes[11] = (uint8_t)crc; sbytes[12] = (uint8_t)(crc >> 8); sbytes[13] = (uint8_t)(crc >> 16); sbytes[14] = (uint8_t)(crc >> 24);
-        sbytes[15] = (uint8_t)MODE_HUFF;
-        so.fused[blk] = 1u;
+    // the payload goes out while warp 0 takes its CRC-32C and then writes the 7-byte block header
+    uint8_t* out = so.dst + so.offsets[f] + so.blk_off[blk];
+    copy_smem_to_global(out + 7, stg, 16, plen);
+    if (wid != 0) return;
+    const uint32_t crc = warp_crc32c(pay, plen, cc);
+    if (lane < 7) {
+        const uint32_t lo = (plen - 1u) | (crc << 16), hi = (crc >> 16) | ((uint32_t)MODE_HUFF << 16);
+        out[lane] = (uint8_t)((lane < 4 ? lo : hi) >> (8u * (lane & 3u)));
     }
-    __syncthreads();
-    copy_smem_to_global(so.dst + so.offsets[f] + so.blk_off[blk], stg, 9, 7u + plen);
+    if (lane == 0) so.fused[blk] = 1u;
 }
 
 }  // namespace rspt

@@ -19,23 +19,21 @@
 //      leaves below every internal node.
 //   C  breadth-first top-down pass, one frontier node per lane: depth, code and pre-order bit
 //      offset of every node.  A subtree with l leaves serialises to 11*l - 1 bits, which places
-//      child_b without walking child_a.
-//   D  leaves in parallel: code table entry, tree bits, payload bit total, maximum code length.
+//      child_b without walking child_a.  Leaves are finished as they are reached: code table
+//      entry, tree bits, payload bit total, maximum code length.
 #pragma once
 
 #include "common.cuh"
 
 namespace rspt {
 
-constexpr int kTreeWarps = 1;  // one tree per CTA: a finished (sparse) tree frees its shared memory at once
+constexpr int kTreeWarps = 2;  // trees per CTA (5.6 KB of shared memory each: 40 trees per SM)
 
 struct TreeWarpSmem {
-    uint32_t key[512];         // sorted leaf keys
+    uint32_t key[264];         // sorted leaf keys
     uint32_t icnt[260];        // B: internal node weight (| bit 31: next node has equal weight); C: node code
     uint32_t child[260];       // child_a | child_b << 10 | leaves below << 20; ids < 512 are leaf ranks, 512 + j internal node j
     uint32_t ninfo[260];       // C: depth | pre-order bit offset << 8
-    uint32_t lcode[264];       // per leaf rank: code
-    uint32_t linfo[264];       // per leaf rank: depth | bit offset << 8
     uint32_t tree[kTreeWords];
     uint16_t front[2][264];    // C: breadth-first frontiers (internal node indices)
 };
@@ -115,24 +113,28 @@ __device__ __forceinline__ BlkInfo warp_build_tree(TreeWarpSmem& S, const uint32
             }
         S.key[lane] = mykey;
     } else {
+        // bitonic network in its all-ascending form (the first step of every merge mirrors the
+        // upper half), so the slots from L up to the next power of two are virtual +infinity
+        // and need no storage: a compare whose upper partner is >= L is a no-op
         uint32_t P = 64;
         while (P < L) P <<= 1;
-        for (uint32_t i = L + lane; i < P; i += 32) S.key[i] = 0xFFFFFFFFu;
-        __syncwarp();
-        for (uint32_t kk = 2; kk <= P; kk <<= 1)
+        for (uint32_t kk = 2; kk <= P; kk <<= 1) {
             for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+                const bool mirror = j == (kk >> 1);
                 for (uint32_t idx = lane; idx < (P >> 1); idx += 32) {
                     const uint32_t i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));
-                    const uint32_t ixj = i | j;
-                    const uint32_t a = S.key[i], c2 = S.key[ixj];
-                    const bool up = (i & kk) == 0;
-                    if ((a > c2) == up) {
-                        S.key[i] = c2;
-                        S.key[ixj] = a;
+                    const uint32_t ixj = mirror ? i ^ (kk - 1u) : i | j;
+                    if (ixj < L) {
+                        const uint32_t a = S.key[i], c2 = S.key[ixj];
+                        if (a > c2) {
+                            S.key[i] = c2;
+                            S.key[ixj] = a;
+                        }
                     }
                 }
                 __syncwarp();
             }
+        }
     }
     for (uint32_t i = lane; i < kTreeWords; i += 32) S.tree[i] = 0;
     __syncwarp();
@@ -218,8 +220,22 @@ __device__ __forceinline__ BlkInfo warp_build_tree(TreeWarpSmem& S, const uint32
     }
     __syncwarp();
 
-    // ---- phase C: breadth-first top-down pass, one frontier node per lane
+    // ---- phase C: breadth-first top-down pass, one frontier node per lane: depth, code and
+    // pre-order bit offset of both children.  A leaf child is finished on the spot: code table
+    // entry, its 10 tree bits (1 + 9-bit symbol), its share of the payload bit total.
+    uint32_t token_bits = 0, maxlen = 0, ntok = 0;
     {
+        auto leaf = [&](uint32_t rank, uint32_t code, uint32_t depth, uint32_t off) {
+            const uint32_t kv = S.key[rank];
+            const uint32_t sym = 511u - (kv & 511u), cnt = kv >> 9;
+            codes_out[sym] = code | (depth << 27);
+            token_bits += cnt * (depth + sym_extra_bits(sym));
+            ntok += cnt;
+            maxlen = max(maxlen, depth);
+            const unsigned long long bits = (unsigned long long)(1u | (sym << 1)) << (off & 31u);
+            atomicOr(&S.tree[off >> 5], (uint32_t)bits);
+            if (bits >> 32) atomicOr(&S.tree[(off >> 5) + 1], (uint32_t)(bits >> 32));
+        };
         uint32_t nf = 1, cur = 0;
         const uint32_t lt = (1u << lane) - 1u;
         while (nf) {
@@ -234,23 +250,20 @@ __device__ __forceinline__ BlkInfo warp_build_tree(TreeWarpSmem& S, const uint32
                     const uint32_t depth = inf & 255u, off = inf >> 8;
                     a = ch & 1023u;
                     bb = (ch >> 10) & 1023u;
-                    const uint32_t st_a = (depth + 1) | ((off + 1) << 8);
                     uint32_t bits_a = 10;
                     if (a < 512u) {
-                        S.lcode[a] = code;
-                        S.linfo[a] = st_a;
+                        leaf(a, code, depth + 1u, off + 1u);
                     } else {
                         bits_a = 11u * (S.child[a - 512u] >> 20) - 1u;
                         S.icnt[a - 512u] = code;
-                        S.ninfo[a - 512u] = st_a;
+                        S.ninfo[a - 512u] = (depth + 1u) | ((off + 1u) << 8);
                     }
-                    const uint32_t code_b = code | (1u << depth), st_b = (depth + 1) | ((off + 1 + bits_a) << 8);
+                    const uint32_t code_b = code | (1u << depth), off_b = off + 1u + bits_a;
                     if (bb < 512u) {
-                        S.lcode[bb] = code_b;
-                        S.linfo[bb] = st_b;
+                        leaf(bb, code_b, depth + 1u, off_b);
                     } else {
                         S.icnt[bb - 512u] = code_b;
-                        S.ninfo[bb - 512u] = st_b;
+                        S.ninfo[bb - 512u] = (depth + 1u) | (off_b << 8);
                     }
                 }
                 const bool ia = act && a >= 512u, ib = act && bb >= 512u;
@@ -264,23 +277,6 @@ __device__ __forceinline__ BlkInfo warp_build_tree(TreeWarpSmem& S, const uint32
             cur ^= 1;
             nf = nn;
         }
-    }
-
-    // ---- phase D: leaves in parallel
-    uint32_t token_bits = 0, maxlen = 0, ntok = 0;
-    uint32_t* my_codes = codes_out;
-    for (uint32_t i = lane; i < L; i += 32) {
-        const uint32_t kv = S.key[i];
-        const uint32_t sym = 511u - (kv & 511u), cnt = kv >> 9;
-        const uint32_t li2 = S.linfo[i], code = S.lcode[i];
-        const uint32_t depth = li2 & 255u, off = li2 >> 8;
-        my_codes[sym] = code | (depth << 27);
-        token_bits += cnt * (depth + sym_extra_bits(sym));
-        ntok += cnt;
-        maxlen = max(maxlen, depth);
-        const unsigned long long bits = (unsigned long long)(1u | (sym << 1)) << (off & 31u);
-        atomicOr(&S.tree[off >> 5], (uint32_t)bits);
-        if (bits >> 32) atomicOr(&S.tree[(off >> 5) + 1], (uint32_t)(bits >> 32));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

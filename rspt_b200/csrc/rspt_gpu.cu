@@ -67,6 +67,11 @@ int ensure_device_constants(int dev)
         for (int b = 0; b < 4; ++b)
             for (uint32_t v = 0; v < 256; ++v) c.zt[t][b][v] = h_multmodp(z, v << (8 * b));
     }
+    {
+        const uint32_t z = h_xpow(32ull * 32);
+        for (int b = 0; b < 4; ++b)
+            for (uint32_t v = 0; v < 256; ++v) c.zt32[b][v] = h_multmodp(z, v << (8 * b));
+    }
     CrcConst* d = nullptr;
     if (cudaMalloc(&d, sizeof(CrcConst)) != cudaSuccess) return RSPT_E_CUDA;
     if (cudaMemcpy(d, &c, sizeof(CrcConst), cudaMemcpyHostToDevice) != cudaSuccess) return RSPT_E_CUDA;
