@@ -41,7 +41,8 @@ enum {
     RSPT_E_CUDA = -2,     /* CUDA runtime error (see rspt_gpu_last_error) */
     RSPT_E_CAPACITY = -3, /* destination or batch capacity too small */
     RSPT_E_STREAM = -4,   /* malformed compressed stream */
-    RSPT_E_NOGPU = -5     /* no usable CUDA device: the library refuses to run */
+    RSPT_E_NOGPU = -5,    /* no usable CUDA device: the library refuses to run */
+    RSPT_E_CRC = -6       /* a block's CRC-32C does not match its payload (verify only) */
 };
 
 typedef struct rspt_gpu_packer rspt_gpu_packer;
@@ -97,6 +98,16 @@ int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_src, const ui
                               size_t n_frames, const uint8_t* d_frame_nb, const void* d_sidecar,
                               uint8_t* d_dst, int32_t* d_status);
 
+/* Integrity check without decoding: replaces hzr_verify (lib_hzr/hzr_decode.c:569-624) applied to
+ * every hzr stream of `n_frames` frames -- frame / chunk / block headers are walked as in
+ * decompress, and the CRC-32C of every block payload is compared with the block header.
+ *   d_status   [n_frames] 0 = ok, RSPT_E_STREAM = malformed framing, RSPT_E_CRC = checksum mismatch
+ * (The reference's decompress never checks the CRC, hzr_decode.c:343; neither does
+ * rspt_gpu_decompress_batch.  This is the separate check a receiver runs on streams from either
+ * implementation.) */
+int rspt_gpu_verify_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets,
+                          size_t n_frames, const uint8_t* d_frame_nb, int32_t* d_status);
+
 size_t rspt_gpu_sidecar_bytes(const rspt_gpu_packer* p, size_t n_frames);
 
 /* Single-frame convenience with HOST buffers -- the exact shape of the reference calls
@@ -122,6 +133,7 @@ typedef struct {
     uint64_t raw_bytes_in, compressed_bytes_out;
     uint64_t blocks_copy, blocks_huff, blocks_fill;
     uint64_t escalations;    /* "Compression needs one more byte to encode." events */
+    uint64_t crc_failures;   /* blocks whose CRC-32C did not match (rspt_gpu_verify_batch) */
     uint64_t kernel_launches;
 } rspt_gpu_counters;
 int rspt_gpu_get_counters(rspt_gpu_packer* p, rspt_gpu_counters* out);

@@ -323,6 +323,16 @@ def hzr_decode(comp, out_size: int, impl: str = "port"):
     return out[:out_size].tobytes(), ok
 
 
+def hzr_verify(comp, impl: str = "port") -> bool:
+    """hzr_verify (hzr_decode.c:569-624): header walk + CRC-32C of every block."""
+    c = np.concatenate([_as_u8(comp), np.zeros(16, np.uint8)])
+    n = len(_as_u8(comp))
+    dec = _sz(0)
+    if impl == "port":
+        return oracle_lib().oracle_hzr_verify(_ptr(c), n, C.byref(dec)) == 0
+    return ref_lib().ref_hzr_verify(_ptr(c), n, C.byref(dec)) == 1
+
+
 def hzr_histogram(block) -> np.ndarray:
     a = _as_u8(block)
     h = np.zeros(NSYM, np.uint32)

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "librspt_gpu.so")
 KINDS = {"xdelta_hzr": 0, "hzr": 1, "hadamard": 2, "dct": 3}
 STAGES = ["transform", "hist", "tree", "layout", "encode", "parse", "decode", "inverse"]
 ERRORS = {0: "ok", -1: "bad argument / unsupported shape", -2: "CUDA error", -3: "capacity too small",
-          -4: "malformed stream", -5: "no CUDA device"}
+          -4: "malformed stream", -5: "no CUDA device", -6: "CRC-32C mismatch"}
 
 # every symbol include/rspt_gpu.h declares
 EXPORTS = [
@@ -21,14 +21,14 @@ EXPORTS = [
     "rspt_gpu_compress_batch_host", "rspt_gpu_decompress_batch_host", "rspt_gpu_sync", "rspt_gpu_last_error",
     "rspt_gpu_get_counters", "rspt_gpu_debug_planes", "rspt_gpu_debug_hzr_tables", "rspt_gpu_crc32c",
     "rspt_gpu_synth_ecg", "rspt_gpu_prdn_terms", "rspt_gpu_rebase_offsets",
-    "rspt_gpu_set_stage_timing", "rspt_gpu_get_stage_times",
+    "rspt_gpu_set_stage_timing", "rspt_gpu_get_stage_times", "rspt_gpu_verify_batch",
 ]
 
 
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "frames_compressed", "frames_decompressed", "raw_bytes_in", "compressed_bytes_out",
-        "blocks_copy", "blocks_huff", "blocks_fill", "escalations", "kernel_launches")]
+        "blocks_copy", "blocks_huff", "blocks_fill", "escalations", "crc_failures", "kernel_launches")]
 
 
 class RsptError(RuntimeError):
@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
     L.rspt_gpu_compress_batch.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp]
     L.rspt_gpu_decompress_batch.restype = C.c_int
     L.rspt_gpu_decompress_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
+    L.rspt_gpu_verify_batch.restype = C.c_int
+    L.rspt_gpu_verify_batch.argtypes = [vp, vp, vp, sz, vp, vp]
     L.rspt_gpu_compress_host.restype = C.c_int
     L.rspt_gpu_compress_host.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     L.rspt_gpu_decompress_host.restype = C.c_int

@@ -424,4 +424,48 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     if (my_err) status[f] = -4;
 }
 
+// ------------------------------------------------------------------------------------------
+// Integrity check without decoding: hzr_verify (lib_hzr/hzr_decode.c:569-624) for every hzr
+// stream of every frame.  The header walk is k_frame_parse's; here one CTA per block stages the
+// payload in shared memory and compares its CRC-32C with the block header's
+// (hzr_decode.c:606-611: "CRC32 check failed").  status[f] = RSPT_E_CRC (-6) on a mismatch.
+// ------------------------------------------------------------------------------------------
+constexpr int kVerifyThreads = 256;
+constexpr int kVerifyZtSel = 1;  // log2(kVerifyThreads / 128)
+
+__global__ void __launch_bounds__(kVerifyThreads) k_hzr_verify(const uint8_t* __restrict__ src, Shape s,
+                                                                const DecBlk* __restrict__ dec,
+                                                                const CrcConst* __restrict__ cc,
+                                                                int32_t* __restrict__ status, Counters* __restrict__ ctr)
+{
+    extern __shared__ __align__(16) uint32_t payw[];
+    __shared__ __align__(16) uint32_t s_zt[1024];
+    __shared__ uint32_t s_red[33];
+    const uint32_t blk = blockIdx.x, tid = threadIdx.x;
+    const DecBlk d = dec[blk];
+    if (d.mode == kModeInactive || d.mode == kModeZero) return;  // not there / frame already flagged
+    for (uint32_t i = tid; i < 256; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_zt)[i] = __ldg(reinterpret_cast<const uint4*>(&cc->zt[kVerifyZtSel][0][0]) + i);
+    const uint8_t* pay = src + d.payload_off;
+    const uintptr_t pa = (uintptr_t)pay;
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3);
+    const uint32_t lead = (uint32_t)(pa & 3u), sh = lead * 8u;
+    const uint32_t plen = d.payload_len, pwords = (plen + 3u) >> 2, naw = (lead + plen + 3u) >> 2;
+    for (uint32_t i = tid; i < pwords; i += blockDim.x) {
+        const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
+        payw[i] = __funnelshift_r(lo, hi, sh);
+    }
+    __syncthreads();
+    const uint32_t crc = block_crc32c(payw, plen, s_zt, cc, s_red);
+    if (tid == 0) {
+        const uint32_t want = ld_le32(pay - 5);  // block header: size u16, crc u32, mode u8
+        if (crc != want) {
+            uint32_t f, k, b;
+            blk_decode(s, blk, f, k, b);
+            status[f] = -6;
+            atomicAdd(&ctr->crc_failures, 1ull);
+        }
+    }
+}
+
 }  // namespace rspt

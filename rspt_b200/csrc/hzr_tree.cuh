@@ -41,6 +41,7 @@ struct TreeWarpSmem {
 struct Counters {
     unsigned long long frames_compressed, frames_decompressed, raw_bytes_in, compressed_bytes_out;
     unsigned long long blocks_copy, blocks_huff, blocks_fill, escalations;
+    unsigned long long crc_failures;
 };
 
 // Block addressing: blk = (f * nb_alloc + k) * nblk + b

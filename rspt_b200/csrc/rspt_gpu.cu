@@ -320,6 +320,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
     p->overlap = !(getenv("RSPT_NO_OVERLAP") && atoi(getenv("RSPT_NO_OVERLAP")));
     if (e == cudaSuccess) e = allow_smem(k_hzr_decode, kDecodeSmem);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_verify, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_crc32c, kEncodeSmem);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
     if (e != cudaSuccess) {
@@ -409,6 +410,7 @@ extern "C" int rspt_gpu_get_counters(rspt_gpu_packer* p, rspt_gpu_counters* out)
     out->blocks_huff = c.blocks_huff;
     out->blocks_fill = c.blocks_fill;
     out->escalations = c.escalations;
+    out->crc_failures = c.crc_failures;
     out->kernel_launches = p->launches;
     return RSPT_OK;
 }
@@ -573,6 +575,25 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
         int rc = launch_inverse_transform(p, d_dst, F);
         if (rc) return rc;
     }
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_verify_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets, size_t n_frames,
+                                     const uint8_t* d_frame_nb, int32_t* d_status)
+{
+    if (!p || !d_src || !d_offsets || !d_status) return RSPT_E_ARG;
+    if (n_frames == 0) return RSPT_OK;
+    if (n_frames > p->max_batch) return fail_arg(p, "n_frames exceeds max_batch_frames"), RSPT_E_CAPACITY;
+    DeviceGuard dg(p->device);
+    const Shape& s = p->s;
+    const size_t F = n_frames;
+    const uint32_t nblocks = total_blocks(p, F);
+    DecBlk* dec = reinterpret_cast<DecBlk*>(p->d_dec);
+    k_frame_parse<<<(unsigned)((F + 127) / 128), 128, 0, p->stream>>>(d_src, d_offsets, s, d_frame_nb, p->d_nb_state, (uint32_t)F, dec,
+                                                                      p->d_headers, p->d_dec_nb, d_status, p->d_ctr);
+    k_hzr_verify<<<nblocks, kVerifyThreads, p->dec_smem, p->stream>>>(d_src, s, dec, p->d_crc, d_status, p->d_ctr);
+    p->launches += 2;
+    RSPT_CUDA_CHECK(cudaGetLastError());
     return RSPT_OK;
 }
 

@@ -171,6 +171,17 @@ class SignalPacker:
         check(rc, self.h, "rspt_gpu_decompress_batch")
         return out
 
+    def verify_batch(self, batch: CompressedBatch, status: torch.Tensor | None = None) -> torch.Tensor:
+        """hzr_verify (hzr_decode.c:569-624) over every block of every frame: int32 status per frame,
+        0 = ok, -4 = malformed framing, -6 = CRC-32C mismatch.  Asynchronous on the current stream."""
+        n = batch.n_frames
+        if status is None:
+            status = torch.zeros(n, dtype=torch.int32, device=self._dev())
+        nbp = batch.frame_nb.data_ptr() if batch.frame_nb is not None else None
+        rc = self.L.rspt_gpu_verify_batch(self.h, batch.stream.data_ptr(), batch.offsets.data_ptr(), n, nbp, status.data_ptr())
+        check(rc, self.h, "rspt_gpu_verify_batch")
+        return status
+
     def decompress_stream(self, stream: bytes, offsets, frame_nb=None) -> tuple[np.ndarray, np.ndarray]:
         """Decode frames produced elsewhere (e.g. by the CPU reference): no decode index."""
         dev = self._dev()

@@ -273,6 +273,51 @@ def test_decodes_streams_from_cpu_reference(R, oracle):
             assert dec[i].tobytes() == cpu.decompress(f)[0]
 
 
+def test_verify_batch_matches_hzr_verify(R, oracle):
+    """rspt_gpu_verify_batch = hzr_verify (hzr_decode.c:569-624) on every plane of every frame: clean
+    streams from the GPU and from the CPU reference pass; a flipped payload byte fails the CRC of
+    that frame only (and the CPU hzr_verify agrees on the damaged plane); broken framing is -4."""
+    from conftest import has_ref
+    impl = "reference" if has_ref() else "port"
+    bps, ch, ns, n = 3, 12, 8192, 6
+    raws = oracle.synth_ecg(3, n, bps, ch, ns)
+    raws[4] = 0  # FILL blocks
+    p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 3, max_batch_frames=n)
+    batch = p.compress_batch(to_dev(raws))
+    st = p.verify_batch(batch)
+    torch.cuda.synchronize()
+    assert not st.cpu().numpy().any()
+    assert p.counters()["crc_failures"] == 0
+    # CPU-produced streams
+    cpu = oracle.make_packer("xdelta_hzr", bps, ch, ns, 3, impl)
+    frames = [bytearray(cpu.compress(r)) for r in raws]
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+
+    def run(frs):
+        buf = torch.from_numpy(np.frombuffer(b"".join(bytes(f) for f in frs) + bytes(16), np.uint8).copy()).cuda()
+        b = R.CompressedBatch(buf, torch.tensor(offs, dtype=torch.int64, device="cuda"), None, None, n)
+        s_ = p.verify_batch(b)
+        torch.cuda.synchronize()
+        return s_.cpu().numpy()
+
+    assert not run(frames).any()
+    # flip one byte inside the last block's payload of frame 2, and one in the first HUFF payload of frame 0
+    frames[2][len(frames[2]) - 3] ^= 0x40
+    frames[0][1 + 8 + 7 + 50] ^= 0x01
+    # frame 5: truncate the chunk length field -> malformed framing
+    frames[5][1] ^= 0xFF
+    st = run(frames)
+    assert list(st) == [-6, 0, -6, 0, 0, -4], st
+    assert p.counters()["crc_failures"] == 2
+    # the CPU's hzr_verify flags the same damaged plane streams
+    f0 = bytes(frames[0])
+    clen = int.from_bytes(f0[1:5], "little")
+    assert oracle.hzr_verify(f0[5:5 + clen], impl) is False
+    good = bytes(frames[1])
+    clen = int.from_bytes(good[1:5], "little")
+    assert oracle.hzr_verify(good[5:5 + clen], impl) is True
+
+
 def test_corrupt_stream_is_reported_not_silent(R, oracle):
     raws = oracle.synth_ecg(0, 2, 3, 4, 2048)
     cpu = oracle.OraclePacker("xdelta_hzr", 3, 4, 2048, 3)
