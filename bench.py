@@ -189,8 +189,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         # keep stdout to the one JSON line: NCCL's own banner / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        RD.init_process_group_quiet(dev)
     sh = SHAPES["A"]
     fb = sh["bps"] * sh["ch"] * sh["ns"]
     F = args.frames
@@ -258,6 +257,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     dec_gbs = nd * raw_step / (d0.elapsed_time(d1) * 1e-3) / 1e9
     roundtrip_ok = bool(torch.equal(dec, inputs[0]))
+    # integrity check (hzr_verify on the GPU: header walk + CRC-32C of every block), device resident
+    vst = torch.zeros(F, dtype=torch.int32, device=dev)
+    p.verify_batch(b, status=vst)
+    torch.cuda.synchronize()
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    v0.record()
+    for _ in range(nd):
+        p.verify_batch(b, status=vst)
+    v1.record()
+    torch.cuda.synchronize()
+    verify_gbs = nd * comp_bytes / (v0.elapsed_time(v1) * 1e-3) / 1e9
+    verify_ok = not bool(vst.any().item())
 
     # per-stage device times -> roofline of the dominant kernel
     p.set_stage_timing(True)
@@ -289,7 +300,7 @@ def run_ours(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": {"transform": "k_xdelta_planes", "hist": "k_hzr_hist", "tree": "k_hzr_tree",
-                                           "layout": "k_scan_offsets", "encode": "k_hzr_encode"}[dom],
+                                           "layout": "k_scan_offsets", "encode": "k_hzr_encode_sparse + k_hzr_encode"}[dom],
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "ms_per_launch": comp_stages[dom],
                 "pipeline": {"algorithmic_bytes_per_step": raw_step + comp_bytes,
@@ -342,6 +353,7 @@ def run_ours(args):
                        "sharding": "contiguous frame ranges per rank; one NCCL all-gather of 8 B/rank per step" if world > 1 else "single GPU",
                        "cr": cr},
             "decompress_raw_GBps": dec_gbs, "roundtrip_bit_exact": roundtrip_ok, "cr": cr,
+            "verify_compressed_GBps": verify_gbs, "verify_ok": verify_ok,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         line.update(extras)

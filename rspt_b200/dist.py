@@ -11,6 +11,26 @@ import torch.distributed as dist
 from . import _lib
 
 
+def init_process_group_quiet(device: torch.device) -> None:
+    """dist.init_process_group("nccl") plus one warm-up collective (communicator creation is lazy and
+    takes seconds), with the process's stdout pointed at stderr meanwhile: NCCL prints its version
+    banner with printf, and a benchmark's stdout must stay one JSON line."""
+    import os
+    import sys
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=device)
+        t = torch.zeros(1, dtype=torch.int64, device=device)
+        dist.all_reduce(t)
+        torch.cuda.synchronize(device)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def shard_range(n_frames: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous shard [lo, hi) of rank `rank`: frames [r*F/W, (r+1)*F/W)."""
     return (rank * n_frames) // world, ((rank + 1) * n_frames) // world

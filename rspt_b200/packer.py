@@ -253,9 +253,15 @@ def synth_ecg(first_frame: int, n_frames: int, bps: int, ch: int, ns: int, seed:
     return out
 
 
-def prdn(orig: torch.Tensor, dec: torch.Tensor, n_frames: int, bps: int, ch: int, ns: int) -> float:
-    """PRDN[%] per lib_rspt_test/rspt_test.cpp:98-111, accumulated over the frames."""
+def prdn_terms(orig: torch.Tensor, dec: torch.Tensor, n_frames: int, bps: int, ch: int, ns: int) -> tuple[float, float]:
+    """Numerator and denominator sums of PRDN (rspt_test.cpp:98-111) over the given frames, so that a
+    caller can accumulate them over batches."""
     out = (C.c_double * 2)()
     check(_lib.lib().rspt_gpu_prdn_terms(orig.data_ptr(), dec.data_ptr(), n_frames, bps, ch, ns, out,
                                          torch.cuda.current_stream().cuda_stream), None, "prdn")
-    return float(np.sqrt(out[0] / out[1]) * 100.0) if out[1] > 0 else 0.0
+    return float(out[0]), float(out[1])
+
+
+def prdn(orig: torch.Tensor, dec: torch.Tensor, n_frames: int, bps: int, ch: int, ns: int) -> float:
+    num, den = prdn_terms(orig, dec, n_frames, bps, ch, ns)
+    return float(np.sqrt(num / den) * 100.0) if den > 0 else 0.0
