@@ -90,8 +90,9 @@ int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src, size_t n_f
  *   d_src      concatenated frames; d_offsets [n_frames + 1] as produced by compress (frames are
  *              self-delimiting but carry no index, signal_packer_base.cpp:121)
  *   d_frame_nb per-frame plane count or NULL = the handle's current count for every frame
- *   d_sidecar  optional decode index produced by compress_batch for these same frames, or NULL
- *              (streams from the CPU reference): decode then walks each hzr block serially
+ *   d_sidecar  optional decode index produced by compress_batch (or rspt_gpu_build_index) for these
+ *              same frames, or NULL (streams from the CPU reference): the index is then rebuilt on
+ *              the device first, into scratch owned by the handle
  *   d_dst      [n_frames][frame_bytes]
  *   d_status   [n_frames] 0 = ok, else RSPT_E_STREAM-style code; may be NULL */
 int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets,
@@ -109,6 +110,14 @@ int rspt_gpu_verify_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64
                           size_t n_frames, const uint8_t* d_frame_nb, int32_t* d_status);
 
 size_t rspt_gpu_sidecar_bytes(const rspt_gpu_packer* p, size_t n_frames);
+
+/* Decode index for frames that came without one (written by the CPU reference, or stored without
+ * the sidecar): header walk, then every HUFF block is cut into bit sub-sequences that are decoded
+ * in parallel from guessed starts until the token boundaries stop moving (a prefix code
+ * re-synchronises by itself).  The result equals the index compress_batch emits and can be kept
+ * next to the stream: build once, decode many times.  d_sidecar: rspt_gpu_sidecar_bytes bytes. */
+int rspt_gpu_build_index(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets,
+                         size_t n_frames, const uint8_t* d_frame_nb, void* d_sidecar, int32_t* d_status);
 
 /* Single-frame convenience with HOST buffers -- the exact shape of the reference calls
  * (signal_packer.h:44,57): stages host<->device, runs the batch path with n_frames = 1 and

@@ -21,7 +21,7 @@ EXPORTS = [
     "rspt_gpu_compress_batch_host", "rspt_gpu_decompress_batch_host", "rspt_gpu_sync", "rspt_gpu_last_error",
     "rspt_gpu_get_counters", "rspt_gpu_debug_planes", "rspt_gpu_debug_hzr_tables", "rspt_gpu_crc32c",
     "rspt_gpu_synth_ecg", "rspt_gpu_prdn_terms", "rspt_gpu_rebase_offsets",
-    "rspt_gpu_set_stage_timing", "rspt_gpu_get_stage_times", "rspt_gpu_verify_batch",
+    "rspt_gpu_set_stage_timing", "rspt_gpu_get_stage_times", "rspt_gpu_verify_batch", "rspt_gpu_build_index",
 ]
 
 
@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
     L.rspt_gpu_compress_batch.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp]
     L.rspt_gpu_decompress_batch.restype = C.c_int
     L.rspt_gpu_decompress_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
+    L.rspt_gpu_build_index.restype = C.c_int
+    L.rspt_gpu_build_index.argtypes = [vp, vp, vp, sz, vp, vp, vp]
     L.rspt_gpu_verify_batch.restype = C.c_int
     L.rspt_gpu_verify_batch.argtypes = [vp, vp, vp, sz, vp, vp]
     L.rspt_gpu_compress_host.restype = C.c_int

@@ -201,12 +201,67 @@ constexpr uint32_t kDecPayWords = kBlock / 4 + 4;
 constexpr size_t kDecodeSmem = (size_t)kDecPayWords * 4;
 constexpr uint32_t kLongFlag = 0x8000u;
 
+// RecoverTree (dec:263-333), iteratively, by ONE thread: pre-order, 0 = branch, 1 + 9-bit symbol =
+// leaf.  Only the code word of every leaf is needed: a stack of (code, depth) of pending right
+// children.  cw[sym] = code | len << 27 (must be zeroed by the caller).  Returns the number of
+// tree bits, or 0xFFFFFFFF on a malformed tree.
+__device__ __forceinline__ uint32_t recover_tree(const uint32_t* payw, uint32_t plen, uint32_t* cw)
+{
+    BitReader r;
+    r.init(payw, 0);
+    uint32_t nodes = 0, leaves = 0, bits_used = 0;
+    uint32_t st_code[40], st_depth[40];
+    int sp = 0;
+    uint32_t code = 0, depth = 0;
+    for (;;) {
+        if (nodes >= 2 * kNumSymbols - 1 || depth > 27u) return 0xFFFFFFFFu;
+        ++nodes;
+        r.refill();
+        const uint32_t leaf = r.take(1);
+        ++bits_used;
+        if (leaf) {
+            const uint32_t sym = r.take(9);
+            bits_used += 9;
+            if (sym >= (uint32_t)kNumSymbols || leaves >= (uint32_t)kNumSymbols || cw[sym] != 0u) return 0xFFFFFFFFu;
+            // lone leaf: 1-bit code (dec:306 `hzr_max(bits, 1)`)
+            cw[sym] = code | (max(depth, 1u) << 27);
+            ++leaves;
+            if (sp == 0) break;
+            --sp;
+            code = st_code[sp]; depth = st_depth[sp];
+        } else {
+            if (sp >= 40) return 0xFFFFFFFFu;
+            st_code[sp] = code | (1u << depth); st_depth[sp] = depth + 1; ++sp;
+            depth = depth + 1;
+        }
+    }
+    return bits_used > plen * 8u ? 0xFFFFFFFFu : bits_used;
+}
+
+// look-up table on the next kLutBits bits (whole CTA): a warp per symbol, lanes over the
+// 2^(12 - len) entries that end in its code; symbols with longer codes go to the list `longs`
+// (*nlong must be 0 on entry).  The caller initialises lut to kLongFlag and synchronises after.
+__device__ __forceinline__ void build_lut(const uint32_t* cw_tab, uint16_t* lut, uint16_t* longs, uint32_t* nlong)
+{
+    const uint32_t lane = lane_id();
+    for (uint32_t sym = warp_id(); sym < (uint32_t)kNumSymbols; sym += (blockDim.x >> 5)) {
+        const uint32_t cw = cw_tab[sym];
+        if (cw == 0u) continue;
+        const uint32_t len = cw >> 27, code = cw & 0x07FFFFFFu;
+        if (len <= (uint32_t)kLutBits) {
+            const uint16_t e = (uint16_t)(sym | (len << 9));
+            for (uint32_t i = lane; i < (1u << (kLutBits - len)); i += 32) lut[(i << len) | code] = e;
+        } else if (lane == 0) {
+            longs[atomicAdd(nlong, 1u)] = (uint16_t)sym;
+        }
+    }
+}
+
 // One CTA per hzr block.  The payload is staged in shared memory (coalesced, re-aligned); the
-// code table comes from the decode index (sc_codes) or, for streams without one, from RecoverTree
-// run by one thread; a 12-bit look-up table maps the next bits to (symbol, length), longer codes
-// are matched against the short list of long code words.  With the index every thread decodes the
-// tokens that start in its 128-byte segment and writes exactly that segment; without it thread 0
-// decodes the whole block.
+// code table comes from the decode index (sc_codes); a 12-bit look-up table maps the next bits to
+// (symbol, length), longer codes are matched against the short list of long code words.  Every
+// thread decodes the tokens that start in its 128-byte segment and writes exactly that segment.
+// Streams that arrive without an index (CPU reference) get one from k_hzr_build_index first.
 __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t* __restrict__ src, Shape s,
                                                                    const DecBlk* __restrict__ dec,
                                                                    const uint32_t* __restrict__ sc_bit,
@@ -264,70 +319,10 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         payw[i] = v;
     }
     for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_lut)[i] = kLongFlag | (kLongFlag << 16);
-    const bool indexed = sc_bit != nullptr;
-    if (indexed) {
-        for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = i < (uint32_t)kNumSymbols ? sc_codes[(size_t)blk * kSymStride + i] : 0u;
-        if (tid == 0) { s_meta[0] = 0; s_meta[1] = 0; s_meta[2] = 0; }
-        __syncthreads();
-    } else {
-        for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = 0;
-        __syncthreads();
-        if (tid == 0) {
-            // RecoverTree (dec:263-333), iteratively: pre-order, 0 = branch, 1 + 9-bit symbol = leaf.
-            // Only the code word of every leaf is needed: a stack of (code, depth) of pending
-            // right children.
-            BitReader r;
-            r.init(payw, 0);
-            uint32_t nodes = 0, leaves = 0, err = 0, bits_used = 0;
-            uint32_t st_code[40], st_depth[40];
-            int sp = 0;
-            uint32_t code = 0, depth = 0;
-            for (;;) {
-                if (nodes >= 2 * kNumSymbols - 1 || depth > 27u) { err = 1; break; }
-                ++nodes;
-                r.refill();
-                const uint32_t leaf = r.take(1);
-                ++bits_used;
-                if (leaf) {
-                    const uint32_t sym = r.take(9);
-                    bits_used += 9;
-                    if (sym >= (uint32_t)kNumSymbols || leaves >= (uint32_t)kNumSymbols || s_cw[sym] != 0u) { err = 1; break; }
-                    // lone leaf: 1-bit code (dec:306 `hzr_max(bits, 1)`)
-                    s_cw[sym] = code | (max(depth, 1u) << 27);
-                    ++leaves;
-                    if (sp == 0) break;
-                    --sp;
-                    code = st_code[sp]; depth = st_depth[sp];
-                } else {
-                    if (sp >= 40) { err = 1; break; }
-                    st_code[sp] = code | (1u << depth); st_depth[sp] = depth + 1; ++sp;
-                    depth = depth + 1;
-                }
-            }
-            if (bits_used > plen * 8u) err = 1;
-            s_meta[0] = bits_used;
-            s_meta[1] = err;
-            s_meta[2] = 0;
-        }
-        __syncthreads();
-    }
-    if (s_meta[1]) {
-        if (tid == 0) status[f] = -4;
-        for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
-        return;
-    }
-    // look-up table: a warp per symbol, lanes over the 2^(12 - len) entries that end in its code
-    for (uint32_t sym = wid; sym < (uint32_t)kNumSymbols; sym += (blockDim.x >> 5)) {
-        const uint32_t cw = s_cw[sym];
-        if (cw == 0u) continue;
-        const uint32_t len = cw >> 27, code = cw & 0x07FFFFFFu;
-        if (len <= (uint32_t)kLutBits) {
-            const uint16_t e = (uint16_t)(sym | (len << 9));
-            for (uint32_t i = lane; i < (1u << (kLutBits - len)); i += 32) s_lut[(i << len) | code] = e;
-        } else if (lane == 0) {
-            s_long[atomicAdd(&s_meta[2], 1u)] = (uint16_t)sym;
-        }
-    }
+    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = i < (uint32_t)kNumSymbols ? sc_codes[(size_t)blk * kSymStride + i] : 0u;
+    if (tid == 0) { s_meta[0] = 0; s_meta[1] = 0; s_meta[2] = 0; }
+    __syncthreads();
+    build_lut(s_cw, s_lut, s_long, &s_meta[2]);
     __syncthreads();
 
     const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
@@ -341,7 +336,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     uint32_t my_err = 0;
     uint32_t bitpos = 0, seg0 = 0, seg_len = 0, skip = 0, end_bit = 0;
     bool mine = false;
-    if (indexed) {
+    {
         if (tid < nseg) {
             bitpos = sc_bit[(size_t)blk * kMaxSegs + tid];
             skip = sc_skip[(size_t)blk * kMaxSegs + tid];
@@ -370,11 +365,6 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
             }
         }
         if (all_zero) mine = false;
-    } else if (tid == 0) {
-        bitpos = s_meta[0];
-        end_bit = 0xFFFFFFFFu;
-        seg_len = n;
-        mine = true;
     }
     if (mine) {
         const uint32_t limit_bits = plen * 8u, nlong = s_meta[2];
@@ -422,6 +412,211 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         wr.finish();
     }
     if (my_err) status[f] = -4;
+}
+
+// ------------------------------------------------------------------------------------------
+// Decode index for streams that arrive without one (written by the CPU reference): one CTA per
+// HUFF block.  The token stream has no sync points, but a prefix code re-synchronises by itself
+// after a few tokens, so the block's payload bits are cut into equal sub-sequences, one per
+// thread, and every thread decodes from a guessed start (the sub-sequence boundary; thread 0
+// from the true start behind the tree) to the first token boundary inside the next
+// sub-sequence, which becomes that neighbour's start.  Threads whose start moved decode again;
+// the starts are exact once nothing moves (each round fixes at least one more sub-sequence,
+// in practice two or three rounds do).  A scan of the bytes every sub-sequence produces gives
+// the output position of every token, and a last walk writes, for every 128-byte output
+// segment, the bit offset of the first token that starts in it and the bytes an earlier zero run
+// still covers -- the same index k_hzr_encode emits -- plus the block's code table.
+// (hzr_decode.c has no counterpart: DecodeSingleBlock :335-567 is a sequential walk.)
+// ------------------------------------------------------------------------------------------
+constexpr int kIndexThreads = 512;
+constexpr uint32_t kSubMinBits = 64;  // sub-sequences are longer than the longest token (27 + 14 bits)
+
+struct TokenDecoder {
+    const uint16_t* lut;
+    const uint32_t* cw;
+    const uint16_t* longs;
+    uint32_t nlong;
+    // one token at the reader's position: bits consumed (0 = no code word matches) and bytes produced
+    __device__ __forceinline__ uint32_t next(BitReader& r, uint32_t& out_bytes) const
+    {
+        r.refill();
+        uint32_t e = lut[r.peek(kLutBits)];
+        if (e & kLongFlag) {
+            e = 0;
+            for (uint32_t j = 0; j < nlong; ++j) {
+                const uint32_t sym = longs[j], c = cw[sym], len = c >> 27;
+                if (((uint32_t)r.buf & ((1u << len) - 1u)) == (c & 0x07FFFFFFu)) {
+                    e = sym | (len << 9);
+                    break;
+                }
+            }
+            if (e == 0u) return 0u;
+        }
+        uint32_t len = e >> 9;
+        const uint32_t sym = e & 511u;
+        r.skip(len);
+        out_bytes = 1u;
+        if (sym >= 256u) {
+            out_bytes = 2u;
+            if (sym > 256u) {
+                const uint32_t eb = sym_extra_bits(sym);
+                r.refill();
+                out_bytes = r.take(eb) + (sym == 257u ? 3u : sym == 258u ? 7u : sym == 259u ? 23u : 279u);
+                len += eb;
+            }
+        }
+        return len;
+    }
+};
+
+__global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint8_t* __restrict__ src, Shape s,
+                                                                       const DecBlk* __restrict__ dec,
+                                                                       uint32_t* __restrict__ sc_bit,
+                                                                       uint16_t* __restrict__ sc_skip,
+                                                                       uint32_t* __restrict__ sc_codes,
+                                                                       int32_t* __restrict__ status)
+{
+    extern __shared__ __align__(16) uint32_t payw[];  // payload words (+ zero slack)
+    __shared__ __align__(16) uint16_t s_lut[1 << kLutBits];
+    __shared__ uint32_t s_cw[kSymStride];
+    __shared__ uint16_t s_long[kSymStride];
+    __shared__ uint32_t s_meta[4];                    // tree bits, error, long count
+    __shared__ uint32_t s_start[kIndexThreads + 1];   // first token boundary of every sub-sequence
+    __shared__ uint32_t s_cnt[kIndexThreads];         // bytes produced by the tokens that start in it
+    __shared__ uint32_t s_wsum[kIndexThreads / 32];
+
+    const uint32_t blk = blockIdx.x, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    const DecBlk d = dec[blk];
+    if (d.mode != MODE_HUFF) return;  // COPY / FILL / unparsed frames need no index
+    uint32_t f, k, b;
+    blk_decode(s, blk, f, k, b);
+    const uint32_t n = d.out_n, nseg = (n + kSegBytes - 1) / kSegBytes;
+    uint32_t* my_bit = sc_bit + (size_t)blk * kMaxSegs;
+    uint16_t* my_skip = sc_skip + (size_t)blk * kMaxSegs;
+    const uint8_t* pay = src + d.payload_off;
+    const uintptr_t pa = (uintptr_t)pay;
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3);
+    const uint32_t lead = (uint32_t)(pa & 3u), sh = lead * 8u;
+    const uint32_t plen = d.payload_len, pwords = (plen + 3u) >> 2, naw = (lead + plen + 3u) >> 2;
+    for (uint32_t i = tid; i < pwords + 4u; i += blockDim.x) {
+        uint32_t v = 0;
+        if (i < pwords) {
+            const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
+            v = __funnelshift_r(lo, hi, sh);
+        }
+        payw[i] = v;
+    }
+    for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_lut)[i] = kLongFlag | (kLongFlag << 16);
+    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t tb = recover_tree(payw, plen, s_cw);
+        s_meta[0] = tb;
+        s_meta[1] = tb == 0xFFFFFFFFu;
+        s_meta[2] = 0;
+    }
+    __syncthreads();
+    bool bad = s_meta[1] != 0u;
+    if (!bad) {
+        build_lut(s_cw, s_lut, s_long, &s_meta[2]);
+        __syncthreads();
+    }
+    const uint32_t limit = plen * 8u, t0 = bad ? 0u : s_meta[0];
+    // sub-sequences: nsub equal pieces of [t0, limit), each longer than any token
+    const uint32_t span = limit - t0;
+    uint32_t nsub = span / kSubMinBits;
+    nsub = nsub < 1u ? 1u : (nsub > (uint32_t)kIndexThreads ? (uint32_t)kIndexThreads : nsub);
+    const uint32_t sub = (span + nsub - 1u) / nsub;
+    const uint32_t lo = t0 + tid * sub, hi = min(limit, lo + sub);  // tokens that START in [lo, hi) are mine
+    const bool live = !bad && tid < nsub && lo < limit;
+    const TokenDecoder td{s_lut, s_cw, s_long, s_meta[2]};
+    if (tid <= nsub) s_start[tid] = min(lo, limit);
+    __syncthreads();
+    uint32_t my_start = 0xFFFFFFFFu, land = 0, cnt = 0;
+    if (!bad) {
+        for (;;) {
+            const uint32_t st = live ? s_start[tid] : 0u;
+            const bool redo = live && st != my_start;
+            if (redo) {
+                my_start = st;
+                BitReader r;
+                uint32_t pos = st;
+                cnt = 0;
+                if (pos < hi) r.init(payw, pos);
+                while (pos < hi) {
+                    uint32_t ob = 0;
+                    uint32_t l = td.next(r, ob);
+                    if (l == 0u) {  // no code word here (only from a wrong start, or a corrupt stream): slip one bit
+                        l = 1u;
+                        ob = 0u;
+                        r.skip(1);
+                    }
+                    pos += l;
+                    cnt += ob;
+                }
+                land = min(pos, limit);
+            }
+            __syncthreads();
+            bool moved = false;
+            if (redo && tid + 1 < nsub && s_start[tid + 1] != land) {
+                s_start[tid + 1] = land;
+                moved = true;
+            }
+            if (!__syncthreads_or(moved)) break;
+        }
+    }
+    // output position of every sub-sequence: exclusive scan of the byte counts
+    uint32_t v = live ? cnt : 0u, inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (uint32_t)o) inc += y;
+    }
+    if (lane == 31) s_wsum[wid] = inc;
+    __syncthreads();
+    uint32_t opos = inc - v, total = 0;
+    for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) {
+        const uint32_t t = s_wsum[w];
+        if (w < wid) opos += t;
+        total += t;
+    }
+    // the tokens must produce at least n bytes (zero padding of the last byte may decode into a
+    // few more: they are ignored, like the reference stops at the output size, dec:440)
+    if (total < n) bad = true;
+    if (bad) {
+        for (uint32_t i = tid; i < nseg; i += blockDim.x) {
+            my_bit[i] = 0xFFFFFFFFu;  // k_hzr_decode reports the frame and writes zeros
+            my_skip[i] = 0;
+        }
+        for (uint32_t i = tid; i < kSymStride; i += blockDim.x) sc_codes[(size_t)blk * kSymStride + i] = 0u;
+        if (tid == 0) status[f] = -4;
+        return;
+    }
+    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) sc_codes[(size_t)blk * kSymStride + i] = s_cw[i];
+    if (live) {
+        BitReader r;
+        uint32_t pos = my_start, op = opos;
+        if (pos < hi) r.init(payw, pos);
+        while (pos < hi && op < n) {
+            uint32_t ob = 0;
+            uint32_t l = td.next(r, ob);
+            if (l == 0u) {  // corrupt stream: the sequential decoder would fail here (dec:431)
+                status[f] = -4;
+                l = 1u;
+                ob = 0u;
+                r.skip(1);
+            }
+            // segment boundaries B in [op, op + ob): B == op -> this token starts the segment;
+            // B inside a zero run -> resume behind the token, with the rest of the run to skip
+            const uint32_t end = min(op + ob, n);
+            for (uint32_t B = (op + kSegBytes - 1u) & ~(uint32_t)(kSegBytes - 1); B < end; B += kSegBytes) {
+                my_bit[B / kSegBytes] = B == op ? pos : pos + l;
+                my_skip[B / kSegBytes] = (uint16_t)(B == op ? 0u : op + ob - B);
+            }
+            pos += l;
+            op += ob;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -60,6 +60,7 @@ struct rspt_gpu_packer {
     void* d_dec;           // block descriptors
     uint8_t* d_dec_nb;     // per-frame plane count used by the last decompress
     int32_t* d_status_tmp;
+    void* d_auto_index;    // decode index built here for streams that came without one (lazy)
     // transform constants (dct twiddles)
     double2* d_twiddle;
     double2* d_post;

@@ -321,6 +321,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     p->overlap = !(getenv("RSPT_NO_OVERLAP") && atoi(getenv("RSPT_NO_OVERLAP")));
     if (e == cudaSuccess) e = allow_smem(k_hzr_decode, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_verify, kDecodeSmem);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_build_index, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_crc32c, kEncodeSmem);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
     if (e != cudaSuccess) {
@@ -340,7 +341,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_fused, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
-                    p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off};
+                    p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p->h_pin) cudaFreeHost(p->h_pin);
@@ -541,6 +542,44 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
 // ---------------------------------------------------------------------------------------------
 // decompress
 // ---------------------------------------------------------------------------------------------
+namespace {
+
+// frame / block header walk + (for streams without a decode index) the index itself
+int launch_parse_and_index(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets, size_t F,
+                           const uint8_t* d_frame_nb, void* d_sidecar_out, int32_t* status)
+{
+    const Shape& s = p->s;
+    const uint32_t nblocks = total_blocks(p, F);
+    DecBlk* dec = reinterpret_cast<DecBlk*>(p->d_dec);
+    {
+        StageTimer t(p, RSPT_STAGE_PARSE);
+        k_frame_parse<<<(unsigned)((F + 127) / 128), 128, 0, p->stream>>>(d_src, d_offsets, s, d_frame_nb, p->d_nb_state,
+                                                                          (uint32_t)F, dec, p->d_headers, p->d_dec_nb, status, p->d_ctr);
+        p->launches += 1;
+        if (d_sidecar_out) {
+            uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar_out);
+            uint16_t* sc_skip = reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs);
+            uint32_t* sc_codes = reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs);
+            k_hzr_build_index<<<nblocks, kIndexThreads, p->dec_smem, p->stream>>>(d_src, s, dec, sc_bit, sc_skip, sc_codes, status);
+            p->launches += 1;
+        }
+    }
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    return RSPT_OK;
+}
+
+}  // namespace
+
+extern "C" int rspt_gpu_build_index(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets, size_t n_frames,
+                                    const uint8_t* d_frame_nb, void* d_sidecar, int32_t* d_status)
+{
+    if (!p || !d_src || !d_offsets || !d_sidecar) return RSPT_E_ARG;
+    if (n_frames == 0) return RSPT_OK;
+    if (n_frames > p->max_batch) return fail_arg(p, "n_frames exceeds max_batch_frames"), RSPT_E_CAPACITY;
+    DeviceGuard dg(p->device);
+    return launch_parse_and_index(p, d_src, d_offsets, n_frames, d_frame_nb, d_sidecar, d_status ? d_status : p->d_status_tmp);
+}
+
 extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets,
                                          size_t n_frames, const uint8_t* d_frame_nb, const void* d_sidecar,
                                          uint8_t* d_dst, int32_t* d_status)
@@ -556,24 +595,28 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
     DecBlk* dec = reinterpret_cast<DecBlk*>(p->d_dec);
     // Without an explicit per-frame plane count every frame uses the instance's current count,
     // as the reference's decompress does (signal_packer_xdelta_hzr.cpp:77).
-    {
-        StageTimer t(p, RSPT_STAGE_PARSE);
-        k_frame_parse<<<(unsigned)((F + 127) / 128), 128, 0, p->stream>>>(d_src, d_offsets, s, d_frame_nb, p->d_nb_state,
-                                                                          (uint32_t)F, dec, p->d_headers, p->d_dec_nb, status, p->d_ctr);
+    void* own_index = nullptr;
+    if (!d_sidecar) {
+        // stream from the CPU reference: build the decode index here first (handle-owned scratch)
+        if (!p->d_auto_index) RSPT_CUDA_CHECK(cudaMalloc(&p->d_auto_index, rspt_gpu_sidecar_bytes(p, p->max_batch)));
+        own_index = p->d_auto_index;
+        d_sidecar = own_index;
     }
+    int rc = launch_parse_and_index(p, d_src, d_offsets, F, d_frame_nb, own_index, status);
+    if (rc) return rc;
     const uint32_t* sc_bit = reinterpret_cast<const uint32_t*>(d_sidecar);
-    const uint16_t* sc_skip = d_sidecar ? reinterpret_cast<const uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
-    const uint32_t* sc_codes = d_sidecar ? reinterpret_cast<const uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
+    const uint16_t* sc_skip = reinterpret_cast<const uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs);
+    const uint32_t* sc_codes = reinterpret_cast<const uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs);
     {
         StageTimer t(p, RSPT_STAGE_DECODE);
         k_hzr_decode<<<nblocks, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec, sc_bit, sc_skip, sc_codes, p->d_planes, status);
     }
-    p->launches += 2;
+    p->launches += 1;
     RSPT_CUDA_CHECK(cudaGetLastError());
     {
         StageTimer t(p, RSPT_STAGE_INVERSE);
-        int rc = launch_inverse_transform(p, d_dst, F);
-        if (rc) return rc;
+        int rc2 = launch_inverse_transform(p, d_dst, F);
+        if (rc2) return rc2;
     }
     return RSPT_OK;
 }

@@ -171,6 +171,16 @@ class SignalPacker:
         check(rc, self.h, "rspt_gpu_decompress_batch")
         return out
 
+    def build_index(self, batch: CompressedBatch, status: torch.Tensor | None = None) -> CompressedBatch:
+        """Give a batch that came without a decode index (CPU-written frames) one, on the device."""
+        n = batch.n_frames
+        sc = torch.empty(self.L.rspt_gpu_sidecar_bytes(self.h, n), dtype=torch.uint8, device=self._dev())
+        nbp = batch.frame_nb.data_ptr() if batch.frame_nb is not None else None
+        rc = self.L.rspt_gpu_build_index(self.h, batch.stream.data_ptr(), batch.offsets.data_ptr(), n, nbp, sc.data_ptr(),
+                                         status.data_ptr() if status is not None else None)
+        check(rc, self.h, "rspt_gpu_build_index")
+        return CompressedBatch(batch.stream, batch.offsets, batch.frame_nb, sc, n)
+
     def verify_batch(self, batch: CompressedBatch, status: torch.Tensor | None = None) -> torch.Tensor:
         """hzr_verify (hzr_decode.c:569-624) over every block of every frame: int32 status per frame,
         0 = ok, -4 = malformed framing, -6 = CRC-32C mismatch.  Asynchronous on the current stream."""

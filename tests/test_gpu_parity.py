@@ -273,6 +273,44 @@ def test_decodes_streams_from_cpu_reference(R, oracle):
             assert dec[i].tobytes() == cpu.decompress(f)[0]
 
 
+def test_index_rebuilt_on_device_for_cpu_streams(R, oracle):
+    """Frames written by the CPU reference carry no decode index: rspt_gpu_build_index rebuilds it by
+    self-synchronising parallel decode, and decoding with it equals the CPU decode.  Crafted planes
+    stress the token kinds: zero runs far beyond the 16 662 chunk cap, isolated zeros, a lone
+    symbol, incompressible bytes (COPY blocks), a ragged tail block."""
+    from conftest import has_ref
+    impl = "reference" if has_ref() else "port"
+    bps, ch, ns, n = 1, 1, 150000, 6   # hzr packer, 1 B/sample: the plane IS the input; 3 blocks, last one ragged
+    rng = np.random.default_rng(5)
+    raws = np.zeros((n, ns), np.uint8)
+    raws[0, [7, 70000, 149999]] = [1, 2, 3]                       # three literals in 150 000 zeros
+    raws[1] = rng.integers(0, 256, ns)                            # incompressible
+    raws[2] = np.where(rng.random(ns) < 0.03, 0, rng.integers(1, 9, ns))   # dense, isolated zeros
+    raws[3] = np.repeat(rng.integers(0, 3, ns // 50), 50)         # runs of 50 of {0,1,2}
+    raws[4] = 0
+    raws[4, 40000:40010] = 255                                    # FILL blocks next to a sparse one
+    raws[5] = (rng.random(ns) < 0.5) * 7                          # two symbols, short runs
+    cpu = oracle.make_packer("hzr", bps, ch, ns, 3, impl)
+    frames = [cpu.compress(r) for r in raws]
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+    p = R.SignalPacker.new_hzr(bps, ch, ns, max_batch_frames=n)
+    buf = torch.from_numpy(np.frombuffer(b"".join(frames) + bytes(16), np.uint8).copy()).cuda()
+    b0 = R.CompressedBatch(buf, torch.tensor(offs, dtype=torch.int64, device="cuda"), None, None, n)
+    st = torch.zeros(n, dtype=torch.int32, device="cuda")
+    b1 = p.build_index(b0, status=st)
+    dec = p.decompress_batch(b1, status=st)
+    torch.cuda.synchronize()
+    assert not st.cpu().numpy().any()
+    assert np.array_equal(dec.cpu().numpy().reshape(n, ns), raws)
+    # and through the implicit path (no index given)
+    dec2, st2 = p.decompress_stream(b"".join(frames), offs)
+    assert not st2.any() and np.array_equal(dec2, raws)
+    # the GPU's own stream of the same frames is byte-identical to the CPU's, index or not
+    gb = p.compress_batch(to_dev(raws))
+    torch.cuda.synchronize()
+    assert bytes(gb.stream[: int(gb.offsets[n].item())].cpu().numpy()) == b"".join(frames)
+
+
 def test_verify_batch_matches_hzr_verify(R, oracle):
     """rspt_gpu_verify_batch = hzr_verify (hzr_decode.c:569-624) on every plane of every frame: clean
     streams from the GPU and from the CPU reference pass; a flipped payload byte fails the CRC of
