@@ -44,7 +44,6 @@ struct Shape {
     uint32_t plane_stride;  // N rounded up to 16
     uint32_t frame_bytes;   // bps * N
     uint32_t method;        // frame method byte (0 hzr/xdelta, 1 dct, 2 hadamard)
-    uint32_t dbg_skip;      // TEMP: 1 = skip plane 0, 2 = skip planes > 0
 };
 
 __host__ __device__ __forceinline__ uint32_t blk_len(const Shape& s, uint32_t b)

@@ -482,7 +482,6 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
     __shared__ uint16_t s_long[kSymStride];
     __shared__ uint32_t s_meta[4];                    // tree bits, error, long count
     __shared__ uint32_t s_start[kIndexThreads + 1];   // first token boundary of every sub-sequence
-    __shared__ uint32_t s_cnt[kIndexThreads];         // bytes produced by the tokens that start in it
     __shared__ uint32_t s_wsum[kIndexThreads / 32];
 
     const uint32_t blk = blockIdx.x, tid = threadIdx.x, lane = lane_id(), wid = warp_id();

@@ -51,7 +51,6 @@ __device__ __forceinline__ void blk_decode(const Shape& s, uint32_t blk, uint32_
     uint32_t fk = blk / s.nblk;
     k = fk % s.nb_alloc;
     f = fk / s.nb_alloc;
-    if (s.dbg_skip && ((s.dbg_skip & 1u) ? k == 0u : k != 0u)) k = 0xFFu;
 }
 
 __device__ __forceinline__ const uint8_t* blk_ptr(const uint8_t* planes, const Shape& s, uint32_t f, uint32_t k, uint32_t b)

@@ -41,9 +41,6 @@ struct rspt_gpu_packer {
     uint32_t* d_lists;     // per block: sorted non-zero bytes (position | value << 16) of sparse blocks, kListCap entries
     uint32_t* d_list_n;    // per block: entries in d_lists, kNoList = dense block
     uint32_t* d_fused;     // per block: 1 = written by k_hzr_encode_sparse, 0 = k_hzr_encode packs the block
-    cudaStream_t side;     // runs k_hzr_encode_sparse beside k_hzr_encode
-    cudaEvent_t ev_fork, ev_join;
-    bool overlap;          // false: everything on `stream` (RSPT_NO_OVERLAP=1)
     uint16_t* d_step_lz;   // per 512-byte step of every block: leading zero count (512 = all zero)
     rspt::BlkInfo* d_info;
     uint8_t* d_frame_nb;

@@ -263,7 +263,6 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     s.plane_stride = (s.N + 15u) & ~15u;
     s.frame_bytes = (uint32_t)(bps * ch * ns);
     s.method = kind == RSPT_DCT ? 1u : (kind == RSPT_HADAMARD ? 2u : 0u);
-    s.dbg_skip = getenv("RSPT_DBG_SKIP") ? (uint32_t)atoi(getenv("RSPT_DBG_SKIP")) : 0u;
     p->ev_free = new std::vector<cudaEvent_t>();
     p->ev_pending = new std::vector<rspt_gpu_packer::Pending>();
     p->device = device;
@@ -315,10 +314,6 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_hist, kHistSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode_sparse, kSparseSmem);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
-    p->overlap = !(getenv("RSPT_NO_OVERLAP") && atoi(getenv("RSPT_NO_OVERLAP")));
     if (e == cudaSuccess) e = allow_smem(k_hzr_decode, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_verify, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_build_index, kDecodeSmem);
@@ -352,9 +347,6 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
         delete p->ev_pending;
         delete p->ev_free;
     }
-    if (p->side) cudaStreamDestroy(p->side);
-    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-    if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
     return RSPT_OK;

@@ -271,6 +271,155 @@ __global__ void __launch_bounds__(256) k_dct_fwd_fast(int32_t* __restrict__ word
     }
 }
 
+// ---- half-size FFT path (n a power of two >= 16) ---------------------------------------------
+// The Makhoul sequence v is real, so its n-point spectrum comes from ONE complex FFT of half the
+// length over z[p] = v[2p] + i v[2p+1] (M = n/2 points) and a butterfly of Z[k] with Z[M-k]; the
+// inverse runs the same steps backwards.  The FFT itself is the radix-2 decimation-in-time
+// network on bit-reversed input, but three stages at a time: a thread keeps 8 points in
+// registers, so the data passes through shared memory ceil(lg M / 3) times instead of lg M
+// times.  Shared memory is padded by one point per 8 (16-byte points: 8 cover all 32 banks), which
+// keeps the stride-8 accesses of the first pass conflict-free.
+__device__ __forceinline__ uint32_t fpad(uint32_t i) { return i + (i >> 3); }
+
+// R fused radix-2 DIT stages starting at butterfly half-width h.  tw = e^{-2 pi i j / n}, j < n/2.
+template <int R, bool INVERSE>
+__device__ __forceinline__ void fft_pass(double2* x, uint32_t M, uint32_t h, uint32_t lgn, const double2* __restrict__ tw)
+{
+    constexpr int Q = 1 << R;
+    const uint32_t lgh = 31 - __clz((int)h);
+    for (uint32_t t = threadIdx.x; t < (M >> R); t += blockDim.x) {
+        const uint32_t jj0 = t & (h - 1);
+        const uint32_t base = ((t & ~(h - 1)) << R) | jj0;
+        double2 a[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) a[q] = x[fpad(base + (uint32_t)q * h)];
+#pragma unroll
+        for (int st = 0; st < R; ++st) {
+            // stage half-width h << st: the twiddle of position pos = jj0 + r h is
+            // e^{-2 pi i pos / (2 (h << st))} = w0 * e^{-i pi r / 2^st}: one table look-up per stage,
+            // the other positions by exact rotations (multiples of pi/4)
+            const uint32_t sh = lgn - 1u - lgh - (uint32_t)st;
+            const double2 w0 = __ldg(tw + ((size_t)jj0 << sh));
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                if (q & (1 << st)) continue;
+                const int r8 = (q & ((1 << st) - 1)) * (4 >> st);  // rotation in units of pi/4 (st <= 2)
+                constexpr double kS = 0.70710678118654752440;
+                double2 w = w0;
+                if (r8 == 1) w = make_double2((w0.x + w0.y) * kS, (w0.y - w0.x) * kS);
+                if (r8 == 2) w = make_double2(w0.y, -w0.x);
+                if (r8 == 3) w = make_double2((w0.y - w0.x) * kS, -(w0.x + w0.y) * kS);
+                if (INVERSE) w.y = -w.y;
+                const double2 u = a[q], v = a[q + (1 << st)];
+                const double2 m = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+                a[q] = make_double2(u.x + m.x, u.y + m.y);
+                a[q + (1 << st)] = make_double2(u.x - m.x, u.y - m.y);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) x[fpad(base + (uint32_t)q * h)] = a[q];
+    }
+}
+
+// in-place M-point FFT (M = 2^lgm >= 8) of bit-reversed input at padded indices; natural-order output
+template <bool INVERSE>
+__device__ __forceinline__ void fft_fused(double2* x, uint32_t lgm, uint32_t lgn, const double2* __restrict__ tw)
+{
+    const uint32_t M = 1u << lgm;
+    uint32_t h = 1, left = lgm;
+    while (left >= 3) {
+        fft_pass<3, INVERSE>(x, M, h, lgn, tw);
+        __syncthreads();
+        h <<= 3;
+        left -= 3;
+    }
+    if (left == 2) {
+        fft_pass<2, INVERSE>(x, M, h, lgn, tw);
+        __syncthreads();
+    } else if (left == 1) {
+        fft_pass<1, INVERSE>(x, M, h, lgn, tw);
+        __syncthreads();
+    }
+}
+
+// index of v[m] in the channel's sample row: v[m] = x[2m] (m < n/2), v[n-1-m] = x[2m+1]
+__device__ __forceinline__ uint32_t makhoul_src(uint32_t m, uint32_t n) { return m < (n >> 1) ? 2u * m : 2u * (n - 1u - m) + 1u; }
+
+// forward DCT of one channel.  post[k] = e^{-i pi k / (2n)}.
+__global__ void __launch_bounds__(256, 4) k_dct_fwd_half(int32_t* __restrict__ words, const long long* __restrict__ sums, Shape s,
+                                                       const double2* __restrict__ tw, const double2* __restrict__ post,
+                                                       uint8_t* __restrict__ headers)
+{
+    extern __shared__ __align__(16) double2 xs[];
+    const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, n = (uint32_t)s.ns, M = n >> 1;
+    const uint32_t lgn = 31 - __clz((int)n), lgm = lgn - 1;
+    const int32_t mean = reference_mean(sums[(size_t)f * s.ch + c], n);
+    int32_t* w = words + (size_t)f * s.N + (size_t)c * n;
+    if (threadIdx.x == 0) store_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c, mean);
+    for (uint32_t p = threadIdx.x; p < M; p += blockDim.x) {
+        const int32_t re = (int32_t)((uint32_t)w[makhoul_src(2u * p, n)] - (uint32_t)mean);
+        const int32_t im = (int32_t)((uint32_t)w[makhoul_src(2u * p + 1u, n)] - (uint32_t)mean);
+        xs[fpad(__brev(p) >> (32 - lgm))] = make_double2((double)re, (double)im);
+    }
+    __syncthreads();
+    fft_fused<false>(xs, lgm, lgn, tw);
+    // V[k] = E[k] + e^{-2 pi i k/n} O[k], E = (Z[k] + conj Z[M-k]) / 2, O = (Z[k] - conj Z[M-k]) / 2i;
+    // V[n-k] = conj V[k];  X[k] = Re(post[k] V[k])
+    const double ratio1 = sqrt(2.0 / (double)(int)n) / 128.0;  // dct.cpp:84 (quality = 128)
+    for (uint32_t k = threadIdx.x; k <= M; k += blockDim.x) {
+        const double2 Zk = xs[fpad(k & (M - 1))], Zm = xs[fpad((M - k) & (M - 1))];
+        const double ex = 0.5 * (Zk.x + Zm.x), ey = 0.5 * (Zk.y - Zm.y);
+        const double ox = 0.5 * (Zk.y + Zm.y), oy = -0.5 * (Zk.x - Zm.x);
+        const double2 t = k < M ? __ldg(tw + k) : make_double2(-1.0, 0.0);
+        const double vx = ex + (t.x * ox - t.y * oy), vy = ey + (t.x * oy + t.y * ox);
+        const double2 pk = __ldg(post + (k < n ? k : 0));
+        double sum = vx * pk.x - vy * pk.y;
+        const float cs = k ? 1.0f : (float)(1 / sqrt(2.0));
+        sum *= (double)cs * ratio1;
+        w[k] = (int32_t)sum;  // truncation toward zero, dct.cpp:85
+        if (k > 0 && k < M) {
+            const double2 pn = __ldg(post + (n - k));
+            w[n - k] = (int32_t)((vx * pn.x + vy * pn.y) * ratio1);
+        }
+    }
+}
+
+// inverse DCT of one channel: U[0] = T[0], U[k] = conj(post[k]) (T[k] - i T[n-k]) / 2 (Hermitian),
+// Zin[k] = (U[k] + conj U[M-k]) + i (U[k] - conj U[M-k]) e^{+2 pi i k/n}, z = M-point inverse FFT,
+// v[2p] = Re z[p], v[2p+1] = Im z[p]; T[k] = Cs[k] * coef[k].
+__global__ void __launch_bounds__(256, 4) k_dct_inv_half(int32_t* __restrict__ words, const uint8_t* __restrict__ headers, Shape s,
+                                                       const double2* __restrict__ tw, const double2* __restrict__ post)
+{
+    extern __shared__ __align__(16) double2 xs[];
+    const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, n = (uint32_t)s.ns, M = n >> 1;
+    const uint32_t lgn = 31 - __clz((int)n), lgm = lgn - 1;
+    int32_t* w = words + (size_t)f * s.N + (size_t)c * n;
+    const double cs0 = (double)(float)(1 / sqrt(2.0));
+    auto U = [&](uint32_t k) {
+        if (k == 0) return make_double2(cs0 * (double)w[0], 0.0);
+        const double a = (double)w[k], b = (double)w[n - k];
+        const double2 p = __ldg(post + k);  // conj(p) * (a - i b) / 2
+        return make_double2(0.5 * (p.x * a - p.y * b), -0.5 * (p.x * b + p.y * a));
+    };
+    for (uint32_t k = threadIdx.x; k < M; k += blockDim.x) {
+        const double2 Uk = U(k), Um = U(M - k);
+        const double ax = Uk.x + Um.x, ay = Uk.y - Um.y;   // U[k] + conj U[M-k]
+        const double dx = Uk.x - Um.x, dy = Uk.y + Um.y;   // U[k] - conj U[M-k]
+        const double2 t = __ldg(tw + k);                    // times conj(t)
+        const double bx = dx * t.x + dy * t.y, by = dy * t.x - dx * t.y;
+        xs[fpad(__brev(k) >> (32 - lgm))] = make_double2(ax - by, ay + bx);
+    }
+    __syncthreads();
+    fft_fused<true>(xs, lgm, lgn, tw);
+    const int32_t mean = load_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c);
+    const double scale = sqrt(2.0 / (double)(int)n) * 128.0;  // dct.cpp:97
+    for (uint32_t p = threadIdx.x; p < M; p += blockDim.x) {
+        const double2 z = xs[fpad(p)];
+        w[makhoul_src(2u * p, n)] = (int32_t)((uint32_t)(int32_t)(z.x * scale) + (uint32_t)mean);
+        w[makhoul_src(2u * p + 1u, n)] = (int32_t)((uint32_t)(int32_t)(z.y * scale) + (uint32_t)mean);
+    }
+}
+
 // forward DCT, direct path: dct.cpp:76-87 verbatim arithmetic.  cosT[x][i] is the float table.
 __global__ void __launch_bounds__(256) k_dct_fwd_direct(int32_t* __restrict__ words, const long long* __restrict__ sums, Shape s,
                                                          const float* __restrict__ cosT, uint8_t* __restrict__ headers)
@@ -347,6 +496,7 @@ __global__ void __launch_bounds__(256) k_dct_inv_direct(int32_t* __restrict__ wo
 }
 
 // ---- host side ----------------------------------------------------------------------------
+inline uint32_t fpad_host(uint32_t m) { return m + (m >> 3) + 1; }
 inline bool dct_use_direct(const rspt_gpu_packer* p) { return p->dct_direct; }
 
 // decided once, when the handle is created: non-power-of-two lengths need the direct path,
@@ -430,9 +580,14 @@ inline int spectral_forward(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
             cudaFuncSetAttribute(k_dct_fwd_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             k_dct_fwd_direct<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_cos, p->d_headers);
         } else {
-            const size_t sm = (size_t)s.ns * 16;
-            cudaFuncSetAttribute(k_dct_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            k_dct_fwd_fast<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_twiddle, p->d_post, p->d_headers);
+            if (s.ns >= 16) {
+                const size_t sm = (size_t)fpad_host((uint32_t)s.ns / 2) * 16;
+                cudaFuncSetAttribute(k_dct_fwd_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                k_dct_fwd_half<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_twiddle, p->d_post, p->d_headers);
+            } else {
+                const size_t sm = (size_t)s.ns * 16;
+                k_dct_fwd_fast<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_twiddle, p->d_post, p->d_headers);
+            }
         }
         const uint32_t chunks = (s.N + 1023) / 1024;
         k_words_stencil_planes<<<(unsigned)(F * chunks), 256, 0, p->stream>>>(p->d_words, s, chunks, p->d_planes);
@@ -519,9 +674,14 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
                 cudaFuncSetAttribute(k_dct_inv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
                 k_dct_inv_direct<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_headers, s, p->d_cos);
             } else {
-                const size_t sm = (size_t)s.ns * 16;
-                cudaFuncSetAttribute(k_dct_inv_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                k_dct_inv_fast<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_headers, s, p->d_twiddle, p->d_post);
+                if (s.ns >= 16) {
+                    const size_t sm = (size_t)fpad_host((uint32_t)s.ns / 2) * 16;
+                    cudaFuncSetAttribute(k_dct_inv_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                    k_dct_inv_half<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_headers, s, p->d_twiddle, p->d_post);
+                } else {
+                    const size_t sm = (size_t)s.ns * 16;
+                    k_dct_inv_fast<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_headers, s, p->d_twiddle, p->d_post);
+                }
             }
             p->launches += 2;
         }
