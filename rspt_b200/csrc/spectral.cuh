@@ -277,9 +277,10 @@ __global__ void __launch_bounds__(256) k_dct_fwd_fast(int32_t* __restrict__ word
 // inverse runs the same steps backwards.  The FFT itself is the radix-2 decimation-in-time
 // network on bit-reversed input, but three stages at a time: a thread keeps 8 points in
 // registers, so the data passes through shared memory ceil(lg M / 3) times instead of lg M
-// times.  Shared memory is padded by one point per 8 (16-byte points: 8 cover all 32 banks), which
-// keeps the stride-8 accesses of the first pass conflict-free.
-__device__ __forceinline__ uint32_t fpad(uint32_t i) { return i + (i >> 3); }
+// times.  Shared memory is padded by one point per 8 and one more per 64 (16-byte points: 8 cover
+// all 32 banks), which keeps the stride-8 accesses of the first pass and the stride-M/32 stores
+// of the bit-reversed load conflict-free.
+__device__ __forceinline__ uint32_t fpad(uint32_t i) { return i + (i >> 3) + (i >> 6); }
 
 // R fused radix-2 DIT stages starting at butterfly half-width h.  tw = e^{-2 pi i j / n}, j < n/2.
 template <int R, bool INVERSE>
@@ -321,12 +322,54 @@ __device__ __forceinline__ void fft_pass(double2* x, uint32_t M, uint32_t h, uin
     }
 }
 
-// in-place M-point FFT (M = 2^lgm >= 8) of bit-reversed input at padded indices; natural-order output
-template <bool INVERSE>
-__device__ __forceinline__ void fft_fused(double2* x, uint32_t lgm, uint32_t lgn, const double2* __restrict__ tw)
+// First three stages (half-widths 1, 2, 4) with the input taken straight from `load(p)` (natural
+// index p) instead of a bit-reversed copy in shared memory: thread t owns the butterfly whose 8
+// inputs are p = t + q M/8, so consecutive lanes load consecutive p; all twiddles of these stages
+// are multiples of pi/4.  Results land at the bit-reversed-order positions 8 brev(t) + q.
+template <bool INVERSE, class Load>
+__device__ __forceinline__ void fft_first_pass(double2* x, uint32_t lgm, Load load)
+{
+    const uint32_t G = 1u << (lgm - 3);
+    constexpr double kS = 0.70710678118654752440;
+    for (uint32_t t = threadIdx.x; t < G; t += blockDim.x) {
+        double2 a[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = load(t + (uint32_t)(((q & 1) << 2) | (q & 2) | (q >> 2)) * G);
+#pragma unroll
+        for (int st = 0; st < 3; ++st) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q & (1 << st)) continue;
+                const int r8 = (q & ((1 << st) - 1)) * (4 >> st);  // twiddle e^{-+ i pi r8 / 4}
+                const double2 u = a[q], v = a[q + (1 << st)];
+                double2 m = v;
+                if (!INVERSE) {
+                    if (r8 == 1) m = make_double2((v.x + v.y) * kS, (v.y - v.x) * kS);
+                    if (r8 == 2) m = make_double2(v.y, -v.x);
+                    if (r8 == 3) m = make_double2((v.y - v.x) * kS, -(v.x + v.y) * kS);
+                } else {
+                    if (r8 == 1) m = make_double2((v.x - v.y) * kS, (v.x + v.y) * kS);
+                    if (r8 == 2) m = make_double2(-v.y, v.x);
+                    if (r8 == 3) m = make_double2(-(v.x + v.y) * kS, (v.x - v.y) * kS);
+                }
+                a[q] = make_double2(u.x + m.x, u.y + m.y);
+                a[q + (1 << st)] = make_double2(u.x - m.x, u.y - m.y);
+            }
+        }
+        const uint32_t base = lgm > 3 ? (__brev(t) >> (32 - (lgm - 3))) << 3 : 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[fpad(base + (uint32_t)q)] = a[q];
+    }
+    __syncthreads();
+}
+
+// M-point FFT (M = 2^lgm >= 8): input through `load(p)`, natural-order output in x at padded indices
+template <bool INVERSE, class Load>
+__device__ __forceinline__ void fft_fused(double2* x, uint32_t lgm, uint32_t lgn, const double2* __restrict__ tw, Load load)
 {
     const uint32_t M = 1u << lgm;
-    uint32_t h = 1, left = lgm;
+    fft_first_pass<INVERSE>(x, lgm, load);
+    uint32_t h = 8, left = lgm - 3;
     while (left >= 3) {
         fft_pass<3, INVERSE>(x, M, h, lgn, tw);
         __syncthreads();
@@ -356,13 +399,11 @@ __global__ void __launch_bounds__(256, 4) k_dct_fwd_half(int32_t* __restrict__ w
     const int32_t mean = reference_mean(sums[(size_t)f * s.ch + c], n);
     int32_t* w = words + (size_t)f * s.N + (size_t)c * n;
     if (threadIdx.x == 0) store_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c, mean);
-    for (uint32_t p = threadIdx.x; p < M; p += blockDim.x) {
+    fft_fused<false>(xs, lgm, lgn, tw, [&](uint32_t p) {
         const int32_t re = (int32_t)((uint32_t)w[makhoul_src(2u * p, n)] - (uint32_t)mean);
         const int32_t im = (int32_t)((uint32_t)w[makhoul_src(2u * p + 1u, n)] - (uint32_t)mean);
-        xs[fpad(__brev(p) >> (32 - lgm))] = make_double2((double)re, (double)im);
-    }
-    __syncthreads();
-    fft_fused<false>(xs, lgm, lgn, tw);
+        return make_double2((double)re, (double)im);
+    });
     // V[k] = E[k] + e^{-2 pi i k/n} O[k], E = (Z[k] + conj Z[M-k]) / 2, O = (Z[k] - conj Z[M-k]) / 2i;
     // V[n-k] = conj V[k];  X[k] = Re(post[k] V[k])
     const double ratio1 = sqrt(2.0 / (double)(int)n) / 128.0;  // dct.cpp:84 (quality = 128)
@@ -401,16 +442,14 @@ __global__ void __launch_bounds__(256, 4) k_dct_inv_half(int32_t* __restrict__ w
         const double2 p = __ldg(post + k);  // conj(p) * (a - i b) / 2
         return make_double2(0.5 * (p.x * a - p.y * b), -0.5 * (p.x * b + p.y * a));
     };
-    for (uint32_t k = threadIdx.x; k < M; k += blockDim.x) {
+    fft_fused<true>(xs, lgm, lgn, tw, [&](uint32_t k) {
         const double2 Uk = U(k), Um = U(M - k);
         const double ax = Uk.x + Um.x, ay = Uk.y - Um.y;   // U[k] + conj U[M-k]
         const double dx = Uk.x - Um.x, dy = Uk.y + Um.y;   // U[k] - conj U[M-k]
         const double2 t = __ldg(tw + k);                    // times conj(t)
         const double bx = dx * t.x + dy * t.y, by = dy * t.x - dx * t.y;
-        xs[fpad(__brev(k) >> (32 - lgm))] = make_double2(ax - by, ay + bx);
-    }
-    __syncthreads();
-    fft_fused<true>(xs, lgm, lgn, tw);
+        return make_double2(ax - by, ay + bx);
+    });
     const int32_t mean = load_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c);
     const double scale = sqrt(2.0 / (double)(int)n) * 128.0;  // dct.cpp:97
     for (uint32_t p = threadIdx.x; p < M; p += blockDim.x) {
@@ -496,7 +535,7 @@ __global__ void __launch_bounds__(256) k_dct_inv_direct(int32_t* __restrict__ wo
 }
 
 // ---- host side ----------------------------------------------------------------------------
-inline uint32_t fpad_host(uint32_t m) { return m + (m >> 3) + 1; }
+inline uint32_t fpad_host(uint32_t m) { return m + (m >> 3) + (m >> 6) + 2; }
 inline bool dct_use_direct(const rspt_gpu_packer* p) { return p->dct_direct; }
 
 // decided once, when the handle is created: non-power-of-two lengths need the direct path,

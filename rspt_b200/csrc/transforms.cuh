@@ -700,6 +700,26 @@ __global__ void __launch_bounds__(256) k_words_stencil_planes(const int32_t* __r
     const uint32_t f = blockIdx.x / chunks, cidx = blockIdx.x % chunks;
     const int32_t* w = words + (size_t)f * s.N;
     uint8_t* out = planes + (size_t)f * s.nb_alloc * s.plane_stride;
+    if ((s.N & 3u) == 0u) {
+        // four consecutive elements per thread: one 128-bit load, the stencil in registers, a 4x4
+        // byte transpose (PRMT) and one 32-bit store per plane
+        const uint32_t i = cidx * 1024u + threadIdx.x * 4u;
+        if (i >= s.N) return;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + i));
+        const uint32_t xm1 = i ? (uint32_t)__ldg(w + i - 1) : 0u, xm2 = i ? (uint32_t)__ldg(w + i - 2) : 0u;
+        const uint32_t dm = i ? xm1 - xm2 - 128u : 0u;
+        const uint32_t d0 = v.x - xm1 - 128u, d1 = v.y - v.x - 128u, d2 = v.z - v.y - 128u, d3 = v.w - v.z - 128u;
+        const uint32_t y0 = d0 ^ dm, y1 = d1 ^ d0, y2 = d2 ^ d1, y3 = d3 ^ d2;
+        const uint32_t a = __byte_perm(y0, y1, 0x5140), b = __byte_perm(y2, y3, 0x5140);
+        *reinterpret_cast<uint32_t*>(out + i) = __byte_perm(a, b, 0x5410);
+        if (s.nb_alloc > 1) *reinterpret_cast<uint32_t*>(out + (size_t)s.plane_stride + i) = __byte_perm(a, b, 0x7632);
+        if (s.nb_alloc > 2) {
+            const uint32_t c = __byte_perm(y0, y1, 0x7362), d = __byte_perm(y2, y3, 0x7362);
+            *reinterpret_cast<uint32_t*>(out + 2 * (size_t)s.plane_stride + i) = __byte_perm(c, d, 0x5410);
+            if (s.nb_alloc > 3) *reinterpret_cast<uint32_t*>(out + 3 * (size_t)s.plane_stride + i) = __byte_perm(c, d, 0x7632);
+        }
+        return;
+    }
     for (uint32_t i = cidx * 1024u + threadIdx.x; i < min(s.N, (cidx + 1) * 1024u); i += blockDim.x) {
         const uint32_t x0 = (uint32_t)w[i], x1 = i >= 1 ? (uint32_t)w[i - 1] : 0u, x2 = i >= 2 ? (uint32_t)w[i - 2] : 0u;
         const uint32_t d0 = x0 - x1 - 128u, d1 = i >= 1 ? x1 - x2 - 128u : 0u;
