@@ -164,24 +164,33 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
         if (so.sc_bit) {
             // decode index entries of the segment boundaries B in [rs, cur], B < n: at B == rs
             // the entry's first token starts; later boundaries lie inside the zero run and
-            // resume at the literal.  The first boundary is written by the entry's own lane,
-            // the rest of a long run by the whole warp.
-            const uint32_t B0 = (rs + kSegBytes - 1u) & ~(uint32_t)(kSegBytes - 1);
-            const bool has = live && B0 <= cur && B0 < n;
-            if (has) {
-                so.sc_bit[(size_t)blk * kMaxSegs + B0 / kSegBytes] = B0 == rs ? o0 : o_lit;
-                so.sc_skip[(size_t)blk * kMaxSegs + B0 / kSegBytes] = (uint16_t)(B0 == rs ? 0u : cur - B0);
+            // resume at the literal.  Up to 8 boundaries are written by the entry's own lane (the
+            // gaps between the bursts of a sparse plane span a few segments), the rest of a very
+            // long run by the whole warp.
+            uint32_t* my_bit = so.sc_bit + (size_t)blk * kMaxSegs;
+            uint16_t* my_skip = so.sc_skip + (size_t)blk * kMaxSegs;
+            uint32_t B = (rs + kSegBytes - 1u) & ~(uint32_t)(kSegBytes - 1);
+            const uint32_t lim = live ? min(cur, n - 1u) : 0u;  // last position a boundary may take
+            if (!live) B = 1u;                                   // nothing to write
+            if (B <= lim && B == rs) {
+                my_bit[B / kSegBytes] = o0;
+                my_skip[B / kSegBytes] = 0;
+                B += kSegBytes;
             }
-            const uint32_t lim = min(cur, n - 1u);  // last position a boundary may take
-            uint32_t more = __ballot_sync(0xFFFFFFFFu, has && B0 + kSegBytes <= lim);
+#pragma unroll 1
+            for (int j = 0; j < 8 && B <= lim; ++j, B += kSegBytes) {
+                my_bit[B / kSegBytes] = o_lit;
+                my_skip[B / kSegBytes] = (uint16_t)(cur - B);
+            }
+            uint32_t more = __ballot_sync(0xFFFFFFFFu, B <= lim);
             while (more) {
                 const uint32_t q = __ffs(more) - 1u;
                 more &= more - 1u;
-                const uint32_t qB = __shfl_sync(0xFFFFFFFFu, B0, q) + kSegBytes, qcur = __shfl_sync(0xFFFFFFFFu, cur, q);
+                const uint32_t qB = __shfl_sync(0xFFFFFFFFu, B, q), qcur = __shfl_sync(0xFFFFFFFFu, cur, q);
                 const uint32_t qlim = __shfl_sync(0xFFFFFFFFu, lim, q), qo = __shfl_sync(0xFFFFFFFFu, o_lit, q);
-                for (uint32_t B = qB + lane * kSegBytes; B <= qlim; B += 32u * kSegBytes) {
-                    so.sc_bit[(size_t)blk * kMaxSegs + B / kSegBytes] = qo;
-                    so.sc_skip[(size_t)blk * kMaxSegs + B / kSegBytes] = (uint16_t)(qcur - B);
+                for (uint32_t Bq = qB + lane * kSegBytes; Bq <= qlim; Bq += 32u * kSegBytes) {
+                    my_bit[Bq / kSegBytes] = qo;
+                    my_skip[Bq / kSegBytes] = (uint16_t)(qcur - Bq);
                 }
             }
         }

@@ -17,9 +17,16 @@ for r in data:
     name = r[hdr.index("Kernel Name")]
     for k, st in stage.items():
         if k in name:
-            res[st] = {"kernel": name.split("(")[0].replace("void ", ""),
-                       "dram_bytes_per_launch": num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"),
-                       "dram_read": num(r, "dram__bytes_read.sum"), "dram_write": num(r, "dram__bytes_write.sum"),
-                       "duration_us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", ""))}
+            kn = name.split("(")[0].replace("void ", "").replace("rspt::", "")
+            e = {"kernel": kn, "dram_bytes_per_launch": num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"),
+                 "dram_read": num(r, "dram__bytes_read.sum"), "dram_write": num(r, "dram__bytes_write.sum"),
+                 "duration_us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", ""))}
+            if st in res and kn not in res[st]["kernel"].split(" + "):
+                # a stage made of several kernels (encode = k_hzr_encode_sparse + k_hzr_encode): add them up
+                for key in ("dram_bytes_per_launch", "dram_read", "dram_write", "duration_us"):
+                    e[key] += res[st][key]
+                e["kernel"] = res[st]["kernel"] + " + " + kn
+            res[st] = e
+            break
 json.dump({"source": rep.split("/")[-1], "frames_per_launch": frames, "kernels": res}, open(out, "w"), indent=1)
 print(json.dumps(res, indent=1))
