@@ -425,7 +425,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--cpu-threads", type=int, default=0)
-    ap.add_argument("--cpu-frames-per-thread", type=int, default=16)
+    ap.add_argument("--cpu-frames-per-thread", type=int, default=64)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
