@@ -350,6 +350,27 @@ def run_ours(args):
     extras = {}
     if rank == 0 and world == 1 and not args.quick:
         extras["packers"] = other_packers(R, torch, args)
+        # the pre-filter step in front of the packers (rspt_test.cpp:116-136), device resident, in place
+        n5 = [1.00000000000, -3.14332095199, 3.70064088865, -1.97083923944, 0.41351972908]
+        d5 = [0.06722876941, 0.00000000000, -0.13445753881, 0.00000000000, 0.06722876941]
+        fir = (np.hanning(33) / np.hanning(33).sum()).tolist()
+        work = inputs[0].clone()
+        pf = {}
+        for name, fn in (("iir_bandpass_5", lambda: p.prefilter_iir(work, n5, d5, 2000)),
+                         ("fir_33", lambda: p.prefilter_fir(work, fir))):
+            fn()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(3):
+                fn()
+            f1.record()
+            torch.cuda.synchronize()
+            pf[name + "_raw_GBps"] = 3 * raw_step / (f0.elapsed_time(f1) * 1e-3) / 1e9
+        pf["note"] = ("bit-identical to i_filter; the IIR walks a frame's channels in sequence like the reference "
+                      "(one thread per frame, latency-bound: its time barely depends on the batch size)")
+        extras["prefilter"] = pf
+        del work
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(inputs[0][: min(F, 4096) * fb].cpu().numpy(), sh, args.cpu_budget)

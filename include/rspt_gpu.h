@@ -133,6 +133,19 @@ int rspt_gpu_compress_batch_host(rspt_gpu_packer* p, const uint8_t* h_src, size_
 int rspt_gpu_decompress_batch_host(rspt_gpu_packer* p, const uint8_t* h_src, const uint64_t* h_offsets,
                                    size_t n_frames, uint8_t* h_dst);
 
+/* Pre-filter step in front of the packers, in place on `n_frames` device-resident frames of the
+ * handle's shape: what the reference's pipeline does per frame with i_filter before packing
+ * (lib_rspt_test/rspt_test.cpp:116-136; lib_rspt/filter.h:23-89) -- native -> int32 matrix, ONE
+ * filter object walked over the channels (init_history_values(first sample, init_nr_samples), then
+ * filter_opt per sample, result truncated to int32), back to native.  Bit-identical to the reference.
+ *   iir: i_filter::new_iir(n, d, nr_coefficients), lib_filter/iir_filter.cpp:46-116; 2..5 coefficients
+ *   fir: i_filter::new_fir(kernel, kernel_size), lib_filter/fir_filter.cpp:26-68
+ * n / d / kernel are HOST arrays (a handful of doubles). */
+int rspt_gpu_prefilter_iir(rspt_gpu_packer* p, uint8_t* d_frames, size_t n_frames, const double* n,
+                           const double* d, int nr_coefficients, int init_nr_samples);
+int rspt_gpu_prefilter_fir(rspt_gpu_packer* p, uint8_t* d_frames, size_t n_frames, const double* kernel,
+                           int kernel_size);
+
 int rspt_gpu_sync(rspt_gpu_packer* p);
 const char* rspt_gpu_last_error(const rspt_gpu_packer* p);
 

@@ -92,6 +92,11 @@ def oracle_lib() -> C.CDLL:
         L.oracle_fwht.argtypes = [C.c_int, _vp, _vp]
         L.oracle_prdn.restype = C.c_double
         L.oracle_prdn.argtypes = [_u8p, _u8p, _sz, _sz, _sz]
+        _dp = C.POINTER(C.c_double)
+        L.oracle_prefilter_iir.restype = C.c_int
+        L.oracle_prefilter_iir.argtypes = [_u8p, _sz, _sz, _sz, _dp, _dp, C.c_int, C.c_int]
+        L.oracle_prefilter_fir.restype = C.c_int
+        L.oracle_prefilter_fir.argtypes = [_u8p, _sz, _sz, _sz, _dp, C.c_int]
         L.oracle_synth_ecg.argtypes = [_u8p, C.c_uint64, _sz, C.c_int, C.c_int, C.c_int,
                                        C.c_uint64, C.c_int32, C.c_int32]
         _oracle = L
@@ -125,6 +130,10 @@ def ref_lib() -> C.CDLL:
         L.ref_hzr_decode.argtypes = [_u8p, _sz, _u8p, _sz]
         L.ref_hzr_verify.restype = C.c_int
         L.ref_hzr_verify.argtypes = [_u8p, _sz, C.POINTER(_sz)]
+        _dp = C.POINTER(C.c_double)
+        if hasattr(L, "ref_prefilter_iir"):
+            L.ref_prefilter_iir.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int]
+            L.ref_prefilter_fir.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
         L.ref_crc32c.restype = C.c_uint32
         L.ref_crc32c.argtypes = [_u8p, _sz]
         _ref = L
@@ -321,6 +330,32 @@ def hzr_decode(comp, out_size: int, impl: str = "port"):
         rc = ref_lib().ref_hzr_decode(_ptr(c), n, _ptr(out), out_size)
         ok = rc == 1
     return out[:out_size].tobytes(), ok
+
+
+def prefilter_iir(frame, bps: int, ch: int, ns: int, n, d, init_nr_samples: int, impl: str = "port") -> np.ndarray:
+    """The pre-filter step of rspt_test.cpp:116-136 (IIR, iir_filter.cpp) on one native frame; returns the filtered frame."""
+    out = np.array(_as_u8(frame), dtype=np.uint8, copy=True)
+    na, da = np.ascontiguousarray(n, np.float64), np.ascontiguousarray(d, np.float64)
+    dp = C.POINTER(C.c_double)
+    if impl == "port":
+        rc = oracle_lib().oracle_prefilter_iir(_ptr(out), bps, ch, ns, na.ctypes.data_as(dp), da.ctypes.data_as(dp), len(na), init_nr_samples)
+        assert rc == 0
+    else:
+        ref_lib().ref_prefilter_iir(_ptr(out), bps, ch, ns, na.ctypes.data_as(dp), da.ctypes.data_as(dp), len(na), init_nr_samples)
+    return out
+
+
+def prefilter_fir(frame, bps: int, ch: int, ns: int, kernel, impl: str = "port") -> np.ndarray:
+    """The same step with a FIR filter (fir_filter.cpp)."""
+    out = np.array(_as_u8(frame), dtype=np.uint8, copy=True)
+    ka = np.ascontiguousarray(kernel, np.float64)
+    dp = C.POINTER(C.c_double)
+    if impl == "port":
+        rc = oracle_lib().oracle_prefilter_fir(_ptr(out), bps, ch, ns, ka.ctypes.data_as(dp), len(ka))
+        assert rc == 0
+    else:
+        ref_lib().ref_prefilter_fir(_ptr(out), bps, ch, ns, ka.ctypes.data_as(dp), len(ka))
+    return out
 
 
 def hzr_verify(comp, impl: str = "port") -> bool:

@@ -4,11 +4,16 @@
 // oracle/Makefile into oracle/_ref/libref.so).  It exposes the reference's own
 // i_signal_packer factories (lib_rspt/signal_packer.h:29-73) and the vendored hzr codec
 // (lib_rspt/lib_hzr/libhzr.h) to ctypes so that tests and bench.py --impl reference can
-// run the real thing.  Nothing here restates any algorithm.
+// run the real thing.  Nothing here restates any algorithm (the pre-filter helper repeats the
+// reference test harness's own calling sequence around i_filter).
 #include <cstddef>
 #include <cstdint>
 #include "signal_packer.h"
 #include "lib_hzr/libhzr.h"
+#include <vector>
+using namespace std;  // filter.h names vector unqualified, like the reference's own sources that include it
+#include "filter.h"
+#include "lib_signalpacker/utils.h"
 extern "C" uint32_t _hzr_crc32(const void* data, size_t length);
 
 extern "C" {
@@ -94,5 +99,37 @@ int ref_hzr_verify(const void* in, size_t in_size, size_t* dec)
 }
 
 uint32_t ref_crc32c(const void* data, size_t n) { return _hzr_crc32(data, n); }
+
+// The reference's pre-filter step exactly as its test harness applies it before packing
+// (lib_rspt_test/rspt_test.cpp:116-136): native -> int32 matrix, ONE i_filter instance walked
+// over the channels (init_history_values(first sample, init_nr_samples), then filter_opt per
+// sample, result truncated to int32), int32 matrix -> native.  In place on one frame.
+static void prefilter(i_filter* filter, uint8_t* frame, int bps, int ch, int ns, int init_nr_samples)
+{
+    std::vector<int32_t> buf((size_t)ch * ns);
+    std::vector<int32_t*> rows(ch);
+    for (int j = 0; j < ch; ++j) rows[j] = buf.data() + (size_t)j * ns;
+    convert_native_to_i32(rows.data(), frame, ns, ch, bps, false);
+    for (int j = 0; j < ch; ++j) {
+        filter->init_history_values(rows[j][0], init_nr_samples);
+        for (int i = 0; i < ns; ++i) rows[j][i] = filter->filter_opt(rows[j][i]);
+    }
+    convert_i32_to_native(frame, rows.data(), ns, ch, bps, false);
+}
+
+void ref_prefilter_iir(uint8_t* frame, int bps, int ch, int ns, const double* n, const double* d, int nr_coefficients,
+                       int init_nr_samples)
+{
+    i_filter* f = i_filter::new_iir(n, d, (size_t)nr_coefficients);
+    prefilter(f, frame, bps, ch, ns, init_nr_samples);
+    i_filter::delete_iir(f);
+}
+
+void ref_prefilter_fir(uint8_t* frame, int bps, int ch, int ns, const double* kernel, int kernel_size)
+{
+    i_filter* f = i_filter::new_fir(kernel, (size_t)kernel_size);
+    prefilter(f, frame, bps, ch, ns, kernel_size);
+    i_filter::delete_fir(f);
+}
 
 }  // extern "C"

@@ -924,3 +924,112 @@ double oracle_prdn(const uint8_t* orig, const uint8_t* dec, size_t bps, size_t c
     free(b);
     return sqrt(mse / den) * 100.0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* pre-filter (lib_filter/iir_filter.cpp, fir_filter.cpp, as driven by rspt_test.cpp:116-136)  */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    double x[5], y[5], n[5], d[5];
+    int nc;
+} iir_state;
+
+static void iir_shift(iir_state* f, double x)
+{
+    /* iir_filter.cpp:60-65 / :77-82 */
+    for (int i = f->nc - 1; i > 0; --i) {
+        f->x[i] = f->x[i - 1];
+        f->y[i] = f->y[i - 1];
+    }
+    f->x[0] = x;
+}
+
+/* iir_filter::filter, iir_filter.cpp:58-73: the d and n terms alternate */
+static double iir_filter_generic(iir_state* f, double x)
+{
+    iir_shift(f, x);
+    double y = f->d[0] * f->x[0];
+    for (int i = 1; i < f->nc; ++i) {
+        y += f->d[i] * f->x[i];
+        y -= f->n[i] * f->y[i];
+    }
+    f->y[0] = y;
+    return y;
+}
+
+/* iir_filter::filter_opt, iir_filter.cpp:75-103 with rolling_iir_filter_N_ :26-44: all d terms
+ * first, then the n terms, left to right */
+static double iir_filter_opt(iir_state* f, double x)
+{
+    iir_shift(f, x);
+    double y = f->d[0] * f->x[0];
+    for (int i = 1; i < f->nc; ++i)
+        y = y + f->d[i] * f->x[i];
+    for (int i = 1; i < f->nc; ++i)
+        y = y - f->n[i] * f->y[i];
+    f->y[0] = y;
+    return y;
+}
+
+int oracle_prefilter_iir(uint8_t* frame, size_t bps, size_t ch, size_t ns, const double* n, const double* d,
+                         int nr_coefficients, int init_nr_samples)
+{
+    if (!frame || !n || !d || nr_coefficients < 2 || nr_coefficients > 5 || bps < 1 || bps > 4)
+        return 1;
+    int32_t* w = (int32_t*)malloc(ch * ns * sizeof(int32_t));
+    if (!w)
+        return 1;
+    native_to_words(frame, w, bps, ch, ns);
+    iir_state f;
+    memset(&f, 0, sizeof f);
+    f.nc = nr_coefficients;
+    memcpy(f.n, n, (size_t)nr_coefficients * sizeof(double));
+    memcpy(f.d, d, (size_t)nr_coefficients * sizeof(double));
+    for (size_t j = 0; j < ch; ++j) {
+        int32_t* row = w + j * ns;
+        /* init_history_values, iir_filter.cpp:105-109: 4 * nr_samples calls of filter(x); the state
+         * of the previous channel is NOT cleared (one object for all channels, rspt_test.cpp:127-133) */
+        const double x0 = (double)row[0];
+        for (int i = 0; i < 4 * init_nr_samples; ++i)
+            iir_filter_generic(&f, x0);
+        for (size_t i = 0; i < ns; ++i)
+            row[i] = (int32_t)iir_filter_opt(&f, (double)row[i]);   /* rspt_test.cpp:132 */
+    }
+    words_to_native(w, frame, bps, ch, ns);
+    free(w);
+    return 0;
+}
+
+int oracle_prefilter_fir(uint8_t* frame, size_t bps, size_t ch, size_t ns, const double* kernel, int kernel_size)
+{
+    if (!frame || !kernel || kernel_size < 1 || bps < 1 || bps > 4)
+        return 1;
+    const size_t K = (size_t)kernel_size;
+    int32_t* w = (int32_t*)malloc(ch * ns * sizeof(int32_t));
+    double* ring = (double*)malloc(K * sizeof(double));
+    if (!w || !ring) {
+        free(w);
+        free(ring);
+        return 1;
+    }
+    native_to_words(frame, w, bps, ch, ns);
+    for (size_t j = 0; j < ch; ++j) {
+        int32_t* row = w + j * ns;
+        /* init_history_values, fir_filter.cpp:58-62: kernel_size calls of filter(x) leave the ring
+         * holding kernel_size copies of x, whatever it held before (:37-46) */
+        for (size_t t = 0; t < K; ++t)
+            ring[t] = (double)row[0];
+        for (size_t i = 0; i < ns; ++i) {
+            /* filter_opt, fir_filter.cpp:48-56: push back, pop front, dot product oldest first */
+            memmove(ring, ring + 1, (K - 1) * sizeof(double));
+            ring[K - 1] = (double)row[i];
+            double y = 0;
+            for (size_t t = 0; t < K; ++t)
+                y += ring[t] * kernel[t];
+            row[i] = (int32_t)y;
+        }
+    }
+    words_to_native(w, frame, bps, ch, ns);
+    free(w);
+    free(ring);
+    return 0;
+}

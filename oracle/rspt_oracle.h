@@ -75,6 +75,14 @@ void oracle_fwht(int n, const int32_t* src, int32_t* dst);              /* lib_f
 /* PRDN as printed by lib_rspt_test/rspt_test.cpp:98-111 (computed in double throughout) */
 double oracle_prdn(const uint8_t* orig, const uint8_t* dec, size_t bps, size_t ch, size_t ns);
 
+/* Pre-filter step in front of the packers, in place on one native frame, as the reference's test
+ * harness applies it (lib_rspt_test/rspt_test.cpp:116-136): one filter object walked over the
+ * channels, init_history_values(first sample), filter_opt per sample, truncation to int32.
+ * IIR: lib_filter/iir_filter.cpp:46-116 (2..5 coefficients); FIR: lib_filter/fir_filter.cpp:26-68. */
+int oracle_prefilter_iir(uint8_t* frame, size_t bps, size_t ch, size_t ns, const double* n, const double* d,
+                         int nr_coefficients, int init_nr_samples);
+int oracle_prefilter_fir(uint8_t* frame, size_t bps, size_t ch, size_t ns, const double* kernel, int kernel_size);
+
 #ifdef __cplusplus
 }
 #endif

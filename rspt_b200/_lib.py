@@ -22,6 +22,7 @@ EXPORTS = [
     "rspt_gpu_get_counters", "rspt_gpu_debug_planes", "rspt_gpu_debug_hzr_tables", "rspt_gpu_crc32c",
     "rspt_gpu_synth_ecg", "rspt_gpu_prdn_terms", "rspt_gpu_rebase_offsets",
     "rspt_gpu_set_stage_timing", "rspt_gpu_get_stage_times", "rspt_gpu_verify_batch", "rspt_gpu_build_index",
+    "rspt_gpu_prefilter_iir", "rspt_gpu_prefilter_fir",
 ]
 
 
@@ -62,6 +63,11 @@ def lib() -> C.CDLL:
     L.rspt_gpu_compress_batch.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp]
     L.rspt_gpu_decompress_batch.restype = C.c_int
     L.rspt_gpu_decompress_batch.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
+    dp = C.POINTER(C.c_double)
+    L.rspt_gpu_prefilter_iir.restype = C.c_int
+    L.rspt_gpu_prefilter_iir.argtypes = [vp, vp, sz, dp, dp, C.c_int, C.c_int]
+    L.rspt_gpu_prefilter_fir.restype = C.c_int
+    L.rspt_gpu_prefilter_fir.argtypes = [vp, vp, sz, dp, C.c_int]
     L.rspt_gpu_build_index.restype = C.c_int
     L.rspt_gpu_build_index.argtypes = [vp, vp, vp, sz, vp, vp, vp]
     L.rspt_gpu_verify_batch.restype = C.c_int

@@ -58,6 +58,8 @@ struct rspt_gpu_packer {
     uint8_t* d_dec_nb;     // per-frame plane count used by the last decompress
     int32_t* d_status_tmp;
     void* d_auto_index;    // decode index built here for streams that came without one (lazy)
+    double* d_fir;         // FIR kernel coefficients of the last rspt_gpu_prefilter_fir call (lazy)
+    size_t fir_cap;
     // transform constants (dct twiddles)
     double2* d_twiddle;
     double2* d_post;

@@ -14,6 +14,7 @@
 #include "transforms.cuh"
 #include "hzr_decode.cuh"
 #include "spectral.cuh"
+#include "filters.cuh"
 
 using namespace rspt;
 
@@ -336,7 +337,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_fused, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
-                    p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index};
+                    p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p->h_pin) cudaFreeHost(p->h_pin);
@@ -630,6 +631,105 @@ extern "C" int rspt_gpu_verify_batch(rspt_gpu_packer* p, const uint8_t* d_src, c
     p->launches += 2;
     RSPT_CUDA_CHECK(cudaGetLastError());
     return RSPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-filter (the step in front of the packers in the reference's pipeline)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int ensure_words(rspt_gpu_packer* p)
+{
+    const Shape& s = p->s;
+    if (!p->d_words) RSPT_CUDA_CHECK(dalloc(p->d_words, p->max_batch * (size_t)s.N));
+    if (!p->d_sums) RSPT_CUDA_CHECK(dalloc(p->d_sums, p->max_batch * (size_t)s.ch));
+    return RSPT_OK;
+}
+
+int launch_words_to_raw(rspt_gpu_packer* p, uint8_t* d_dst, size_t F)
+{
+    const Shape& s = p->s;
+    const uint32_t tiles = ((uint32_t)s.ns + kPiece - 1) / kPiece;
+    const size_t tile_bytes = (size_t)kPiece * s.ch * s.bps + 48;
+    if (tile_bytes > 200 * 1024) return fail_arg(p, "too many channels");
+    switch (s.bps) {
+    case 1: cudaFuncSetAttribute(k_words_to_raw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
+    case 2: cudaFuncSetAttribute(k_words_to_raw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
+    case 3: cudaFuncSetAttribute(k_words_to_raw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
+    default: cudaFuncSetAttribute(k_words_to_raw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
+    }
+    SPECTRAL_BPS_SWITCH(k_words_to_raw, <<<(unsigned)(F * tiles), 256, tile_bytes, p->stream>>>(p->d_words, s, tiles, d_dst));
+    p->launches += 1;
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    return RSPT_OK;
+}
+
+}  // namespace
+
+extern "C" int rspt_gpu_prefilter_iir(rspt_gpu_packer* p, uint8_t* d_frames, size_t n_frames, const double* n, const double* d,
+                                      int nr_coefficients, int init_nr_samples)
+{
+    if (!p || !d_frames || !n || !d || init_nr_samples < 0) return RSPT_E_ARG;
+    if (nr_coefficients < 2 || nr_coefficients > 5) return fail_arg(p, "iir: 2..5 coefficients (iir_filter.cpp:84-100)");
+    if (n_frames == 0) return RSPT_OK;
+    if (n_frames > p->max_batch) return fail_arg(p, "n_frames exceeds max_batch_frames"), RSPT_E_CAPACITY;
+    DeviceGuard dg(p->device);
+    const Shape& s = p->s;
+    const size_t F = n_frames;
+    int rc = ensure_words(p);
+    if (rc) return rc;
+    const uint32_t tiles = ((uint32_t)s.ns + kPiece - 1) / kPiece;
+    const size_t tile_smem = (size_t)kPiece * s.ch * s.bps + 48;
+    if (tile_smem > 200 * 1024) return fail_arg(p, "too many channels");
+    switch (s.bps) {
+    case 1: cudaFuncSetAttribute(k_raw_to_words<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    case 2: cudaFuncSetAttribute(k_raw_to_words<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    case 3: cudaFuncSetAttribute(k_raw_to_words<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    default: cudaFuncSetAttribute(k_raw_to_words<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    }
+    SPECTRAL_BPS_SWITCH(k_raw_to_words, <<<(unsigned)(F * tiles), 256, tile_smem, p->stream>>>(d_frames, s, tiles, p->d_words, p->d_sums));
+    IirCoef c;
+    memset(&c, 0, sizeof c);
+    c.nc = nr_coefficients;
+    c.init_calls = 4 * init_nr_samples;
+    for (int i = 0; i < nr_coefficients; ++i) {
+        c.n[i] = n[i];
+        c.d[i] = d[i];
+    }
+    const unsigned grid = (unsigned)((F + 31) / 32);
+    switch (nr_coefficients) {
+    case 2: k_iir_frames<2><<<grid, 32, 0, p->stream>>>(p->d_words, s, (uint32_t)F, c); break;
+    case 3: k_iir_frames<3><<<grid, 32, 0, p->stream>>>(p->d_words, s, (uint32_t)F, c); break;
+    case 4: k_iir_frames<4><<<grid, 32, 0, p->stream>>>(p->d_words, s, (uint32_t)F, c); break;
+    default: k_iir_frames<5><<<grid, 32, 0, p->stream>>>(p->d_words, s, (uint32_t)F, c); break;
+    }
+    p->launches += 2;
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    return launch_words_to_raw(p, d_frames, F);
+}
+
+extern "C" int rspt_gpu_prefilter_fir(rspt_gpu_packer* p, uint8_t* d_frames, size_t n_frames, const double* kernel, int kernel_size)
+{
+    if (!p || !d_frames || !kernel || kernel_size < 1 || kernel_size > 65536) return RSPT_E_ARG;
+    if (n_frames == 0) return RSPT_OK;
+    if (n_frames > p->max_batch) return fail_arg(p, "n_frames exceeds max_batch_frames"), RSPT_E_CAPACITY;
+    DeviceGuard dg(p->device);
+    const Shape& s = p->s;
+    const size_t F = n_frames;
+    int rc = ensure_words(p);
+    if (rc) return rc;
+    if (p->fir_cap < (size_t)kernel_size) {
+        if (p->d_fir) cudaFree(p->d_fir);
+        p->d_fir = nullptr;
+        RSPT_CUDA_CHECK(dalloc(p->d_fir, (size_t)kernel_size));
+        p->fir_cap = (size_t)kernel_size;
+    }
+    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_fir, kernel, sizeof(double) * (size_t)kernel_size, cudaMemcpyHostToDevice, p->stream));
+    const size_t total = F * (size_t)s.N;
+    SPECTRAL_BPS_SWITCH(k_fir_frames, <<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(d_frames, s, (uint32_t)F, p->d_fir, kernel_size, p->d_words));
+    p->launches += 1;
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    return launch_words_to_raw(p, d_frames, F);
 }
 
 // ---------------------------------------------------------------------------------------------

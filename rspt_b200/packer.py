@@ -171,6 +171,23 @@ class SignalPacker:
         check(rc, self.h, "rspt_gpu_decompress_batch")
         return out
 
+    def prefilter_iir(self, frames: torch.Tensor, n, d, init_nr_samples: int) -> torch.Tensor:
+        """In place on device frames: the IIR pre-filter step of rspt_test.cpp:116-136 (i_filter::new_iir)."""
+        na, da = np.ascontiguousarray(n, np.float64), np.ascontiguousarray(d, np.float64)
+        dp = C.POINTER(C.c_double)
+        rc = self.L.rspt_gpu_prefilter_iir(self.h, frames.data_ptr(), frames.numel() // self.frame_bytes,
+                                           na.ctypes.data_as(dp), da.ctypes.data_as(dp), len(na), init_nr_samples)
+        check(rc, self.h, "rspt_gpu_prefilter_iir")
+        return frames
+
+    def prefilter_fir(self, frames: torch.Tensor, kernel) -> torch.Tensor:
+        """In place on device frames: the same step with i_filter::new_fir(kernel)."""
+        ka = np.ascontiguousarray(kernel, np.float64)
+        rc = self.L.rspt_gpu_prefilter_fir(self.h, frames.data_ptr(), frames.numel() // self.frame_bytes,
+                                           ka.ctypes.data_as(C.POINTER(C.c_double)), len(ka))
+        check(rc, self.h, "rspt_gpu_prefilter_fir")
+        return frames
+
     def build_index(self, batch: CompressedBatch, status: torch.Tensor | None = None) -> CompressedBatch:
         """Give a batch that came without a decode index (CPU-written frames) one, on the device."""
         n = batch.n_frames

@@ -273,6 +273,44 @@ def test_decodes_streams_from_cpu_reference(R, oracle):
             assert dec[i].tobytes() == cpu.decompress(f)[0]
 
 
+def test_prefilter_bit_exact(R, oracle):
+    """rspt_gpu_prefilter_iir / _fir (the step in front of the packers, rspt_test.cpp:116-136) give the
+    bytes the CPU side gives, for the reference's own band-pass and for shorter filters."""
+    from conftest import has_ref
+    impl = "reference" if has_ref() else "port"
+    n5 = [1.00000000000, -3.14332095199, 3.70064088865, -1.97083923944, 0.41351972908]
+    d5 = [0.06722876941, 0.00000000000, -0.13445753881, 0.00000000000, 0.06722876941]
+    rng = np.random.default_rng(9)
+    for bps, ch, ns, nfr in ((3, 12, 8192, 5), (4, 3, 1000, 3), (2, 5, 300, 4)):
+        raws = oracle.synth_ecg(21, nfr, bps, ch, ns, amplitude=20000 if bps >= 3 else 3000)
+        p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, bps, max_batch_frames=nfr)
+        # 2nd / 1st order Butterworth low-passes, and the band-pass cut to 3 taps (unstable: the output
+        # leaves the int32 range and must turn into 0x80000000 like the reference's x86 conversion)
+        filters = ((n5, d5, 2000), ([1.0, -1.1429805, 0.4128016], [0.06745527, 0.13491055, 0.06745527], 50),
+                   ([1.0, -0.5095254], [0.2452373, 0.2452373], 0), (n5[:3], d5[:3], 10))
+        for nn, dd, init in filters:
+            nc = len(nn)
+            got = p.prefilter_iir(to_dev(raws), nn, dd, init)
+            torch.cuda.synchronize()
+            got = got.cpu().numpy().reshape(nfr, -1)
+            for i in range(nfr):
+                want = oracle.prefilter_iir(raws[i], bps, ch, ns, nn, dd, init, impl)
+                assert np.array_equal(got[i], want), ("iir", bps, ch, ns, nc, i)
+        for K in (1, 9, 64):
+            k = rng.normal(size=K)
+            k /= np.abs(k).sum()
+            got = p.prefilter_fir(to_dev(raws), k)
+            torch.cuda.synchronize()
+            got = got.cpu().numpy().reshape(nfr, -1)
+            for i in range(nfr):
+                assert np.array_equal(got[i], oracle.prefilter_fir(raws[i], bps, ch, ns, k, impl)), ("fir", bps, ch, ns, K, i)
+        # filtered frames then go through the packer like any other input
+        f = p.prefilter_iir(to_dev(raws), n5, d5, 2000)
+        b = p.compress_batch(f)
+        assert torch.equal(p.decompress_batch(b), f)
+        p.close()
+
+
 def test_index_rebuilt_on_device_for_cpu_streams(R, oracle):
     """Frames written by the CPU reference carry no decode index: rspt_gpu_build_index rebuilds it by
     self-synchronising parallel decode, and decoding with it equals the CPU decode.  Crafted planes

@@ -113,3 +113,28 @@ def test_full_12ch_fixture_known_answers(oracle):
     for c in want["cases"]:
         comp = oracle.OraclePacker(c["kind"], 4, 12, 34199, c["nb"]).compress(data)
         assert len(comp) == c["len"] and "%08x" % zlib.crc32(comp) == c["crc32"]
+
+
+# the band-pass the reference's own pipeline uses (rspt_test.cpp:123-125) and two shorter filters
+IIR5_N = [1.00000000000, -3.14332095199, 3.70064088865, -1.97083923944, 0.41351972908]
+IIR5_D = [0.06722876941, 0.00000000000, -0.13445753881, 0.00000000000, 0.06722876941]
+
+
+@needs_ref
+def test_prefilter_restatement_equals_reference(oracle):
+    """oracle_prefilter_iir / _fir vs the compiled i_filter (lib_filter/*.cpp) driven the way
+    rspt_test.cpp:116-136 drives it: same bytes, including the state that leaks from one channel
+    into the next through the single filter object."""
+    rng = np.random.default_rng(3)
+    for bps, ch, ns in ((3, 12, 8192), (4, 3, 1000), (2, 2, 500), (1, 1, 64)):
+        raws = oracle.synth_ecg(5, 2, bps, ch, ns, amplitude=20000 if bps >= 3 else (3000 if bps == 2 else 50))
+        for f in raws:
+            for nc, init in ((5, 2000), (3, 100), (2, 0), (4, 7)):
+                n, d = IIR5_N[:nc], IIR5_D[:nc]
+                assert np.array_equal(oracle.prefilter_iir(f, bps, ch, ns, n, d, init, "port"),
+                                      oracle.prefilter_iir(f, bps, ch, ns, n, d, init, "reference")), (bps, ch, ns, nc)
+            for K in (1, 5, 31):
+                k = rng.normal(size=K)
+                k /= np.abs(k).sum()
+                assert np.array_equal(oracle.prefilter_fir(f, bps, ch, ns, k, "port"),
+                                      oracle.prefilter_fir(f, bps, ch, ns, k, "reference")), (bps, ch, ns, K)
