@@ -23,6 +23,7 @@ struct SparseOut {
     uint8_t* dst;         // output stream
     const uint64_t* offsets;   // byte offset of every frame in dst
     const uint32_t* blk_off;   // per block: offset of its header from the frame start
+    uint32_t stage_bytes;      // largest payload packed here (<= kSpStageBytes; smaller values only in tests)
     uint32_t* sc_bit;     // decode index (may be null)
     uint16_t* sc_skip;
     uint32_t* sc_codes;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
         return;
     }
     const uint32_t* glist = lists + (size_t)blk * kListCap;
-    if (bi.payload_len > kSpStageBytes) {
+    if (bi.payload_len > so.stage_bytes) {
         // too large for the staging here (rare): k_hzr_encode packs the block from the plane; it
         // needs the leading zero count of every 512-byte step, which the list gives directly
         const uint32_t nsteps = (n + kStepBytes - 1) / kStepBytes;

@@ -315,6 +315,12 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_hist, kHistSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode_sparse, kSparseSmem);
+    {
+        // test hook: a smaller staging limit sends listed blocks down the hand-over path to k_hzr_encode
+        const char* ev = getenv("RSPT_SPARSE_STAGE_BYTES");
+        const long v = ev ? atol(ev) : (long)kSpStageBytes;
+        p->sp_stage = (uint32_t)(v < 1 ? 1 : (v > (long)kSpStageBytes ? (long)kSpStageBytes : v));
+    }
     if (e == cudaSuccess) e = allow_smem(k_hzr_decode, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_verify, kDecodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_build_index, kDecodeSmem);
@@ -519,7 +525,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     {
         // sparse blocks from their lists, then everything else from the planes
         StageTimer t(p, RSPT_STAGE_ENCODE);
-        const SparseOut so{p->d_fused, d_dst, d_offsets, p->d_blk_off, sc_bit, sc_skip, sc_codes};
+        const SparseOut so{p->d_fused, d_dst, d_offsets, p->d_blk_off, p->sp_stage, sc_bit, sc_skip, sc_codes};
         k_hzr_encode_sparse<<<nblocks, kSpThreads, kSparseSmem, p->stream>>>(s, p->d_frame_nb, p->d_info, p->d_codes, p->d_tree, p->d_lists,
                                                                              p->d_list_n, p->d_step_lz, p->d_crc, so);
         k_hzr_encode<<<nblocks, kEncThreads, p->enc_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,

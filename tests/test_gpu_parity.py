@@ -273,6 +273,46 @@ def test_decodes_streams_from_cpu_reference(R, oracle):
             assert dec[i].tobytes() == cpu.decompress(f)[0]
 
 
+def test_listed_block_handed_to_general_encoder(R, oracle, monkeypatch):
+    """A sparse block whose payload exceeds k_hzr_encode_sparse's staging is handed to k_hzr_encode,
+    which needs the per-step leading-zero counts rebuilt from the list.  That size is out of reach of
+    real data (5120 entries x ~15 bits), so the limit is lowered for this test."""
+    monkeypatch.setenv("RSPT_SPARSE_STAGE_BYTES", "300")
+    bps, ch, ns, n = 3, 12, 8192, 6
+    raws = oracle.synth_ecg(40, n, bps, ch, ns)
+    raws[5] = 0
+    p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 3, max_batch_frames=n)
+    batch = p.compress_batch(to_dev(raws))
+    torch.cuda.synchronize()
+    offs = batch.offsets.cpu().numpy()
+    stream = batch.stream.cpu().numpy()
+    o = oracle.OraclePacker("xdelta_hzr", bps, ch, ns, 3)
+    for i in range(n):
+        assert stream[offs[i]:offs[i + 1]].tobytes() == o.compress(raws[i]), i
+    for use_sc in (True, False):
+        dec = p.decompress_batch(batch, use_sidecar=use_sc)
+        assert np.array_equal(dec.cpu().numpy().reshape(n, -1), raws)
+    # ragged single-channel planes: short last block, long zero runs across the step boundaries
+    rng = np.random.default_rng(8)
+    x = np.zeros((3, 70001), np.uint8)
+    for r in x:
+        idx = rng.choice(70001, 900, replace=False)
+        r[idx] = rng.integers(1, 256, 900)
+    # bursts: few chunks are touched (the density probe says "sparse") but the list overflows its 5120
+    # entries, so the block falls back to the dense scan half-way through
+    x[2] = 0
+    for c0 in rng.choice(4000, 450, replace=False):
+        x[2, c0 * 16:(c0 + 1) * 16] = rng.integers(1, 256, 16)
+    ph = R.SignalPacker.new_hzr(1, 1, 70001, max_batch_frames=3)
+    bh = ph.compress_batch(to_dev(x))
+    torch.cuda.synchronize()
+    oh = oracle.OraclePacker("hzr", 1, 1, 70001, 3)
+    so, st = bh.offsets.cpu().numpy(), bh.stream.cpu().numpy()
+    for i in range(3):
+        assert st[so[i]:so[i + 1]].tobytes() == oh.compress(x[i]), i
+    assert np.array_equal(ph.decompress_batch(bh).cpu().numpy().reshape(3, -1), x)
+
+
 def test_prefilter_bit_exact(R, oracle):
     """rspt_gpu_prefilter_iir / _fir (the step in front of the packers, rspt_test.cpp:116-136) give the
     bytes the CPU side gives, for the reference's own band-pass and for shorter filters."""
