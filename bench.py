@@ -367,10 +367,29 @@ def run_ours(args):
             f1.record()
             torch.cuda.synchronize()
             pf[name + "_raw_GBps"] = 3 * raw_step / (f0.elapsed_time(f1) * 1e-3) / 1e9
+        del work
+        # the IIR chain is serial per frame (latency-bound, one warp per 32 frames): a larger batch takes
+        # about the same time, so its throughput scales with the batch
+        try:
+            Fb = 8 * F
+            pb = R.SignalPacker.new_xdelta_hzr(sh["bps"], sh["ch"], sh["ns"], 3, max_batch_frames=Fb)
+            big = R.synth_ecg(first, Fb, **sh)
+            pb.prefilter_iir(big, n5, d5, 2000)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            pb.prefilter_iir(big, n5, d5, 2000)
+            f1.record()
+            torch.cuda.synchronize()
+            pf["iir_bandpass_5_raw_GBps_at_%d_frames" % Fb] = Fb * fb / (f0.elapsed_time(f1) * 1e-3) / 1e9
+            pb.close()
+            del big
+            torch.cuda.empty_cache()
+        except Exception as ex:  # out of memory on a shared box: the figure is optional
+            pf["iir_large_batch_error"] = str(ex)[:120]
         pf["note"] = ("bit-identical to i_filter; the IIR walks a frame's channels in sequence like the reference "
                       "(one thread per frame, latency-bound: its time barely depends on the batch size)")
         extras["prefilter"] = pf
-        del work
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(inputs[0][: min(F, 4096) * fb].cpu().numpy(), sh, args.cpu_budget)

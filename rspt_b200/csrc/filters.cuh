@@ -34,77 +34,114 @@ struct IirCoef {
     int init_calls;  // 4 * nr_samples (iir_filter.cpp:105-109)
 };
 
+// One warp per 32 frames, lane = frame.  The words of the 32 frames are moved through a 32 x 32
+// shared-memory tile (row = frame, padded to 33) so that global loads and stores are coalesced
+// 128-byte rows; the next tile is fetched into registers while the current one is filtered, so the
+// memory latency hides behind the serial chain.
 template <int NC>
 __global__ void __launch_bounds__(32) k_iir_frames(int32_t* __restrict__ words, Shape s, uint32_t n_frames, IirCoef c)
 {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= n_frames) return;
-    int32_t* w = words + (size_t)f * s.N;
+    __shared__ int32_t tile[32][33];
+    const uint32_t lane = threadIdx.x, f0 = blockIdx.x * 32u;
+    const uint32_t nf = min(32u, n_frames - f0);  // frames of this warp
+    const bool live = lane < nf;
+    int32_t* w0 = words + (size_t)f0 * s.N;
+    const uint32_t ns = (uint32_t)s.ns;
     double x[NC], y[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) x[i] = y[i] = 0.0;
-    for (int j = 0; j < s.ch; ++j) {
-        int32_t* row = w + (size_t)j * s.ns;
-        const double x0 = (double)row[0];
-        // init_history_values: iir_filter::filter (iir_filter.cpp:58-73), d and n terms alternating
-        for (int it = 0; it < c.init_calls; ++it) {
+    auto fetch = [&](int32_t (&v)[32], uint32_t j, uint32_t i0) {
 #pragma unroll
-            for (int i = NC - 1; i > 0; --i) {
-                x[i] = x[i - 1];
-                y[i] = y[i - 1];
+        for (uint32_t r = 0; r < 32; ++r)
+            v[r] = (r < nf && i0 + lane < ns) ? w0[(size_t)r * s.N + (size_t)j * ns + i0 + lane] : 0;
+    };
+    int32_t nxt[32];
+    fetch(nxt, 0, 0);
+    for (uint32_t j = 0; j < (uint32_t)s.ch; ++j) {
+        for (uint32_t i0 = 0; i0 < ns; i0 += 32) {
+#pragma unroll
+            for (uint32_t r = 0; r < 32; ++r) tile[r][lane] = nxt[r];
+            __syncwarp();
+            // the tile after this one (same channel, or the start of the next channel)
+            {
+                const uint32_t ni = i0 + 32 < ns ? i0 + 32 : 0u, nj = i0 + 32 < ns ? j : j + 1;
+                if (nj < (uint32_t)s.ch) fetch(nxt, nj, ni);
             }
-            x[0] = x0;
-            double acc = __dmul_rn(c.d[0], x[0]);
+            if (i0 == 0 && live) {
+                // init_history_values: iir_filter::filter (iir_filter.cpp:58-73), d and n terms alternating
+                const double x0 = (double)tile[lane][0];
+                for (int it = 0; it < c.init_calls; ++it) {
 #pragma unroll
-            for (int i = 1; i < NC; ++i) {
-                acc = __dadd_rn(acc, __dmul_rn(c.d[i], x[i]));
-                acc = __dsub_rn(acc, __dmul_rn(c.n[i], y[i]));
+                    for (int i = NC - 1; i > 0; --i) {
+                        x[i] = x[i - 1];
+                        y[i] = y[i - 1];
+                    }
+                    x[0] = x0;
+                    double acc = __dmul_rn(c.d[0], x[0]);
+#pragma unroll
+                    for (int i = 1; i < NC; ++i) {
+                        acc = __dadd_rn(acc, __dmul_rn(c.d[i], x[i]));
+                        acc = __dsub_rn(acc, __dmul_rn(c.n[i], y[i]));
+                    }
+                    y[0] = acc;
+                }
             }
-            y[0] = acc;
-        }
-        // filter_opt (iir_filter.cpp:75-103, rolling_iir_filter_N_ :26-44): d terms, then n terms
-        for (int i0 = 0; i0 < s.ns; ++i0) {
+            // filter_opt (iir_filter.cpp:75-103, rolling_iir_filter_N_ :26-44): d terms, then n terms
+            const uint32_t cnt = min(32u, ns - i0);
+            if (live) {
+                for (uint32_t k = 0; k < cnt; ++k) {
 #pragma unroll
-            for (int i = NC - 1; i > 0; --i) {
-                x[i] = x[i - 1];
-                y[i] = y[i - 1];
+                    for (int i = NC - 1; i > 0; --i) {
+                        x[i] = x[i - 1];
+                        y[i] = y[i - 1];
+                    }
+                    x[0] = (double)tile[lane][k];
+                    double acc = __dmul_rn(c.d[0], x[0]);
+#pragma unroll
+                    for (int i = 1; i < NC; ++i) acc = __dadd_rn(acc, __dmul_rn(c.d[i], x[i]));
+#pragma unroll
+                    for (int i = 1; i < NC; ++i) acc = __dsub_rn(acc, __dmul_rn(c.n[i], y[i]));
+                    y[0] = acc;
+                    tile[lane][k] = to_i32_x86(acc);  // rspt_test.cpp:132: double -> int32, toward zero
+                }
             }
-            x[0] = (double)row[i0];
-            double acc = __dmul_rn(c.d[0], x[0]);
+            __syncwarp();
 #pragma unroll
-            for (int i = 1; i < NC; ++i) acc = __dadd_rn(acc, __dmul_rn(c.d[i], x[i]));
-#pragma unroll
-            for (int i = 1; i < NC; ++i) acc = __dsub_rn(acc, __dmul_rn(c.n[i], y[i]));
-            y[0] = acc;
-            row[i0] = to_i32_x86(acc);  // rspt_test.cpp:132: double -> int32, toward zero
+            for (uint32_t r = 0; r < 32; ++r)
+                if (r < nf && i0 + lane < ns) w0[(size_t)r * s.N + (size_t)j * ns + i0 + lane] = tile[r][lane];
+            __syncwarp();
         }
     }
 }
 
-// one thread per output sample, reading the interleaved little-endian frame directly
-template <int BPS>
-__global__ void __launch_bounds__(256) k_fir_frames(const uint8_t* __restrict__ frames, Shape s, uint32_t n_frames,
-                                                     const double* __restrict__ kernel, int K, int32_t* __restrict__ words)
+// FIR over the int32 words ([frame][channel][sample], from k_raw_to_words): one CTA per 256 samples
+// of one channel, the tile and its kernel_size - 1 predecessors staged in shared memory as doubles,
+// the coefficients too; one thread per output sample.  Out of place (a tile's halo is its
+// neighbour's data).
+constexpr int kFirTile = 256;
+
+__global__ void __launch_bounds__(kFirTile) k_fir_words(const int32_t* __restrict__ in, Shape s, uint32_t tiles,
+                                                        const double* __restrict__ kernel, int K, int32_t* __restrict__ out)
 {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (size_t)n_frames * s.N) return;
-    const uint32_t f = (uint32_t)(e / s.N), r = (uint32_t)(e % s.N);
-    const int j = (int)(r / (uint32_t)s.ns), i = (int)(r % (uint32_t)s.ns);
-    const uint8_t* fr = frames + (size_t)f * s.frame_bytes;
-    auto sample = [&](int t) {
-        const uint8_t* q = fr + ((size_t)t * s.ch + j) * BPS;
-        uint32_t v = 0;
-#pragma unroll
-        for (int b = 0; b < BPS; ++b) v |= (uint32_t)q[b] << (8 * b);
-        return (double)((int32_t)(v << (32 - 8 * BPS)) >> (32 - 8 * BPS));
-    };
-    // ring[t] = x[i - (K - 1) + t], samples before the channel start = its first sample
-    double acc = 0.0;
-    for (int t = 0; t < K; ++t) {
-        const int src = i - (K - 1) + t;
-        acc = __dadd_rn(acc, __dmul_rn(sample(src < 0 ? 0 : src), kernel[t]));  // fir_filter.cpp:52-54
+    extern __shared__ __align__(16) double fir_sm[];  // [K] coefficients, then [kFirTile + K - 1] samples
+    double* kc = fir_sm;
+    double* xs = fir_sm + K;
+    const uint32_t t = blockIdx.x % tiles, row = blockIdx.x / tiles;  // row = frame * ch + channel
+    const int32_t* src = in + (size_t)row * s.ns;
+    const int i0 = (int)(t * kFirTile);
+    for (int q = (int)threadIdx.x; q < K; q += kFirTile) kc[q] = kernel[q];
+    for (int q = (int)threadIdx.x; q < kFirTile + K - 1; q += kFirTile) {
+        int src_i = i0 - (K - 1) + q;  // samples before the channel start = its first sample
+        src_i = src_i < 0 ? 0 : (src_i >= s.ns ? s.ns - 1 : src_i);
+        xs[q] = (double)src[src_i];
     }
-    words[e] = to_i32_x86(acc);
+    __syncthreads();
+    const int i = i0 + (int)threadIdx.x;
+    if (i >= s.ns) return;
+    double acc = 0.0;
+    for (int q = 0; q < K; ++q)
+        acc = __dadd_rn(acc, __dmul_rn(xs[threadIdx.x + q], kc[q]));  // fir_filter.cpp:52-54, oldest first
+    out[(size_t)row * s.ns + i] = to_i32_x86(acc);
 }
 
 }  // namespace rspt

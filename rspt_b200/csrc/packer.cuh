@@ -60,6 +60,7 @@ struct rspt_gpu_packer {
     void* d_auto_index;    // decode index built here for streams that came without one (lazy)
     double* d_fir;         // FIR kernel coefficients of the last rspt_gpu_prefilter_fir call (lazy)
     size_t fir_cap;
+    int32_t* d_words2;     // second word buffer (FIR is out of place), lazy
     uint32_t sp_stage;     // payload limit of k_hzr_encode_sparse (kSpStageBytes; lower only under RSPT_SPARSE_STAGE_BYTES)
     // transform constants (dct twiddles)
     double2* d_twiddle;

@@ -343,7 +343,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_fused, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
-                    p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir};
+                    p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p->h_pin) cudaFreeHost(p->h_pin);
@@ -652,7 +652,7 @@ int ensure_words(rspt_gpu_packer* p)
     return RSPT_OK;
 }
 
-int launch_words_to_raw(rspt_gpu_packer* p, uint8_t* d_dst, size_t F)
+int launch_words_to_raw(rspt_gpu_packer* p, const int32_t* d_words, uint8_t* d_dst, size_t F)
 {
     const Shape& s = p->s;
     const uint32_t tiles = ((uint32_t)s.ns + kPiece - 1) / kPiece;
@@ -664,7 +664,25 @@ int launch_words_to_raw(rspt_gpu_packer* p, uint8_t* d_dst, size_t F)
     case 3: cudaFuncSetAttribute(k_words_to_raw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
     default: cudaFuncSetAttribute(k_words_to_raw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
     }
-    SPECTRAL_BPS_SWITCH(k_words_to_raw, <<<(unsigned)(F * tiles), 256, tile_bytes, p->stream>>>(p->d_words, s, tiles, d_dst));
+    SPECTRAL_BPS_SWITCH(k_words_to_raw, <<<(unsigned)(F * tiles), 256, tile_bytes, p->stream>>>(d_words, s, tiles, d_dst));
+    p->launches += 1;
+    RSPT_CUDA_CHECK(cudaGetLastError());
+    return RSPT_OK;
+}
+
+int launch_raw_to_words(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
+{
+    const Shape& s = p->s;
+    const uint32_t tiles = ((uint32_t)s.ns + kPiece - 1) / kPiece;
+    const size_t tile_smem = (size_t)kPiece * s.ch * s.bps + 48;
+    if (tile_smem > 200 * 1024) return fail_arg(p, "too many channels");
+    switch (s.bps) {
+    case 1: cudaFuncSetAttribute(k_raw_to_words<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    case 2: cudaFuncSetAttribute(k_raw_to_words<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    case 3: cudaFuncSetAttribute(k_raw_to_words<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    default: cudaFuncSetAttribute(k_raw_to_words<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    }
+    SPECTRAL_BPS_SWITCH(k_raw_to_words, <<<(unsigned)(F * tiles), 256, tile_smem, p->stream>>>(d_src, s, tiles, p->d_words, p->d_sums));
     p->launches += 1;
     RSPT_CUDA_CHECK(cudaGetLastError());
     return RSPT_OK;
@@ -684,16 +702,8 @@ extern "C" int rspt_gpu_prefilter_iir(rspt_gpu_packer* p, uint8_t* d_frames, siz
     const size_t F = n_frames;
     int rc = ensure_words(p);
     if (rc) return rc;
-    const uint32_t tiles = ((uint32_t)s.ns + kPiece - 1) / kPiece;
-    const size_t tile_smem = (size_t)kPiece * s.ch * s.bps + 48;
-    if (tile_smem > 200 * 1024) return fail_arg(p, "too many channels");
-    switch (s.bps) {
-    case 1: cudaFuncSetAttribute(k_raw_to_words<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
-    case 2: cudaFuncSetAttribute(k_raw_to_words<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
-    case 3: cudaFuncSetAttribute(k_raw_to_words<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
-    default: cudaFuncSetAttribute(k_raw_to_words<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
-    }
-    SPECTRAL_BPS_SWITCH(k_raw_to_words, <<<(unsigned)(F * tiles), 256, tile_smem, p->stream>>>(d_frames, s, tiles, p->d_words, p->d_sums));
+    rc = launch_raw_to_words(p, d_frames, F);
+    if (rc) return rc;
     IirCoef c;
     memset(&c, 0, sizeof c);
     c.nc = nr_coefficients;
@@ -709,9 +719,9 @@ extern "C" int rspt_gpu_prefilter_iir(rspt_gpu_packer* p, uint8_t* d_frames, siz
     case 4: k_iir_frames<4><<<grid, 32, 0, p->stream>>>(p->d_words, s, (uint32_t)F, c); break;
     default: k_iir_frames<5><<<grid, 32, 0, p->stream>>>(p->d_words, s, (uint32_t)F, c); break;
     }
-    p->launches += 2;
+    p->launches += 1;
     RSPT_CUDA_CHECK(cudaGetLastError());
-    return launch_words_to_raw(p, d_frames, F);
+    return launch_words_to_raw(p, p->d_words, d_frames, F);
 }
 
 extern "C" int rspt_gpu_prefilter_fir(rspt_gpu_packer* p, uint8_t* d_frames, size_t n_frames, const double* kernel, int kernel_size)
@@ -731,11 +741,17 @@ extern "C" int rspt_gpu_prefilter_fir(rspt_gpu_packer* p, uint8_t* d_frames, siz
         p->fir_cap = (size_t)kernel_size;
     }
     RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_fir, kernel, sizeof(double) * (size_t)kernel_size, cudaMemcpyHostToDevice, p->stream));
-    const size_t total = F * (size_t)s.N;
-    SPECTRAL_BPS_SWITCH(k_fir_frames, <<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(d_frames, s, (uint32_t)F, p->d_fir, kernel_size, p->d_words));
+    if (!p->d_words2) RSPT_CUDA_CHECK(dalloc(p->d_words2, p->max_batch * (size_t)s.N));
+    rc = launch_raw_to_words(p, d_frames, F);
+    if (rc) return rc;
+    const size_t sm = (size_t)(2 * kernel_size + kFirTile) * sizeof(double);
+    if (sm > 200 * 1024) return fail_arg(p, "fir kernel too long for the shared-memory tile");
+    RSPT_CUDA_CHECK(allow_smem(k_fir_words, sm));
+    const uint32_t tiles = ((uint32_t)s.ns + kFirTile - 1) / kFirTile;
+    k_fir_words<<<(unsigned)(F * s.ch * tiles), kFirTile, sm, p->stream>>>(p->d_words, s, tiles, p->d_fir, kernel_size, p->d_words2);
     p->launches += 1;
     RSPT_CUDA_CHECK(cudaGetLastError());
-    return launch_words_to_raw(p, d_frames, F);
+    return launch_words_to_raw(p, p->d_words2, d_frames, F);
 }
 
 // ---------------------------------------------------------------------------------------------
