@@ -126,12 +126,16 @@ constexpr uint32_t kNoList = 0xFFFFFFFFu;           // list_n value of a block t
 constexpr size_t kHistSmem = (size_t)kListCap * 4;
 constexpr int kHistSteps = kMaxSteps / (kHistThreads / 32);      // steps per warp: 16
 
-__global__ void __launch_bounds__(kHistThreads, 4) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
+// Two launches per batch: PART 1 (sparse attempt: writes the list and the histogram, or marks the
+// block kNoList) and PART 2 (dense scan of the blocks marked kNoList).  The split lets each part
+// have the register budget and occupancy that suits it (the dense scan is issue-bound and gains
+// from 6 CTAs per SM; the sparse part keeps 16 mask/prefix registers per lane).
+template <int PART>
+__global__ void __launch_bounds__(kHistThreads, PART == 2 ? 8 : 5) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
                                                                const uint8_t* __restrict__ frame_nb,
                                                                uint32_t* __restrict__ hist,
                                                                uint16_t* __restrict__ step_lz,
-                                                               uint32_t* __restrict__ lists, uint32_t* __restrict__ list_n,
-                                                               int allow_list)
+                                                               uint32_t* __restrict__ lists, uint32_t* __restrict__ list_n)
 {
     extern __shared__ __align__(16) uint32_t s_list[];  // sparse list under construction
     __shared__ uint32_t s_lit[256];  // raw byte counts; [0] is scratch (zeros are tokenised as runs)
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(kHistThreads, 4) k_hzr_hist(const uint8_t* __r
     const uint32_t blk = blockIdx.x;
     blk_decode(s, blk, f, k, b);
     if (k >= frame_nb[f]) return;
+    if (PART == 2 && list_n[blk] != kNoList) return;
     const uint32_t n = blk_len(s, b);
     const uint8_t* src = blk_ptr(planes, s, f, k, b);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = 0;
@@ -153,8 +158,8 @@ __global__ void __launch_bounds__(kHistThreads, 4) k_hzr_hist(const uint8_t* __r
     const uint32_t s_lo = min(nsteps, wid * spw), s_hi = min(nsteps, s_lo + spw);
 
     // ---- sparse path
+    if (PART == 1) {
     do {
-        if (!allow_list) break;
         // density probe: the first chunk of every warp range (spread over the block)
         const Chunk probe = load_chunk(src, n, s_lo * kStepBytes + lane * 16u);
         const int dense_chunks = __syncthreads_count(__popc(probe.nz) >= 2);
@@ -245,6 +250,8 @@ __global__ void __launch_bounds__(kHistThreads, 4) k_hzr_hist(const uint8_t* __r
         return;
     } while (0);
     if (tid == 0) list_n[blk] = kNoList;
+    return;
+    }
     __syncthreads();
 
     // ---- dense blocks

@@ -313,7 +313,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ctr, 0, sizeof(Counters), p->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_nb_state, &s.nb_init, 4, cudaMemcpyHostToDevice, p->stream);
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
-    if (e == cudaSuccess) e = allow_smem(k_hzr_hist, kHistSmem);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_hist<1>, kHistSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode_sparse, kSparseSmem);
     {
         // test hook: a smaller staging limit sends listed blocks down the hand-over path to k_hzr_encode
@@ -510,7 +510,8 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     uint32_t* sc_codes = d_sidecar ? reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
     {
         StageTimer t(p, RSPT_STAGE_HIST);
-        k_hzr_hist<<<nblocks, kHistThreads, kHistSmem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n, 1);
+        k_hzr_hist<1><<<nblocks, kHistThreads, kHistSmem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
+        k_hzr_hist<2><<<nblocks, kHistThreads, 0, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
     }
     {
         StageTimer t(p, RSPT_STAGE_TREE);
@@ -532,7 +533,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
                                                                         p->d_codes, p->d_tree, p->d_step_lz, p->d_fused, d_offsets,
                                                                         p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip, sc_codes);
     }
-    p->launches += 6;
+    p->launches += 7;
     RSPT_CUDA_CHECK(cudaGetLastError());
     if (d_frame_nb) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_frame_nb, p->d_frame_nb, F, cudaMemcpyDeviceToDevice, p->stream));
     return RSPT_OK;
@@ -981,9 +982,10 @@ extern "C" int rspt_gpu_debug_hzr_tables(rspt_gpu_packer* p, const uint8_t* d_bl
     DeviceGuard dg(p->device);
     Shape s = p->s;
     s.N = (uint32_t)n; s.nblk = 1; s.nb_alloc = 1; s.plane_stride = (uint32_t)((n + 15) & ~(size_t)15);
-    k_hzr_hist<<<1, kHistThreads, kHistSmem, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n, 1);
+    k_hzr_hist<1><<<1, kHistThreads, kHistSmem, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
+    k_hzr_hist<2><<<1, kHistThreads, 0, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
     k_hzr_tree<<<1, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, 1, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
-    p->launches += 2;
+    p->launches += 3;
     RSPT_CUDA_CHECK(cudaGetLastError());
     if (d_hist) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_hist, p->d_hist, kNumSymbols * 4, cudaMemcpyDeviceToDevice, p->stream));
     if (d_codes) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_codes, p->d_codes, kNumSymbols * 4, cudaMemcpyDeviceToDevice, p->stream));
