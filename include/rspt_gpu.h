@@ -146,6 +146,25 @@ int rspt_gpu_prefilter_iir(rspt_gpu_packer* p, uint8_t* d_frames, size_t n_frame
 int rspt_gpu_prefilter_fir(rspt_gpu_packer* p, uint8_t* d_frames, size_t n_frames, const double* kernel,
                            int kernel_size);
 
+/* Streaming ingest: a packet ring in PINNED host memory in front of a packer, modelled on the
+ * reference's io_buffer (lib_ring_buffer/ring_buffers.h:150-201): one packet = one frame, the same
+ * single-producer / single-consumer protocol and slot states (0 free, 1 being filled, 2 filled,
+ * 3 consumed).  The producer (an acquisition thread) asks for the next address to fill exactly as with
+ * io_buffer::get_next_address_to_fill -- NULL means the ring is full; a packet counts as filled once the
+ * producer asks for the next one (:186-187), or when `flush` is set.  The consumer does not take the
+ * filled packets one by one (get_next_filled_address) but drains them in batches: every run of filled
+ * packets goes through the pipelined host-buffer path (H2D of chunk i+1, kernels of chunk i, D2H of chunk
+ * i-1) and the compressed frames are appended to h_dst.
+ *   h_offsets   [max frames of this drain + 1] offsets of the frames inside h_dst, starting at 0
+ *   *n_frames   in: capacity of h_offsets - 1 (frames to take at most); out: frames compressed
+ * The handle `p` must not be used for anything else while the ring exists. */
+typedef struct rspt_gpu_ingest rspt_gpu_ingest;
+int rspt_gpu_ingest_create(rspt_gpu_packer* p, size_t nr_max_packets, rspt_gpu_ingest** out);
+int rspt_gpu_ingest_destroy(rspt_gpu_ingest* g);
+uint8_t* rspt_gpu_ingest_next_address_to_fill(rspt_gpu_ingest* g);
+int rspt_gpu_ingest_drain(rspt_gpu_ingest* g, int flush, uint8_t* h_dst, size_t dst_capacity,
+                          uint64_t* h_offsets, size_t* n_frames);
+
 int rspt_gpu_sync(rspt_gpu_packer* p);
 const char* rspt_gpu_last_error(const rspt_gpu_packer* p);
 

@@ -23,6 +23,7 @@ EXPORTS = [
     "rspt_gpu_synth_ecg", "rspt_gpu_prdn_terms", "rspt_gpu_rebase_offsets",
     "rspt_gpu_set_stage_timing", "rspt_gpu_get_stage_times", "rspt_gpu_verify_batch", "rspt_gpu_build_index",
     "rspt_gpu_prefilter_iir", "rspt_gpu_prefilter_fir",
+    "rspt_gpu_ingest_create", "rspt_gpu_ingest_destroy", "rspt_gpu_ingest_next_address_to_fill", "rspt_gpu_ingest_drain",
 ]
 
 
@@ -68,6 +69,14 @@ def lib() -> C.CDLL:
     L.rspt_gpu_prefilter_iir.argtypes = [vp, vp, sz, dp, dp, C.c_int, C.c_int]
     L.rspt_gpu_prefilter_fir.restype = C.c_int
     L.rspt_gpu_prefilter_fir.argtypes = [vp, vp, sz, dp, C.c_int]
+    L.rspt_gpu_ingest_create.restype = C.c_int
+    L.rspt_gpu_ingest_create.argtypes = [vp, sz, C.POINTER(vp)]
+    L.rspt_gpu_ingest_destroy.restype = C.c_int
+    L.rspt_gpu_ingest_destroy.argtypes = [vp]
+    L.rspt_gpu_ingest_next_address_to_fill.restype = vp
+    L.rspt_gpu_ingest_next_address_to_fill.argtypes = [vp]
+    L.rspt_gpu_ingest_drain.restype = C.c_int
+    L.rspt_gpu_ingest_drain.argtypes = [vp, C.c_int, vp, sz, vp, C.POINTER(sz)]
     L.rspt_gpu_build_index.restype = C.c_int
     L.rspt_gpu_build_index.argtypes = [vp, vp, vp, sz, vp, vp, vp]
     L.rspt_gpu_verify_batch.restype = C.c_int

@@ -6,6 +6,7 @@
 
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -637,6 +638,106 @@ extern "C" int rspt_gpu_verify_batch(rspt_gpu_packer* p, const uint8_t* d_src, c
     k_hzr_verify<<<nblocks, kVerifyThreads, p->dec_smem, p->stream>>>(d_src, s, dec, p->d_crc, d_status, p->d_ctr);
     p->launches += 2;
     RSPT_CUDA_CHECK(cudaGetLastError());
+    return RSPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming ingest ring (io_buffer, lib_ring_buffer/ring_buffers.h:150-201, with pinned packets)
+// ---------------------------------------------------------------------------------------------
+struct rspt_gpu_ingest {
+    rspt_gpu_packer* p;
+    size_t packet_bytes, nr_max_packets;
+    uint8_t* buffer;                   // pinned, nr_max_packets * packet_bytes
+    std::atomic<uint8_t>* rw_states;   // 0 free, 1 being filled, 2 filled, 3 consumed
+    size_t it_read, it_write, it_write_last;
+};
+
+extern "C" int rspt_gpu_ingest_create(rspt_gpu_packer* p, size_t nr_max_packets, rspt_gpu_ingest** out)
+{
+    if (!p || !out || nr_max_packets < 2) return RSPT_E_ARG;
+    *out = nullptr;
+    DeviceGuard dg(p->device);
+    rspt_gpu_ingest* g = new (std::nothrow) rspt_gpu_ingest();
+    if (!g) return RSPT_E_ARG;
+    g->p = p;
+    g->packet_bytes = p->s.frame_bytes;
+    g->nr_max_packets = nr_max_packets;
+    g->it_read = g->it_write = g->it_write_last = 0;
+    g->buffer = nullptr;
+    g->rw_states = new (std::nothrow) std::atomic<uint8_t>[nr_max_packets];
+    if (!g->rw_states || cudaMallocHost(reinterpret_cast<void**>(&g->buffer), nr_max_packets * g->packet_bytes) != cudaSuccess) {
+        delete[] g->rw_states;
+        delete g;
+        return RSPT_E_CUDA;
+    }
+    for (size_t i = 0; i < nr_max_packets; ++i) g->rw_states[i].store(0, std::memory_order_relaxed);
+    *out = g;
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_ingest_destroy(rspt_gpu_ingest* g)
+{
+    if (!g) return RSPT_E_ARG;
+    DeviceGuard dg(g->p->device);
+    cudaStreamSynchronize(g->p->stream);
+    if (g->buffer) cudaFreeHost(g->buffer);
+    delete[] g->rw_states;
+    delete g;
+    return RSPT_OK;
+}
+
+// io_buffer::get_next_address_to_fill, ring_buffers.h:182-199 (producer side)
+extern "C" uint8_t* rspt_gpu_ingest_next_address_to_fill(rspt_gpu_ingest* g)
+{
+    if (!g) return nullptr;
+    const uint8_t st = g->rw_states[g->it_write].load(std::memory_order_acquire);
+    if (st != 0 && st != 3) return nullptr;
+    if (g->rw_states[g->it_write_last].load(std::memory_order_relaxed) == 1)
+        g->rw_states[g->it_write_last].store(2, std::memory_order_release);  // the previous packet is complete
+    uint8_t* res = g->buffer + g->it_write * g->packet_bytes;
+    g->rw_states[g->it_write].store(1, std::memory_order_relaxed);
+    g->it_write_last = g->it_write;
+    if (++g->it_write == g->nr_max_packets) g->it_write = 0;
+    return res;
+}
+
+// consumer side: what a loop over io_buffer::get_next_filled_address (:168-180) + compress would do,
+// in batches of contiguous filled packets
+extern "C" int rspt_gpu_ingest_drain(rspt_gpu_ingest* g, int flush, uint8_t* h_dst, size_t dst_capacity, uint64_t* h_offsets,
+                                     size_t* n_frames)
+{
+    if (!g || !h_dst || !h_offsets || !n_frames) return RSPT_E_ARG;
+    rspt_gpu_packer* p = g->p;
+    if (flush && g->rw_states[g->it_write_last].load(std::memory_order_relaxed) == 1)
+        g->rw_states[g->it_write_last].store(2, std::memory_order_release);  // only safe once the producer has stopped
+    const size_t want = *n_frames, maxc = rspt_gpu_max_compressed_size(p);
+    size_t done = 0;
+    uint64_t bytes = 0;
+    h_offsets[0] = 0;
+    while (done < want) {
+        // the run of filled packets that starts at it_read and does not wrap
+        size_t run = 0;
+        while (done + run < want && g->it_read + run < g->nr_max_packets && run < p->max_batch &&
+               g->rw_states[g->it_read + run].load(std::memory_order_acquire) == 2)
+            ++run;
+        if (run == 0) break;
+        if (dst_capacity - bytes < run * maxc) {
+            if (done == 0) return fail_arg(p, "dst_capacity too small for the filled packets"), RSPT_E_CAPACITY;
+            break;
+        }
+        const int rc = rspt_gpu_compress_batch_host(p, g->buffer + g->it_read * g->packet_bytes, run, h_dst + bytes,
+                                                    dst_capacity - bytes, h_offsets + done);
+        if (rc != RSPT_OK) return rc;
+        // compress_batch_host numbers its offsets from 0: rebase onto what this drain has written so far
+        const uint64_t chunk_bytes = h_offsets[done + run];
+        for (size_t i = 0; i <= run; ++i) h_offsets[done + i] += bytes;
+        bytes += chunk_bytes;
+        for (size_t i = 0; i < run; ++i) g->rw_states[g->it_read + i].store(3, std::memory_order_release);
+        g->it_read += run;
+        if (g->it_read == g->nr_max_packets) g->it_read = 0;
+        done += run;
+    }
+    *n_frames = done;
     return RSPT_OK;
 }
 

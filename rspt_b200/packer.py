@@ -262,6 +262,36 @@ class SignalPacker:
                 info.cpu().numpy().view(np.uint32))
 
 
+class IngestRing:
+    """Pinned-host packet ring in front of a packer (the reference's io_buffer, ring_buffers.h:150-201):
+    the producer writes frames into `next_packet()`, the consumer calls `drain()`."""
+
+    def __init__(self, packer: SignalPacker, nr_max_packets: int):
+        self.p = packer
+        self.L = packer.L
+        self.h = C.c_void_p()
+        check(self.L.rspt_gpu_ingest_create(packer.h, nr_max_packets, C.byref(self.h)), packer.h, "rspt_gpu_ingest_create")
+
+    def close(self):
+        if self.h:
+            self.L.rspt_gpu_ingest_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def next_packet(self):
+        """numpy view of the next packet to fill (frame_bytes bytes), or None when the ring is full."""
+        addr = self.L.rspt_gpu_ingest_next_address_to_fill(self.h)
+        if not addr:
+            return None
+        return np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_uint8)), shape=(self.p.frame_bytes,))
+
+    def drain(self, dst: np.ndarray, offsets: np.ndarray, max_frames: int | None = None, flush: bool = False) -> int:
+        """Compress the filled packets into dst; offsets[0..n] are filled in.  Returns n."""
+        n = C.c_size_t(offsets.size - 1 if max_frames is None else min(max_frames, offsets.size - 1))
+        rc = self.L.rspt_gpu_ingest_drain(self.h, int(flush), dst.ctypes.data, dst.size, offsets.ctypes.data, C.byref(n))
+        check(rc, self.p.h, "rspt_gpu_ingest_drain")
+        return int(n.value)
+
+
 def crc32c(data: np.ndarray) -> int:
     t = torch.from_numpy(np.array(data, dtype=np.uint8, copy=True)).cuda() if data.size else torch.zeros(1, dtype=torch.uint8, device="cuda")
     out = C.c_uint32(0)

@@ -313,6 +313,76 @@ def test_listed_block_handed_to_general_encoder(R, oracle, monkeypatch):
     assert np.array_equal(ph.decompress_batch(bh).cpu().numpy().reshape(3, -1), x)
 
 
+def test_ingest_ring_streams_frames_in_order(R, oracle):
+    """The pinned packet ring (io_buffer protocol, ring_buffers.h:150-201): a packet becomes visible to
+    the consumer when the producer asks for the next one, a full ring refuses, wrap-around keeps the frame
+    order, and every drained frame is byte-identical to the oracle's."""
+    bps, ch, ns, total, slots = 3, 4, 2048, 23, 6
+    raws = oracle.synth_ecg(77, total, bps, ch, ns)
+    p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 3, max_batch_frames=4)  # smaller than the ring: several batches per drain
+    ring = R.IngestRing(p, slots)
+    o = oracle.OraclePacker("xdelta_hzr", bps, ch, ns, 3)
+    dst = np.zeros(slots * p.max_compressed_size, np.uint8)
+    offs = np.zeros(slots + 1, np.uint64)
+    got = []
+    produced = 0
+
+    def take(flush=False):
+        n = ring.drain(dst, offs, flush=flush)
+        for i in range(n):
+            got.append(dst[int(offs[i]):int(offs[i + 1])].tobytes())
+        return n
+
+    # nothing filled yet; the first packet alone stays "being filled"
+    assert take() == 0
+    pk = ring.next_packet()
+    pk[:] = raws[produced]; produced += 1
+    assert take() == 0
+    while produced < total:
+        pk = ring.next_packet()
+        if pk is None:                 # ring full: the consumer has to run
+            assert take() >= 1
+            continue
+        pk[:] = raws[produced]; produced += 1
+        if produced % 5 == 0:
+            take()
+    take(flush=True)                   # the last packet is only released by flush
+    assert take(flush=True) == 0
+    assert len(got) == total
+    for i in range(total):
+        assert got[i] == o.compress(raws[i]), i
+    # the same with the producer on its own thread (single producer / single consumer, like io_buffer)
+    import threading
+    import time
+    got.clear()
+
+    def producer():
+        sent = 0
+        while sent < total:
+            pk2 = ring.next_packet()
+            if pk2 is None:
+                time.sleep(0.0005)
+                continue
+            pk2[:] = raws[sent]
+            sent += 1
+
+    th = threading.Thread(target=producer)
+    th.start()
+    deadline = time.time() + 60
+    while th.is_alive() and time.time() < deadline:
+        if take() == 0:
+            time.sleep(0.0005)
+    th.join(timeout=5)
+    assert not th.is_alive()
+    while take(flush=True):
+        pass
+    assert len(got) == total
+    for i in range(total):
+        assert got[i] == o.compress(raws[i]), i
+    ring.close()
+    p.close()
+
+
 def test_prefilter_bit_exact(R, oracle):
     """rspt_gpu_prefilter_iir / _fir (the step in front of the packers, rspt_test.cpp:116-136) give the
     bytes the CPU side gives, for the reference's own band-pass and for shorter filters."""
