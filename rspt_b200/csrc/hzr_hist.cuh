@@ -123,19 +123,25 @@ __device__ __forceinline__ void scatter_chunks(const Chunk& c, uint32_t off, uin
 // reading the plane again.  Blocks that are too dense for the list take the dense scan below.
 constexpr uint32_t kListCap = 5120;                 // entries of a block's sparse list
 constexpr uint32_t kNoList = 0xFFFFFFFFu;           // list_n value of a block that has no sparse list
+constexpr uint8_t kClassSparse = 0, kClassDense = 1;  // blk_class: which histogram launch (and tree launch) owns the block
 constexpr size_t kHistSmem = (size_t)kListCap * 4;
 constexpr int kHistSteps = kMaxSteps / (kHistThreads / 32);      // steps per warp: 16
 
-// Two launches per batch: PART 1 (sparse attempt: writes the list and the histogram, or marks the
-// block kNoList) and PART 2 (dense scan of the blocks marked kNoList).  The split lets each part
-// have the register budget and occupancy that suits it (the dense scan is issue-bound and gains
-// from 6 CTAs per SM; the sparse part keeps 16 mask/prefix registers per lane).
+// Two independent launches per batch, each over all blocks; the density probe (deterministic, the
+// same in both) assigns every block to exactly one of them and is recorded in blk_class:
+//   PART 1 takes the sparse-looking blocks (list + histogram; if the list overflows after all, the
+//          dense scan runs here too -- rare);
+//   PART 2 takes the dense-looking blocks (dense scan).
+// They run on two streams: the tree build of the dense class (long, latency-bound) then overlaps
+// with PART 1.  The split also lets the dense scan run at 8 CTAs per SM (30 registers) while the
+// sparse part keeps 16 mask/prefix registers per lane.
 template <int PART>
 __global__ void __launch_bounds__(kHistThreads, PART == 2 ? 8 : 5) k_hzr_hist(const uint8_t* __restrict__ planes, Shape s,
                                                                const uint8_t* __restrict__ frame_nb,
                                                                uint32_t* __restrict__ hist,
                                                                uint16_t* __restrict__ step_lz,
-                                                               uint32_t* __restrict__ lists, uint32_t* __restrict__ list_n)
+                                                               uint32_t* __restrict__ lists, uint32_t* __restrict__ list_n,
+                                                               uint8_t* __restrict__ blk_class)
 {
     extern __shared__ __align__(16) uint32_t s_list[];  // sparse list under construction
     __shared__ uint32_t s_lit[256];  // raw byte counts; [0] is scratch (zeros are tokenised as runs)
@@ -146,7 +152,6 @@ __global__ void __launch_bounds__(kHistThreads, PART == 2 ? 8 : 5) k_hzr_hist(co
     const uint32_t blk = blockIdx.x;
     blk_decode(s, blk, f, k, b);
     if (k >= frame_nb[f]) return;
-    if (PART == 2 && list_n[blk] != kNoList) return;
     const uint32_t n = blk_len(s, b);
     const uint8_t* src = blk_ptr(planes, s, f, k, b);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lit[i] = 0;
@@ -157,14 +162,18 @@ __global__ void __launch_bounds__(kHistThreads, PART == 2 ? 8 : 5) k_hzr_hist(co
     const uint32_t spw = (nsteps + nwarps - 1) / nwarps;
     const uint32_t s_lo = min(nsteps, wid * spw), s_hi = min(nsteps, s_lo + spw);
 
-    // ---- sparse path
-    if (PART == 1) {
-    do {
-        // density probe: the first chunk of every warp range (spread over the block)
+    // density probe: the first chunk of every warp range (spread over the block)
+    {
         const Chunk probe = load_chunk(src, n, s_lo * kStepBytes + lane * 16u);
         const int dense_chunks = __syncthreads_count(__popc(probe.nz) >= 2);
         const int probed = __syncthreads_count(probe.valid > 0);
-        if (dense_chunks * 4 > probed) break;
+        const bool dense_class = dense_chunks * 4 > probed;
+        if (tid == 0) blk_class[blk] = dense_class ? kClassDense : kClassSparse;  // both parts write the same value
+        if (dense_class != (PART == 2)) return;  // the other launch owns this block
+    }
+    // ---- sparse path
+    if (PART == 1) {
+    do {
 
         // 1. masks and in-warp prefix counts of every step of my warp's range
         uint32_t pk[kHistSteps];  // nz mask | entries of my warp before this chunk << 16
@@ -249,9 +258,12 @@ __global__ void __launch_bounds__(kHistThreads, PART == 2 ? 8 : 5) k_hzr_hist(co
             out[i] = i == 0 ? s_run[0] : (i < 256 ? s_lit[i] : (i < (uint32_t)kNumSymbols ? s_run[i - 255] : 0u));
         return;
     } while (0);
-    if (tid == 0) list_n[blk] = kNoList;
-    return;
+    // the list overflowed: undo the partial counts and take the dense scan
+    __syncthreads();
+    for (uint32_t i = tid; i < 256; i += blockDim.x) s_lit[i] = 0;
+    if (tid < 8) s_run[tid] = 0;
     }
+    if (tid == 0) list_n[blk] = kNoList;
     __syncthreads();
 
     // ---- dense blocks

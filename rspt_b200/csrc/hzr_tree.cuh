@@ -306,9 +306,10 @@ __device__ __forceinline__ void count_block_mode(Counters* ctr, uint32_t mode)
     atomicAdd(mode == MODE_FILL ? &ctr->blocks_fill : (mode == MODE_COPY ? &ctr->blocks_copy : &ctr->blocks_huff), 1ull);
 }
 
-// One CTA (one warp) per block.
+// One warp per block of the class `cls` (blk_class is written by the histogram launches).
 __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __restrict__ hist, Shape s,
                                                                const uint8_t* __restrict__ frame_nb,
+                                                               const uint8_t* __restrict__ blk_class, uint32_t cls,
                                                                uint32_t total_blocks,
                                                                uint32_t* __restrict__ codes,
                                                                uint32_t* __restrict__ tree,
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
     if (blk >= total_blocks) return;
     uint32_t f, k, b;
     blk_decode(s, blk, f, k, b);
-    if (k >= frame_nb[f]) return;
+    if (k >= frame_nb[f] || blk_class[blk] != cls) return;
     const BlkInfo bi = warp_build_tree(S, hist + (size_t)blk * kSymStride, blk_len(s, b),
                                        codes + (size_t)blk * kSymStride, tree + (size_t)blk * kTreeWords);
     if (lane_id() == 0) {

@@ -286,6 +286,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_lists, nblocks * (size_t)kListCap));
     A(dalloc(p->d_list_n, nblocks));
     A(dalloc(p->d_fused, nblocks));
+    A(dalloc(p->d_blk_class, nblocks));
     A(dalloc(p->d_info, nblocks));
     A(dalloc(p->d_frame_nb, F));
     A(dalloc(p->d_need, F));
@@ -315,6 +316,9 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_nb_state, &s.nb_init, 4, cudaMemcpyHostToDevice, p->stream);
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_hist<1>, kHistSmem);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode_sparse, kSparseSmem);
     {
         // test hook: a smaller staging limit sends listed blocks down the hand-over path to k_hzr_encode
@@ -341,7 +345,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     if (!p) return RSPT_E_ARG;
     DeviceGuard dg(p->device);
     cudaStreamSynchronize(p->stream);
-    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_fused, p->d_info, p->d_frame_nb,
+    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_fused, p->d_blk_class, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
                     p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2};
@@ -355,6 +359,9 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
         delete p->ev_pending;
         delete p->ev_free;
     }
+    if (p->side) cudaStreamDestroy(p->side);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
     return RSPT_OK;
@@ -510,14 +517,25 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     uint16_t* sc_skip = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
     uint32_t* sc_codes = d_sidecar ? reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
     {
-        StageTimer t(p, RSPT_STAGE_HIST);
-        k_hzr_hist<1><<<nblocks, kHistThreads, kHistSmem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
-        k_hzr_hist<2><<<nblocks, kHistThreads, 0, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
-    }
-    {
-        StageTimer t(p, RSPT_STAGE_TREE);
-        k_hzr_tree<<<(nblocks + kTreeWarps - 1) / kTreeWarps, 32 * kTreeWarps, 0, p->stream>>>(
-            p->d_hist, s, p->d_frame_nb, nblocks, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
+        // Two classes of blocks (density probe): the sparse-looking ones go through histogram + tree on
+        // the side stream while this stream does the dense-looking ones, whose tree build is long and
+        // latency-bound and overlaps with the sparse histogram.  RSPT_STAGE_HIST times the dense
+        // histogram, RSPT_STAGE_TREE everything from there to the join.
+        const unsigned tgrid = (nblocks + kTreeWarps - 1) / kTreeWarps;
+        RSPT_CUDA_CHECK(cudaEventRecord(p->ev_fork, p->stream));
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+        k_hzr_hist<1><<<nblocks, kHistThreads, kHistSmem, p->side>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class);
+        k_hzr_tree<<<tgrid, 32 * kTreeWarps, 0, p->side>>>(p->d_hist, s, p->d_frame_nb, p->d_blk_class, kClassSparse, nblocks, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
+        RSPT_CUDA_CHECK(cudaEventRecord(p->ev_join, p->side));
+        {
+            StageTimer t(p, RSPT_STAGE_HIST);
+            k_hzr_hist<2><<<nblocks, kHistThreads, 0, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class);
+        }
+        {
+            StageTimer t(p, RSPT_STAGE_TREE);
+            k_hzr_tree<<<tgrid, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, p->d_blk_class, kClassDense, nblocks, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
+            RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+        }
     }
     {
         StageTimer t(p, RSPT_STAGE_LAYOUT);
@@ -534,7 +552,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
                                                                         p->d_codes, p->d_tree, p->d_step_lz, p->d_fused, d_offsets,
                                                                         p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip, sc_codes);
     }
-    p->launches += 7;
+    p->launches += 8;
     RSPT_CUDA_CHECK(cudaGetLastError());
     if (d_frame_nb) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_frame_nb, p->d_frame_nb, F, cudaMemcpyDeviceToDevice, p->stream));
     return RSPT_OK;
@@ -1083,10 +1101,11 @@ extern "C" int rspt_gpu_debug_hzr_tables(rspt_gpu_packer* p, const uint8_t* d_bl
     DeviceGuard dg(p->device);
     Shape s = p->s;
     s.N = (uint32_t)n; s.nblk = 1; s.nb_alloc = 1; s.plane_stride = (uint32_t)((n + 15) & ~(size_t)15);
-    k_hzr_hist<1><<<1, kHistThreads, kHistSmem, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
-    k_hzr_hist<2><<<1, kHistThreads, 0, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n);
-    k_hzr_tree<<<1, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, 1, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
-    p->launches += 3;
+    k_hzr_hist<1><<<1, kHistThreads, kHistSmem, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class);
+    k_hzr_hist<2><<<1, kHistThreads, 0, p->stream>>>(d_block, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class);
+    k_hzr_tree<<<1, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, p->d_blk_class, kClassSparse, 1, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
+    k_hzr_tree<<<1, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, p->d_blk_class, kClassDense, 1, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
+    p->launches += 4;
     RSPT_CUDA_CHECK(cudaGetLastError());
     if (d_hist) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_hist, p->d_hist, kNumSymbols * 4, cudaMemcpyDeviceToDevice, p->stream));
     if (d_codes) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_codes, p->d_codes, kNumSymbols * 4, cudaMemcpyDeviceToDevice, p->stream));
