@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                                                                 const uint32_t* __restrict__ codes,
                                                                 const uint32_t* __restrict__ tree,
                                                                 const uint16_t* __restrict__ step_lz,
-                                                                const uint32_t* __restrict__ fused,
+                                                                const uint32_t* __restrict__ lists,
+                                                                const uint32_t* __restrict__ list_n, uint32_t sparse_stage,
                                                                 const uint64_t* __restrict__ offsets,
                                                                 const uint8_t* __restrict__ headers,
                                                                 const CrcConst* __restrict__ cc,
@@ -197,7 +198,9 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             for (uint32_t i = tid; i < s.hdr_bytes; i += blockDim.x) dst[frame_off + 1 + i] = headers[(size_t)f * s.hdr_bytes + i];
     }
 
-    if (fused[blk]) return;  // k_hzr_encode_sparse wrote this block
+    // a block with a list is k_hzr_encode_sparse's, unless its payload does not fit that kernel's staging
+    const uint32_t list_m = list_n[blk];
+    if (sparse_block_is_packed_from_list(list_m, bi, sparse_stage)) return;
     if (bi.mode == MODE_FILL) {
         if (tid == 0) {
             const uint32_t crc = ~(0x00FFFFFFu ^ __ldg(&cc->byte_tab[0xFFu ^ bi.fill]));
@@ -243,6 +246,19 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             for (int j = 0; j < 4; ++j) {
                 const uint32_t st = 4u * lane + j;
                 lz[j] = st < nsteps ? (uint32_t)lzp[st] : 0u;  // beyond the block: a stop at once
+                if (list_m != kNoList && st < nsteps) {
+                    // listed block handed over by the sparse encoder (payload beyond its staging, rare):
+                    // it never went through the dense scan, so its leading-zero counts come from the list
+                    const uint32_t* gl = lists + (size_t)blk * kListCap;
+                    uint32_t lo = 0, hi = list_m;  // first entry at or after the step start
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if ((__ldg(gl + mid) & 0xFFFFu) < st * kStepBytes) lo = mid + 1u;
+                        else hi = mid;
+                    }
+                    const uint32_t pos = lo < list_m ? __ldg(gl + lo) & 0xFFFFu : n;
+                    lz[j] = min(min(pos, n) - st * kStepBytes, (uint32_t)kStepBytes);
+                }
             }
             // leading zeros counted from the start of my 4 steps, and whether all 4 are zero
             uint32_t mine = 0;

@@ -19,7 +19,6 @@ constexpr uint32_t kSpStageWords = kSpStageBytes / 4 + 8;
 constexpr size_t kSparseSmem = (size_t)(kListCap + 4 + kSpStageWords) * 4;
 
 struct SparseOut {
-    uint32_t* fused;      // [blocks] 1 = block written here, 0 = k_hzr_encode packs the block
     uint8_t* dst;         // output stream
     const uint64_t* offsets;   // byte offset of every frame in dst
     const uint32_t* blk_off;   // per block: offset of its header from the frame start
@@ -35,7 +34,6 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
                                                                      const uint32_t* __restrict__ tree,
                                                                      const uint32_t* __restrict__ lists,
                                                                      const uint32_t* __restrict__ list_n,
-                                                                     uint16_t* __restrict__ step_lz,
                                                                      const CrcConst* __restrict__ cc, SparseOut so)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];  // the list, then the payload staging
@@ -49,28 +47,8 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
     const uint32_t n = blk_len(s, b);
     const uint32_t m = list_n[blk];
     const BlkInfo bi = info[blk];
-    if (m == kNoList || bi.mode != MODE_HUFF) {
-        if (tid == 0) so.fused[blk] = 0u;
-        return;
-    }
+    if (!sparse_block_is_packed_from_list(m, bi, so.stage_bytes)) return;  // k_hzr_encode packs it from the plane
     const uint32_t* glist = lists + (size_t)blk * kListCap;
-    if (bi.payload_len > so.stage_bytes) {
-        // too large for the staging here (rare): k_hzr_encode packs the block from the plane; it
-        // needs the leading zero count of every 512-byte step, which the list gives directly
-        const uint32_t nsteps = (n + kStepBytes - 1) / kStepBytes;
-        for (uint32_t st = tid; st < nsteps; st += blockDim.x) {
-            uint32_t lo = 0, hi = m;  // first entry at or after the step start
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if ((__ldg(glist + mid) & 0xFFFFu) < st * kStepBytes) lo = mid + 1u;
-                else hi = mid;
-            }
-            const uint32_t pos = lo < m ? __ldg(glist + lo) & 0xFFFFu : n;
-            step_lz[(size_t)blk * kMaxSteps + st] = (uint16_t)min(min(pos, n) - st * kStepBytes, (uint32_t)kStepBytes);
-        }
-        if (tid == 0) so.fused[blk] = 0u;
-        return;
-    }
     uint32_t* list = s_dyn;
     uint32_t* stg = s_dyn + kListCap;  // block header at bytes 9..15, payload from byte 16
     uint32_t* pay = stg + 4;
@@ -207,7 +185,6 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
         const uint32_t lo = (plen - 1u) | (crc << 16), hi = (crc >> 16) | ((uint32_t)MODE_HUFF << 16);
         out[lane] = (uint8_t)((lane < 4 ? lo : hi) >> (8u * (lane & 3u)));
     }
-    if (lane == 0) so.fused[blk] = 1u;
 }
 
 }  // namespace rspt

@@ -42,8 +42,7 @@ struct rspt_gpu_packer {
     uint32_t* d_list_n;    // per block: entries in d_lists, kNoList = dense block
     uint8_t* d_blk_class;  // per block: kClassSparse / kClassDense (density probe of the histogram launches)
     cudaStream_t side;     // sparse-class histogram + trees run here, beside the dense class on `stream`
-    cudaEvent_t ev_fork, ev_join;
-    uint32_t* d_fused;     // per block: 1 = written by k_hzr_encode_sparse, 0 = k_hzr_encode packs the block
+    cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2;
     uint16_t* d_step_lz;   // per 512-byte step of every block: leading zero count (512 = all zero)
     rspt::BlkInfo* d_info;
     uint8_t* d_frame_nb;

@@ -285,7 +285,6 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_step_lz, nblocks * kMaxSteps));
     A(dalloc(p->d_lists, nblocks * (size_t)kListCap));
     A(dalloc(p->d_list_n, nblocks));
-    A(dalloc(p->d_fused, nblocks));
     A(dalloc(p->d_blk_class, nblocks));
     A(dalloc(p->d_info, nblocks));
     A(dalloc(p->d_frame_nb, F));
@@ -319,6 +318,8 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork2, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode_sparse, kSparseSmem);
     {
         // test hook: a smaller staging limit sends listed blocks down the hand-over path to k_hzr_encode
@@ -345,7 +346,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     if (!p) return RSPT_E_ARG;
     DeviceGuard dg(p->device);
     cudaStreamSynchronize(p->stream);
-    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_fused, p->d_blk_class, p->d_info, p->d_frame_nb,
+    void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
                     p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2};
@@ -362,6 +363,8 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     if (p->side) cudaStreamDestroy(p->side);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
+    if (p->ev_fork2) cudaEventDestroy(p->ev_fork2);
+    if (p->ev_join2) cudaEventDestroy(p->ev_join2);
     if (p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
     return RSPT_OK;
@@ -543,14 +546,19 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         k_scan_offsets<<<1, 1024, 0, p->stream>>>(p->d_sizes, (uint32_t)F, d_offsets, p->d_ctr, s.frame_bytes);
     }
     {
-        // sparse blocks from their lists, then everything else from the planes
+        // sparse blocks from their lists (side stream) beside everything else from the planes: both kernels
+        // decide with the same predicate which of them writes a block
         StageTimer t(p, RSPT_STAGE_ENCODE);
-        const SparseOut so{p->d_fused, d_dst, d_offsets, p->d_blk_off, p->sp_stage, sc_bit, sc_skip, sc_codes};
-        k_hzr_encode_sparse<<<nblocks, kSpThreads, kSparseSmem, p->stream>>>(s, p->d_frame_nb, p->d_info, p->d_codes, p->d_tree, p->d_lists,
-                                                                             p->d_list_n, p->d_step_lz, p->d_crc, so);
+        const SparseOut so{d_dst, d_offsets, p->d_blk_off, p->sp_stage, sc_bit, sc_skip, sc_codes};
+        RSPT_CUDA_CHECK(cudaEventRecord(p->ev_fork2, p->stream));
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_fork2, 0));
+        k_hzr_encode_sparse<<<nblocks, kSpThreads, kSparseSmem, p->side>>>(s, p->d_frame_nb, p->d_info, p->d_codes, p->d_tree, p->d_lists,
+                                                                           p->d_list_n, p->d_crc, so);
+        RSPT_CUDA_CHECK(cudaEventRecord(p->ev_join2, p->side));
         k_hzr_encode<<<nblocks, kEncThreads, p->enc_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
-                                                                        p->d_codes, p->d_tree, p->d_step_lz, p->d_fused, d_offsets,
-                                                                        p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip, sc_codes);
+                                                                        p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->sp_stage,
+                                                                        d_offsets, p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip, sc_codes);
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_join2, 0));
     }
     p->launches += 8;
     RSPT_CUDA_CHECK(cudaGetLastError());
