@@ -149,10 +149,19 @@ struct BitReader {
 struct SegWriter {
     uint8_t* dst;
     uint32_t len, pos, w, sh;
-    bool cleared;  // the destination already holds zeros: zero runs are skipped, not written
+    uint32_t xacc;  // xor of all words written (zero runs contribute nothing): the segment's xor total
+    bool cleared;   // the destination already holds zeros: zero runs are skipped, not written
     __device__ __forceinline__ void init(uint8_t* d, uint32_t l, bool pre_cleared)
     {
-        dst = d; len = l; pos = 0; w = 0; sh = 0; cleared = pre_cleared;
+        dst = d; len = l; pos = 0; w = 0; sh = 0; xacc = 0; cleared = pre_cleared;
+    }
+    // xor of the segment's bytes
+    __device__ __forceinline__ uint32_t xor_byte() const
+    {
+        uint32_t x = xacc ^ w;
+        x ^= x >> 16;
+        x ^= x >> 8;
+        return x & 0xFFu;
     }
     __device__ __forceinline__ void put(uint32_t byte)
     {
@@ -161,6 +170,7 @@ struct SegWriter {
         ++pos;
         if (sh == 32u) {
             *reinterpret_cast<uint32_t*>(dst + pos - 4u) = w;
+            xacc ^= w;
             w = 0;
             sh = 0;
         }
@@ -173,6 +183,7 @@ struct SegWriter {
             const uint32_t np = pos + z;
             if ((np >> 2) != (pos >> 2)) {  // the run leaves the open word
                 if (sh) *reinterpret_cast<uint32_t*>(dst + (pos & ~3u)) = w;
+                xacc ^= w;
                 w = 0;
             }
             pos = np;
@@ -267,10 +278,11 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                                                                    const uint32_t* __restrict__ sc_bit,
                                                                    const uint16_t* __restrict__ sc_skip,
                                                                    const uint32_t* __restrict__ sc_codes,
-                                                                   uint8_t* __restrict__ planes, int32_t* __restrict__ status)
+                                                                   uint8_t* __restrict__ planes, int32_t* __restrict__ status,
+                                                                   uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane)
 {
     extern __shared__ __align__(16) uint32_t payw[];  // payload words (+ zero slack)
-    __shared__ __align__(16) uint16_t s_lut[1 << kLutBits];  // sym | len << 9, or kLongFlag; serial path: tree scratch first
+    __shared__ __align__(16) uint16_t s_lut[1 << kLutBits];  // sym | len << 9, or kLongFlag
     __shared__ uint32_t s_cw[kSymStride];            // code | len << 27 per symbol, 0 = unused
     __shared__ uint16_t s_long[kSymStride];          // symbols whose code is longer than the table
     __shared__ uint32_t s_meta[4];                   // tree_end_bit, error, long count
@@ -284,10 +296,17 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     uint4* out4 = reinterpret_cast<uint4*>(out);
     const uint32_t n = d.out_n, nq = (n + 15u) >> 4;
     const uint8_t* pay = src + d.payload_off;
+    // xor of the bytes of every 128-byte output segment, for the inverse transform's first scan
+    // (k_planes_to_samples_fast: a segment is one of its pieces), so that it need not read the planes for it
+    uint8_t* my_xor = seg_xor ? seg_xor + ((size_t)f * s.nb_alloc + k) * segs_per_plane + (size_t)b * kMaxSegs : nullptr;
+    const uint32_t nseg_all = (n + kSegBytes - 1) / kSegBytes;
 
     if (d.mode == MODE_FILL || d.mode == kModeZero) {
         const uint32_t v = d.mode == MODE_FILL ? pay[0] * 0x01010101u : 0u;  // memset (dec:362-370)
         for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(v, v, v, v);
+        if (my_xor)
+            for (uint32_t i = tid; i < nseg_all; i += blockDim.x)
+                my_xor[i] = (uint8_t)((min((uint32_t)kSegBytes, n - i * kSegBytes) & 1u) ? (v & 0xFFu) : 0u);
         return;
     }
     const uintptr_t pa = (uintptr_t)pay;
@@ -297,6 +316,8 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         if (d.payload_len != n) {  // "Encoded / decoded size mismatch (COPY)" dec:351-355
             if (tid == 0) status[f] = -4;
             for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
+            if (my_xor)
+                for (uint32_t i = tid; i < nseg_all; i += blockDim.x) my_xor[i] = 0;
             return;
         }
         const uint32_t naw = (lead + n + 3u) >> 2, nw = (n + 3u) >> 2;
@@ -304,6 +325,21 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         for (uint32_t i = tid; i < nw; i += blockDim.x) {
             const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
             out32[i] = __funnelshift_r(lo, hi, sh);
+        }
+        if (my_xor) {
+            for (uint32_t sg = tid; sg < nseg_all; sg += blockDim.x) {
+                const uint32_t w0 = sg * (kSegBytes / 4), w1 = min(nw, w0 + kSegBytes / 4);
+                uint32_t x = 0;
+                for (uint32_t i = w0; i < w1; ++i) {
+                    const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
+                    uint32_t v = __funnelshift_r(lo, hi, sh);
+                    if (4u * i + 4u > n) v &= (1u << (8u * (n - 4u * i))) - 1u;  // bytes beyond the block
+                    x ^= v;
+                }
+                x ^= x >> 16;
+                x ^= x >> 8;
+                my_xor[sg] = (uint8_t)x;
+            }
         }
         return;
     }
@@ -364,7 +400,10 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                 if (q < nq) out4[q] = make_uint4(0, 0, 0, 0);
             }
         }
-        if (all_zero) mine = false;
+        if (all_zero) {
+            mine = false;
+            if (my_xor) my_xor[tid] = 0;
+        }
     }
     if (mine) {
         const uint32_t limit_bits = plen * 8u, nlong = s_meta[2];
@@ -409,7 +448,9 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
             }
         }
         if (bitpos > limit_bits) my_err = 1;
+        const uint32_t xb = wr.xor_byte();  // before finish(): the padding it adds is zeros anyway
         wr.finish();
+        if (my_xor) my_xor[tid] = (uint8_t)xb;
     }
     if (my_err) status[f] = -4;
 }

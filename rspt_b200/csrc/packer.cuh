@@ -59,6 +59,8 @@ struct rspt_gpu_packer {
     void* d_dec;           // block descriptors
     uint8_t* d_dec_nb;     // per-frame plane count used by the last decompress
     int32_t* d_status_tmp;
+    uint8_t* d_seg_xor;    // per 128-byte segment of every decoded plane: xor of its bytes (k_hzr_decode -> inverse transform)
+    uint32_t segs_per_plane;
     void* d_auto_index;    // decode index built here for streams that came without one (lazy)
     double* d_fir;         // FIR kernel coefficients of the last rspt_gpu_prefilter_fir call (lazy)
     size_t fir_cap;

@@ -296,6 +296,8 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_ctr, 1));
     A(dalloc(p->d_status_tmp, F));
     A(dalloc(p->d_dec_nb, F));
+    p->segs_per_plane = s.nblk * (uint32_t)kMaxSegs;
+    A(dalloc(p->d_seg_xor, F * s.nb_alloc * (size_t)p->segs_per_plane));
     A(cudaMalloc(&p->d_dec, nblocks * sizeof(DecBlk) + 64));
     if (kind == RSPT_HADAMARD || kind == RSPT_DCT) {
         A(dalloc(p->d_words, F * (size_t)s.N));
@@ -349,7 +351,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
-                    p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2};
+                    p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2, p->d_seg_xor};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p->h_pin) cudaFreeHost(p->h_pin);
@@ -636,7 +638,8 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
     const uint32_t* sc_codes = reinterpret_cast<const uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs);
     {
         StageTimer t(p, RSPT_STAGE_DECODE);
-        k_hzr_decode<<<nblocks, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec, sc_bit, sc_skip, sc_codes, p->d_planes, status);
+        k_hzr_decode<<<nblocks, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec, sc_bit, sc_skip, sc_codes, p->d_planes, status,
+                                                                          p->d_seg_xor, p->segs_per_plane);
     }
     p->launches += 1;
     RSPT_CUDA_CHECK(cudaGetLastError());

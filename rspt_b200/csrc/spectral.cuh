@@ -659,7 +659,8 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
 #define INVF_LAUNCH(B, SC)                                                                                            \
     do {                                                                                                              \
         cudaFuncSetAttribute(k_planes_to_samples_fast<B, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf); \
-        k_planes_to_samples_fast<B, SC><<<gf, kInvThreads, smf, p->stream>>>(p->d_planes, s, p->d_dec_nb, tpg, d_dst);   \
+        k_planes_to_samples_fast<B, SC><<<gf, kInvThreads, smf, p->stream>>>(p->d_planes, s, p->d_dec_nb, tpg, d_dst,    \
+                                                                       p->d_seg_xor, p->segs_per_plane);       \
     } while (0)
             const bool sc = s.kind == 0;
             switch (s.bps) {

@@ -504,7 +504,8 @@ template <int BPS, bool SCAN>
 __global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const uint8_t* __restrict__ planes, Shape s,
                                                                             const uint8_t* __restrict__ dec_nb,
                                                                             uint32_t tiles_per_group,
-                                                                            uint8_t* __restrict__ dst_raw)
+                                                                            uint8_t* __restrict__ dst_raw,
+                                                                            const uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane)
 {
     extern __shared__ __align__(16) uint32_t sm32[];
     const uint32_t f = blockIdx.x;
@@ -531,7 +532,16 @@ __global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const
     };
     constexpr int U = 4;  // pieces in flight per warp
     if (SCAN) {
-        // pass 1: xor of all words of a piece = byte-wise fold of the plane words
+        // pass 1: xor of all words of a piece = byte-wise fold of the plane words.  k_hzr_decode leaves
+        // exactly that per 128-byte segment (= piece) of every plane, so the planes are not read here.
+        if (seg_xor) {
+            const uint8_t* sx = seg_xor + (size_t)f * s.nb_alloc * segs_per_plane;
+            for (uint32_t p = threadIdx.x; p < np; p += blockDim.x) {
+                uint32_t x = 0;
+                for (uint32_t k = 0; k < nb; ++k) x |= (uint32_t)sx[(size_t)k * segs_per_plane + p] << (8 * k);
+                pxor[p] = (uint32_t)((int32_t)(x << sext) >> sext);
+            }
+        } else
         for (uint32_t p0 = wid * U; p0 < np; p0 += nwarps * U) {
             uint32_t q[U][4];
 #pragma unroll
