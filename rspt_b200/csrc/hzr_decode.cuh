@@ -211,6 +211,7 @@ struct SegWriter {
 constexpr uint32_t kDecPayWords = kBlock / 4 + 4;
 constexpr size_t kDecodeSmem = (size_t)kDecPayWords * 4;
 constexpr uint32_t kLongFlag = 0x8000u;
+constexpr uint32_t kLongEnd = 0x1FFu;  // flagged table entries: index of the first long symbol of the chain, kLongEnd = none
 
 // RecoverTree (dec:263-333), iteratively, by ONE thread: pre-order, 0 = branch, 1 + 9-bit symbol =
 // leaf.  Only the code word of every leaf is needed: a stack of (code, depth) of pending right
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     __shared__ __align__(16) uint16_t s_lut[1 << kLutBits];  // sym | len << 9, or kLongFlag
     __shared__ uint32_t s_cw[kSymStride];            // code | len << 27 per symbol, 0 = unused
     __shared__ uint16_t s_long[kSymStride];          // symbols whose code is longer than the table
+    __shared__ uint16_t s_next[kSymStride];          // chains of the long symbols that share their first kLutBits bits
     __shared__ uint32_t s_meta[4];                   // tree_end_bit, error, long count
 
     const uint32_t blk = blockIdx.x, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
@@ -354,11 +356,26 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         }
         payw[i] = v;
     }
-    for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_lut)[i] = kLongFlag | (kLongFlag << 16);
+    for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_lut)[i] = (kLongFlag | kLongEnd) * 0x00010001u;
     for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = i < (uint32_t)kNumSymbols ? sc_codes[(size_t)blk * kSymStride + i] : 0u;
     if (tid == 0) { s_meta[0] = 0; s_meta[1] = 0; s_meta[2] = 0; }
     __syncthreads();
     build_lut(s_cw, s_lut, s_long, &s_meta[2]);
+    __syncthreads();
+    // long codes: the table entry of their first kLutBits bits (kLongFlag | index) heads a chain through
+    // s_next of the long symbols that share those bits, so a long code costs a compare or two instead of
+    // a scan of all long symbols (a lane on this path stalls its whole warp)
+    for (uint32_t j = tid; j < s_meta[2]; j += blockDim.x) {
+        const uint32_t prefix = s_cw[s_long[j]] & ((1u << kLutBits) - 1u);
+        uint32_t* word = reinterpret_cast<uint32_t*>(s_lut) + (prefix >> 1);
+        const uint32_t shift = (prefix & 1u) * 16u;
+        uint32_t old = *word, seen;
+        do {
+            seen = old;
+            old = atomicCAS(word, seen, (seen & ~(0xFFFFu << shift)) | ((kLongFlag | j) << shift));
+        } while (old != seen);
+        s_next[j] = (uint16_t)((seen >> shift) & kLongEnd);
+    }
     __syncthreads();
 
     const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
@@ -406,7 +423,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         }
     }
     if (mine) {
-        const uint32_t limit_bits = plen * 8u, nlong = s_meta[2];
+        const uint32_t limit_bits = plen * 8u;
         if (bitpos > limit_bits) { my_err = 1; bitpos = 0; }
         end_bit = min(end_bit, limit_bits);
         SegWriter wr;
@@ -419,13 +436,15 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
             uint32_t e = s_lut[r.peek(kLutBits)];
             if (e & kLongFlag) {
                 // code longer than the table: match the few long code words (dec:418-431 walks the tree)
+                uint32_t j = e & kLongEnd;
                 e = 0;
-                for (uint32_t j = 0; j < nlong; ++j) {
+                while (j != kLongEnd) {
                     const uint32_t sym = s_long[j], cw = s_cw[sym], len = cw >> 27;
                     if (((uint32_t)r.buf & ((1u << len) - 1u)) == (cw & 0x07FFFFFFu)) {
                         e = sym | (len << 9);
                         break;
                     }
+                    j = s_next[j];
                 }
                 if (e == 0u) { my_err = 1; break; }
             }
