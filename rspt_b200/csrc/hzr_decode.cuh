@@ -269,6 +269,26 @@ __device__ __forceinline__ void build_lut(const uint32_t* cw_tab, uint16_t* lut,
     }
 }
 
+// Long codes: the table entry of their first kLutBits bits (kLongFlag | index) heads a chain through
+// `next` of the long symbols that share those bits, so a long code costs a compare or two instead of
+// a scan of all long symbols (a lane on this path stalls its whole warp).  Whole CTA; the table must have
+// been initialised to kLongFlag | kLongEnd; synchronise after.
+__device__ __forceinline__ void chain_long_codes(const uint32_t* cw_tab, uint16_t* lut, const uint16_t* longs, uint16_t* next,
+                                                 uint32_t nlong)
+{
+    for (uint32_t j = threadIdx.x; j < nlong; j += blockDim.x) {
+        const uint32_t prefix = cw_tab[longs[j]] & ((1u << kLutBits) - 1u);
+        uint32_t* word = reinterpret_cast<uint32_t*>(lut) + (prefix >> 1);
+        const uint32_t shift = (prefix & 1u) * 16u;
+        uint32_t old = *word, seen;
+        do {
+            seen = old;
+            old = atomicCAS(word, seen, (seen & ~(0xFFFFu << shift)) | ((kLongFlag | j) << shift));
+        } while (old != seen);
+        next[j] = (uint16_t)((seen >> shift) & kLongEnd);
+    }
+}
+
 // One CTA per hzr block.  The payload is staged in shared memory (coalesced, re-aligned); the
 // code table comes from the decode index (sc_codes); a 12-bit look-up table maps the next bits to
 // (symbol, length), longer codes are matched against the short list of long code words.  Every
@@ -362,20 +382,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     __syncthreads();
     build_lut(s_cw, s_lut, s_long, &s_meta[2]);
     __syncthreads();
-    // long codes: the table entry of their first kLutBits bits (kLongFlag | index) heads a chain through
-    // s_next of the long symbols that share those bits, so a long code costs a compare or two instead of
-    // a scan of all long symbols (a lane on this path stalls its whole warp)
-    for (uint32_t j = tid; j < s_meta[2]; j += blockDim.x) {
-        const uint32_t prefix = s_cw[s_long[j]] & ((1u << kLutBits) - 1u);
-        uint32_t* word = reinterpret_cast<uint32_t*>(s_lut) + (prefix >> 1);
-        const uint32_t shift = (prefix & 1u) * 16u;
-        uint32_t old = *word, seen;
-        do {
-            seen = old;
-            old = atomicCAS(word, seen, (seen & ~(0xFFFFu << shift)) | ((kLongFlag | j) << shift));
-        } while (old != seen);
-        s_next[j] = (uint16_t)((seen >> shift) & kLongEnd);
-    }
+    chain_long_codes(s_cw, s_lut, s_long, s_next, s_meta[2]);
     __syncthreads();
 
     const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
@@ -495,20 +502,22 @@ struct TokenDecoder {
     const uint16_t* lut;
     const uint32_t* cw;
     const uint16_t* longs;
-    uint32_t nlong;
+    const uint16_t* chain;
     // one token at the reader's position: bits consumed (0 = no code word matches) and bytes produced
     __device__ __forceinline__ uint32_t next(BitReader& r, uint32_t& out_bytes) const
     {
         r.refill();
         uint32_t e = lut[r.peek(kLutBits)];
         if (e & kLongFlag) {
+            uint32_t j = e & kLongEnd;
             e = 0;
-            for (uint32_t j = 0; j < nlong; ++j) {
+            while (j != kLongEnd) {
                 const uint32_t sym = longs[j], c = cw[sym], len = c >> 27;
                 if (((uint32_t)r.buf & ((1u << len) - 1u)) == (c & 0x07FFFFFFu)) {
                     e = sym | (len << 9);
                     break;
                 }
+                j = chain[j];
             }
             if (e == 0u) return 0u;
         }
@@ -540,6 +549,7 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
     __shared__ __align__(16) uint16_t s_lut[1 << kLutBits];
     __shared__ uint32_t s_cw[kSymStride];
     __shared__ uint16_t s_long[kSymStride];
+    __shared__ uint16_t s_next[kSymStride];
     __shared__ uint32_t s_meta[4];                    // tree bits, error, long count
     __shared__ uint32_t s_start[kIndexThreads + 1];   // first token boundary of every sub-sequence
     __shared__ uint32_t s_wsum[kIndexThreads / 32];
@@ -565,7 +575,7 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
         }
         payw[i] = v;
     }
-    for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_lut)[i] = kLongFlag | (kLongFlag << 16);
+    for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_lut)[i] = (kLongFlag | kLongEnd) * 0x00010001u;
     for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = 0;
     __syncthreads();
     if (tid == 0) {
@@ -579,6 +589,8 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
     if (!bad) {
         build_lut(s_cw, s_lut, s_long, &s_meta[2]);
         __syncthreads();
+        chain_long_codes(s_cw, s_lut, s_long, s_next, s_meta[2]);
+        __syncthreads();
     }
     const uint32_t limit = plen * 8u, t0 = bad ? 0u : s_meta[0];
     // sub-sequences: nsub equal pieces of [t0, limit), each longer than any token
@@ -588,7 +600,7 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
     const uint32_t sub = (span + nsub - 1u) / nsub;
     const uint32_t lo = t0 + tid * sub, hi = min(limit, lo + sub);  // tokens that START in [lo, hi) are mine
     const bool live = !bad && tid < nsub && lo < limit;
-    const TokenDecoder td{s_lut, s_cw, s_long, s_meta[2]};
+    const TokenDecoder td{s_lut, s_cw, s_long, s_next};
     if (tid <= nsub) s_start[tid] = min(lo, limit);
     __syncthreads();
     uint32_t my_start = 0xFFFFFFFFu, land = 0, cnt = 0;
