@@ -5,7 +5,9 @@ csv.field_size_limit(10**9)
 rep, kre = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 sortkey = sys.argv[4] if len(sys.argv) > 4 else "samples"
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kre],
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
+                      "--kernel-name-base", "mangled" if "ILi" in kre else "function",  # template instantiations: match the mangled name
+                      "--kernel-name", "regex:" + kre],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 fname = None; hdr = None

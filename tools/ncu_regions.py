@@ -8,7 +8,9 @@ for a in sys.argv[3:]:
     parts = a.split(":")
     lo, hi = parts[1].split("-")
     regions.append((parts[0], int(lo), int(hi), parts[2] if len(parts) > 2 else a))
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kre],
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
+                      "--kernel-name-base", "mangled" if "ILi" in kre else "function",  # template instantiations: match the mangled name
+                      "--kernel-name", "regex:" + kre],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 fname = None; hdr = None; cur = None
