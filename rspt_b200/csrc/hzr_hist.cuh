@@ -1,10 +1,13 @@
 // hzr token histogram for sm_100a: one CTA per hzr block, 16 bytes per lane, 512 bytes per
-// warp-step.  Replaces Histogram (lib_hzr/hzr_encode.c:133-173).
+// warp-step.  Replaces Histogram (lib_hzr/hzr_encode.c:133-173).  Two launches (k_hzr_hist<1>,
+// k_hzr_hist<2>) split the blocks by a density probe: sparse-looking blocks are tokenised from a
+// sorted list of their non-zero bytes (described at the kernel), dense-looking ones by the scan
+// described here.
 //
 // Tokens (hzr_encode.c:140-170): every non-zero byte is a literal; every maximal zero run inside
 // the block is cut greedily into chunks of <= 16662 and each chunk becomes one of the symbols
 // 0 (run of 1), 256 (run of 2), 257..260 (longer runs, with extra bits).  The literal counts are
-// order-free; only the zero runs need structure:
+// order-free; only the zero runs need structure (dense scan):
 //   * a warp owns a CONTIGUOUS range of steps and walks it in order, so the zeros pending at the
 //     end of one step are simply carried in a (warp-uniform) register to the next;
 //   * inside a step every lane turns its 16 bytes into a 16-bit "stop" mask (non-zero or beyond

@@ -1,5 +1,5 @@
 // Bit-packing and CRC-32C helpers shared by the kernels that produce hzr payloads
-// (k_hzr_hist finishes sparse blocks itself, k_hzr_encode does the rest).
+// (k_hzr_encode_sparse for blocks with a list of non-zero bytes, k_hzr_encode for the rest).
 // WriteBits / FlushBitCache: lib_hzr/hzr_encode.c:63-113; CRC-32C: lib_hzr/hzr_crc32c.c:77-97.
 #pragma once
 
