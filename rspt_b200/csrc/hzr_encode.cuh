@@ -173,34 +173,19 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
 
     uint32_t f, k, b;
     const uint32_t blk = blockIdx.x;
+    // a block with a list is k_hzr_encode_sparse's (framing included), unless its payload does not fit that
+    // kernel's staging: those CTAs (2/3 of the grid on delta-coded signals) leave at once
+    const BlkInfo bi = info[blk];
+    const uint32_t list_m = list_n[blk];
+    if (sparse_block_is_packed_from_list(list_m, bi, sparse_stage)) return;
     blk_decode(s, blk, f, k, b);
     const uint32_t nb = frame_nb[f];
     if (k >= nb) return;
     const uint32_t n = blk_len(s, b);
-    const BlkInfo bi = info[blk];
     const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     const unsigned long long frame_off = offsets[f];
     uint8_t* out = dst + frame_off + blk_off[blk];
-
-    // frame / chunk framing, written by the CTA that owns the chunk's first block
-    // (signal_packer_base.cpp:78,83-95; hzr_encode.c:521)
-    if (b == 0) {
-        if (tid == 0) {
-            uint32_t clen = 4;
-            const size_t row = ((size_t)f * s.nb_alloc + k) * s.nblk;
-            for (uint32_t bb = 0; bb < s.nblk; ++bb) clen += 7u + info[row + bb].payload_len;
-            uint8_t* q = out - 8;
-            q[0] = (uint8_t)clen; q[1] = (uint8_t)(clen >> 8); q[2] = (uint8_t)(clen >> 16); q[3] = (uint8_t)(clen >> 24);
-            q[4] = (uint8_t)s.N; q[5] = (uint8_t)(s.N >> 8); q[6] = (uint8_t)(s.N >> 16); q[7] = (uint8_t)(s.N >> 24);
-            if (k == 0) dst[frame_off] = (uint8_t)s.method;
-        }
-        if (k == 0)
-            for (uint32_t i = tid; i < s.hdr_bytes; i += blockDim.x) dst[frame_off + 1 + i] = headers[(size_t)f * s.hdr_bytes + i];
-    }
-
-    // a block with a list is k_hzr_encode_sparse's, unless its payload does not fit that kernel's staging
-    const uint32_t list_m = list_n[blk];
-    if (sparse_block_is_packed_from_list(list_m, bi, sparse_stage)) return;
+    if (b == 0) write_chunk_framing(s, info, f, k, dst, frame_off, out, headers);
     if (bi.mode == MODE_FILL) {
         if (tid == 0) {
             const uint32_t crc = ~(0x00FFFFFFu ^ __ldg(&cc->byte_tab[0xFFu ^ bi.fill]));

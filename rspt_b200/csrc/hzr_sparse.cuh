@@ -18,11 +18,32 @@ constexpr uint32_t kSpStageBytes = 12288;                // largest payload pack
 constexpr uint32_t kSpStageWords = kSpStageBytes / 4 + 8;
 constexpr size_t kSparseSmem = (size_t)(kListCap + 4 + kSpStageWords) * 4;
 
+// frame / chunk framing, written by the CTA that owns the chunk's first block (whichever encoder that is):
+// chunk length and hzr decoded size in front of the block, method byte and header at the frame start
+// (signal_packer_base.cpp:78,83-95; hzr_encode.c:521)
+__device__ __forceinline__ void write_chunk_framing(const Shape& s, const BlkInfo* __restrict__ info, uint32_t f, uint32_t k,
+                                                    uint8_t* __restrict__ dst, unsigned long long frame_off, uint8_t* out,
+                                                    const uint8_t* __restrict__ headers)
+{
+    if (threadIdx.x == 0) {
+        uint32_t clen = 4;
+        const size_t row = ((size_t)f * s.nb_alloc + k) * s.nblk;
+        for (uint32_t bb = 0; bb < s.nblk; ++bb) clen += 7u + info[row + bb].payload_len;
+        uint8_t* q = out - 8;
+        q[0] = (uint8_t)clen; q[1] = (uint8_t)(clen >> 8); q[2] = (uint8_t)(clen >> 16); q[3] = (uint8_t)(clen >> 24);
+        q[4] = (uint8_t)s.N; q[5] = (uint8_t)(s.N >> 8); q[6] = (uint8_t)(s.N >> 16); q[7] = (uint8_t)(s.N >> 24);
+        if (k == 0) dst[frame_off] = (uint8_t)s.method;
+    }
+    if (k == 0)
+        for (uint32_t i = threadIdx.x; i < s.hdr_bytes; i += blockDim.x) dst[frame_off + 1 + i] = headers[(size_t)f * s.hdr_bytes + i];
+}
+
 struct SparseOut {
     uint8_t* dst;         // output stream
     const uint64_t* offsets;   // byte offset of every frame in dst
     const uint32_t* blk_off;   // per block: offset of its header from the frame start
     uint32_t stage_bytes;      // largest payload packed here (<= kSpStageBytes; smaller values only in tests)
+    const uint8_t* headers;    // per frame: the packer's header bytes (hadamard / dct means)
     uint32_t* sc_bit;     // decode index (may be null)
     uint16_t* sc_skip;
     uint32_t* sc_codes;
@@ -41,13 +62,13 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
     __shared__ uint32_t s_wtot[kSpThreads / 32];
     uint32_t f, k, b;
     const uint32_t blk = blockIdx.x;
+    const uint32_t m = list_n[blk];
+    const BlkInfo bi = info[blk];
+    if (!sparse_block_is_packed_from_list(m, bi, so.stage_bytes)) return;  // k_hzr_encode packs it from the plane
     blk_decode(s, blk, f, k, b);
     if (k >= frame_nb[f]) return;
     const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
     const uint32_t n = blk_len(s, b);
-    const uint32_t m = list_n[blk];
-    const BlkInfo bi = info[blk];
-    if (!sparse_block_is_packed_from_list(m, bi, so.stage_bytes)) return;  // k_hzr_encode packs it from the plane
     const uint32_t* glist = lists + (size_t)blk * kListCap;
     uint32_t* list = s_dyn;
     uint32_t* stg = s_dyn + kListCap;  // block header at bytes 9..15, payload from byte 16
@@ -177,7 +198,9 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
     __syncthreads();
 
     // the payload goes out while warp 0 takes its CRC-32C and then writes the 7-byte block header
-    uint8_t* out = so.dst + so.offsets[f] + so.blk_off[blk];
+    const unsigned long long frame_off = so.offsets[f];
+    uint8_t* out = so.dst + frame_off + so.blk_off[blk];
+    if (b == 0) write_chunk_framing(s, info, f, k, so.dst, frame_off, out, so.headers);
     copy_smem_to_global(out + 7, stg, 16, plen);
     if (wid != 0) return;
     const uint32_t crc = warp_crc32c(pay, plen, cc);

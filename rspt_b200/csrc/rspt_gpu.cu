@@ -551,7 +551,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         // sparse blocks from their lists (side stream) beside everything else from the planes: both kernels
         // decide with the same predicate which of them writes a block
         StageTimer t(p, RSPT_STAGE_ENCODE);
-        const SparseOut so{d_dst, d_offsets, p->d_blk_off, p->sp_stage, sc_bit, sc_skip, sc_codes};
+        const SparseOut so{d_dst, d_offsets, p->d_blk_off, p->sp_stage, p->d_headers, sc_bit, sc_skip, sc_codes};
         RSPT_CUDA_CHECK(cudaEventRecord(p->ev_fork2, p->stream));
         RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_fork2, 0));
         k_hzr_encode_sparse<<<nblocks, kSpThreads, kSparseSmem, p->side>>>(s, p->d_frame_nb, p->d_info, p->d_codes, p->d_tree, p->d_lists,
