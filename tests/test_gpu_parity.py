@@ -391,8 +391,8 @@ def test_prefilter_bit_exact(R, oracle):
     n5 = [1.00000000000, -3.14332095199, 3.70064088865, -1.97083923944, 0.41351972908]
     d5 = [0.06722876941, 0.00000000000, -0.13445753881, 0.00000000000, 0.06722876941]
     rng = np.random.default_rng(9)
-    for bps, ch, ns, nfr in ((3, 12, 8192, 5), (4, 3, 1000, 3), (2, 5, 300, 4)):
-        raws = oracle.synth_ecg(21, nfr, bps, ch, ns, amplitude=20000 if bps >= 3 else 3000)
+    for bps, ch, ns, nfr in ((3, 12, 8192, 5), (4, 3, 1000, 3), (2, 5, 300, 4), (1, 1, 1, 2), (2, 3, 33, 35), (4, 1, 257, 3)):
+        raws = oracle.synth_ecg(21, nfr, bps, ch, ns, amplitude=20000 if bps >= 3 else (3000 if bps == 2 else 40))
         p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, bps, max_batch_frames=nfr)
         # 2nd / 1st order Butterworth low-passes, and the band-pass cut to 3 taps (unstable: the output
         # leaves the int32 range and must turn into 0x80000000 like the reference's x86 conversion)
@@ -406,7 +406,7 @@ def test_prefilter_bit_exact(R, oracle):
             for i in range(nfr):
                 want = oracle.prefilter_iir(raws[i], bps, ch, ns, nn, dd, init, impl)
                 assert np.array_equal(got[i], want), ("iir", bps, ch, ns, nc, i)
-        for K in (1, 9, 64):
+        for K in (1, 9, 64, 300):
             k = rng.normal(size=K)
             k /= np.abs(k).sum()
             got = p.prefilter_fir(to_dev(raws), k)
