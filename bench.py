@@ -460,7 +460,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=4096, help="frames per step per GPU")
-    ap.add_argument("--e2e-frames", type=int, default=1024)
+    ap.add_argument("--e2e-frames", type=int, default=4096)
     ap.add_argument("--quick", action="store_true", help="skip the other packers")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
