@@ -58,16 +58,16 @@ __device__ __forceinline__ const uint8_t* blk_ptr(const uint8_t* planes, const S
     return planes + ((size_t)f * s.nb_alloc + k) * s.plane_stride + (size_t)b * kBlock;
 }
 
-// Build the tree of one block with one warp.  h = the block's 261 token counts (global or shared
-// memory), n = block length.  Writes the code table (code | length << 27, 0 = unused symbol) to
-// codes_out[0..263] and the serialised tree to tree_out (global or shared memory).  Returns the
-// block's plan in every lane.  Touches no counters.
-__device__ __forceinline__ BlkInfo warp_build_tree(TreeWarpSmem& S, const uint32_t* h, uint32_t n,
-                                                   uint32_t* codes_out, uint32_t* tree_out)
+// The tree build of one block in three parts (several trees sharing a warp for the serial part was
+// measured and is slower: 4 merges side by side in one warp's lanes diverge on every pick and leave
+// too few warps to hide the latency of the cooperative parts).  h = the block's 261 token counts (global or shared memory), n = block length.
+// tree_prepare and tree_assign are warp-cooperative; tree_merge is ONE thread's job.
+
+// Part 1: classify (FILL?), compact the used symbols into sort keys, sort.  Returns true when the
+// block is a FILL (bi is final then).  Unused symbols get code table entry 0.
+__device__ __forceinline__ bool tree_prepare(TreeWarpSmem& S, const uint32_t* h, uint32_t* codes_out, uint32_t& L_out, BlkInfo& bi)
 {
     const uint32_t lane = lane_id();
-    BlkInfo bi;
-
     // ---- phase A: classify and compact
     uint32_t L = 0, nz = 0, nzsym = 0, zero_class = 0;
     uint32_t mykey = 0xFFFFFFFFu;  // register copy for the <= 32 symbol network
@@ -97,7 +97,8 @@ __device__ __forceinline__ BlkInfo warp_build_tree(TreeWarpSmem& S, const uint32
         // single value class -> FILL (OnlySingleCode); payload is in[0]
         bi.payload_len = 1; bi.total_bits = 8; bi.tree_nbits = 0;
         bi.mode = MODE_FILL; bi.fill = (uint8_t)(nz ? nzsym : 0u); bi.n_used = (uint16_t)L; bi.n_tokens = 0;
-        return bi;
+        L_out = L;
+        return true;
     }
     __syncwarp();
     if (L <= 32) {
@@ -139,87 +140,97 @@ __device__ __forceinline__ BlkInfo warp_build_tree(TreeWarpSmem& S, const uint32
     for (uint32_t i = lane; i < kTreeWords; i += 32) S.tree[i] = 0;
     __syncwarp();
 
-    // ---- phase B: lane 0, two-queue merge.  Registers hold both queue heads; an internal node's
-    // weight word carries a flag "the node created right after me has the same weight", so the
-    // common pick (a run of one) needs no look-ahead load.
-    constexpr uint32_t kInf = 0x7FFFFFFFu, kEqNext = 0x80000000u;
-    if (lane == 0) {
-        uint32_t li = 0, lc = S.key[0] >> 9;          // leaf queue head
-        uint32_t fr = 0, ni = 0, ic = kInf;           // internal queue: head index, count, head weight
-        uint32_t icf = 0;                             // head has an equal-weight successor (flag bit)
-        uint32_t last_w = kInf;
-        // one pick: the lighter head; ties go to the internal node.  Branch-free unless the
-        // internal head starts a run of equal weights (then the latest of the run goes first).
-        uint32_t top = 0, run_end = 0;
-        bool in_run = false;
-        auto pick = [&](uint32_t& id, uint32_t& wt, uint32_t& lv) {
-            const bool take_int = ic <= lc;
-            if (take_int && (in_run || icf)) {
-                uint32_t pk;
-                bool advance;
-                if (!in_run) {
-                    top = fr + 1;
-                    while (top < ni && (S.icnt[top] & kInf) == ic) ++top;
-                    run_end = top;
-                    in_run = true;
-                    pk = --top;
-                    advance = false;  // a flagged run has >= 2 nodes
-                } else {
-                    pk = --top;
-                    advance = top == fr;
-                }
-                id = 512u + pk;
-                wt = ic;
-                lv = S.child[pk] >> 20;
-                if (advance) {
-                    in_run = false;
-                    fr = run_end;
-                    const uint32_t raw = fr < ni ? S.icnt[fr] : kInf;
-                    ic = raw & kInf;
-                    icf = raw & kEqNext;
-                }
-                return;
-            }
-            // heads after this pick, loaded unconditionally (indices stay inside the arrays)
-            const uint32_t nfr = fr + (take_int ? 1u : 0u), nli = li + (take_int ? 0u : 1u);
-            const uint32_t raw = S.icnt[nfr], nk = S.key[nli], ch = S.child[fr];
-            id = take_int ? 512u + fr : li;
-            wt = take_int ? ic : lc;
-            lv = take_int ? ch >> 20 : 1u;
-            if (take_int) {
-                ic = nfr < ni ? raw & kInf : kInf;
-                icf = nfr < ni ? raw & kEqNext : 0u;
-            } else {
-                lc = nli < L ? nk >> 9 : kInf;
-            }
-            fr = nfr;
-            li = nli;
-        };
-        for (uint32_t round = 0; round + 1 < L; ++round) {
-            uint32_t id0, id1, w0, w1, lv0, lv1;
-            pick(id0, w0, lv0);
-            pick(id1, w1, lv1);
-            const uint32_t w = w0 + w1;
-            if (w == last_w) {
-                S.icnt[ni - 1] = w | kEqNext;
-                if (ni - 1 == fr) icf = kEqNext;
-            }
-            if (fr == ni) {
-                ic = w;
-                icf = 0;
-            }
-            S.icnt[ni] = w;
-            S.child[ni] = id0 | (id1 << 10) | ((lv0 + lv1) << 20);
-            last_w = w;
-            ++ni;
-        }
-        // root = last internal node: depth 0, code 0, pre-order offset 0
-        S.icnt[L - 2] = 0;
-        S.ninfo[L - 2] = 0;
-        S.front[0][0] = (uint16_t)(L - 2);
-    }
-    __syncwarp();
+    L_out = L;
+    return false;
+}
 
+// Part 2 (one thread): two-queue merge.
+// Phase B: two-queue merge.  Registers hold both queue heads; an internal node's
+// weight word carries a flag "the node created right after me has the same weight", so the
+// common pick (a run of one) needs no look-ahead load.
+__device__ __forceinline__ void tree_merge(TreeWarpSmem& S, const uint32_t L)
+{
+    constexpr uint32_t kInf = 0x7FFFFFFFu, kEqNext = 0x80000000u;
+    uint32_t li = 0, lc = S.key[0] >> 9;          // leaf queue head
+    uint32_t fr = 0, ni = 0, ic = kInf;           // internal queue: head index, count, head weight
+    uint32_t icf = 0;                             // head has an equal-weight successor (flag bit)
+    uint32_t last_w = kInf;
+    // one pick: the lighter head; ties go to the internal node.  Branch-free unless the
+    // internal head starts a run of equal weights (then the latest of the run goes first).
+    uint32_t top = 0, run_end = 0;
+    bool in_run = false;
+    auto pick = [&](uint32_t& id, uint32_t& wt, uint32_t& lv) {
+        const bool take_int = ic <= lc;
+        if (take_int && (in_run || icf)) {
+            uint32_t pk;
+            bool advance;
+            if (!in_run) {
+                top = fr + 1;
+                while (top < ni && (S.icnt[top] & kInf) == ic) ++top;
+                run_end = top;
+                in_run = true;
+                pk = --top;
+                advance = false;  // a flagged run has >= 2 nodes
+            } else {
+                pk = --top;
+                advance = top == fr;
+            }
+            id = 512u + pk;
+            wt = ic;
+            lv = S.child[pk] >> 20;
+            if (advance) {
+                in_run = false;
+                fr = run_end;
+                const uint32_t raw = fr < ni ? S.icnt[fr] : kInf;
+                ic = raw & kInf;
+                icf = raw & kEqNext;
+            }
+            return;
+        }
+        // heads after this pick, loaded unconditionally (indices stay inside the arrays)
+        const uint32_t nfr = fr + (take_int ? 1u : 0u), nli = li + (take_int ? 0u : 1u);
+        const uint32_t raw = S.icnt[nfr], nk = S.key[nli], ch = S.child[fr];
+        id = take_int ? 512u + fr : li;
+        wt = take_int ? ic : lc;
+        lv = take_int ? ch >> 20 : 1u;
+        if (take_int) {
+            ic = nfr < ni ? raw & kInf : kInf;
+            icf = nfr < ni ? raw & kEqNext : 0u;
+        } else {
+            lc = nli < L ? nk >> 9 : kInf;
+        }
+        fr = nfr;
+        li = nli;
+    };
+    for (uint32_t round = 0; round + 1 < L; ++round) {
+        uint32_t id0, id1, w0, w1, lv0, lv1;
+        pick(id0, w0, lv0);
+        pick(id1, w1, lv1);
+        const uint32_t w = w0 + w1;
+        if (w == last_w) {
+            S.icnt[ni - 1] = w | kEqNext;
+            if (ni - 1 == fr) icf = kEqNext;
+        }
+        if (fr == ni) {
+            ic = w;
+            icf = 0;
+        }
+        S.icnt[ni] = w;
+        S.child[ni] = id0 | (id1 << 10) | ((lv0 + lv1) << 20);
+        last_w = w;
+        ++ni;
+    }
+    // root = last internal node: depth 0, code 0, pre-order offset 0
+    S.icnt[L - 2] = 0;
+    S.ninfo[L - 2] = 0;
+    S.front[0][0] = (uint16_t)(L - 2);
+}
+
+// Part 3: codes, tree bits and the block's plan (returned in every lane).
+__device__ __forceinline__ BlkInfo tree_assign(TreeWarpSmem& S, const uint32_t L, uint32_t n, uint32_t* codes_out, uint32_t* tree_out)
+{
+    const uint32_t lane = lane_id();
+    BlkInfo bi;
     // ---- phase C: breadth-first top-down pass, one frontier node per lane: depth, code and
     // pre-order bit offset of both children.  A leaf child is finished on the spot: code table
     // entry, its 10 tree bits (1 + 9-bit symbol), its share of the payload bit total.
@@ -299,6 +310,20 @@ __device__ __forceinline__ BlkInfo warp_build_tree(TreeWarpSmem& S, const uint32
     bi.n_used = (uint16_t)L;
     bi.n_tokens = (uint16_t)min(ntok, 65535u);
     return bi;
+}
+
+// Build the tree of one block with one warp.  Writes the code table (code | length << 27, 0 = unused
+// symbol) to codes_out[0..263] and the serialised tree to tree_out (global or shared memory).
+// Returns the block's plan in every lane.  Touches no counters.
+__device__ __forceinline__ BlkInfo warp_build_tree(TreeWarpSmem& S, const uint32_t* h, uint32_t n,
+                                                   uint32_t* codes_out, uint32_t* tree_out)
+{
+    BlkInfo bi;
+    uint32_t L;
+    if (tree_prepare(S, h, codes_out, L, bi)) return bi;
+    if (lane_id() == 0) tree_merge(S, L);
+    __syncwarp();
+    return tree_assign(S, L, n, codes_out, tree_out);
 }
 
 __device__ __forceinline__ void count_block_mode(Counters* ctr, uint32_t mode)
