@@ -101,15 +101,16 @@ __global__ void __launch_bounds__(256) k_fwht_inv(const uint8_t* __restrict__ pl
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) w[i] = (int32_t)(a[i] + (uint32_t)mean);
 }
 
-// ---- n = 4096 fast path: three radix-16 passes in registers ---------------------------------
-// 256 threads x 16 elements.  Pass 1 takes index bits 8..11 (elements t + 256 j, read straight
-// from global memory), pass 2 bits 4..7, pass 3 bits 0..3 (elements 16 t + j, so a thread ends
-// up with 16 consecutive coefficients and writes one 128-bit word per plane).  Between passes
-// the data sits in shared memory at i + (i >> 5) (one pad word per 32), which keeps the stride-16
-// accesses of pass 3 conflict-free.  Butterfly order is irrelevant mod 2^32, so the result is the
-// reference's natural-order transform (fwht.c:15-25).
-constexpr uint32_t kFwhtFastN = 4096;
+// ---- n = 4096 / 8192 fast path: three radix-16 passes in registers ---------------------------
+// n/16 threads x 16 elements.  Pass 1 takes the top four index bits (elements t + (n/16) j, read
+// straight from global memory), pass 2 the next four, pass 3 bits 0..3 (elements 16 t + j, so a
+// thread ends up with 16 consecutive coefficients and writes one 128-bit word per plane); for
+// n = 8192 the thirteenth bit (bit 4) is a butterfly between neighbouring lanes (one shuffle per
+// element).  Between passes the data sits in shared memory at i + (i >> 5) (one pad word per 32),
+// which keeps the stride-16 accesses of pass 3 conflict-free.  Butterfly order is irrelevant mod
+// 2^32, so the result is the reference's natural-order transform (fwht.c:15-25).
 __device__ __forceinline__ uint32_t fwht_phys(uint32_t i) { return i + (i >> 5); }
+inline bool fwht_fast_len(int ns) { return ns == 4096 || ns == 8192; }
 
 __device__ __forceinline__ void radix16(uint32_t (&r)[16])
 {
@@ -124,34 +125,48 @@ __device__ __forceinline__ void radix16(uint32_t (&r)[16])
             }
 }
 
-__global__ void __launch_bounds__(256) k_fwht4096_fwd(const int32_t* __restrict__ words, const long long* __restrict__ sums,
-                                                       Shape s, uint8_t* __restrict__ planes, uint8_t* __restrict__ headers)
+// butterfly on index bit 4 = bit 0 of the thread index (elements 16 t + j and 16 (t ^ 1) + j)
+__device__ __forceinline__ void lane_pair_butterfly(uint32_t (&r)[16])
 {
-    __shared__ uint32_t a[kFwhtFastN + kFwhtFastN / 32];
+    const bool upper = threadIdx.x & 1u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, r[j], 1);
+        r[j] = upper ? o - r[j] : r[j] + o;
+    }
+}
+
+template <int LG>
+__global__ void __launch_bounds__((1 << LG) / 16) k_fwht_fast_fwd(const int32_t* __restrict__ words, const long long* __restrict__ sums,
+                                                                   Shape s, uint8_t* __restrict__ planes, uint8_t* __restrict__ headers)
+{
+    constexpr uint32_t N = 1u << LG, T = N / 16, S2 = N / 256;  // threads; element stride of pass 2
+    __shared__ uint32_t a[N + N / 32];
     const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, t = threadIdx.x;
-    const int32_t mean = reference_mean(sums[(size_t)f * s.ch + c], kFwhtFastN);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(words) + (size_t)f * s.N + (size_t)c * kFwhtFastN;
+    const int32_t mean = reference_mean(sums[(size_t)f * s.ch + c], N);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(words) + (size_t)f * s.N + (size_t)c * N;
     if (t == 0) store_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c, mean);
     uint32_t r[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r[j] = __ldg(w + t + 256 * j);
+    for (int j = 0; j < 16; ++j) r[j] = __ldg(w + t + T * j);
     radix16(r);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[fwht_phys(t + 256 * j)] = r[j];
+    for (int j = 0; j < 16; ++j) a[fwht_phys(t + T * j)] = r[j];
     __syncthreads();
-    const uint32_t b2 = (t >> 4) * 256 + (t & 15);
+    const uint32_t b2 = (t / S2) * (16 * S2) + (t % S2);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(b2 + 16 * j)];
+    for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(b2 + S2 * j)];
     radix16(r);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[fwht_phys(b2 + 16 * j)] = r[j];
+    for (int j = 0; j < 16; ++j) a[fwht_phys(b2 + S2 * j)] = r[j];
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(16 * t + j)];
     radix16(r);
+    if (LG == 13) lane_pair_butterfly(r);
     // the per-channel mean is removed before the transform (hadamard.cpp:60-65); by linearity mod
     // 2^32 that only changes the DC coefficient
-    if (t == 0) r[0] -= kFwhtFastN * (uint32_t)mean;
+    if (t == 0) r[0] -= N * (uint32_t)mean;
     uint32_t pl[4][4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(256) k_fwht4096_fwd(const int32_t* __restrict_
         for (int i = 0; i < 4; ++i) {
             const int32_t X = (int32_t)r[4 * g + i];
             // (int)(X / (double)n): truncation toward zero of an exact power-of-two quotient (fwht.c:33)
-            q[i] = (uint32_t)((X + ((X >> 31) & (int32_t)(kFwhtFastN - 1))) >> 12);
+            q[i] = (uint32_t)((X + ((X >> 31) & (int32_t)(N - 1))) >> LG);
         }
         const uint32_t t01 = prmt(q[0], q[1], 0x5140u), t23 = prmt(q[2], q[3], 0x5140u);
         const uint32_t u01 = prmt(q[0], q[1], 0x7362u), u23 = prmt(q[2], q[3], 0x7362u);
@@ -169,20 +184,22 @@ __global__ void __launch_bounds__(256) k_fwht4096_fwd(const int32_t* __restrict_
         pl[2][g] = prmt(u01, u23, 0x5410u);
         pl[3][g] = prmt(u01, u23, 0x7632u);
     }
-    uint8_t* out = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)c * kFwhtFastN + 16 * t;
+    uint8_t* out = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)c * N + 16 * t;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if ((uint32_t)k < s.nb_alloc)
             *reinterpret_cast<uint4*>(out + (size_t)k * s.plane_stride) = make_uint4(pl[k][0], pl[k][1], pl[k][2], pl[k][3]);
 }
 
-__global__ void __launch_bounds__(256) k_fwht4096_inv(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ headers,
-                                                       const uint8_t* __restrict__ dec_nb, Shape s, int32_t* __restrict__ words)
+template <int LG>
+__global__ void __launch_bounds__((1 << LG) / 16) k_fwht_fast_inv(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ headers,
+                                                                   const uint8_t* __restrict__ dec_nb, Shape s, int32_t* __restrict__ words)
 {
-    __shared__ uint32_t a[kFwhtFastN + kFwhtFastN / 32];
+    constexpr uint32_t N = 1u << LG, T = N / 16, S2 = N / 256;
+    __shared__ uint32_t a[N + N / 32];
     const uint32_t f = blockIdx.x / s.ch, c = blockIdx.x % s.ch, t = threadIdx.x;
     const uint32_t nb = dec_nb[f];
-    const uint8_t* in = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)c * kFwhtFastN + 16 * t;
+    const uint8_t* in = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)c * N + 16 * t;
     uint4 pv[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -200,23 +217,24 @@ __global__ void __launch_bounds__(256) k_fwht4096_inv(const uint8_t* __restrict_
         r[12] = y[0]; r[13] = y[1]; r[14] = y[2]; r[15] = y[3];
     }
     radix16(r);
+    if (LG == 13) lane_pair_butterfly(r);
 #pragma unroll
     for (int j = 0; j < 16; ++j) a[fwht_phys(16 * t + j)] = r[j];
     __syncthreads();
-    const uint32_t b2 = (t >> 4) * 256 + (t & 15);
+    const uint32_t b2 = (t / S2) * (16 * S2) + (t % S2);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(b2 + 16 * j)];
+    for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(b2 + S2 * j)];
     radix16(r);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[fwht_phys(b2 + 16 * j)] = r[j];
+    for (int j = 0; j < 16; ++j) a[fwht_phys(b2 + S2 * j)] = r[j];
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(t + 256 * j)];
+    for (int j = 0; j < 16; ++j) r[j] = a[fwht_phys(t + T * j)];
     radix16(r);
     const uint32_t mean = (uint32_t)load_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c);
-    uint32_t* w = reinterpret_cast<uint32_t*>(words) + (size_t)f * s.N + (size_t)c * kFwhtFastN;
+    uint32_t* w = reinterpret_cast<uint32_t*>(words) + (size_t)f * s.N + (size_t)c * N;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) w[t + 256 * j] = r[j] + mean;
+    for (int j = 0; j < 16; ++j) w[t + T * j] = r[j] + mean;
 }
 
 // ---- FP64 complex FFT in shared memory ------------------------------------------------------
@@ -606,8 +624,10 @@ inline int spectral_forward(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
     const dim3 g2((unsigned)(F * s.ch));
     if (s.kind == 2 /*RSPT_HADAMARD*/) {
         const size_t sm = (size_t)s.ns * 4;
-        if ((uint32_t)s.ns == kFwhtFastN) {
-            k_fwht4096_fwd<<<g2, 256, 0, p->stream>>>(p->d_words, p->d_sums, s, p->d_planes, p->d_headers);
+        if (s.ns == 4096) {
+            k_fwht_fast_fwd<12><<<g2, 256, 0, p->stream>>>(p->d_words, p->d_sums, s, p->d_planes, p->d_headers);
+        } else if (s.ns == 8192) {
+            k_fwht_fast_fwd<13><<<g2, 512, 0, p->stream>>>(p->d_words, p->d_sums, s, p->d_planes, p->d_headers);
         } else {
             cudaFuncSetAttribute(k_fwht_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             k_fwht_fwd<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_planes, p->d_headers);
@@ -700,8 +720,10 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
         const dim3 g2((unsigned)(F * s.ch));
         if (s.kind == 2) {
             const size_t sm = (size_t)s.ns * 4;
-            if ((uint32_t)s.ns == kFwhtFastN) {
-                k_fwht4096_inv<<<g2, 256, 0, p->stream>>>(p->d_planes, p->d_headers, p->d_dec_nb, s, p->d_words);
+            if (s.ns == 4096) {
+                k_fwht_fast_inv<12><<<g2, 256, 0, p->stream>>>(p->d_planes, p->d_headers, p->d_dec_nb, s, p->d_words);
+            } else if (s.ns == 8192) {
+                k_fwht_fast_inv<13><<<g2, 512, 0, p->stream>>>(p->d_planes, p->d_headers, p->d_dec_nb, s, p->d_words);
             } else {
                 cudaFuncSetAttribute(k_fwht_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
                 k_fwht_inv<<<g2, 256, sm, p->stream>>>(p->d_planes, p->d_headers, p->d_dec_nb, s, p->d_words);

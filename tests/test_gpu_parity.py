@@ -137,6 +137,7 @@ STREAM_CASES = [
     ("xdelta_hzr", 4, 2, 70001, 4, 2),
     ("hzr", 3, 12, 8192, 0, 3), ("hzr", 4, 12, 4096, 0, 2), ("hzr", 1, 2, 999, 0, 3), ("hzr", 2, 1, 140000, 0, 2),
     ("hadamard", 4, 12, 4096, 0, 3), ("hadamard", 3, 3, 16384, 0, 2), ("hadamard", 2, 2, 8, 0, 3), ("hadamard", 2, 3, 4096, 0, 2),
+    ("hadamard", 3, 12, 8192, 0, 3), ("hadamard", 4, 1, 8192, 0, 2),
 ]
 
 
