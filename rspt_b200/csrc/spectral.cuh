@@ -730,7 +730,15 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
             }
             p->launches += 1;
         } else {
-            INV_LAUNCH(4, true, false);  // coefficient words (BPS unused for word output)
+            // coefficient words (BPS unused for word output)
+            const size_t smw = (size_t)2 * ((uint32_t)s.ns / kInvPiece) * s.ch * 4;
+            if ((s.ns % (int)kInvPiece) == 0 && smw <= 200 * 1024) {
+                cudaFuncSetAttribute(k_planes_to_samples_fast<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);
+                k_planes_to_samples_fast<4, true, true><<<gf, kInvThreads, smw, p->stream>>>(p->d_planes, s, p->d_dec_nb, 1, nullptr,
+                                                                                             p->d_seg_xor, p->segs_per_plane, p->d_words);
+            } else {
+                INV_LAUNCH(4, true, false);
+            }
             if (dct_use_direct(p)) {
                 const size_t sm = (size_t)s.ns * 4;
                 cudaFuncSetAttribute(k_dct_inv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

@@ -460,7 +460,9 @@ __global__ void __launch_bounds__(512) k_planes_to_samples(const uint8_t* __rest
 //           sign-extended words, lane-local + warp xor scan, +128, lane-local + warp add scan;
 //           the four channels' samples are packed row-wise with PRMT into a shared-memory tile
 //           (quad stride row + 1 words, conflict-free) that the CTA then copies out coalesced.
-// SCAN = false is the plain hzr packer (no chain).
+// SCAN = false is the plain hzr packer (no chain).  WORDS = true stops after the scans and stores
+// the int32 words in flat order (the coefficient words of the inverse DCT): pass 3 then walks the
+// pieces like pass 2 and every lane writes its 4 consecutive words with one 128-bit store.
 // ------------------------------------------------------------------------------------------
 constexpr int kInvThreads = 256;
 constexpr uint32_t kInvPiece = 128;
@@ -500,12 +502,13 @@ __device__ __forceinline__ uint32_t warp_add_inclusive(uint32_t v)
     return v;
 }
 
-template <int BPS, bool SCAN>
+template <int BPS, bool SCAN, bool WORDS = false>
 __global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const uint8_t* __restrict__ planes, Shape s,
                                                                             const uint8_t* __restrict__ dec_nb,
                                                                             uint32_t tiles_per_group,
                                                                             uint8_t* __restrict__ dst_raw,
-                                                                            const uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane)
+                                                                            const uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane,
+                                                                            int32_t* __restrict__ dst_words = nullptr)
 {
     extern __shared__ __align__(16) uint32_t sm32[];
     const uint32_t f = blockIdx.x;
@@ -589,6 +592,35 @@ __global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const
         __syncthreads();
         smem_exclusive_scan<false>(psum, np);
         __syncthreads();
+    }
+
+    if (WORDS) {
+        // pass 3, word output: piece by piece, 4 consecutive words per lane
+        uint4* wout = reinterpret_cast<uint4*>(dst_words + (size_t)f * s.N);
+        for (uint32_t p0 = wid * U; p0 < np; p0 += nwarps * U) {
+            uint32_t q[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (p0 + u < np) load_piece(p0 + u, q[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (p0 + u >= np) break;
+                uint32_t y[4];
+                planes_to_words(q[u][0], q[u][1], q[u][2], q[u][3], nb, y);
+                if (SCAN) {
+                    y[1] ^= y[0]; y[2] ^= y[1]; y[3] ^= y[2];
+                    const uint32_t before = pxor[p0 + u] ^ warp_xor_inclusive(y[3]) ^ y[3];
+                    y[0] = (y[0] ^ before) + 128u;
+                    y[1] = (y[1] ^ before) + 128u + y[0];
+                    y[2] = (y[2] ^ before) + 128u + y[1];
+                    y[3] = (y[3] ^ before) + 128u + y[2];
+                    const uint32_t base = psum[p0 + u] + warp_add_inclusive(y[3]) - y[3];
+                    y[0] += base; y[1] += base; y[2] += base; y[3] += base;
+                }
+                wout[(size_t)(p0 + u) * 32u + lane] = make_uint4(y[0], y[1], y[2], y[3]);
+            }
+        }
+        return;
     }
 
     // pass 3: groups of `tiles_per_group` sample tiles (128 samples each); work item = (tile, channel group)
