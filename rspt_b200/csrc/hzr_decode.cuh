@@ -386,96 +386,81 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     __syncthreads();
 
     const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
-    // blocks that are mostly zeros (payload < 1/4 of the output): clear the whole output once,
-    // coalesced; zero runs then cost nothing.  Dense blocks write their zeros in place instead.
-    const bool pre_clear = plen * 4u < n;
-    if (pre_clear) {
-        for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-    }
+    // The whole output block is cleared first (coalesced 128-bit stores that the L2 merges with the word
+    // stores below), so a zero run only advances the write position and the token loop is the same
+    // straight-line code for literals and runs.
+    for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
     uint32_t my_err = 0;
-    uint32_t bitpos = 0, seg0 = 0, seg_len = 0, skip = 0, end_bit = 0;
-    bool mine = false;
-    {
-        if (tid < nseg) {
-            bitpos = sc_bit[(size_t)blk * kMaxSegs + tid];
-            skip = sc_skip[(size_t)blk * kMaxSegs + tid];
-            end_bit = tid + 1 < nseg ? sc_bit[(size_t)blk * kMaxSegs + tid + 1] : 0xFFFFFFFFu;
-            seg0 = tid * kSegBytes;
-            seg_len = min((uint32_t)kSegBytes, n - seg0);
-            mine = true;
-        }
-        // segments that lie entirely inside a zero run: cleared by the warp, several per store
-        constexpr uint32_t kQ = kSegBytes / 16, kPer = 32 / kQ;  // 16-byte chunks per segment, segments per store
-        const bool all_zero = mine && skip >= seg_len;
-        uint32_t zm = pre_clear ? 0u : __ballot_sync(0xFFFFFFFFu, all_zero);
-        while (zm) {
-            uint32_t sl = 32u;
-#pragma unroll
-            for (uint32_t j = 0; j < kPer; ++j) {
-                if (zm) {
-                    const uint32_t l = __ffs(zm) - 1u;
-                    zm &= zm - 1u;
-                    if (lane / kQ == j) sl = l;
-                }
-            }
-            if (sl < 32u) {
-                const uint32_t sg = (tid & ~31u) + sl, q = sg * kQ + (lane % kQ);
-                if (q < nq) out4[q] = make_uint4(0, 0, 0, 0);
-            }
-        }
-        if (all_zero) {
-            mine = false;
-            if (my_xor) my_xor[tid] = 0;
-        }
-    }
-    if (mine) {
-        const uint32_t limit_bits = plen * 8u;
-        if (bitpos > limit_bits) { my_err = 1; bitpos = 0; }
-        end_bit = min(end_bit, limit_bits);
-        SegWriter wr;
-        wr.init(out + seg0, seg_len, pre_clear);
-        wr.zeros(skip);  // bytes covered by a zero run that started in an earlier segment
-        BitReader r;
-        r.init(payw, bitpos);
-        while (!my_err && bitpos < end_bit && wr.pos < seg_len) {
-            r.refill();
-            uint32_t e = s_lut[r.peek(kLutBits)];
-            if (e & kLongFlag) {
-                // code longer than the table: match the few long code words (dec:418-431 walks the tree)
-                uint32_t j = e & kLongEnd;
-                e = 0;
-                while (j != kLongEnd) {
-                    const uint32_t sym = s_long[j], cw = s_cw[sym], len = cw >> 27;
-                    if (((uint32_t)r.buf & ((1u << len) - 1u)) == (cw & 0x07FFFFFFu)) {
-                        e = sym | (len << 9);
-                        break;
+    if (tid < nseg) {
+        uint32_t bitpos = sc_bit[(size_t)blk * kMaxSegs + tid];
+        const uint32_t skip = sc_skip[(size_t)blk * kMaxSegs + tid];  // bytes covered by a zero run that started earlier
+        uint32_t end_bit = tid + 1 < nseg ? sc_bit[(size_t)blk * kMaxSegs + tid + 1] : 0xFFFFFFFFu;
+        const uint32_t seg0 = tid * kSegBytes, seg_len = min((uint32_t)kSegBytes, n - seg0);
+        uint32_t xb = 0;
+        if (skip < seg_len) {
+            const uint32_t limit_bits = plen * 8u;
+            if (bitpos > limit_bits) { my_err = 1; bitpos = 0; }
+            end_bit = min(end_bit, limit_bits);
+            // the thread's bytes are gathered into the open word w (bytes of the word at and beyond pos are
+            // zero); a word goes out with one 32-bit store when the position leaves it, unless it is empty
+            uint8_t* dst = out + seg0;
+            uint32_t pos = skip, w = 0, xacc = 0;
+            BitReader r;
+            r.init(payw, bitpos);
+            while (!my_err && bitpos < end_bit && pos < seg_len) {
+                r.refill();
+                uint32_t e = s_lut[r.peek(kLutBits)];
+                if (e & kLongFlag) {
+                    // code longer than the table: match the few long code words (dec:418-431 walks the tree)
+                    uint32_t j = e & kLongEnd;
+                    e = 0;
+                    while (j != kLongEnd) {
+                        const uint32_t sym = s_long[j], cw = s_cw[sym], len = cw >> 27;
+                        if (((uint32_t)r.buf & ((1u << len) - 1u)) == (cw & 0x07FFFFFFu)) {
+                            e = sym | (len << 9);
+                            break;
+                        }
+                        j = s_next[j];
                     }
-                    j = s_next[j];
-                }
-                if (e == 0u) { my_err = 1; break; }
-            }
-            const uint32_t len = e >> 9, sym = e & 511u;
-            r.skip(len);
-            bitpos += len;
-            if (sym < 256u) {
-                wr.put(sym);  // literal; symbol 0 is a zero run of one
-            } else {
-                uint32_t z = 2u;
-                if (sym > 256u) {
-                    const uint32_t eb = sym_extra_bits(sym);
+                    if (e == 0u) { my_err = 1; break; }
+                    // consume it here and top the window up, so that the extra bits of a run are there
+                    r.skip(e >> 9);
+                    bitpos += e >> 9;
                     r.refill();
-                    const uint32_t ev = r.take(eb);
-                    bitpos += eb;
-                    z = ev + (sym == 257u ? 3u : sym == 258u ? 7u : sym == 259u ? 23u : 279u);
+                    e &= 511u;
                 }
-                if (seg0 + wr.pos + z > n) { my_err = 1; break; }  // "Output buffer full" dec:473-476
-                wr.zeros(z);
+                const uint32_t len = e >> 9, sym = e & 511u;
+                r.skip(len);  // <= kLutBits bits: at least 21 are left in the window
+                bitpos += len;
+                const bool run = sym >= 256u;  // symbol 0 (a zero run of one) is handled as a literal
+                uint32_t adv = 1u;
+                if (run) {
+                    const uint32_t kk = sym - 256u;                              // run class 0..4 (hzr_internal.h:117-121)
+                    const uint32_t eb = (0xE8420u >> (4u * kk)) & 15u;             // 0, 2, 4, 8, 14 extra bits
+                    const uint32_t ev = (uint32_t)r.buf & ((1u << eb) - 1u);
+                    r.skip(eb);
+                    bitpos += eb;
+                    const uint32_t z = ev + (kk == 4u ? 279u : (0x17070302u >> (8u * kk)) & 255u);
+                    if (seg0 + pos + z > n) { my_err = 1; break; }  // "Output buffer full" dec:473-476
+                    adv = min(z, seg_len - pos);  // the rest of the run is the next segment's `skip`
+                }
+                const uint32_t np = pos + adv;
+                const uint32_t wv = run ? w : w | (sym << ((pos & 3u) * 8u));
+                const bool cross = (np >> 2) != (pos >> 2);
+                if (cross) {
+                    if (wv) *reinterpret_cast<uint32_t*>(dst + (pos & ~3u)) = wv;
+                    xacc ^= wv;
+                }
+                w = cross ? 0u : wv;
+                pos = np;
             }
+            if (bitpos > limit_bits) my_err = 1;
+            if (w) *reinterpret_cast<uint32_t*>(dst + (pos & ~3u)) = w;
+            xb = xacc ^ w;  // xor of the segment's bytes
+            xb ^= xb >> 16;
+            xb ^= xb >> 8;
         }
-        if (bitpos > limit_bits) my_err = 1;
-        const uint32_t xb = wr.xor_byte();  // before finish(): the padding it adds is zeros anyway
-        wr.finish();
         if (my_xor) my_xor[tid] = (uint8_t)xb;
     }
     if (my_err) status[f] = -4;

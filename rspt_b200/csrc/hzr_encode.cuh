@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
     __shared__ uint32_t s_after[kMaxSteps];          // zeros that follow the end of every step
     __shared__ uint32_t s_tot[2][kEncWarps];
     __shared__ uint32_t s_red[33];
+    __shared__ uint32_t s_rc[2][32];                 // the two slots (code word, extra bits) of a zero run of 2..31
 
     uint32_t f, k, b;
     const uint32_t blk = blockIdx.x;
@@ -216,6 +217,12 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             const uint32_t cw = __ldg(codes + (size_t)blk * kSymStride + i);
             s_codes[i] = cw;
             if (sc_codes) sc_codes[(size_t)blk * kSymStride + i] = cw;  // decode index: the block's code table
+        }
+        if (tid >= 2u && tid < 32u) {
+            uint32_t sym, ev, eb;
+            run_token(tid, sym, ev, eb);
+            s_rc[0][tid] = __ldg(codes + (size_t)blk * kSymStride + sym);
+            s_rc[1][tid] = ev | (eb << 27);
         }
         const uint32_t tw = (bi.tree_nbits + 31u) >> 5, pw = (plen + 3u) >> 2;
         // staging: tree words, then zeros (the code words are OR-ed in)
@@ -351,9 +358,16 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                         if (len > kRunCap) {
                             slow |= 1u << r;  // several tokens: general path
                         } else {
-                            uint32_t sym, ev, eb;
-                            run_token(len, sym, ev, eb);
-                            const uint32_t c0 = s_codes[sym], c1 = ev | (eb << 27);
+                            uint32_t c0, c1;
+                            if (len < 32u) {  // the usual case on a dense plane: both slots from the block's run table
+                                c0 = s_rc[0][len];
+                                c1 = s_rc[1][len];
+                            } else {
+                                uint32_t sym, ev, eb;
+                                run_token(len, sym, ev, eb);
+                                c0 = s_codes[sym];
+                                c1 = ev | (eb << 27);
+                            }
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
                                 if ((uint32_t)jj == j) cw[r][jj] = c0;

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kHistThreads, PART == 2 ? 8 : 5) k_hzr_hist(co
 
     // ---- dense blocks
     uint16_t* my_lz = step_lz + (size_t)blk * kMaxSteps;
-    uint32_t pending = 0, lead = 0, cnt0 = 0;
+    uint32_t pending = 0, lead = 0, cnt_a = 0, cnt_b = 0;  // packed per-thread counts of the short run classes
     bool seen = false;
     for (uint32_t st = s_lo; st < s_hi; ++st) {
         const Chunk c = load_chunk(src, n, st * kStepBytes + lane * 16u);
@@ -311,23 +311,26 @@ __global__ void __launch_bounds__(kHistThreads, PART == 2 ? 8 : 5) k_hzr_hist(co
         neighbour_zero(c.z, prevz, nextz);
         const uint32_t starts = c.z & ~((c.z << 1) | prevz);
         const uint32_t cont = (c.z >> 1) | (nextz << 15);  // the byte after is a zero too
-        cnt0 += __popc(starts & ~cont);
-        uint32_t rs2 = starts & cont;
+        const uint32_t rs2 = starts & cont;                // first zero of a run of >= 2
+        // runs that END inside the chunk are classified for all 16 positions at once: aK has bit p set when
+        // the K bytes from p on are zeros of this chunk (hzr_encode.c:152-166; such a run is < 16 long)
+        const uint32_t a2 = c.z & (c.z >> 1), a3 = a2 & (c.z >> 2), a4 = a2 & (a2 >> 2), a7 = a4 & (a3 >> 4);
+        // the run that reaches the chunk's last byte (if any) is measured across lanes below
+        const uint32_t top = c.stop ? 32u - (uint32_t)__clz((int)c.stop) : 0u;  // first byte after the last stop
+        const uint32_t open_bit = (c.z >> 15) << top;
+        const uint32_t closed = rs2 & ~open_bit;
+        cnt_a += __popc(starts & ~cont) | (__popc(closed & ~a3) << 16);            // runs of 1 | runs of 2
+        cnt_b += __popc(closed & a3 & ~a7) | (__popc(closed & a7) << 16);          // runs of 3-6 | 7-22
         // position of the first / last stop bit of every lane, for the neighbours
         const uint32_t first_stop = c.stop ? (uint32_t)__ffs(c.stop) - 1u : 16u;
-        if (__any_sync(0xFFFFFFFFu, rs2 != 0u)) {
+        const bool open_run = (rs2 & open_bit) != 0u;
+        if (__any_sync(0xFFFFFFFFu, open_run)) {
             const uint32_t above = lane < 31 ? anyt & ~((2u << lane) - 1u) : 0u;
             const uint32_t q = above ? (uint32_t)__ffs(above) - 1u : 0u;
             const uint32_t fq = __shfl_sync(0xFFFFFFFFu, first_stop, q);
-            const uint32_t fwd = 16u * (q - lane - 1u) + fq;  // zeros after my chunk (valid iff above != 0)
-            while (rs2) {
-                const uint32_t p = __ffs(rs2) - 1u;
-                rs2 &= rs2 - 1u;
-                const uint32_t sb = c.stop >> p;
-                if (sb) hist_run((uint32_t)__ffs(sb) - 1u, s_run);
-                else if (above) hist_run(16u - p + fwd, s_run);
-                // else: the run leaves the step; it is part of the step's trailing zeros
-            }
+            // zeros after my chunk up to the next stop; without one the run leaves the step and is part of
+            // the step's trailing zeros
+            if (open_run && above) hist_run(16u - top + 16u * (q - lane - 1u) + fq, s_run);
         }
         // chain the step's leading / trailing zeros along the warp's range
         const uint32_t qf = (uint32_t)__ffs(anyt) - 1u, ql = 31u - (uint32_t)__clz((int)anyt);
@@ -345,9 +348,15 @@ __global__ void __launch_bounds__(kHistThreads, PART == 2 ? 8 : 5) k_hzr_hist(co
         pending = tz;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt0 += __shfl_xor_sync(0xFFFFFFFFu, cnt0, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt_a += __shfl_xor_sync(0xFFFFFFFFu, cnt_a, o);  // <= 16 steps x 8 runs x 32 lanes per field
+        cnt_b += __shfl_xor_sync(0xFFFFFFFFu, cnt_b, o);
+    }
     if (lane == 0) {
-        if (cnt0) atomicAdd(&s_run[0], cnt0);
+        if (cnt_a & 0xFFFFu) atomicAdd(&s_run[0], cnt_a & 0xFFFFu);
+        if (cnt_a >> 16) atomicAdd(&s_run[1], cnt_a >> 16);
+        if (cnt_b & 0xFFFFu) atomicAdd(&s_run[2], cnt_b & 0xFFFFu);
+        if (cnt_b >> 16) atomicAdd(&s_run[3], cnt_b >> 16);
         s_wsum[wid][0] = seen;
         s_wsum[wid][1] = lead;
         s_wsum[wid][2] = pending;

@@ -237,6 +237,183 @@ __global__ void __launch_bounds__((1 << LG) / 16) k_fwht_fast_inv(const uint8_t*
     for (int j = 0; j < 16; ++j) w[t + T * j] = r[j] + mean;
 }
 
+// ---- fused fast path: interleaved samples <-> planes without the int32 word matrix ------------
+// ch % 4 == 0: a CTA takes FOUR channels of one frame.  The 4 x BPS bytes of a sample row that belong
+// to them are contiguous in the interleaved input, so thread t reads them for its 16 samples
+// t + T j (one 128-bit load per sample for 4-byte samples; the other channel groups of the frame
+// read the neighbouring bytes of the same lines at the same time and find them in L2), unpacks them
+// with PRMT and runs the three radix-16 passes of k_fwht_fast_* on four shared-memory buffers.
+// k_raw_to_words / k_words_to_raw and the word matrix (2 x 4 bytes of traffic per sample) drop out.
+// The channel mean needs the 64-bit sum (average_32, utils.cpp:30-40): its low 32 bits are the DC
+// coefficient X[0] of the transform itself, the rest follows from the sum of the samples' upper
+// halves (one warp reduction per channel): sum = 65536 * S_hi + ((X[0] - 65536 * S_hi) mod 2^32).
+template <int LG, int BPS>
+__global__ void __launch_bounds__((1 << LG) / 16) k_fwht_raw_fwd(const uint8_t* __restrict__ src, Shape s,
+                                                                  uint8_t* __restrict__ planes, uint8_t* __restrict__ headers)
+{
+    constexpr uint32_t N = 1u << LG, T = N / 16, S2 = N / 256, A = N + N / 32;
+    extern __shared__ __align__(16) uint32_t a4[];  // [4][A]
+    __shared__ int s_hi[4];
+    const uint32_t G = (uint32_t)s.ch >> 2, f = blockIdx.x / G, g = blockIdx.x % G, t = threadIdx.x;
+    const uint32_t roww = ((uint32_t)s.ch * BPS) >> 2;  // words per sample row
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(src + (size_t)f * s.frame_bytes) + g * BPS;
+    if (t < 4) s_hi[t] = 0;
+    uint32_t v[4][16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t* p = base + (size_t)(t + T * j) * roww;
+        uint32_t w[4], x[4];
+        if (BPS == 4) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+            w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < BPS; ++i) w[i] = __ldg(p + i);
+        }
+        unpack4<BPS>(w, x);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) v[cc][j] = x[cc];
+    }
+    __syncthreads();  // s_hi cleared
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        int hi = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hi += (int32_t)v[cc][j] >> 16;
+        hi = __reduce_add_sync(0xFFFFFFFFu, hi);
+        if ((t & 31u) == 0) atomicAdd(&s_hi[cc], hi);
+        radix16(v[cc]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a4[cc * A + fwht_phys(t + T * j)] = v[cc][j];
+    }
+    __syncthreads();
+    const uint32_t b2 = (t / S2) * (16 * S2) + (t % S2);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = a4[cc * A + fwht_phys(b2 + S2 * j)];
+        radix16(r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a4[cc * A + fwht_phys(b2 + S2 * j)] = r[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const uint32_t c = 4 * g + cc;
+        uint32_t r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = a4[cc * A + fwht_phys(16 * t + j)];
+        radix16(r);
+        if (LG == 13) lane_pair_butterfly(r);
+        if (t == 0) {
+            const int shi = s_hi[cc];
+            const uint32_t lo = r[0] - ((uint32_t)shi << 16);  // sum of the samples' lower halves (< 2^29)
+            const int32_t mean = reference_mean((long long)shi * 65536ll + (long long)lo, N);
+            store_mean24(headers + (size_t)f * s.hdr_bytes + 3 * c, mean);
+            // the mean is removed before the transform (hadamard.cpp:60-65): only the DC coefficient changes
+            r[0] -= N * (uint32_t)mean;
+        }
+        uint32_t pl[4][4];
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+            uint32_t q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int32_t X = (int32_t)r[4 * gq + i];
+                q[i] = (uint32_t)((X + ((X >> 31) & (int32_t)(N - 1))) >> LG);  // trunc(X / n), fwht.c:33
+            }
+            const uint32_t t01 = prmt(q[0], q[1], 0x5140u), t23 = prmt(q[2], q[3], 0x5140u);
+            const uint32_t u01 = prmt(q[0], q[1], 0x7362u), u23 = prmt(q[2], q[3], 0x7362u);
+            pl[0][gq] = prmt(t01, t23, 0x5410u);
+            pl[1][gq] = prmt(t01, t23, 0x7632u);
+            pl[2][gq] = prmt(u01, u23, 0x5410u);
+            pl[3][gq] = prmt(u01, u23, 0x7632u);
+        }
+        uint8_t* out = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)c * N + 16 * t;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((uint32_t)k < s.nb_alloc)
+                *reinterpret_cast<uint4*>(out + (size_t)k * s.plane_stride) = make_uint4(pl[k][0], pl[k][1], pl[k][2], pl[k][3]);
+    }
+}
+
+template <int LG, int BPS>
+__global__ void __launch_bounds__((1 << LG) / 16) k_fwht_raw_inv(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ headers,
+                                                                  const uint8_t* __restrict__ dec_nb, Shape s, uint8_t* __restrict__ dst)
+{
+    constexpr uint32_t N = 1u << LG, T = N / 16, S2 = N / 256, A = N + N / 32;
+    extern __shared__ __align__(16) uint32_t a4[];  // [4][A]
+    const uint32_t G = (uint32_t)s.ch >> 2, f = blockIdx.x / G, g = blockIdx.x % G, t = threadIdx.x;
+    const uint32_t nb = dec_nb[f];
+    uint4 pv[4][4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const uint8_t* in = planes + (size_t)f * s.nb_alloc * s.plane_stride + (size_t)(4 * g + cc) * N + 16 * t;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            pv[cc][k] = (uint32_t)k < s.nb_alloc ? __ldg(reinterpret_cast<const uint4*>(in + (size_t)k * s.plane_stride)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[16], y[4];
+        planes_to_words(pv[cc][0].x, pv[cc][1].x, pv[cc][2].x, pv[cc][3].x, nb, y);
+        r[0] = y[0]; r[1] = y[1]; r[2] = y[2]; r[3] = y[3];
+        planes_to_words(pv[cc][0].y, pv[cc][1].y, pv[cc][2].y, pv[cc][3].y, nb, y);
+        r[4] = y[0]; r[5] = y[1]; r[6] = y[2]; r[7] = y[3];
+        planes_to_words(pv[cc][0].z, pv[cc][1].z, pv[cc][2].z, pv[cc][3].z, nb, y);
+        r[8] = y[0]; r[9] = y[1]; r[10] = y[2]; r[11] = y[3];
+        planes_to_words(pv[cc][0].w, pv[cc][1].w, pv[cc][2].w, pv[cc][3].w, nb, y);
+        r[12] = y[0]; r[13] = y[1]; r[14] = y[2]; r[15] = y[3];
+        radix16(r);
+        if (LG == 13) lane_pair_butterfly(r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a4[cc * A + fwht_phys(16 * t + j)] = r[j];
+    }
+    __syncthreads();
+    const uint32_t b2 = (t / S2) * (16 * S2) + (t % S2);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = a4[cc * A + fwht_phys(b2 + S2 * j)];
+        radix16(r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a4[cc * A + fwht_phys(b2 + S2 * j)] = r[j];
+    }
+    __syncthreads();
+    uint32_t x[4][16];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[cc][j] = a4[cc * A + fwht_phys(t + T * j)];
+        radix16(x[cc]);
+        const uint32_t mean = (uint32_t)load_mean24(headers + (size_t)f * s.hdr_bytes + 3 * (4 * g + cc));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[cc][j] += mean;
+    }
+    // the 4 channels of a sample row, low BPS bytes each (convert_i32_to_native, utils.cpp:51-121)
+    const uint32_t roww = ((uint32_t)s.ch * BPS) >> 2;
+    uint32_t* base = reinterpret_cast<uint32_t*>(dst + (size_t)f * s.frame_bytes) + g * BPS;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        uint32_t* p = base + (size_t)(t + T * j) * roww;
+        const uint32_t a = x[0][j], b = x[1][j], c2 = x[2][j], d = x[3][j];
+        if (BPS == 4) {
+            *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c2, d);
+        } else if (BPS == 3) {
+            p[0] = prmt(a, b, 0x4210u);
+            p[1] = prmt(b, c2, 0x5421u);
+            p[2] = prmt(c2, d, 0x6542u);
+        } else if (BPS == 2) {
+            p[0] = prmt(a, b, 0x5410u);
+            p[1] = prmt(c2, d, 0x5410u);
+        } else {
+            p[0] = prmt(prmt(a, b, 0x0040u), prmt(c2, d, 0x0040u), 0x5410u);
+        }
+    }
+}
+
 // ---- FP64 complex FFT in shared memory ------------------------------------------------------
 // x[0..n) complex, n = 2^lg.  Input must already be in bit-reversed order.  tw[j] = e^{-2 pi i j/n}
 // for j < n/2; INVERSE conjugates it.  Radix-2 decimation in time.
@@ -605,10 +782,52 @@ inline cudaError_t dct_build_tables(rspt_gpu_packer* p)
     default: KERNEL<4> __VA_ARGS__; break;                   \
     }
 
+// the fused hadamard kernels apply: four-channel groups, a transform length with a register path,
+// 16-byte aligned frames
+inline bool fwht_raw_ok(const Shape& s, const void* d_raw)
+{
+    return s.kind == 2 && (s.ch & 3) == 0 && fwht_fast_len(s.ns) && ((uintptr_t)d_raw & 15) == 0 && (s.frame_bytes & 15) == 0 &&
+           getenv("RSPT_FWHT_FUSED") != nullptr;
+}
+
+// the four-channel-group word kernels apply (a warp's 32 sample quads stay inside one channel group)
+inline bool words_g4_ok(const Shape& s, const void* d_raw)
+{
+    return (s.ch & 3) == 0 && (s.ns % 1024) == 0 && ((uintptr_t)d_raw & 15) == 0 && (s.frame_bytes & 15) == 0 &&
+           getenv("RSPT_WORDS_G4") != nullptr;
+}
+
+#define FWHT_RAW_LAUNCH(KERNEL, ...)                                                                              \
+    do {                                                                                                          \
+        const size_t smr = (size_t)4 * ((size_t)s.ns + s.ns / 32) * 4;                                            \
+        const unsigned gr = (unsigned)(F * (s.ch >> 2));                                                          \
+        if (s.ns == 4096) {                                                                                       \
+            switch (s.bps) {                                                                                      \
+            case 1: cudaFuncSetAttribute(KERNEL<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<12, 1><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
+            case 2: cudaFuncSetAttribute(KERNEL<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<12, 2><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
+            case 3: cudaFuncSetAttribute(KERNEL<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<12, 3><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
+            default: cudaFuncSetAttribute(KERNEL<12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<12, 4><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
+            }                                                                                                     \
+        } else {                                                                                                  \
+            switch (s.bps) {                                                                                      \
+            case 1: cudaFuncSetAttribute(KERNEL<13, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<13, 1><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
+            case 2: cudaFuncSetAttribute(KERNEL<13, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<13, 2><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
+            case 3: cudaFuncSetAttribute(KERNEL<13, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<13, 3><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
+            default: cudaFuncSetAttribute(KERNEL<13, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<13, 4><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
+            }                                                                                                     \
+        }                                                                                                         \
+    } while (0)
+
 // hadamard / dct: samples -> planes + header
 inline int spectral_forward(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
 {
     const Shape& s = p->s;
+    if (fwht_raw_ok(s, d_src)) {
+        FWHT_RAW_LAUNCH(k_fwht_raw_fwd, d_src, s, p->d_planes, p->d_headers);
+        p->launches += 1;
+        RSPT_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     const uint32_t tiles = ((uint32_t)s.ns + kPiece - 1) / kPiece;
     const size_t tile_smem = (size_t)kPiece * s.ch * s.bps + 48;
     if (tile_smem > 200 * 1024) return fail_arg(p, "too many channels");
@@ -620,7 +839,12 @@ inline int spectral_forward(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
     case 3: cudaFuncSetAttribute(k_raw_to_words<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
     default: cudaFuncSetAttribute(k_raw_to_words<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
     }
-    SPECTRAL_BPS_SWITCH(k_raw_to_words, <<<g1, 256, tile_smem, p->stream>>>(d_src, s, tiles, p->d_words, p->d_sums));
+    if (words_g4_ok(s, d_src)) {
+        const unsigned gb = (unsigned)(F * (s.ch >> 2) * (size_t)(s.ns >> 2) / 256);
+        SPECTRAL_BPS_SWITCH(k_raw_to_words_g4, <<<gb, 256, 0, p->stream>>>(d_src, s, p->d_words, p->d_sums));
+    } else {
+        SPECTRAL_BPS_SWITCH(k_raw_to_words, <<<g1, 256, tile_smem, p->stream>>>(d_src, s, tiles, p->d_words, p->d_sums));
+    }
     const dim3 g2((unsigned)(F * s.ch));
     if (s.kind == 2 /*RSPT_HADAMARD*/) {
         const size_t sm = (size_t)s.ns * 4;
@@ -718,6 +942,12 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
         p->launches += 1;
     } else {
         const dim3 g2((unsigned)(F * s.ch));
+        if (fwht_raw_ok(s, d_dst)) {
+            FWHT_RAW_LAUNCH(k_fwht_raw_inv, p->d_planes, p->d_headers, p->d_dec_nb, s, d_dst);
+            p->launches += 1;
+            RSPT_CUDA_CHECK(cudaGetLastError());
+            return 0;
+        }
         if (s.kind == 2) {
             const size_t sm = (size_t)s.ns * 4;
             if (s.ns == 4096) {
@@ -762,7 +992,12 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
         case 3: cudaFuncSetAttribute(k_words_to_raw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
         default: cudaFuncSetAttribute(k_words_to_raw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
         }
-        SPECTRAL_BPS_SWITCH(k_words_to_raw, <<<(unsigned)(F * tiles), 256, tile_bytes, p->stream>>>(p->d_words, s, tiles, d_dst));
+        if (words_g4_ok(s, d_dst)) {
+            const unsigned gb = (unsigned)(F * (s.ch >> 2) * (size_t)(s.ns >> 2) / 256);
+            SPECTRAL_BPS_SWITCH(k_words_to_raw_g4, <<<gb, 256, 0, p->stream>>>(p->d_words, s, d_dst));
+        } else {
+            SPECTRAL_BPS_SWITCH(k_words_to_raw, <<<(unsigned)(F * tiles), 256, tile_bytes, p->stream>>>(p->d_words, s, tiles, d_dst));
+        }
         p->launches += 1;
     }
 #undef INV_LAUNCH

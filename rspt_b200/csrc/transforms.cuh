@@ -734,6 +734,93 @@ __global__ void __launch_bounds__(256) k_raw_to_words(const uint8_t* __restrict_
     }
 }
 
+// ---- four-channel-group variants (ch % 4 == 0, ns % 4 == 0, 16-byte aligned frames) -------------
+// The 4 x BPS bytes that four neighbouring channels contribute to a sample row are contiguous, so a
+// thread that owns 4 consecutive samples of a channel group moves them between the interleaved frame
+// (BPS words per sample, at the row stride) and the word matrix (one 128-bit access per channel,
+// lanes along the samples) in registers -- no shared-memory tile.  The other channel groups touch the
+// neighbouring bytes of the same lines at the same time; the L2 merges them.
+template <int BPS>
+__global__ void __launch_bounds__(256) k_words_to_raw_g4(const int32_t* __restrict__ words, Shape s, uint8_t* __restrict__ dst)
+{
+    const uint32_t nq = (uint32_t)s.ns >> 2, G = (uint32_t)s.ch >> 2;
+    const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (frame, group, sample quad)
+    const uint32_t jq = (uint32_t)(item % nq), g = (uint32_t)((item / nq) % G);
+    const size_t f = item / ((size_t)nq * G);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(words) + f * s.N + (size_t)(4 * g) * s.ns + 4 * jq;
+    uint4 x[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) x[cc] = __ldg(reinterpret_cast<const uint4*>(w + (size_t)cc * s.ns));
+    const uint32_t roww = ((uint32_t)s.ch * BPS) >> 2;
+    uint32_t* base = reinterpret_cast<uint32_t*>(dst + f * s.frame_bytes) + (size_t)(4 * jq) * roww + g * BPS;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t a = i == 0 ? x[0].x : i == 1 ? x[0].y : i == 2 ? x[0].z : x[0].w;
+        const uint32_t b = i == 0 ? x[1].x : i == 1 ? x[1].y : i == 2 ? x[1].z : x[1].w;
+        const uint32_t c2 = i == 0 ? x[2].x : i == 1 ? x[2].y : i == 2 ? x[2].z : x[2].w;
+        const uint32_t d = i == 0 ? x[3].x : i == 1 ? x[3].y : i == 2 ? x[3].z : x[3].w;
+        uint32_t* p = base + (size_t)i * roww;
+        if (BPS == 4) {
+            *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c2, d);
+        } else if (BPS == 3) {
+            p[0] = prmt(a, b, 0x4210u);
+            p[1] = prmt(b, c2, 0x5421u);
+            p[2] = prmt(c2, d, 0x6542u);
+        } else if (BPS == 2) {
+            p[0] = prmt(a, b, 0x5410u);
+            p[1] = prmt(c2, d, 0x5410u);
+        } else {
+            p[0] = prmt(prmt(a, b, 0x0040u), prmt(c2, d, 0x0040u), 0x5410u);
+        }
+    }
+}
+
+// nq % 32 == 0 (a warp stays inside one frame and channel group), so the per-channel sums of a warp's
+// 128 samples go out with one 64-bit atomic per channel
+template <int BPS>
+__global__ void __launch_bounds__(256) k_raw_to_words_g4(const uint8_t* __restrict__ src, Shape s, int32_t* __restrict__ words,
+                                                          long long* __restrict__ sums)
+{
+    const uint32_t nq = (uint32_t)s.ns >> 2, G = (uint32_t)s.ch >> 2;
+    const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t jq = (uint32_t)(item % nq), g = (uint32_t)((item / nq) % G);
+    const size_t f = item / ((size_t)nq * G);
+    const uint32_t roww = ((uint32_t)s.ch * BPS) >> 2;
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(src + f * s.frame_bytes) + (size_t)(4 * jq) * roww + g * BPS;
+    uint32_t x[4][4];  // [sample][channel]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t* p = base + (size_t)i * roww;
+        uint32_t w[4];
+        if (BPS == 4) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+            w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < BPS; ++t) w[t] = __ldg(p + t);
+        }
+        unpack4<BPS>(w, x[i]);
+    }
+    uint32_t* wout = reinterpret_cast<uint32_t*>(words) + f * s.N + (size_t)(4 * g) * s.ns + 4 * jq;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        *reinterpret_cast<uint4*>(wout + (size_t)cc * s.ns) = make_uint4(x[0][cc], x[1][cc], x[2][cc], x[3][cc]);
+        // 64-bit channel sum from two 32-bit warp reductions: upper halves (signed) and lower halves
+        int hi = 0;
+        uint32_t lo = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            hi += (int32_t)x[i][cc] >> 16;
+            lo += x[i][cc] & 0xFFFFu;
+        }
+        hi = __reduce_add_sync(0xFFFFFFFFu, hi);
+        lo = __reduce_add_sync(0xFFFFFFFFu, lo);
+        if (lane_id() == 0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(sums + f * s.ch + 4 * g + cc),
+                      (unsigned long long)((long long)hi * 65536ll + (long long)lo));
+    }
+}
+
 // flat int32 words -> byte planes with the delta / offset / xor stencil (dct coefficients,
 // signal_packer_dct.cpp:117-119); one CTA per (frame, 1024-element chunk)
 __global__ void __launch_bounds__(256) k_words_stencil_planes(const int32_t* __restrict__ words, Shape s, uint32_t chunks,
