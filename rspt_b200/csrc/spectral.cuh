@@ -787,14 +787,14 @@ inline cudaError_t dct_build_tables(rspt_gpu_packer* p)
 inline bool fwht_raw_ok(const Shape& s, const void* d_raw)
 {
     return s.kind == 2 && (s.ch & 3) == 0 && fwht_fast_len(s.ns) && ((uintptr_t)d_raw & 15) == 0 && (s.frame_bytes & 15) == 0 &&
-           getenv("RSPT_FWHT_FUSED") != nullptr;
+           getenv("RSPT_FWHT_UNFUSED") == nullptr;
 }
 
 // the four-channel-group word kernels apply (a warp's 32 sample quads stay inside one channel group)
 inline bool words_g4_ok(const Shape& s, const void* d_raw)
 {
     return (s.ch & 3) == 0 && (s.ns % 1024) == 0 && ((uintptr_t)d_raw & 15) == 0 && (s.frame_bytes & 15) == 0 &&
-           getenv("RSPT_WORDS_G4") != nullptr;
+           getenv("RSPT_WORDS_TILED") == nullptr;
 }
 
 #define FWHT_RAW_LAUNCH(KERNEL, ...)                                                                              \

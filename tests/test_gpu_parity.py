@@ -138,6 +138,9 @@ STREAM_CASES = [
     ("hzr", 3, 12, 8192, 0, 3), ("hzr", 4, 12, 4096, 0, 2), ("hzr", 1, 2, 999, 0, 3), ("hzr", 2, 1, 140000, 0, 2),
     ("hadamard", 4, 12, 4096, 0, 3), ("hadamard", 3, 3, 16384, 0, 2), ("hadamard", 2, 2, 8, 0, 3), ("hadamard", 2, 3, 4096, 0, 2),
     ("hadamard", 3, 12, 8192, 0, 3), ("hadamard", 4, 1, 8192, 0, 2),
+    # fused raw <-> planes kernels (ch % 4 == 0, ns 4096 / 8192), every sample width
+    ("hadamard", 2, 4, 4096, 0, 2), ("hadamard", 1, 8, 8192, 0, 2), ("hadamard", 4, 4, 8192, 0, 2), ("hadamard", 3, 4, 4096, 0, 3),
+    ("hadamard", 1, 4, 4096, 0, 2), ("hadamard", 2, 8, 8192, 0, 2),
 ]
 
 
@@ -517,7 +520,33 @@ def test_corrupt_stream_is_reported_not_silent(R, oracle):
     assert dec[0].tobytes() == raws[0].tobytes()
 
 
-DCT_CASES = [(4, 12, 4096, 4), (3, 3, 4096, 2), (4, 2, 512, 6), (2, 3, 64, 4)]
+@pytest.mark.parametrize("bps,ch,ns", [(4, 4, 4096), (4, 8, 8192), (3, 4, 8192), (2, 4, 4096)])
+def test_hadamard_extreme_sample_values(R, oracle, bps, ch, ns):
+    """The fused hadamard kernel rebuilds the 64-bit channel sum (average_32, utils.cpp:30-40) from the
+    transform's DC coefficient and the sum of the samples' upper halves: full-range random samples and
+    constant frames at the extremes must give the reference's means and stream."""
+    rng = np.random.default_rng(5 * ns + bps)
+    lo, hi = -(1 << (8 * bps - 1)), (1 << (8 * bps - 1)) - 1
+    vals = [rng.integers(lo, hi + 1, size=(ns, ch), dtype=np.int64),
+            np.full((ns, ch), lo, np.int64), np.full((ns, ch), hi, np.int64), np.full((ns, ch), -1, np.int64),
+            np.where(rng.random((ns, ch)) < 0.5, lo, hi).astype(np.int64),
+            rng.integers(lo, lo // 2, size=(ns, ch), dtype=np.int64)]
+    raws = np.stack([v.astype("<i4").view(np.uint8).reshape(ns, ch, 4)[:, :, :bps].reshape(-1) for v in vals])
+    nfr, fb = len(vals), bps * ch * ns
+    p = R.SignalPacker.new_hadamard(bps, ch, ns, max_batch_frames=nfr)
+    batch = p.compress_batch(to_dev(raws))
+    dec = p.decompress_batch(batch).cpu().numpy().reshape(nfr, fb)
+    torch.cuda.synchronize()
+    offs = batch.offsets.cpu().numpy()
+    stream = batch.stream.cpu().numpy()
+    o = oracle.OraclePacker("hadamard", bps, ch, ns)
+    for i in range(nfr):
+        want = o.compress(raws[i])
+        assert stream[offs[i]:offs[i + 1]].tobytes() == want, i
+        assert dec[i].tobytes() == o.decompress(want)[0], i
+
+
+DCT_CASES = [(4, 12, 4096, 4), (3, 3, 4096, 2), (4, 2, 512, 6), (2, 3, 64, 4), (3, 4, 1024, 3), (2, 8, 2048, 2)]
 
 
 @pytest.mark.parametrize("bps,ch,ns,nfr", DCT_CASES)
