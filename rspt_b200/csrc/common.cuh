@@ -55,6 +55,29 @@ __host__ __device__ __forceinline__ uint32_t blk_len(const Shape& s, uint32_t b)
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
 
+// Shared-memory accesses through a 32-bit shared-window address taken once (__cvta_generic_to_shared).
+// ptxas otherwise re-derives the address of a __shared__ array at every use inside a loop whose
+// registers are tight (S2R SR_CgaCtaId + MOV + LEA in front of each LDS / ATOMS on sm_100).
+__device__ __forceinline__ uint32_t smem_addr(const void* p)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));  // opaque, so that the address stays in its register instead of being re-derived
+    return a;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // Extra bits carried by the zero-run symbols 256..260 (hzr_internal.h:117-121).
 __device__ __forceinline__ uint32_t sym_extra_bits(uint32_t sym)
 {

@@ -408,9 +408,10 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
             uint32_t pos = skip, w = 0, xacc = 0;
             BitReader r;
             r.init(payw, bitpos);
+            const uint32_t lut_s = smem_addr(s_lut);
             while (!my_err && bitpos < end_bit && pos < seg_len) {
                 r.refill();
-                uint32_t e = s_lut[r.peek(kLutBits)];
+                uint32_t e = lds_u16(lut_s + 2u * r.peek(kLutBits));
                 if (e & kLongFlag) {
                     // code longer than the table: match the few long code words (dec:418-431 walks the tree)
                     uint32_t j = e & kLongEnd;

@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
 
         uint32_t base = bi.tree_nbits;  // bit offset of the group (same in every thread)
         const uint32_t ngroups = (nsteps + kEncWarps - 1) / kEncWarps;
+        const uint32_t codes_s = smem_addr(s_codes), pay_s = smem_addr(pay);  // see common.cuh
         {
         // ---- dense blocks: a lane owns 16 consecutive bytes (4 words) of its warp's 512-byte step
         // (the chunk of the next group and the byte before its step are fetched one group ahead, so
@@ -338,10 +339,10 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             uint32_t cw[4][4], xs[4], bits[4], slow = 0;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                cw[r][0] = s_codes[x[r] & 0xFFu];
-                cw[r][1] = s_codes[(x[r] >> 8) & 0xFFu];
-                cw[r][2] = s_codes[(x[r] >> 16) & 0xFFu];
-                cw[r][3] = s_codes[x[r] >> 24];
+                cw[r][0] = lds_u32(codes_s + 4u * (x[r] & 0xFFu));
+                cw[r][1] = lds_u32(codes_s + 4u * ((x[r] >> 8) & 0xFFu));
+                cw[r][2] = lds_u32(codes_s + 4u * ((x[r] >> 16) & 0xFFu));
+                cw[r][3] = lds_u32(codes_s + 4u * (x[r] >> 24));
                 xs[r] = 0;
                 const uint32_t sp = (special >> (4 * r)) & 0xFu;
                 if (sp) {
@@ -432,11 +433,11 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                             lo = (lo << l) | (cw[r][j] & 0x07FFFFFFu);
                         }
                         const uint32_t sh = o & 31u;
-                        uint32_t* w = pay + (o >> 5);
+                        const uint32_t wa = pay_s + 4u * (o >> 5);
                         const uint32_t v0 = lo << sh, v1 = __funnelshift_l(lo, hi, sh), v2 = __funnelshift_l(hi, 0u, sh);
-                        atomicOr(w, v0);
-                        if (v1) atomicOr(w + 1, v1);
-                        if (v2) atomicOr(w + 2, v2);
+                        reds_or(wa, v0);
+                        if (v1) reds_or(wa + 4u, v1);
+                        if (v2) reds_or(wa + 8u, v2);
                     }
                 }
                 o += bits[r];
