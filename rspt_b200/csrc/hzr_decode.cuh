@@ -12,6 +12,8 @@
 // decoded by a single thread per block.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "hzr_encode.cuh"
 
@@ -19,6 +21,7 @@ namespace rspt {
 
 constexpr int kDecodeThreads = kMaxSegs;  // one thread per decode segment
 constexpr int kLutBits = 12;
+constexpr int kPairBits = 11;  // index width of the pair table (32-bit entries in the same 8 KB)
 constexpr uint32_t kModeZero = 3;      // frame failed to parse: emit zeros
 constexpr uint32_t kModeInactive = 255;
 
@@ -253,16 +256,17 @@ __device__ __forceinline__ uint32_t recover_tree(const uint32_t* payw, uint32_t 
 // look-up table on the next kLutBits bits (whole CTA): a warp per symbol, lanes over the
 // 2^(12 - len) entries that end in its code; symbols with longer codes go to the list `longs`
 // (*nlong must be 0 on entry).  The caller initialises lut to kLongFlag and synchronises after.
-__device__ __forceinline__ void build_lut(const uint32_t* cw_tab, uint16_t* lut, uint16_t* longs, uint32_t* nlong)
+template <class T, int BITS = kLutBits>
+__device__ __forceinline__ void build_lut(const uint32_t* cw_tab, T* lut, uint16_t* longs, uint32_t* nlong)
 {
     const uint32_t lane = lane_id();
     for (uint32_t sym = warp_id(); sym < (uint32_t)kNumSymbols; sym += (blockDim.x >> 5)) {
         const uint32_t cw = cw_tab[sym];
         if (cw == 0u) continue;
         const uint32_t len = cw >> 27, code = cw & 0x07FFFFFFu;
-        if (len <= (uint32_t)kLutBits) {
-            const uint16_t e = (uint16_t)(sym | (len << 9));
-            for (uint32_t i = lane; i < (1u << (kLutBits - len)); i += 32) lut[(i << len) | code] = e;
+        if (len <= (uint32_t)BITS) {
+            const T e = (T)(sym | (len << 9));
+            for (uint32_t i = lane; i < (1u << (BITS - len)); i += 32) lut[(i << len) | code] = e;
         } else if (lane == 0) {
             longs[atomicAdd(nlong, 1u)] = (uint16_t)sym;
         }
@@ -273,11 +277,16 @@ __device__ __forceinline__ void build_lut(const uint32_t* cw_tab, uint16_t* lut,
 // `next` of the long symbols that share those bits, so a long code costs a compare or two instead of
 // a scan of all long symbols (a lane on this path stalls its whole warp).  Whole CTA; the table must have
 // been initialised to kLongFlag | kLongEnd; synchronise after.
-__device__ __forceinline__ void chain_long_codes(const uint32_t* cw_tab, uint16_t* lut, const uint16_t* longs, uint16_t* next,
+template <class T, int BITS = kLutBits>
+__device__ __forceinline__ void chain_long_codes(const uint32_t* cw_tab, T* lut, const uint16_t* longs, uint16_t* next,
                                                  uint32_t nlong)
 {
     for (uint32_t j = threadIdx.x; j < nlong; j += blockDim.x) {
-        const uint32_t prefix = cw_tab[longs[j]] & ((1u << kLutBits) - 1u);
+        const uint32_t prefix = cw_tab[longs[j]] & ((1u << BITS) - 1u);
+        if (sizeof(T) == 4) {  // 32-bit entries: one exchange
+            next[j] = (uint16_t)(atomicExch(reinterpret_cast<uint32_t*>(lut) + prefix, kLongFlag | j) & kLongEnd);
+            continue;
+        }
         uint32_t* word = reinterpret_cast<uint32_t*>(lut) + (prefix >> 1);
         const uint32_t shift = (prefix & 1u) * 16u;
         uint32_t old = *word, seen;
@@ -303,13 +312,18 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                                                                    uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane)
 {
     extern __shared__ __align__(16) uint32_t payw[];  // payload words (+ zero slack)
-    __shared__ __align__(16) uint16_t s_lut[1 << kLutBits];  // sym | len << 9, or kLongFlag
+    // 8 KB of look-up table in one of two shapes, chosen per block:
+    //   kLutBits bits -> 16-bit entries: sym | len << 9, or kLongFlag | chain head
+    //   kPairBits bits -> 32-bit entries: the same in the low half; high half: a second literal whose whole
+    //   code the same bits also hold -- bit 31, both lengths << 24, its byte << 16
+    __shared__ __align__(16) uint16_t s_lut[1 << kLutBits];
+    uint32_t* s_lut32 = reinterpret_cast<uint32_t*>(s_lut);
     __shared__ uint32_t s_cw[kSymStride];            // code | len << 27 per symbol, 0 = unused
     __shared__ uint16_t s_long[kSymStride];          // symbols whose code is longer than the table
     __shared__ uint16_t s_next[kSymStride];          // chains of the long symbols that share their first kLutBits bits
     __shared__ uint32_t s_meta[4];                   // tree_end_bit, error, long count
 
-    const uint32_t blk = blockIdx.x, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+    const uint32_t blk = blockIdx.x, tid = threadIdx.x;
     const DecBlk d = dec[blk];
     if (d.mode == kModeInactive) return;
     uint32_t f, k, b;
@@ -376,21 +390,43 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         }
         payw[i] = v;
     }
-    for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_lut)[i] = (kLongFlag | kLongEnd) * 0x00010001u;
+    // Pairs are worth it where codes are short and tokens many (1/2 .. 4 payload bits per output byte):
+    // quantised coefficient planes, smooth upper planes.  Sparse blocks would only pay for the extra pass, and
+    // planes with ~6-bit codes rarely hold two codes in the window and want the longer single-symbol table.
+    const bool use_pairs = plen * 16u >= d.out_n && plen * 2u <= d.out_n;
     for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = i < (uint32_t)kNumSymbols ? sc_codes[(size_t)blk * kSymStride + i] : 0u;
     if (tid == 0) { s_meta[0] = 0; s_meta[1] = 0; s_meta[2] = 0; }
-    __syncthreads();
-    build_lut(s_cw, s_lut, s_long, &s_meta[2]);
-    __syncthreads();
-    chain_long_codes(s_cw, s_lut, s_long, s_next, s_meta[2]);
-    __syncthreads();
-
-    const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
+    if (!use_pairs) {
+        for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) s_lut32[i] = (kLongFlag | kLongEnd) * 0x00010001u;
+        __syncthreads();
+        build_lut(s_cw, s_lut, s_long, &s_meta[2]);
+        __syncthreads();
+        chain_long_codes(s_cw, s_lut, s_long, s_next, s_meta[2]);
+    } else {
+        for (uint32_t i = tid; i < (1u << kPairBits); i += blockDim.x) s_lut32[i] = kLongFlag | kLongEnd;
+        __syncthreads();
+        build_lut<uint32_t, kPairBits>(s_cw, s_lut32, s_long, &s_meta[2]);
+        __syncthreads();
+        chain_long_codes<uint32_t, kPairBits>(s_cw, s_lut32, s_long, s_next, s_meta[2]);
+        __syncthreads();
+        // pair pass: only the high half of an entry changes, so the look-ups of the other threads into the
+        // low halves stay valid while it runs
+        for (uint32_t i = tid; i < (1u << kPairBits); i += blockDim.x) {
+            const uint32_t e1 = s_lut32[i], len1 = (e1 >> 9) & 15u;
+            if (!(e1 & kLongFlag) && (e1 & 511u) < 256u && len1 < (uint32_t)kPairBits) {
+                const uint32_t e2 = s_lut32[i >> len1] & 0xFFFFu, len2 = (e2 >> 9) & 15u;
+                if (!(e2 & kLongFlag) && (e2 & 511u) < 256u && len1 + len2 <= (uint32_t)kPairBits)
+                    s_lut32[i] = e1 | 0x80000000u | ((len1 + len2) << 24) | ((e2 & 255u) << 16);
+            }
+        }
+    }
     // The whole output block is cleared first (coalesced 128-bit stores that the L2 merges with the word
     // stores below), so a zero run only advances the write position and the token loop is the same
     // straight-line code for literals and runs.
     for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+
+    const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
     uint32_t my_err = 0;
     if (tid < nseg) {
         uint32_t bitpos = sc_bit[(size_t)blk * kMaxSegs + tid];
@@ -409,9 +445,11 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
             BitReader r;
             r.init(payw, bitpos);
             const uint32_t lut_s = smem_addr(s_lut);
+            auto token_loop = [&](auto pairs_t) {
+            constexpr bool PAIRS = decltype(pairs_t)::value;
             while (!my_err && bitpos < end_bit && pos < seg_len) {
                 r.refill();
-                uint32_t e = lds_u16(lut_s + 2u * r.peek(kLutBits));
+                uint32_t e = PAIRS ? lds_u32(lut_s + 4u * r.peek(kPairBits)) : lds_u16(lut_s + 2u * r.peek(kLutBits));
                 if (e & kLongFlag) {
                     // code longer than the table: match the few long code words (dec:418-431 walks the tree)
                     uint32_t j = e & kLongEnd;
@@ -431,11 +469,13 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                     r.refill();
                     e &= 511u;
                 }
-                const uint32_t len = e >> 9, sym = e & 511u;
+                // two literals at once when the entry has them and both belong to this segment
+                const bool two = PAIRS && (e >> 31) != 0u && pos + 2u <= seg_len;
+                const uint32_t len = (two ? e >> 24 : e >> 9) & 15u, sym = e & 511u;
                 r.skip(len);  // <= kLutBits bits: at least 21 are left in the window
                 bitpos += len;
                 const bool run = sym >= 256u;  // symbol 0 (a zero run of one) is handled as a literal
-                uint32_t adv = 1u;
+                uint32_t adv = two ? 2u : 1u;
                 if (run) {
                     const uint32_t kk = sym - 256u;                              // run class 0..4 (hzr_internal.h:117-121)
                     const uint32_t eb = (0xE8420u >> (4u * kk)) & 15u;             // 0, 2, 4, 8, 14 extra bits
@@ -446,16 +486,21 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                     if (seg0 + pos + z > n) { my_err = 1; break; }  // "Output buffer full" dec:473-476
                     adv = min(z, seg_len - pos);  // the rest of the run is the next segment's `skip`
                 }
-                const uint32_t np = pos + adv;
-                const uint32_t wv = run ? w : w | (sym << ((pos & 3u) * 8u));
+                const uint32_t np = pos + adv, sh = (pos & 3u) * 8u;
+                const uint32_t val = two ? sym | ((e >> 8) & 0xFF00u) : sym;  // the literal byte(s)
+                const uint32_t wv = run ? w : w | (val << sh);
                 const bool cross = (np >> 2) != (pos >> 2);
                 if (cross) {
                     if (wv) *reinterpret_cast<uint32_t*>(dst + (pos & ~3u)) = wv;
                     xacc ^= wv;
                 }
-                w = cross ? 0u : wv;
+                // a pair that starts in a word's last byte leaves its second byte in the next word
+                w = cross ? ((!PAIRS || run) ? 0u : __funnelshift_l(val, 0u, sh)) : wv;
                 pos = np;
             }
+            };
+            if (use_pairs) token_loop(std::true_type{});
+            else token_loop(std::false_type{});
             if (bitpos > limit_bits) my_err = 1;
             if (w) *reinterpret_cast<uint32_t*>(dst + (pos & ~3u)) = w;
             xb = xacc ^ w;  // xor of the segment's bytes
