@@ -143,74 +143,6 @@ struct BitReader {
     }
 };
 
-// Writes one thread's output range [0, len) of a 16-byte aligned destination in order: bytes are
-// gathered into a word and every completed word goes out with one 32-bit store (lanes drift out
-// of phase after zero runs, so a wider per-lane window would only add divergent bookkeeping;
-// the L2 merges the partial sectors).  Zero runs use 128-bit stores where they are aligned.
-// Every byte of the range is written exactly once, so the destination needs no clearing; the
-// last word may run up to 3 bytes past `len` (plane rows are padded to 16).
-struct SegWriter {
-    uint8_t* dst;
-    uint32_t len, pos, w, sh;
-    uint32_t xacc;  // xor of all words written (zero runs contribute nothing): the segment's xor total
-    bool cleared;   // the destination already holds zeros: zero runs are skipped, not written
-    __device__ __forceinline__ void init(uint8_t* d, uint32_t l, bool pre_cleared)
-    {
-        dst = d; len = l; pos = 0; w = 0; sh = 0; xacc = 0; cleared = pre_cleared;
-    }
-    // xor of the segment's bytes
-    __device__ __forceinline__ uint32_t xor_byte() const
-    {
-        uint32_t x = xacc ^ w;
-        x ^= x >> 16;
-        x ^= x >> 8;
-        return x & 0xFFu;
-    }
-    __device__ __forceinline__ void put(uint32_t byte)
-    {
-        w |= byte << sh;
-        sh += 8u;
-        ++pos;
-        if (sh == 32u) {
-            *reinterpret_cast<uint32_t*>(dst + pos - 4u) = w;
-            xacc ^= w;
-            w = 0;
-            sh = 0;
-        }
-    }
-    // z zero bytes, clipped to the range
-    __device__ __forceinline__ void zeros(uint32_t z)
-    {
-        z = min(z, len - pos);
-        if (cleared) {
-            const uint32_t np = pos + z;
-            if ((np >> 2) != (pos >> 2)) {  // the run leaves the open word
-                if (sh) *reinterpret_cast<uint32_t*>(dst + (pos & ~3u)) = w;
-                xacc ^= w;
-                w = 0;
-            }
-            pos = np;
-            sh = (pos & 3u) * 8u;
-            return;
-        }
-        if (z < 8u) {  // short runs (dense planes): byte by byte, no alignment bookkeeping
-            for (; z; --z) put(0u);
-            return;
-        }
-        for (; z && sh; --z) put(0u);                    // close the open word
-        for (; z >= 4u && (pos & 15u); z -= 4u, pos += 4u) *reinterpret_cast<uint32_t*>(dst + pos) = 0u;
-        for (; z >= 16u; z -= 16u, pos += 16u) *reinterpret_cast<uint4*>(dst + pos) = make_uint4(0, 0, 0, 0);
-        for (; z >= 4u; z -= 4u, pos += 4u) *reinterpret_cast<uint32_t*>(dst + pos) = 0u;
-        for (; z; --z) put(0u);
-    }
-    // pad the open word with zeros and store it
-    __device__ __forceinline__ void finish()
-    {
-        zeros(len - pos);
-        while (sh) put(0u);
-    }
-};
-
 constexpr uint32_t kDecPayWords = kBlock / 4 + 4;
 constexpr size_t kDecodeSmem = (size_t)kDecPayWords * 4;
 constexpr uint32_t kLongFlag = 0x8000u;
