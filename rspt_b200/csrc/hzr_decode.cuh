@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                                                                    const uint16_t* __restrict__ sc_skip,
                                                                    const uint32_t* __restrict__ sc_codes,
                                                                    uint8_t* __restrict__ planes, int32_t* __restrict__ status,
-                                                                   uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane)
+                                                                   uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane,
+                                                                   uint32_t pair_max_bits)
 {
     extern __shared__ __align__(16) uint32_t payw[];  // payload words (+ zero slack)
     // 8 KB of look-up table in one of two shapes, chosen per block:
@@ -322,10 +323,10 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         }
         payw[i] = v;
     }
-    // Pairs are worth it where codes are short and tokens many (1/2 .. 4 payload bits per output byte):
+    // Pairs are worth it where codes are short and tokens many (1/2 .. pair_max_bits payload bits per output byte):
     // quantised coefficient planes, smooth upper planes.  Sparse blocks would only pay for the extra pass, and
     // planes with ~6-bit codes rarely hold two codes in the window and want the longer single-symbol table.
-    const bool use_pairs = plen * 16u >= d.out_n && plen * 2u <= d.out_n;
+    const bool use_pairs = plen * 16u >= d.out_n && plen * 8u <= pair_max_bits * d.out_n;
     for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = i < (uint32_t)kNumSymbols ? sc_codes[(size_t)blk * kSymStride + i] : 0u;
     if (tid == 0) { s_meta[0] = 0; s_meta[1] = 0; s_meta[2] = 0; }
     if (!use_pairs) {

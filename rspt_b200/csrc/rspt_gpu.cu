@@ -609,6 +609,17 @@ extern "C" int rspt_gpu_build_index(rspt_gpu_packer* p, const uint8_t* d_src, co
     return launch_parse_and_index(p, d_src, d_offsets, n_frames, d_frame_nb, d_sidecar, d_status ? d_status : p->d_status_tmp);
 }
 
+// payload bits per output byte up to which k_hzr_decode uses its two-literals-per-look-up table (measured: 4;
+// RSPT_PAIR_MAX_BITS overrides it for experiments)
+static uint32_t decode_pair_max_bits()
+{
+    static const uint32_t v = [] {
+        const char* e = getenv("RSPT_PAIR_MAX_BITS");
+        return e ? (uint32_t)atoi(e) : 4u;
+    }();
+    return v;
+}
+
 extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets,
                                          size_t n_frames, const uint8_t* d_frame_nb, const void* d_sidecar,
                                          uint8_t* d_dst, int32_t* d_status)
@@ -639,7 +650,7 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
     {
         StageTimer t(p, RSPT_STAGE_DECODE);
         k_hzr_decode<<<nblocks, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec, sc_bit, sc_skip, sc_codes, p->d_planes, status,
-                                                                          p->d_seg_xor, p->segs_per_plane);
+                                                                          p->d_seg_xor, p->segs_per_plane, decode_pair_max_bits());
     }
     p->launches += 1;
     RSPT_CUDA_CHECK(cudaGetLastError());
