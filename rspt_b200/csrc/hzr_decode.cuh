@@ -143,7 +143,7 @@ struct BitReader {
     }
 };
 
-constexpr uint32_t kDecPayWords = kBlock / 4 + 4;
+constexpr uint32_t kDecPayWords = kBlock / 4 + 16;  // cap of the payload staging: 16-byte chunks at any alignment + slack
 constexpr size_t kDecodeSmem = (size_t)kDecPayWords * 4;
 constexpr uint32_t kLongFlag = 0x8000u;
 constexpr uint32_t kLongEnd = 0x1FFu;  // flagged table entries: index of the first long symbol of the chain, kLongEnd = none
@@ -313,15 +313,18 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         return;
     }
 
-    // ---- MODE_HUFF: stage the payload
-    const uint32_t plen = d.payload_len, pwords = (plen + 3u) >> 2, naw = (lead + plen + 3u) >> 2;
-    for (uint32_t i = tid; i < pwords + 4u; i += blockDim.x) {
-        uint32_t v = 0;
-        if (i < pwords) {
-            const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
-            v = __funnelshift_r(lo, hi, sh);
-        }
-        payw[i] = v;
+    // ---- MODE_HUFF: stage the payload, asynchronously (cp.async) and as it lies in the stream: the 16-byte
+    // chunks that hold it go to shared memory unshifted, the payload starts lead16 bytes into the staging and
+    // the bit reader starts that much later.  The copies land while the tables are built.
+    const uint32_t plen = d.payload_len;
+    const uint32_t lead16 = (uint32_t)(pa & 15u), n16 = (lead16 + plen + 15u) >> 4;
+    {
+        const uint4* a16 = reinterpret_cast<const uint4*>(pa & ~(uintptr_t)15);
+        const uint32_t pay_s = smem_addr(payw);
+        for (uint32_t i = tid; i < n16; i += blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pay_s + 16u * i), "l"(a16 + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (tid < 8u) payw[4u * n16 + tid] = 0u;  // the bit reader looks two words ahead
     }
     // Pairs are worth it where codes are short and tokens many (1/2 .. pair_max_bits payload bits per output byte):
     // quantised coefficient planes, smooth upper planes.  Sparse blocks would only pay for the extra pass, and
@@ -357,6 +360,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     // stores below), so a zero run only advances the write position and the token loop is the same
     // straight-line code for literals and runs.
     for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
             uint8_t* dst = out + seg0;
             uint32_t pos = skip, w = 0, xacc = 0;
             BitReader r;
-            r.init(payw, bitpos);
+            r.init(payw, bitpos + 8u * lead16);
             const uint32_t lut_s = smem_addr(s_lut);
             auto token_loop = [&](auto pairs_t) {
             constexpr bool PAIRS = decltype(pairs_t)::value;
