@@ -74,7 +74,15 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
     uint32_t* stg = s_dyn + kListCap;  // block header at bytes 9..15, payload from byte 16
     uint32_t* pay = stg + 4;
     const uint32_t plen = bi.payload_len, tw = (bi.tree_nbits + 31u) >> 5, pw = (plen + 3u) >> 2;
-    for (uint32_t i = tid; i < m; i += blockDim.x) list[i] = __ldg(glist + i);
+    // the list arrives asynchronously (16-byte chunks; its slot in d_lists is kListCap entries, a multiple of 4)
+    // while the code table, the tree bits and the zeroed staging are set up
+    {
+        const uint32_t list_s = smem_addr(list);
+        const uint4* g4 = reinterpret_cast<const uint4*>(glist);
+        for (uint32_t i = tid; i < (m + 3u) / 4u; i += blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(list_s + 16u * i), "l"(g4 + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (uint32_t i = tid; i < kSymStride; i += blockDim.x) {
         const uint32_t cw = __ldg(codes + (size_t)blk * kSymStride + i);
         s_codes[i] = cw;
@@ -82,6 +90,7 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
     }
     // staging: tree words, then zeros (the code words are OR-ed in)
     for (uint32_t i = tid; i < pw + 2u; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // bit packing: warp w owns the entries [w * R, (w + 1) * R), one entry per lane and pass;
