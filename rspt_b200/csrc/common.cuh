@@ -33,6 +33,14 @@ struct BlkInfo {
     uint16_t n_tokens;     // tokens of the block, saturated at 65535 (selects the encoder path)
 };
 
+constexpr uint32_t kNoList = 0xFFFFFFFFu;           // list_n value of a block that has no sparse list
+// which encoder writes a block: the list-based one iff there is a list, the block is HUFF and its payload
+// fits that kernel's staging; both encoders evaluate this same predicate, so they need no hand-shake
+__device__ __forceinline__ bool sparse_block_is_packed_from_list(uint32_t list_m, const BlkInfo& bi, uint32_t stage_bytes)
+{
+    return list_m != kNoList && bi.mode == MODE_HUFF && bi.payload_len <= stage_bytes;
+}
+
 struct Shape {
     int kind;
     int bps, ch, ns;

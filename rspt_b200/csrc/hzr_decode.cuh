@@ -86,6 +86,12 @@ __global__ void __launch_bounds__(128) k_frame_parse(const uint8_t* __restrict__
             const uint32_t plen = ((uint32_t)src[q] | ((uint32_t)src[q + 1] << 8)) + 1u;  // dec:342
             const uint32_t mode = src[q + 6];
             if (mode > MODE_FILL || q + 7 + plen > cend) { err = 1; break; }
+            // A legitimate block stream is capped at header + in_size (hzr_encode.c:377-382), COPY carries
+            // exactly the block (:307-339) and FILL one byte (:352-364).  Anything else is rejected here:
+            // the decode / index / verify kernels stage payload_len bytes in shared memory sized for the
+            // largest legitimate payload.
+            const uint32_t bl = blk_len(s, b);
+            if ((mode == MODE_HUFF && plen > bl) || (mode == MODE_COPY && plen != bl) || (mode == MODE_FILL && plen != 1u)) { err = 1; break; }
             DecBlk& d = row[k * s.nblk + b];
             d.payload_off = q + 7;
             d.payload_len = plen;

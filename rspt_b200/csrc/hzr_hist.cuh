@@ -125,14 +125,6 @@ __device__ __forceinline__ void scatter_chunks(const Chunk& c, uint32_t off, uin
 // The list goes to global memory for k_hzr_encode_sparse, which packs the block's payload without
 // reading the plane again.  Blocks that are too dense for the list take the dense scan below.
 constexpr uint32_t kListCap = 5120;                 // entries of a block's sparse list
-constexpr uint32_t kNoList = 0xFFFFFFFFu;           // list_n value of a block that has no sparse list
-// which encoder writes a block: the list-based one iff there is a list, the block is HUFF and its payload
-// fits that kernel's staging; both encoders evaluate this same predicate, so they need no hand-shake
-__device__ __forceinline__ bool sparse_block_is_packed_from_list(uint32_t list_m, const BlkInfo& bi, uint32_t stage_bytes)
-{
-    return list_m != kNoList && bi.mode == MODE_HUFF && bi.payload_len <= stage_bytes;
-}
-
 constexpr uint8_t kClassSparse = 0, kClassDense = 1;  // blk_class: which histogram launch (and tree launch) owns the block
 constexpr size_t kHistSmem = (size_t)kListCap * 4;
 constexpr int kHistSteps = kMaxSteps / (kHistThreads / 32);      // steps per warp: 16

@@ -36,6 +36,7 @@ struct TreeWarpSmem {
     uint32_t ninfo[260];       // C: depth | pre-order bit offset << 8
     uint32_t tree[kTreeWords];
     uint16_t front[2][264];    // C: breadth-first frontiers (internal node indices)
+    uint32_t hist[264];        // token histogram of a listed block, taken from its list (blocks that come from k_front)
 };
 
 struct Counters {
@@ -331,7 +332,34 @@ __device__ __forceinline__ void count_block_mode(Counters* ctr, uint32_t mode)
     atomicAdd(mode == MODE_FILL ? &ctr->blocks_fill : (mode == MODE_COPY ? &ctr->blocks_copy : &ctr->blocks_huff), 1ull);
 }
 
-// One warp per block of the class `cls` (blk_class is written by the histogram launches).
+// Token histogram of a block from the sorted list of its non-zero bytes (position | value << 16): one
+// literal per entry, one zero run per gap (hzr_encode.c:140-170).  h[0] = runs of one, h[1..255] literals,
+// h[256..260] the longer run classes.  One warp; h must be zeroed.
+__device__ __forceinline__ void warp_hist_from_list(const uint32_t* __restrict__ list, uint32_t m, uint32_t n, uint32_t* h)
+{
+    for (uint32_t i = lane_id(); i <= m; i += 32) {
+        const uint32_t rs = i ? (list[i - 1] & 0xFFFFu) + 1u : 0u;
+        uint32_t cur = n;
+        if (i < m) {
+            const uint32_t e = list[i];
+            cur = e & 0xFFFFu;
+            atomicAdd(&h[e >> 16], 1u);
+        }
+        uint32_t z = cur > rs ? cur - rs : 0u;
+        while (z > kRunCap) {
+            atomicAdd(&h[260], 1u);
+            z -= kRunCap;
+        }
+        if (z) {
+            const uint32_t idx = (z >= 2u) + (z >= 3u) + (z >= 7u) + (z >= 23u) + (z >= 279u);
+            atomicAdd(&h[idx ? 255u + idx : 0u], 1u);
+        }
+    }
+}
+
+// One warp per block of the class `cls` (blk_class is written by the histogram launches; null = every block).
+// Behind k_front (sub_n given) a listed block first gets its list: the sub-lists of the channel rows it spans,
+// concatenated (they are sorted and block-relative already), and its token histogram from that list.
 __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __restrict__ hist, Shape s,
                                                                const uint8_t* __restrict__ frame_nb,
                                                                const uint8_t* __restrict__ blk_class, uint32_t cls,
@@ -339,7 +367,12 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
                                                                uint32_t* __restrict__ codes,
                                                                uint32_t* __restrict__ tree,
                                                                BlkInfo* __restrict__ info,
-                                                               Counters* __restrict__ ctr)
+                                                               Counters* __restrict__ ctr,
+                                                               const uint32_t* __restrict__ list_n = nullptr, uint32_t sparse_stage = 0,
+                                                               uint8_t* __restrict__ redo = nullptr,
+                                                               const uint32_t* __restrict__ sub_n = nullptr,
+                                                               const uint8_t* __restrict__ planes = nullptr,
+                                                               uint32_t* __restrict__ lists = nullptr, uint32_t list_cap = 0)
 {
     __shared__ TreeWarpSmem s_all[kTreeWarps];
     TreeWarpSmem& S = s_all[warp_id()];
@@ -347,12 +380,34 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
     if (blk >= total_blocks) return;
     uint32_t f, k, b;
     blk_decode(s, blk, f, k, b);
-    if (k >= frame_nb[f] || blk_class[blk] != cls) return;
-    const BlkInfo bi = warp_build_tree(S, hist + (size_t)blk * kSymStride, blk_len(s, b),
-                                       codes + (size_t)blk * kSymStride, tree + (size_t)blk * kTreeWords);
+    if (k >= frame_nb[f] || (blk_class && blk_class[blk] != cls)) return;
+    const uint32_t n = blk_len(s, b);
+    const uint32_t* h = hist + (size_t)blk * kSymStride;
+    if (sub_n && list_n[blk] != kNoList) {
+        const uint32_t lane = lane_id();
+        const uint32_t ns = (uint32_t)s.ns, c0 = (b * kBlock) / ns, c1 = (b * kBlock + n) / ns;
+        uint32_t* dst = lists + (size_t)blk * list_cap;
+        uint32_t at = 0;
+        for (uint32_t c = c0; c < c1; ++c) {
+            const uint32_t nc = sub_n[((size_t)f * s.nb_alloc + k) * s.ch + c];
+            const uint32_t* sub = reinterpret_cast<const uint32_t*>(planes + ((size_t)f * s.nb_alloc + k) * s.plane_stride + (size_t)c * ns);
+            for (uint32_t i = lane; i < nc; i += 32) dst[at + i] = sub[i];
+            at += nc;
+        }
+        for (uint32_t i = lane; i < (uint32_t)kSymStride; i += 32) S.hist[i] = 0;
+        __syncwarp();
+        warp_hist_from_list(dst, at, n, S.hist);
+        __syncwarp();
+        h = S.hist;
+    }
+    const BlkInfo bi = warp_build_tree(S, h, n, codes + (size_t)blk * kSymStride, tree + (size_t)blk * kTreeWords);
     if (lane_id() == 0) {
         info[blk] = bi;
         count_block_mode(ctr, bi.mode);
+        // behind k_front a listed block has no plane bytes in memory: if it turns out not to be one the list
+        // encoder packs (COPY, or a payload beyond that kernel's staging) the frame runs through k_front again
+        if (redo && bi.mode != MODE_FILL && list_n[blk] != kNoList && !sparse_block_is_packed_from_list(list_n[blk], bi, sparse_stage))
+            redo[f] = 1;
     }
 }
 

@@ -65,6 +65,12 @@ struct rspt_gpu_packer {
     double* d_fir;         // FIR kernel coefficients of the last rspt_gpu_prefilter_fir call (lazy)
     size_t fir_cap;
     int32_t* d_words2;     // second word buffer (FIR is out of place), lazy
+    uint8_t* d_redo;       // per frame: k_front flagged a sparse-mode plane as too dense (the frame runs again, forced dense)
+    uint8_t* d_redo2;      // per frame: the tree kernel found a listed block the list encoder cannot take (same remedy)
+    uint32_t* d_sub_n;     // k_front: entries in every (frame, plane, channel) sub-list
+    bool front_ok;         // shape is eligible for the fused front end (k_front)
+    int front_grid;        // persistent CTAs of k_front (SMs x resident CTAs)
+    size_t front_smem;
     uint32_t sp_stage;     // payload limit of k_hzr_encode_sparse (kSpStageBytes; lower only under RSPT_SPARSE_STAGE_BYTES)
     // transform constants (dct twiddles)
     double2* d_twiddle;

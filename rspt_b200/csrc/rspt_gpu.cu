@@ -13,6 +13,7 @@
 
 #include "packer.cuh"
 #include "transforms.cuh"
+#include "front.cuh"
 #include "hzr_decode.cuh"
 #include "spectral.cuh"
 #include "filters.cuh"
@@ -147,6 +148,77 @@ bool xdelta_fast_tile(const Shape& s, const uint8_t* d_src, uint32_t& tsq, size_
         }
     }
     return false;
+}
+
+
+// ---- fused front end (front.cuh) ----------------------------------------------------------------
+#define RSPT_FRONT_SHAPES(X) X(2, 4) X(2, 8) X(2, 12) X(3, 4) X(3, 8) X(3, 12) X(4, 4) X(4, 8) X(4, 12)
+
+bool front_shape_ok(const Shape& s)
+{
+    if (s.kind != RSPT_XDELTA_HZR && s.kind != RSPT_HZR) return false;
+    if (s.bps < 2 || s.bps > 4 || (s.ch != 4 && s.ch != 8 && s.ch != 12)) return false;
+    if (s.ns % kStepBytes != 0 || (uint32_t)s.ns / kStepBytes > kFrontMaxTiles) return false;
+    if (s.nb_alloc < 2 || s.nb_alloc * s.nblk > kFrontMaxHist) return false;
+    if (s.N > kBlock && kBlock % (uint32_t)s.ns != 0) return false;  // hzr blocks must start on channel rows
+    // measured (profiles/r02_front_*.txt): 1.22 ms per 4096 shape-A frames against 0.49 + 0.99 ms for the three
+    // kernels it replaces when those overlap with the tree build -- no gain yet, so it is opt-in
+    if (const char* e = getenv("RSPT_FRONT")) return atoi(e) != 0;
+    return false;
+}
+
+template <int B, int C>
+cudaError_t front_prepare(bool stencil, size_t smem, int* ctas_per_sm)
+{
+    cudaError_t e;
+    if (stencil) {
+        e = cudaFuncSetAttribute(k_front<B, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_front<B, C, true>, kFrontThreads, smem);
+    } else {
+        e = cudaFuncSetAttribute(k_front<B, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_front<B, C, false>, kFrontThreads, smem);
+    }
+    return e;
+}
+
+// decides whether the handle uses k_front and sizes its launch (called once, from rspt_gpu_create)
+cudaError_t front_setup(rspt_gpu_packer* p)
+{
+    const Shape& s = p->s;
+    p->front_ok = false;
+    if (p->can_escalate || !front_shape_ok(s)) return cudaSuccess;
+    p->front_smem = front_smem_bytes(s.bps, s.ch, s.nb_alloc, s.nblk, (uint32_t)s.ns / kStepBytes);
+    if (p->front_smem > 200 * 1024) return cudaSuccess;
+    int per_sm = 0, sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    if (e != cudaSuccess) return e;
+    const bool st = s.kind == RSPT_XDELTA_HZR;
+#define X(B, C) if (s.bps == B && s.ch == C) e = front_prepare<B, C>(st, p->front_smem, &per_sm);
+    RSPT_FRONT_SHAPES(X)
+#undef X
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaSuccess;
+    p->front_grid = sms * per_sm;
+    p->front_ok = true;
+    return cudaSuccess;
+}
+
+// pass 0: every frame; pass 1 / 2: the frames flagged in d_redo / d_redo2, every plane forced dense
+void front_launch(rspt_gpu_packer* p, const uint8_t* d_src, size_t F, int pass)
+{
+    const Shape& s = p->s;
+    const FrontOut o{p->d_planes, p->d_hist, p->d_step_lz, p->d_sub_n, p->d_list_n, p->d_redo, p->d_redo2};
+    const unsigned grid = (unsigned)(F < (size_t)p->front_grid ? F : (size_t)p->front_grid);
+    const bool st = s.kind == RSPT_XDELTA_HZR;
+    const uint8_t* only = pass == 0 ? nullptr : (pass == 1 ? p->d_redo : p->d_redo2);
+    const int force = pass != 0;
+#define X(B, C)                                                                                               \
+    if (s.bps == B && s.ch == C) {                                                                            \
+        if (st) k_front<B, C, true><<<grid, kFrontThreads, p->front_smem, p->stream>>>(d_src, s, (uint32_t)F, o, only, force);  \
+        else k_front<B, C, false><<<grid, kFrontThreads, p->front_smem, p->stream>>>(d_src, s, (uint32_t)F, o, only, force);    \
+    }
+    RSPT_FRONT_SHAPES(X)
+#undef X
 }
 
 }  // namespace
@@ -289,6 +361,9 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_info, nblocks));
     A(dalloc(p->d_frame_nb, F));
     A(dalloc(p->d_need, F));
+    A(dalloc(p->d_redo, F));
+    A(dalloc(p->d_redo2, F));
+    A(dalloc(p->d_sub_n, F * s.nb_alloc * ch));
     A(dalloc(p->d_nb_state, 4));
     A(dalloc(p->d_sizes, F));
     A(dalloc(p->d_blk_off, nblocks));
@@ -323,6 +398,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode_sparse, kSparseSmem);
+    if (e == cudaSuccess) e = front_setup(p);
     {
         // test hook: a smaller staging limit sends listed blocks down the hand-over path to k_hzr_encode
         const char* ev = getenv("RSPT_SPARSE_STAGE_BYTES");
@@ -351,7 +427,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
-                    p->d_one_off, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2, p->d_seg_xor};
+                    p->d_one_off, p->d_redo, p->d_redo2, p->d_sub_n, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2, p->d_seg_xor};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p->h_pin) cudaFreeHost(p->h_pin);
@@ -435,7 +511,7 @@ extern "C" int rspt_gpu_get_counters(rspt_gpu_packer* p, rspt_gpu_counters* out)
 namespace {
 
 // stage 1: samples -> byte planes (+ header, + need flags)
-int launch_forward_transform(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
+int launch_forward_transform(rspt_gpu_packer* p, const uint8_t* d_src, size_t F, const uint8_t* only = nullptr)
 {
     const Shape& s = p->s;
     if (s.kind == RSPT_XDELTA_HZR || s.kind == RSPT_HZR) {
@@ -450,7 +526,7 @@ int launch_forward_transform(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
 #define LAUNCH_F(B, ST)                                                                                   \
     do {                                                                                                  \
         RSPT_CUDA_CHECK(allow_smem(k_xdelta_planes_fast<B, ST>, fsmem));                                  \
-        k_xdelta_planes_fast<B, ST><<<grid, 128, fsmem, p->stream>>>(d_src, s, tsq, tiles, p->d_planes, need); \
+        k_xdelta_planes_fast<B, ST><<<grid, 128, fsmem, p->stream>>>(d_src, s, tsq, tiles, p->d_planes, need, only); \
     } while (0)
             switch (s.bps) {
             case 1: if (st) LAUNCH_F(1, true); else LAUNCH_F(1, false); break;
@@ -511,6 +587,30 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     const size_t F = n_frames;
     const uint32_t nblocks = total_blocks(p, F);
     int rc = 0;
+    uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar);
+    uint16_t* sc_skip = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
+    uint32_t* sc_codes = d_sidecar ? reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
+    const unsigned tgrid = (nblocks + kTreeWarps - 1) / kTreeWarps;
+    if (p->front_ok && !((uintptr_t)d_src & 15)) {
+        // fused front end: transform + token histograms + sparse lists in one pass over the raw frames
+        // (front.cuh); a frame whose sparse-looking plane turned out dense gets its planes from the
+        // stand-alone transform kernel afterwards (flag per frame, normally no CTA does any work)
+        {
+            StageTimer t(p, RSPT_STAGE_TRANSFORM);
+            front_launch(p, d_src, F, 0);
+            front_launch(p, d_src, F, 1);   // frames whose sub-lists overflowed (normally none: the CTAs read a flag each and leave)
+            p->launches += 2;
+            RSPT_CUDA_CHECK(cudaGetLastError());
+        }
+        {
+            StageTimer t(p, RSPT_STAGE_TREE);
+            k_hzr_tree<<<tgrid, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, nullptr, 0, nblocks, p->d_codes, p->d_tree, p->d_info, p->d_ctr,
+                                                                 p->d_list_n, p->sp_stage, p->d_redo2, p->d_sub_n, p->d_planes, p->d_lists, kListCap);
+            front_launch(p, d_src, F, 2);   // frames with a listed block the list encoder cannot take
+            p->launches += 2;
+            RSPT_CUDA_CHECK(cudaGetLastError());
+        }
+    } else {
     {
         StageTimer t(p, RSPT_STAGE_TRANSFORM);
         rc = launch_forward_transform(p, d_src, F);
@@ -518,15 +618,11 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         rc = launch_frame_nb(p, F);
         if (rc) return rc;
     }
-    uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar);
-    uint16_t* sc_skip = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
-    uint32_t* sc_codes = d_sidecar ? reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
     {
         // Two classes of blocks (density probe): the sparse-looking ones go through histogram + tree on
         // the side stream while this stream does the dense-looking ones, whose tree build is long and
         // latency-bound and overlaps with the sparse histogram.  RSPT_STAGE_HIST times the dense
         // histogram, RSPT_STAGE_TREE everything from there to the join.
-        const unsigned tgrid = (nblocks + kTreeWarps - 1) / kTreeWarps;
         RSPT_CUDA_CHECK(cudaEventRecord(p->ev_fork, p->stream));
         RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
         k_hzr_hist<1><<<nblocks, kHistThreads, kHistSmem, p->side>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class);
@@ -541,6 +637,8 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
             k_hzr_tree<<<tgrid, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, p->d_blk_class, kClassDense, nblocks, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
             RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
         }
+        p->launches += 4;
+    }
     }
     {
         StageTimer t(p, RSPT_STAGE_LAYOUT);
@@ -562,7 +660,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
                                                                         d_offsets, p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip, sc_codes);
         RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_join2, 0));
     }
-    p->launches += 8;
+    p->launches += 4;
     RSPT_CUDA_CHECK(cudaGetLastError());
     if (d_frame_nb) RSPT_CUDA_CHECK(cudaMemcpyAsync(d_frame_nb, p->d_frame_nb, F, cudaMemcpyDeviceToDevice, p->stream));
     return RSPT_OK;

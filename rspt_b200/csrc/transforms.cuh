@@ -162,10 +162,11 @@ __device__ __forceinline__ void unpack4(const uint32_t* w, uint32_t (&x)[4])
 template <int BPS, bool STENCIL>
 __global__ void __launch_bounds__(128) k_xdelta_planes_fast(const uint8_t* __restrict__ src, Shape s, uint32_t tsq,
                                                              uint32_t tiles_per_frame, uint8_t* __restrict__ planes,
-                                                             uint32_t* __restrict__ need)
+                                                             uint32_t* __restrict__ need, const uint8_t* __restrict__ only = nullptr)
 {
     extern __shared__ __align__(16) uint32_t smw[];
     const uint32_t f = blockIdx.x / tiles_per_frame, tile = blockIdx.x % tiles_per_frame;
+    if (only && !only[f]) return;                    // second pass behind k_front: flagged frames only
     const uint32_t row = (uint32_t)s.ch * BPS;       // bytes per sample row == words per quad
     const uint32_t qstride = row + 1;                // words
     const uint32_t cpq = row >> 2;                   // 16-byte chunks per quad

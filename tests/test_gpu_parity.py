@@ -520,6 +520,37 @@ def test_corrupt_stream_is_reported_not_silent(R, oracle):
     assert dec[0].tobytes() == raws[0].tobytes()
 
 
+def test_oversized_block_size_field_is_rejected(R, oracle):
+    """A block whose 16-bit size field exceeds the block it decodes to (inside a consistently lengthened
+    chunk) must come back as a stream error from decompress, index build and verify -- the kernels stage
+    payload_len bytes in shared memory sized for the largest LEGITIMATE payload (hzr_encode.c:377-382)."""
+    bps, ch, ns = 3, 4, 1000                      # N = 4000: staging is ~4 KB, the forged payload 64 KB
+    raws = oracle.synth_ecg(9, 3, bps, ch, ns)
+    cpu = oracle.OraclePacker("xdelta_hzr", bps, ch, ns, 3)
+    frames = [bytearray(cpu.compress(r)) for r in raws]
+    for mode in (0, 1, 2):                        # forged COPY, HUFF and FILL headers
+        f = bytearray(frames[1])
+        clen = int.from_bytes(f[1:5], "little")
+        q = 1 + 4 + 4                             # first block header of plane 0
+        plen = int.from_bytes(f[q:q + 2], "little") + 1
+        grow = 65536 - plen
+        body = f[q + 7:q + 7 + plen] + bytes(grow)
+        f2 = f[:1] + (clen + grow).to_bytes(4, "little") + f[5:q] + (0xFFFF).to_bytes(2, "little") + f[q + 2:q + 6] + bytes([mode]) + body + f[q + 7 + plen:]
+        fr = [frames[0], f2, frames[2]]
+        offs = np.concatenate([[0], np.cumsum([len(x) for x in fr])])
+        p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 3, max_batch_frames=3)
+        blob = b"".join(bytes(x) for x in fr)
+        dec, status = p.decompress_stream(blob, offs)
+        assert status[0] == 0 and status[1] == -4 and status[2] == 0, (mode, status)
+        assert dec[0].tobytes() == raws[0].tobytes() and dec[2].tobytes() == raws[2].tobytes()
+        buf = torch.from_numpy(np.frombuffer(blob + bytes(16), np.uint8).copy()).cuda()
+        b = R.CompressedBatch(buf, torch.tensor(offs, dtype=torch.int64, device="cuda"), None, None, 3)
+        st = p.verify_batch(b)
+        torch.cuda.synchronize()
+        assert list(st.cpu().numpy()) == [0, -4, 0], (mode, st)
+        p.close()
+
+
 @pytest.mark.parametrize("bps,ch,ns", [(4, 4, 4096), (4, 8, 8192), (3, 4, 8192), (2, 4, 4096)])
 def test_hadamard_extreme_sample_values(R, oracle, bps, ch, ns):
     """The fused hadamard kernel rebuilds the 64-bit channel sum (average_32, utils.cpp:30-40) from the
@@ -547,43 +578,53 @@ def test_hadamard_extreme_sample_values(R, oracle, bps, ch, ns):
 
 
 DCT_CASES = [(4, 12, 4096, 4), (3, 3, 4096, 2), (4, 2, 512, 6), (2, 3, 64, 4), (3, 4, 1024, 3), (2, 8, 2048, 2)]
+DCT_EQUAL_FRACTION = 0.9999   # stated fraction of quantised coefficients that equal the reference's
+
+
+def unstencil16(words16):
+    """Coefficients mod 2^16 from the post-stencil plane words (signal_packer_dct.cpp:117-119 undone):
+    d = prefix-xor(y), x = prefix-sum(d + 128).  Both scans only carry upwards, so they are closed
+    under mod 2^16 -- exactly the two byte planes the dct packer keeps."""
+    d = np.bitwise_xor.accumulate(words16.astype(np.uint32) & 0xFFFF)
+    return (np.cumsum((d + 128) & 0xFFFF, dtype=np.uint64) & 0xFFFF).astype(np.uint32)
+
+
+def dct_coefficient_diff(oracle_words, planes):
+    """Signed difference (GPU - reference) of the quantised coefficients, mod 2^16, from the reference's
+    post-stencil words and the GPU's two byte planes of one frame."""
+    want = unstencil16(oracle_words.view(np.uint32) & 0xFFFF)
+    got = unstencil16(planes[0].astype(np.uint32) | (planes[1].astype(np.uint32) << 8))
+    return ((got.astype(np.int64) - want.astype(np.int64) + 0x8000) & 0xFFFF) - 0x8000
 
 
 @pytest.mark.parametrize("bps,ch,ns,nfr", DCT_CASES)
 def test_dct_fast_path_tolerance(R, oracle, bps, ch, ns, nfr):
-    """dct, FFT-based FP64 path: quantised coefficients equal the reference's on >= 99.9 % of
-    values and never differ by more than 1 LSB; reconstruction PRDN within 0.01 percentage points."""
+    """dct, FFT-based FP64 path (signal_packer_dct.cpp:76-100 is an O(n^2) float-product sum): the
+    QUANTISED COEFFICIENTS (stencil undone) never differ from the reference's by more than 1 LSB and
+    are equal on >= 99.99 % of values; reconstruction PRDN within 0.01 percentage points."""
     raws = oracle.synth_ecg(3, nfr, bps, ch, ns, amplitude=20000 if bps >= 3 else 3000)
     fb = bps * ch * ns
     p = R.SignalPacker.new_dct(bps, ch, ns, max_batch_frames=nfr)
     batch = p.compress_batch(to_dev(raws))
     dec = p.decompress_batch(batch).cpu().numpy().reshape(nfr, fb)
     torch.cuda.synchronize()
-    offs = batch.offsets.cpu().numpy()
-    stream = batch.stream.cpu().numpy()
+    planes, gh = p.debug_planes(to_dev(raws))
     o = oracle.OraclePacker("dct", bps, ch, ns)
-    o2 = oracle.OraclePacker("dct", bps, ch, ns)
     n_all = n_bad = 0
     for i in range(nfr):
         want = o.compress(raws[i])
-        got = stream[offs[i]:offs[i + 1]].tobytes()
-        # compare the coefficients both decoders reconstruct from the two streams
         wd, _ = o.decompress(want)
-        gd, _ = o2.decompress(got)
-        # coefficient-level: undo the entropy coding only (oracle planes -> words) via transform()
         ww, wh = o.transform(raws[i])
-        planes, gh = p.debug_planes(to_dev(raws[i]))
-        gw = (planes[0, 0].astype(np.uint32) | (planes[0, 1].astype(np.uint32) << 8))
-        diff = ((ww.view(np.uint32) & 0xFFFF) != gw)
+        diff = dct_coefficient_diff(ww, planes[i])
+        assert np.abs(diff).max() <= 1, (i, int(np.abs(diff).max()))   # the +-1 LSB clause
         n_all += diff.size
-        n_bad += int(diff.sum())
-        assert np.array_equal(gh[0], wh)                       # the means are integer: exact
+        n_bad += int((diff != 0).sum())
+        assert np.array_equal(gh[i], wh)                               # the means are integer: exact
         prd_ref = oracle.prdn(raws[i], wd, bps, ch, ns)
         prd_gpu = oracle.prdn(raws[i], dec[i], bps, ch, ns)
         assert abs(prd_ref - prd_gpu) < 0.01, (prd_ref, prd_gpu)
-        d = np.frombuffer(wd, np.uint8).astype(np.int64) - dec[i].astype(np.int64)
-    # a differing coefficient perturbs the xor/delta-coded neighbours too, hence the loose word bound
-    assert n_bad <= max(3, n_all // 1000), (n_bad, n_all)
+    # the stated fraction; a case smaller than 10 000 coefficients may hold one such coefficient
+    assert n_bad <= max(1, int(n_all * (1.0 - DCT_EQUAL_FRACTION))), (n_bad, n_all)
 
 
 def test_dct_direct_path_bit_exact(R, oracle):
