@@ -74,7 +74,8 @@ int rspt_gpu_nb(rspt_gpu_packer* p, unsigned* nb);
 /* Replaces i_signal_packer::compress (signal_packer.h:44) for `n_frames` frames at once.
  *   d_src      [n_frames][frame_bytes]  interleaved little-endian samples ([ns][ch][bps])
  *   d_dst      the frames' streams, concatenated back to back, each byte-identical to what the
- *              reference writes for that frame
+ *              reference writes for that frame (xdelta_hzr, hzr, hadamard; dct: on its exact path,
+ *              see rspt_gpu_set_dct_exact -- its default FFT path is held to a tolerance instead)
  *   d_offsets  [n_frames + 1] byte offset of every frame in d_dst; d_offsets[n_frames] = total
  *   d_frame_nb [n_frames] planes used per frame (the reference does not store this in the
  *              stream; decompress needs it); may be NULL
@@ -109,7 +110,16 @@ int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_src, const ui
 int rspt_gpu_verify_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets,
                           size_t n_frames, const uint8_t* d_frame_nb, int32_t* d_status);
 
+/* Decode index ("sidecar"), out of band: one 32-bit entry per 1024 payload bits of every HUFF block (a token
+ * boundary and the output byte it starts at), addressed by the block's position in the batch's stream, so it
+ * is valid only together with the d_src / d_offsets layout it was produced for.  rspt_gpu_sidecar_bytes is the
+ * buffer size to allocate (worst-case stream); the entries of a batch whose stream has `stream_bytes` bytes fill
+ * the first rspt_gpu_sidecar_used_bytes of it (about 3 % of the compressed size) -- that prefix is what has to
+ * be stored next to the stream.  Code tables are NOT part of it: the decoder recovers them from the tree bits
+ * in the stream (hzr_decode.c:263-333).  Entries are range-checked on use; a wrong index yields RSPT_E_STREAM
+ * or wrong bytes in that frame, never an out-of-bounds access. */
 size_t rspt_gpu_sidecar_bytes(const rspt_gpu_packer* p, size_t n_frames);
+size_t rspt_gpu_sidecar_used_bytes(const rspt_gpu_packer* p, size_t n_frames, size_t stream_bytes);
 
 /* Decode index for frames that came without one (written by the CPU reference, or stored without
  * the sidecar): header walk, then every HUFF block is cut into bit sub-sequences that are decoded
@@ -214,12 +224,41 @@ int rspt_gpu_synth_ecg(uint8_t* d_dst, uint64_t first_frame, size_t n_frames, in
 int rspt_gpu_prdn_terms(const uint8_t* d_orig, const uint8_t* d_dec, size_t n_frames, int bps, int ch,
                         int ns, double* h_out, void* stream);
 
-/* Multi-GPU placement of the concatenated stream: given every rank's compressed byte total
- * (exchanged by the caller with ONE all-gather of a uint64 per rank -- ncclAllGather through
- * torch.distributed in rspt_b200, or rspt_nccl_allgather_totals below), rebase this rank's
- * frame offsets by the exclusive prefix of the totals.  d_all_totals [world]. */
+/* ---- multi-GPU placement of the concatenated stream ---------------------------------
+ * Frames shard over ranks; the path's only collective is ONE all-gather of a uint64 per rank (each rank's
+ * compressed byte total).  NCCL is reached through its C API, resolved at run time from libnccl.so.2 (the copy
+ * already loaded in the process, e.g. torch's, else the system one): no link-time dependency.
+ *
+ * rspt_gpu_comm_unique_id / _init / _destroy are ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy for a
+ * caller that has no NCCL communicator of its own (`id`: 128 bytes, produced on rank 0 and handed to the other
+ * ranks by whatever means the host program has).  `comm` is an ncclComm_t; one created elsewhere works too. */
+int rspt_gpu_comm_unique_id(uint8_t id[128]);
+int rspt_gpu_comm_init(int world, const uint8_t id[128], int rank, int device, void** comm);
+int rspt_gpu_comm_destroy(void* comm);
+
+/* ncclAllGather(sendcount = 1, ncclUint64) of d_total into d_all_totals [world], on `stream`. */
+int rspt_gpu_allgather_totals(void* comm, const uint64_t* d_total, uint64_t* d_all_totals, void* stream);
+
+/* Rebase this rank's frame offsets by the exclusive prefix of the totals.  d_all_totals [world]. */
 int rspt_gpu_rebase_offsets(uint64_t* d_offsets, size_t n_frames_plus_1, const uint64_t* d_all_totals,
                             int rank, void* stream);
+
+/* Both steps for the batch rspt_gpu_compress_batch has just produced into d_offsets, OFF the handle's stream:
+ * they run on a side stream of the handle ordered behind the compress, so the next batch's kernels start at
+ * once (its offsets must go to a different buffer).  rspt_gpu_place_join makes the handle's stream wait for
+ * every placement issued so far. */
+int rspt_gpu_place_offsets_async(rspt_gpu_packer* p, void* comm, uint64_t* d_offsets, size_t n_frames, int rank, int world);
+int rspt_gpu_place_join(rspt_gpu_packer* p);
+
+/* All later work of the handle is ordered on `stream` (a cudaStream_t) instead of the one given at create;
+ * the caller orders the two streams against each other if work is still in flight. */
+int rspt_gpu_set_stream(rspt_gpu_packer* p, void* stream);
+
+/* dct only: 1 = the O(n^2) float-product / double-accumulate path over the reference's cosine table, whose
+ * stream is byte-identical to the reference's (signal_packer_dct.cpp:76-100); 0 = the FP64 FFT path (default
+ * for power-of-two lengths), held to the stated tolerance.  The RSPT_DCT_DIRECT environment variable sets
+ * the default at create time. */
+int rspt_gpu_set_dct_exact(rspt_gpu_packer* p, int exact);
 
 #ifdef __cplusplus
 }

@@ -17,13 +17,15 @@ ERRORS = {0: "ok", -1: "bad argument / unsupported shape", -2: "CUDA error", -3:
 EXPORTS = [
     "rspt_gpu_create", "rspt_gpu_destroy", "rspt_gpu_frame_bytes", "rspt_gpu_header_bytes",
     "rspt_gpu_max_compressed_size", "rspt_gpu_nb", "rspt_gpu_compress_batch", "rspt_gpu_decompress_batch",
-    "rspt_gpu_sidecar_bytes", "rspt_gpu_compress_host", "rspt_gpu_decompress_host",
+    "rspt_gpu_sidecar_bytes", "rspt_gpu_sidecar_used_bytes", "rspt_gpu_compress_host", "rspt_gpu_decompress_host",
     "rspt_gpu_compress_batch_host", "rspt_gpu_decompress_batch_host", "rspt_gpu_sync", "rspt_gpu_last_error",
     "rspt_gpu_get_counters", "rspt_gpu_debug_planes", "rspt_gpu_debug_hzr_tables", "rspt_gpu_crc32c",
     "rspt_gpu_synth_ecg", "rspt_gpu_prdn_terms", "rspt_gpu_rebase_offsets",
     "rspt_gpu_set_stage_timing", "rspt_gpu_get_stage_times", "rspt_gpu_verify_batch", "rspt_gpu_build_index",
     "rspt_gpu_prefilter_iir", "rspt_gpu_prefilter_fir",
     "rspt_gpu_ingest_create", "rspt_gpu_ingest_destroy", "rspt_gpu_ingest_next_address_to_fill", "rspt_gpu_ingest_drain",
+    "rspt_gpu_comm_unique_id", "rspt_gpu_comm_init", "rspt_gpu_comm_destroy", "rspt_gpu_allgather_totals",
+    "rspt_gpu_place_offsets_async", "rspt_gpu_place_join", "rspt_gpu_set_stream", "rspt_gpu_set_dct_exact",
 ]
 
 
@@ -58,6 +60,8 @@ def lib() -> C.CDLL:
         getattr(L, name).argtypes = [vp]
     L.rspt_gpu_sidecar_bytes.restype = sz
     L.rspt_gpu_sidecar_bytes.argtypes = [vp, sz]
+    L.rspt_gpu_sidecar_used_bytes.restype = sz
+    L.rspt_gpu_sidecar_used_bytes.argtypes = [vp, sz, sz]
     L.rspt_gpu_nb.restype = C.c_int
     L.rspt_gpu_nb.argtypes = [vp, C.POINTER(C.c_uint)]
     L.rspt_gpu_compress_batch.restype = C.c_int
@@ -111,6 +115,22 @@ def lib() -> C.CDLL:
     L.rspt_gpu_set_stage_timing.argtypes = [vp, C.c_int]
     L.rspt_gpu_get_stage_times.restype = C.c_int
     L.rspt_gpu_get_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.c_int]
+    L.rspt_gpu_comm_unique_id.restype = C.c_int
+    L.rspt_gpu_comm_unique_id.argtypes = [vp]
+    L.rspt_gpu_comm_init.restype = C.c_int
+    L.rspt_gpu_comm_init.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.rspt_gpu_comm_destroy.restype = C.c_int
+    L.rspt_gpu_comm_destroy.argtypes = [vp]
+    L.rspt_gpu_allgather_totals.restype = C.c_int
+    L.rspt_gpu_allgather_totals.argtypes = [vp, vp, vp, vp]
+    L.rspt_gpu_place_offsets_async.restype = C.c_int
+    L.rspt_gpu_place_offsets_async.argtypes = [vp, vp, vp, sz, C.c_int, C.c_int]
+    L.rspt_gpu_place_join.restype = C.c_int
+    L.rspt_gpu_place_join.argtypes = [vp]
+    L.rspt_gpu_set_stream.restype = C.c_int
+    L.rspt_gpu_set_stream.argtypes = [vp, vp]
+    L.rspt_gpu_set_dct_exact.restype = C.c_int
+    L.rspt_gpu_set_dct_exact.argtypes = [vp, C.c_int]
     _lib = L
     return L
 

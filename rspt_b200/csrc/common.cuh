@@ -17,8 +17,20 @@ constexpr int kSymStride = 264;        // padded row for per-block tables
 constexpr int kTreeWords = 92;         // >= ceil((11*261-1)/32)
 constexpr uint32_t kBlock = 65536;     // HZR_MAX_BLOCK_SIZE, hzr_internal.h:109
 constexpr uint32_t kRunCap = 16662;    // hzr_encode.c:149
-constexpr int kSegBytes = 128;         // decode segment: one entry of the decode index, one decoder thread
-constexpr int kMaxSegs = kBlock / kSegBytes;  // 512 per block
+// Decode index (out of band, never part of the stream): one 32-bit entry per kIdxBits payload bits of a
+// HUFF block.  Entry k names a token boundary at or shortly after bit k * kIdxBits of the block's payload:
+//   bits 0..11  start bit of that token minus k * kIdxBits     bits 12..  output byte the token starts at
+// A decoder thread takes the tokens from its entry's boundary up to the next entry's.  The entries of a
+// block sit at slot (payload byte offset in the batch's stream >> 7) + block ordinal + k, so the index of
+// a batch is a prefix of the sidecar buffer whose length follows the compressed size (4 bytes per 128).
+constexpr uint32_t kIdxShift = 10;
+constexpr uint32_t kIdxBits = 1u << kIdxShift;
+constexpr uint32_t kIdxPosShift = 12;
+constexpr int kMaxSegs = (kBlock * 8) / kIdxBits;  // 512 intervals per block at most: one decoder thread each
+__host__ __device__ __forceinline__ size_t idx_slot_base(unsigned long long payload_rel, uint32_t blk)
+{
+    return (size_t)(payload_rel >> 7) + blk;
+}
 
 enum : uint32_t { MODE_COPY = 0, MODE_HUFF = 1, MODE_FILL = 2 };  // hzr_internal.h:98-101
 
@@ -83,6 +95,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
 }
 __device__ __forceinline__ void reds_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 

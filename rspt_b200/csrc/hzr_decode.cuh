@@ -4,22 +4,29 @@
 // checked on decode (hzr_decode.c:343).
 //
 // Parallelism: frames and hzr blocks are located by a cheap header walk (one thread per frame);
-// each block is decoded by one CTA.  Inside a block the token stream has no sync points, so the
-// decoder is seeded from the encoder's out-of-band index (per 256 output bytes: the bit offset of
-// the first token that starts there + the leading bytes covered by a zero run that started
-// earlier; rspt_gpu_compress_batch's d_sidecar) and every thread decodes one segment
-// through a 10-bit lookup table.  Streams without an index (produced by the CPU reference) are
-// decoded by a single thread per block.
+// the code table of every HUFF block is recovered from the tree bits in its payload (one warp per
+// block, k_hzr_recover_codes); each block is decoded by one CTA.  Inside a block the token stream
+// has no sync points, so the decoder is seeded from the out-of-band decode index (common.cuh: one
+// token boundary and its output position per 1024 payload bits; rspt_gpu_compress_batch's
+// d_sidecar) and every thread decodes the tokens between two boundaries through a 12-bit look-up
+// table.  Streams without an index (produced by the CPU reference) get one from
+// k_hzr_build_index first.
 #pragma once
 
 #include <type_traits>
 
+#include "bulk.cuh"
 #include "common.cuh"
 #include "hzr_encode.cuh"
 
 namespace rspt {
 
 constexpr int kDecodeThreads = kMaxSegs;  // one thread per decode segment
+// decode classes: HUFF payloads up to kClassPayload[c] bytes are decoded by CTAs of kClassPayload[c] * 8 / kIdxBits
+// threads; class 0 takes everything else (longer payloads, COPY / FILL blocks)
+constexpr uint32_t kSmallPayload = 8192, kMediumPayload = 32768;
+__host__ __device__ constexpr int decode_class_threads(uint32_t payload) { return (int)(payload * 8 / kIdxBits); }
+__host__ __device__ constexpr size_t decode_class_smem(uint32_t payload) { return payload + 64; }
 constexpr int kLutBits = 12;
 constexpr int kPairBits = 11;  // index width of the pair table (32-bit entries in the same 8 KB)
 constexpr uint32_t kModeZero = 3;      // frame failed to parse: emit zeros
@@ -32,6 +39,12 @@ struct DecBlk {
     uint32_t mode;
     uint32_t pad;
 };
+
+__device__ __forceinline__ uint32_t decode_class(const DecBlk& d)
+{
+    if (d.mode != MODE_HUFF) return 0u;
+    return d.payload_len <= kSmallPayload ? 1u : (d.payload_len <= kMediumPayload ? 2u : 0u);
+}
 
 __device__ __forceinline__ uint32_t ld_le32(const uint8_t* p)
 {
@@ -154,41 +167,90 @@ constexpr size_t kDecodeSmem = (size_t)kDecPayWords * 4;
 constexpr uint32_t kLongFlag = 0x8000u;
 constexpr uint32_t kLongEnd = 0x1FFu;  // flagged table entries: index of the first long symbol of the chain, kLongEnd = none
 
-// RecoverTree (dec:263-333), iteratively, by ONE thread: pre-order, 0 = branch, 1 + 9-bit symbol =
-// leaf.  Only the code word of every leaf is needed: a stack of (code, depth) of pending right
-// children.  cw[sym] = code | len << 27 (must be zeroed by the caller).  Returns the number of
-// tree bits, or 0xFFFFFFFF on a malformed tree.
+// RecoverTree (dec:263-333) by ONE thread: the tree bits are pre-order, 0 = branch, 1 + 9-bit symbol =
+// leaf, and only the code word of every leaf is needed.  One step per LEAF: the zeros in front of a leaf
+// are that many descents to the left; after a leaf the walk resumes at the right child of the deepest
+// ancestor that was entered to the left, which is the highest zero bit of the path (code words are
+// LSB-first: bit i of the code is the turn taken at depth i).  cw[sym] = code | len << 27 (must be
+// zeroed by the caller).  Returns the number of tree bits (11 per leaf - 1), or 0xFFFFFFFF on a malformed tree;
+// the caller checks that as many code words came out as there were leaves (no symbol twice).
 __device__ __forceinline__ uint32_t recover_tree(const uint32_t* payw, uint32_t plen, uint32_t* cw)
 {
     BitReader r;
     r.init(payw, 0);
-    uint32_t nodes = 0, leaves = 0, bits_used = 0;
-    uint32_t st_code[40], st_depth[40];
-    int sp = 0;
-    uint32_t code = 0, depth = 0;
+    uint32_t leaves = 0, bits_used = 0, code = 0, depth = 0;
+    const uint32_t limit = plen * 8u;
     for (;;) {
-        if (nodes >= 2 * kNumSymbols - 1 || depth > 27u) return 0xFFFFFFFFu;
-        ++nodes;
         r.refill();
-        const uint32_t leaf = r.take(1);
-        ++bits_used;
-        if (leaf) {
-            const uint32_t sym = r.take(9);
-            bits_used += 9;
-            if (sym >= (uint32_t)kNumSymbols || leaves >= (uint32_t)kNumSymbols || cw[sym] != 0u) return 0xFFFFFFFFu;
-            // lone leaf: 1-bit code (dec:306 `hzr_max(bits, 1)`)
-            cw[sym] = code | (max(depth, 1u) << 27);
-            ++leaves;
-            if (sp == 0) break;
-            --sp;
-            code = st_code[sp]; depth = st_depth[sp];
-        } else {
-            if (sp >= 40) return 0xFFFFFFFFu;
-            st_code[sp] = code | (1u << depth); st_depth[sp] = depth + 1; ++sp;
-            depth = depth + 1;
-        }
+        const uint32_t w = (uint32_t)r.buf;
+        if (w == 0u) return 0xFFFFFFFFu;                  // 32 branches in a row: deeper than any code word
+        const uint32_t z = (uint32_t)__ffs(w) - 1u;
+        depth += z;
+        if (depth > 27u) return 0xFFFFFFFFu;
+        r.skip(z + 1u);
+        r.refill();
+        const uint32_t sym = r.take(9);
+        bits_used += z + 10u;
+        if (bits_used > limit || sym >= (uint32_t)kNumSymbols || leaves >= (uint32_t)kNumSymbols) return 0xFFFFFFFFu;
+        cw[sym] = code | (max(depth, 1u) << 27);          // lone leaf: 1-bit code (dec:306 `hzr_max(bits, 1)`)
+        ++leaves;                                         // (a symbol named twice shows up in the caller's count)
+        const uint32_t m = ~code & ((1u << depth) - 1u);  // levels entered to the left
+        if (m == 0u) break;                               // the tree is complete
+        const uint32_t i = 31u - (uint32_t)__clz((int)m);
+        code = (code & ((1u << i) - 1u)) | (1u << i);
+        depth = i + 1u;
     }
-    return bits_used > plen * 8u ? 0xFFFFFFFFu : bits_used;
+    return bits_used;
+}
+
+// One warp per block: the code table of every HUFF block from its in-stream tree (k_hzr_decode and
+// k_hzr_build_index read it from `codes`).  status[f] = -4 on a malformed tree; the block then decodes to zeros.
+constexpr int kRecoverWarps = 4;
+constexpr uint32_t kTreeMaxWords = (11u * kNumSymbols + 31u) / 32u + 2u;
+__global__ void __launch_bounds__(32 * kRecoverWarps) k_hzr_recover_codes(const uint8_t* __restrict__ src, uint32_t total_blocks,
+                                                                          DecBlk* __restrict__ dec, uint32_t* __restrict__ codes,
+                                                                          Shape s, int32_t* __restrict__ status)
+{
+    __shared__ uint32_t s_w[kRecoverWarps][kTreeMaxWords + 2];
+    __shared__ uint32_t s_c[kRecoverWarps][kSymStride];
+    const uint32_t blk = blockIdx.x * kRecoverWarps + warp_id(), lane = lane_id();
+    if (blk >= total_blocks) return;
+    const DecBlk d = dec[blk];
+    if (d.mode != MODE_HUFF) return;
+    uint32_t* w = s_w[warp_id()];
+    uint32_t* c = s_c[warp_id()];
+    const uintptr_t pa = (uintptr_t)(src + d.payload_off);
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(pa & 3u) * 8u;
+    const uint32_t pwords = min((d.payload_len + 3u) >> 2, kTreeMaxWords), naw = (uint32_t)(((pa & 3u) + d.payload_len + 3u) >> 2);
+    for (uint32_t i = lane; i < kTreeMaxWords + 2u; i += 32) {
+        uint32_t v = 0;
+        if (i < pwords) {
+            const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
+            v = __funnelshift_r(lo, hi, sh);
+        }
+        w[i] = v;
+    }
+    for (uint32_t i = lane; i < (uint32_t)kSymStride; i += 32) c[i] = 0;
+    __syncwarp();
+    uint32_t tb = 0;
+    if (lane == 0) tb = recover_tree(w, d.payload_len, c);
+    tb = __shfl_sync(0xFFFFFFFFu, tb, 0);
+    __syncwarp();
+    uint32_t used = 0;
+    for (uint32_t i = lane; i < (uint32_t)kSymStride; i += 32) used += c[i] != 0u;
+    used = __reduce_add_sync(0xFFFFFFFFu, used);
+    if (tb != 0xFFFFFFFFu && 11u * used != tb + 1u) tb = 0xFFFFFFFFu;  // a symbol had two leaves
+    if (tb == 0xFFFFFFFFu) {
+        if (lane == 0) {
+            uint32_t f, k, b;
+            blk_decode(s, blk, f, k, b);
+            status[f] = -4;
+            dec[blk].mode = kModeZero;
+        }
+        return;
+    }
+    for (uint32_t i = lane; i < (uint32_t)kSymStride; i += 32) codes[(size_t)blk * kSymStride + i] = c[i];
 }
 
 // look-up table on the next kLutBits bits (whole CTA): a warp per symbol, lanes over the
@@ -236,19 +298,19 @@ __device__ __forceinline__ void chain_long_codes(const uint32_t* cw_tab, T* lut,
     }
 }
 
-// One CTA per hzr block.  The payload is staged in shared memory (coalesced, re-aligned); the
-// code table comes from the decode index (sc_codes); a 12-bit look-up table maps the next bits to
-// (symbol, length), longer codes are matched against the short list of long code words.  Every
-// thread decodes the tokens that start in its 128-byte segment and writes exactly that segment.
-// Streams that arrive without an index (CPU reference) get one from k_hzr_build_index first.
+// One CTA per hzr block.  The payload is staged in shared memory with ONE bulk asynchronous copy (the
+// 16-byte chunks of the stream that hold it, unshifted; the bit reader starts 8 * (address mod 16) bits
+// later) that lands while the tables are built; the code table comes from k_hzr_recover_codes; a 12-bit
+// look-up table maps the next bits to (symbol, length), longer codes are matched against the short list
+// of long code words.  Thread k decodes the tokens between the k-th and the (k + 1)-th boundary of the
+// decode index (common.cuh) and writes the bytes they produce.
 __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t* __restrict__ src, Shape s,
                                                                    const DecBlk* __restrict__ dec,
-                                                                   const uint32_t* __restrict__ sc_bit,
-                                                                   const uint16_t* __restrict__ sc_skip,
-                                                                   const uint32_t* __restrict__ sc_codes,
+                                                                   const uint64_t* __restrict__ offsets,
+                                                                   const uint32_t* __restrict__ sidecar,
+                                                                   const uint32_t* __restrict__ codes,
                                                                    uint8_t* __restrict__ planes, int32_t* __restrict__ status,
-                                                                   uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane,
-                                                                   uint32_t pair_max_bits)
+                                                                   uint32_t pair_max_bits, uint32_t small_class)
 {
     extern __shared__ __align__(16) uint32_t payw[];  // payload words (+ zero slack)
     // 8 KB of look-up table in one of two shapes, chosen per block:
@@ -260,84 +322,61 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     __shared__ uint32_t s_cw[kSymStride];            // code | len << 27 per symbol, 0 = unused
     __shared__ uint16_t s_long[kSymStride];          // symbols whose code is longer than the table
     __shared__ uint16_t s_next[kSymStride];          // chains of the long symbols that share their first kLutBits bits
-    __shared__ uint32_t s_meta[4];                   // tree_end_bit, error, long count
+    __shared__ uint32_t s_meta[4];                   // -, error, long count
+    __shared__ __align__(8) uint64_t s_bar;
 
     const uint32_t blk = blockIdx.x, tid = threadIdx.x;
     const DecBlk d = dec[blk];
     if (d.mode == kModeInactive) return;
+    // three launches share the blocks by payload size (decode_class): a CTA has as many threads as its class has
+    // index intervals and stages no more than its class's payload, so that short payloads (the sparse planes: a
+    // handful of busy threads) and half-size blocks do not hold a full-size CTA's shared memory
+    if (decode_class(d) != small_class) return;
     uint32_t f, k, b;
     blk_decode(s, blk, f, k, b);
     uint8_t* out = planes + ((size_t)f * s.nb_alloc + k) * s.plane_stride + (size_t)b * kBlock;
     uint4* out4 = reinterpret_cast<uint4*>(out);
     const uint32_t n = d.out_n, nq = (n + 15u) >> 4;
     const uint8_t* pay = src + d.payload_off;
-    // xor of the bytes of every 128-byte output segment, for the inverse transform's first scan
-    // (k_planes_to_samples_fast: a segment is one of its pieces), so that it need not read the planes for it
-    uint8_t* my_xor = seg_xor ? seg_xor + ((size_t)f * s.nb_alloc + k) * segs_per_plane + (size_t)b * kMaxSegs : nullptr;
-    const uint32_t nseg_all = (n + kSegBytes - 1) / kSegBytes;
 
     if (d.mode == MODE_FILL || d.mode == kModeZero) {
         const uint32_t v = d.mode == MODE_FILL ? pay[0] * 0x01010101u : 0u;  // memset (dec:362-370)
         for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(v, v, v, v);
-        if (my_xor)
-            for (uint32_t i = tid; i < nseg_all; i += blockDim.x)
-                my_xor[i] = (uint8_t)((min((uint32_t)kSegBytes, n - i * kSegBytes) & 1u) ? (v & 0xFFu) : 0u);
         return;
     }
     const uintptr_t pa = (uintptr_t)pay;
-    const uint32_t* aw = reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3);
-    const uint32_t lead = (uint32_t)(pa & 3u), sh = lead * 8u;
     if (d.mode == MODE_COPY) {
         if (d.payload_len != n) {  // "Encoded / decoded size mismatch (COPY)" dec:351-355
             if (tid == 0) status[f] = -4;
             for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
-            if (my_xor)
-                for (uint32_t i = tid; i < nseg_all; i += blockDim.x) my_xor[i] = 0;
             return;
         }
+        const uint32_t* aw = reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3);
+        const uint32_t lead = (uint32_t)(pa & 3u), sh = lead * 8u;
         const uint32_t naw = (lead + n + 3u) >> 2, nw = (n + 3u) >> 2;
         uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
         for (uint32_t i = tid; i < nw; i += blockDim.x) {
             const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
             out32[i] = __funnelshift_r(lo, hi, sh);
         }
-        if (my_xor) {
-            for (uint32_t sg = tid; sg < nseg_all; sg += blockDim.x) {
-                const uint32_t w0 = sg * (kSegBytes / 4), w1 = min(nw, w0 + kSegBytes / 4);
-                uint32_t x = 0;
-                for (uint32_t i = w0; i < w1; ++i) {
-                    const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
-                    uint32_t v = __funnelshift_r(lo, hi, sh);
-                    if (4u * i + 4u > n) v &= (1u << (8u * (n - 4u * i))) - 1u;  // bytes beyond the block
-                    x ^= v;
-                }
-                x ^= x >> 16;
-                x ^= x >> 8;
-                my_xor[sg] = (uint8_t)x;
-            }
-        }
         return;
     }
 
-    // ---- MODE_HUFF: stage the payload, asynchronously (cp.async) and as it lies in the stream: the 16-byte
-    // chunks that hold it go to shared memory unshifted, the payload starts lead16 bytes into the staging and
-    // the bit reader starts that much later.  The copies land while the tables are built.
-    const uint32_t plen = d.payload_len;
+    // ---- MODE_HUFF
+    const uint32_t plen = d.payload_len;   // <= n (k_frame_parse), so it fits the staging sized for the largest block
     const uint32_t lead16 = (uint32_t)(pa & 15u), n16 = (lead16 + plen + 15u) >> 4;
-    {
-        const uint4* a16 = reinterpret_cast<const uint4*>(pa & ~(uintptr_t)15);
-        const uint32_t pay_s = smem_addr(payw);
-        for (uint32_t i = tid; i < n16; i += blockDim.x)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pay_s + 16u * i), "l"(a16 + i) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (tid < 8u) payw[4u * n16 + tid] = 0u;  // the bit reader looks two words ahead
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(&s_bar, 16u * n16);
+        bulk_g2s(payw, reinterpret_cast<const void*>(pa & ~(uintptr_t)15), 16u * n16, &s_bar);
+        s_meta[0] = 0; s_meta[1] = 0; s_meta[2] = 0;
     }
     // Pairs are worth it where codes are short and tokens many (1/2 .. pair_max_bits payload bits per output byte):
     // quantised coefficient planes, smooth upper planes.  Sparse blocks would only pay for the extra pass, and
     // planes with ~6-bit codes rarely hold two codes in the window and want the longer single-symbol table.
     const bool use_pairs = plen * 16u >= d.out_n && plen * 8u <= pair_max_bits * d.out_n;
-    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = i < (uint32_t)kNumSymbols ? sc_codes[(size_t)blk * kSymStride + i] : 0u;
-    if (tid == 0) { s_meta[0] = 0; s_meta[1] = 0; s_meta[2] = 0; }
+    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = i < (uint32_t)kNumSymbols ? codes[(size_t)blk * kSymStride + i] : 0u;
     if (!use_pairs) {
         for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) s_lut32[i] = (kLongFlag | kLongEnd) * 0x00010001u;
         __syncthreads();
@@ -366,31 +405,39 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     // stores below), so a zero run only advances the write position and the token loop is the same
     // straight-line code for literals and runs.
     for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+    // the bit reader looks two words past the payload: keep what follows it in the stream out of the window
+    if (tid < 8u) {
+        const uint32_t endb = lead16 + plen;                      // first byte behind the payload
+        uint8_t* pb = reinterpret_cast<uint8_t*>(payw);
+        if (tid == 0)
+            for (uint32_t i = endb; i < 16u * n16; ++i) pb[i] = 0;
+        payw[4u * n16 + tid] = 0u;
+    }
     __syncthreads();
 
-    const uint32_t nseg = (n + kSegBytes - 1) / kSegBytes;
+    const uint32_t limit = plen * 8u, nint = (limit + kIdxBits - 1u) >> kIdxShift;
+    const uint32_t* my_idx = sidecar + idx_slot_base(d.payload_off - offsets[0], blk);
     uint32_t my_err = 0;
-    if (tid < nseg) {
-        uint32_t bitpos = sc_bit[(size_t)blk * kMaxSegs + tid];
-        const uint32_t skip = sc_skip[(size_t)blk * kMaxSegs + tid];  // bytes covered by a zero run that started earlier
-        uint32_t end_bit = tid + 1 < nseg ? sc_bit[(size_t)blk * kMaxSegs + tid + 1] : 0xFFFFFFFFu;
-        const uint32_t seg0 = tid * kSegBytes, seg_len = min((uint32_t)kSegBytes, n - seg0);
-        uint32_t xb = 0;
-        if (skip < seg_len) {
-            const uint32_t limit_bits = plen * 8u;
-            if (bitpos > limit_bits) { my_err = 1; bitpos = 0; }
-            end_bit = min(end_bit, limit_bits);
+    if (tid < nint) {
+        const uint32_t e0 = my_idx[tid];
+        uint32_t bitpos = (tid << kIdxShift) + (e0 & ((1u << kIdxPosShift) - 1u)), pos = e0 >> kIdxPosShift;
+        uint32_t end_bit = limit;
+        if (tid + 1 < nint) end_bit = min(limit, ((tid + 1u) << kIdxShift) + (my_idx[tid + 1] & ((1u << kIdxPosShift) - 1u)));
+        if (bitpos > limit || pos > n) { my_err = 1; bitpos = end_bit; }   // an index that does not belong to this stream
+        if (bitpos < end_bit && pos < n) {
             // the thread's bytes are gathered into the open word w (bytes of the word at and beyond pos are
-            // zero); a word goes out with one 32-bit store when the position leaves it, unless it is empty
-            uint8_t* dst = out + seg0;
-            uint32_t pos = skip, w = 0, xacc = 0;
+            // zero); a word goes out when the position leaves it, unless it is empty.  The first word may be
+            // shared with the thread before (it is OR-ed in), and so may the last one.
+            const uint32_t first_w = (pos & 3u) ? pos >> 2 : 0xFFFFFFFFu;
+            uint32_t w = 0;
             BitReader r;
             r.init(payw, bitpos + 8u * lead16);
             const uint32_t lut_s = smem_addr(s_lut);
             auto token_loop = [&](auto pairs_t) {
             constexpr bool PAIRS = decltype(pairs_t)::value;
-            while (!my_err && bitpos < end_bit && pos < seg_len) {
+            while (!my_err && bitpos < end_bit && pos < n) {
                 r.refill();
                 uint32_t e = PAIRS ? lds_u32(lut_s + 4u * r.peek(kPairBits)) : lds_u16(lut_s + 2u * r.peek(kLutBits));
                 if (e & kLongFlag) {
@@ -412,8 +459,8 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                     r.refill();
                     e &= 511u;
                 }
-                // two literals at once when the entry has them and both belong to this segment
-                const bool two = PAIRS && (e >> 31) != 0u && pos + 2u <= seg_len;
+                // two literals at once when the entry has them and both belong to this thread
+                const bool two = PAIRS && (e >> 31) != 0u && pos + 2u <= n && bitpos + ((e >> 24) & 15u) <= end_bit;
                 const uint32_t len = (two ? e >> 24 : e >> 9) & 15u, sym = e & 511u;
                 r.skip(len);  // <= kLutBits bits: at least 21 are left in the window
                 bitpos += len;
@@ -425,17 +472,17 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                     const uint32_t ev = (uint32_t)r.buf & ((1u << eb) - 1u);
                     r.skip(eb);
                     bitpos += eb;
-                    const uint32_t z = ev + (kk == 4u ? 279u : (0x17070302u >> (8u * kk)) & 255u);
-                    if (seg0 + pos + z > n) { my_err = 1; break; }  // "Output buffer full" dec:473-476
-                    adv = min(z, seg_len - pos);  // the rest of the run is the next segment's `skip`
+                    adv = ev + (kk == 4u ? 279u : (0x17070302u >> (8u * kk)) & 255u);
+                    if (pos + adv > n) { my_err = 1; break; }  // "Output buffer full" dec:473-476
                 }
                 const uint32_t np = pos + adv, sh = (pos & 3u) * 8u;
                 const uint32_t val = two ? sym | ((e >> 8) & 0xFF00u) : sym;  // the literal byte(s)
                 const uint32_t wv = run ? w : w | (val << sh);
                 const bool cross = (np >> 2) != (pos >> 2);
-                if (cross) {
-                    if (wv) *reinterpret_cast<uint32_t*>(dst + (pos & ~3u)) = wv;
-                    xacc ^= wv;
+                if (cross && wv) {
+                    uint32_t* q = reinterpret_cast<uint32_t*>(out + (pos & ~3u));
+                    if ((pos >> 2) == first_w) atomicOr(q, wv);
+                    else *q = wv;
                 }
                 // a pair that starts in a word's last byte leaves its second byte in the next word
                 w = cross ? ((!PAIRS || run) ? 0u : __funnelshift_l(val, 0u, sh)) : wv;
@@ -444,13 +491,9 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
             };
             if (use_pairs) token_loop(std::true_type{});
             else token_loop(std::false_type{});
-            if (bitpos > limit_bits) my_err = 1;
-            if (w) *reinterpret_cast<uint32_t*>(dst + (pos & ~3u)) = w;
-            xb = xacc ^ w;  // xor of the segment's bytes
-            xb ^= xb >> 16;
-            xb ^= xb >> 8;
+            if (bitpos > limit) my_err = 1;
+            if (w) atomicOr(reinterpret_cast<uint32_t*>(out + (pos & ~3u)), w);
         }
-        if (my_xor) my_xor[tid] = (uint8_t)xb;
     }
     if (my_err) status[f] = -4;
 }
@@ -458,19 +501,15 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
 // ------------------------------------------------------------------------------------------
 // Decode index for streams that arrive without one (written by the CPU reference): one CTA per
 // HUFF block.  The token stream has no sync points, but a prefix code re-synchronises by itself
-// after a few tokens, so the block's payload bits are cut into equal sub-sequences, one per
-// thread, and every thread decodes from a guessed start (the sub-sequence boundary; thread 0
-// from the true start behind the tree) to the first token boundary inside the next
-// sub-sequence, which becomes that neighbour's start.  Threads whose start moved decode again;
-// the starts are exact once nothing moves (each round fixes at least one more sub-sequence,
-// in practice two or three rounds do).  A scan of the bytes every sub-sequence produces gives
-// the output position of every token, and a last walk writes, for every 128-byte output
-// segment, the bit offset of the first token that starts in it and the bytes an earlier zero run
-// still covers -- the same index k_hzr_encode emits -- plus the block's code table.
-// (hzr_decode.c has no counterpart: DecodeSingleBlock :335-567 is a sequential walk.)
+// after a few tokens, so thread k decodes from a guessed start -- bit k * kIdxBits of the payload
+// (the first thread that has tokens from the true start behind the tree) -- to the first token
+// boundary inside the next interval, which becomes that neighbour's start.  Threads whose start
+// moved decode again; the starts are exact once nothing moves (each round fixes at least one more
+// interval, in practice two or three rounds do).  A scan of the bytes every interval produces
+// gives the output position of its first token: together the entry of the decode index
+// (common.cuh).  (hzr_decode.c has no counterpart: DecodeSingleBlock :335-567 is a sequential walk.)
 // ------------------------------------------------------------------------------------------
-constexpr int kIndexThreads = 512;
-constexpr uint32_t kSubMinBits = 64;  // sub-sequences are longer than the longest token (27 + 14 bits)
+constexpr int kIndexThreads = kMaxSegs;
 
 struct TokenDecoder {
     const uint16_t* lut;
@@ -514,9 +553,9 @@ struct TokenDecoder {
 
 __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint8_t* __restrict__ src, Shape s,
                                                                        const DecBlk* __restrict__ dec,
-                                                                       uint32_t* __restrict__ sc_bit,
-                                                                       uint16_t* __restrict__ sc_skip,
-                                                                       uint32_t* __restrict__ sc_codes,
+                                                                       const uint64_t* __restrict__ offsets,
+                                                                       const uint32_t* __restrict__ codes,
+                                                                       uint32_t* __restrict__ sidecar,
                                                                        int32_t* __restrict__ status)
 {
     extern __shared__ __align__(16) uint32_t payw[];  // payload words (+ zero slack)
@@ -524,8 +563,8 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
     __shared__ uint32_t s_cw[kSymStride];
     __shared__ uint16_t s_long[kSymStride];
     __shared__ uint16_t s_next[kSymStride];
-    __shared__ uint32_t s_meta[4];                    // tree bits, error, long count
-    __shared__ uint32_t s_start[kIndexThreads + 1];   // first token boundary of every sub-sequence
+    __shared__ uint32_t s_meta[4];                    // -, -, long count
+    __shared__ uint32_t s_start[kIndexThreads + 1];   // first token boundary of every interval
     __shared__ uint32_t s_wsum[kIndexThreads / 32];
 
     const uint32_t blk = blockIdx.x, tid = threadIdx.x, lane = lane_id(), wid = warp_id();
@@ -533,9 +572,8 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
     if (d.mode != MODE_HUFF) return;  // COPY / FILL / unparsed frames need no index
     uint32_t f, k, b;
     blk_decode(s, blk, f, k, b);
-    const uint32_t n = d.out_n, nseg = (n + kSegBytes - 1) / kSegBytes;
-    uint32_t* my_bit = sc_bit + (size_t)blk * kMaxSegs;
-    uint16_t* my_skip = sc_skip + (size_t)blk * kMaxSegs;
+    const uint32_t n = d.out_n;
+    uint32_t* my_idx = sidecar + idx_slot_base(d.payload_off - offsets[0], blk);
     const uint8_t* pay = src + d.payload_off;
     const uintptr_t pa = (uintptr_t)pay;
     const uint32_t* aw = reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3);
@@ -546,36 +584,36 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
         if (i < pwords) {
             const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
             v = __funnelshift_r(lo, hi, sh);
+            if (4u * i + 4u > plen) v &= (1u << (8u * (plen - 4u * i))) - 1u;  // bytes behind the payload
         }
         payw[i] = v;
     }
     for (uint32_t i = tid; i < (1u << kLutBits) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(s_lut)[i] = (kLongFlag | kLongEnd) * 0x00010001u;
-    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_cw[i] = 0;
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t tb = recover_tree(payw, plen, s_cw);
-        s_meta[0] = tb;
-        s_meta[1] = tb == 0xFFFFFFFFu;
-        s_meta[2] = 0;
+    uint32_t mytb = 0;  // tree bits: 11 per leaf - 1 (StoreTree, hzr_encode.c:177-219)
+    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) {
+        const uint32_t c = i < (uint32_t)kNumSymbols ? codes[(size_t)blk * kSymStride + i] : 0u;
+        s_cw[i] = c;
+        mytb += c ? 11u : 0u;
     }
+    if (tid == 0) s_meta[2] = 0;
+    mytb = __reduce_add_sync(0xFFFFFFFFu, mytb);
+    if (lane == 0) s_wsum[wid] = mytb;
     __syncthreads();
-    bool bad = s_meta[1] != 0u;
-    if (!bad) {
-        build_lut(s_cw, s_lut, s_long, &s_meta[2]);
-        __syncthreads();
-        chain_long_codes(s_cw, s_lut, s_long, s_next, s_meta[2]);
-        __syncthreads();
-    }
-    const uint32_t limit = plen * 8u, t0 = bad ? 0u : s_meta[0];
-    // sub-sequences: nsub equal pieces of [t0, limit), each longer than any token
-    const uint32_t span = limit - t0;
-    uint32_t nsub = span / kSubMinBits;
-    nsub = nsub < 1u ? 1u : (nsub > (uint32_t)kIndexThreads ? (uint32_t)kIndexThreads : nsub);
-    const uint32_t sub = (span + nsub - 1u) / nsub;
-    const uint32_t lo = t0 + tid * sub, hi = min(limit, lo + sub);  // tokens that START in [lo, hi) are mine
-    const bool live = !bad && tid < nsub && lo < limit;
+    uint32_t t0 = 0;
+    for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t0 += s_wsum[w];
+    t0 = t0 ? t0 - 1u : 0u;
+    __syncthreads();
+    build_lut(s_cw, s_lut, s_long, &s_meta[2]);
+    __syncthreads();
+    chain_long_codes(s_cw, s_lut, s_long, s_next, s_meta[2]);
+    __syncthreads();
+    const uint32_t limit = plen * 8u, nint = (limit + kIdxBits - 1u) >> kIdxShift;
+    bool bad = t0 > limit;
+    // interval k: tokens that START in [lo, hi); the intervals in front of the first token have none
+    const uint32_t lo = max(tid << kIdxShift, t0), hi = min(limit, (tid + 1u) << kIdxShift);
+    const bool live = !bad && tid < nint && lo < hi;
     const TokenDecoder td{s_lut, s_cw, s_long, s_next};
-    if (tid <= nsub) s_start[tid] = min(lo, limit);
+    if (tid <= nint) s_start[tid] = min(lo, limit);
     __syncthreads();
     uint32_t my_start = 0xFFFFFFFFu, land = 0, cnt = 0;
     if (!bad) {
@@ -603,20 +641,21 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
             }
             __syncthreads();
             bool moved = false;
-            if (redo && tid + 1 < nsub && s_start[tid + 1] != land) {
+            if (redo && tid + 1 < nint && s_start[tid + 1] != land) {
                 s_start[tid + 1] = land;
                 moved = true;
             }
             if (!__syncthreads_or(moved)) break;
         }
     }
-    // output position of every sub-sequence: exclusive scan of the byte counts
+    // output position of every interval: exclusive scan of the byte counts
     uint32_t v = live ? cnt : 0u, inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
         if (lane >= (uint32_t)o) inc += y;
     }
+    __syncthreads();
     if (lane == 31) s_wsum[wid] = inc;
     __syncthreads();
     uint32_t opos = inc - v, total = 0;
@@ -629,38 +668,13 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
     // few more: they are ignored, like the reference stops at the output size, dec:440)
     if (total < n) bad = true;
     if (bad) {
-        for (uint32_t i = tid; i < nseg; i += blockDim.x) {
-            my_bit[i] = 0xFFFFFFFFu;  // k_hzr_decode reports the frame and writes zeros
-            my_skip[i] = 0;
-        }
-        for (uint32_t i = tid; i < kSymStride; i += blockDim.x) sc_codes[(size_t)blk * kSymStride + i] = 0u;
+        if (tid < nint) my_idx[tid] = 0xFFFFFFFFu;  // k_hzr_decode reports the frame and writes zeros
         if (tid == 0) status[f] = -4;
         return;
     }
-    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) sc_codes[(size_t)blk * kSymStride + i] = s_cw[i];
-    if (live) {
-        BitReader r;
-        uint32_t pos = my_start, op = opos;
-        if (pos < hi) r.init(payw, pos);
-        while (pos < hi && op < n) {
-            uint32_t ob = 0;
-            uint32_t l = td.next(r, ob);
-            if (l == 0u) {  // corrupt stream: the sequential decoder would fail here (dec:431)
-                status[f] = -4;
-                l = 1u;
-                ob = 0u;
-                r.skip(1);
-            }
-            // segment boundaries B in [op, op + ob): B == op -> this token starts the segment;
-            // B inside a zero run -> resume behind the token, with the rest of the run to skip
-            const uint32_t end = min(op + ob, n);
-            for (uint32_t B = (op + kSegBytes - 1u) & ~(uint32_t)(kSegBytes - 1); B < end; B += kSegBytes) {
-                my_bit[B / kSegBytes] = B == op ? pos : pos + l;
-                my_skip[B / kSegBytes] = (uint16_t)(B == op ? 0u : op + ob - B);
-            }
-            pos += l;
-            op += ob;
-        }
+    if (tid < nint) {
+        const uint32_t st = min(max(s_start[tid], lo), limit);
+        my_idx[tid] = (st - (tid << kIdxShift)) | (min(opos, n) << kIdxPosShift);
     }
 }
 

@@ -114,13 +114,17 @@ __global__ void __launch_bounds__(1024) k_scan_offsets(const uint32_t* __restric
 // (8 KiB); in a group every lane owns 16 consecutive bytes and the tokens that START in them:
 // its literals and the zero runs whose first zero lies in the chunk (a run that continues into
 // later chunks is measured with the lane's forward zero count: stop bits of the following lanes,
-// then the per-step leading-zero counts left by k_hzr_hist).  Per group:
-//   1. lane bit length (dense chunks -- 16 tokens, one per byte -- keep their 16 table entries
-//      in registers; other chunks walk their tokens)
-//   2. warp scan + one __syncthreads: exclusive bit offset of every lane in the block's payload
-//   3. the lane appends its code words into the shared-memory staging buffer: 64-bit
-//      accumulator, 32-bit flushes; the first and the last (partial) word are OR-ed atomically
-//      because they are shared with the neighbouring lanes.
+// then the per-step leading-zero counts left by the histogram pass).
+//
+// Every byte becomes one look-up in a per-block table of (value, bit length):
+//   entries 0..255   the byte's code word (entry 0: symbol 0, a zero run of one)
+//   entry 256        nothing -- zeros inside a run, bytes beyond the block end
+//   entries 257..383 the whole token of a zero run of 2..128: run symbol + extra bits
+// so the per-byte work is the same straight line for literals and runs: a lane with zero runs only
+// rewrites the index bytes of the affected positions first (rare per lane).  The four slots of a
+// word are concatenated last-first into 64 bits; lane bit lengths -> warp scan + one
+// __syncthreads per group -> each word is shifted to its bit offset and OR-ed into <= 3 staging
+// words.  Words that do not fit (> 64 bits, runs > 128) take a generic token walker.
 // The block's bytes [7-byte header | payload] are staged in shared memory starting at byte 9
 // (payload 16-byte aligned at byte 16); the CRC-32C is taken from the staged payload and the
 // whole thing is copied to its final, arbitrarily aligned position in the output stream
@@ -129,6 +133,10 @@ __global__ void __launch_bounds__(1024) k_scan_offsets(const uint32_t* __restric
 constexpr int kEncThreads = 512;
 constexpr int kEncWarps = kEncThreads / 32;
 constexpr int kEncZtSel = 2;  // log2(kEncThreads / 128)
+constexpr uint32_t kTabNull = 256;       // table entry that contributes no bits
+constexpr uint32_t kTabMaxRun = 128;     // longest zero run that has a table entry (257 + L - 2)
+constexpr uint32_t kTabSize = 256 + kTabMaxRun;
+constexpr uint32_t kTabSlow = 255;       // bit length of an entry that cannot be used (forces the generic path)
 
 // tokens that start in one 4-byte word, in stream order (general path: any run length)
 template <class Sink>
@@ -143,6 +151,26 @@ __device__ __forceinline__ void walk_word(uint32_t x, uint32_t nz, uint32_t star
             emit_run(sb ? (uint32_t)__ffs(sb) - 1u : 4u - j + fwd, sink);
         }
     }
+}
+
+__device__ __forceinline__ uint2 lds_v2(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+// shifts whose amount may reach 32 (PTX clamps, C++ does not define them)
+__device__ __forceinline__ uint32_t shl_c(uint32_t a, uint32_t n)
+{
+    uint32_t d;
+    asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(n));
+    return d;
+}
+__device__ __forceinline__ uint32_t shf_l_c(uint32_t lo, uint32_t hi, uint32_t n)
+{
+    uint32_t d;
+    asm("shf.l.clamp.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(n));
+    return d;
 }
 
 constexpr uint32_t kStgWords = 4 + kBlock / 4 + 8;
@@ -161,16 +189,15 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                                                                 const uint8_t* __restrict__ headers,
                                                                 const CrcConst* __restrict__ cc,
                                                                 uint8_t* __restrict__ dst,
-                                                                uint32_t* __restrict__ sc_bit, uint16_t* __restrict__ sc_skip,
-                                                                uint32_t* __restrict__ sc_codes)
+                                                                uint32_t* __restrict__ sidecar)
 {
     extern __shared__ __align__(16) uint32_t stg[];  // header at bytes 9..15, payload from byte 16
     __shared__ uint32_t s_codes[kSymStride];
+    __shared__ __align__(8) uint2 s_tab[kTabSize];
     __shared__ __align__(16) uint32_t s_zt[1024];
     __shared__ uint32_t s_after[kMaxSteps];          // zeros that follow the end of every step
     __shared__ uint32_t s_tot[2][kEncWarps];
     __shared__ uint32_t s_red[33];
-    __shared__ uint32_t s_rc[2][32];                 // the two slots (code word, extra bits) of a zero run of 2..31
 
     uint32_t f, k, b;
     const uint32_t blk = blockIdx.x;
@@ -213,22 +240,31 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
         __syncthreads();
     } else {
         const uint32_t nsteps = (n + kStepBytes - 1) / kStepBytes;
-        for (uint32_t i = tid; i < kSymStride; i += blockDim.x) {
-            const uint32_t cw = __ldg(codes + (size_t)blk * kSymStride + i);
-            s_codes[i] = cw;
-            if (sc_codes) sc_codes[(size_t)blk * kSymStride + i] = cw;  // decode index: the block's code table
-        }
-        if (tid >= 2u && tid < 32u) {
-            uint32_t sym, ev, eb;
-            run_token(tid, sym, ev, eb);
-            s_rc[0][tid] = __ldg(codes + (size_t)blk * kSymStride + sym);
-            s_rc[1][tid] = ev | (eb << 27);
+        const uint32_t* gc = codes + (size_t)blk * kSymStride;
+        for (uint32_t i = tid; i < kTabSize; i += blockDim.x) {
+            if (i < (uint32_t)kSymStride) s_codes[i] = __ldg(gc + i);
+            uint2 e;
+            if (i < 256u) {
+                const uint32_t cw = __ldg(gc + i);
+                e = make_uint2(cw & 0x07FFFFFFu, cw >> 27);
+            } else if (i == kTabNull) {
+                e = make_uint2(0u, 0u);
+            } else {
+                uint32_t sym, ev, eb;
+                run_token(i - 255u, sym, ev, eb);
+                const uint32_t cw = __ldg(gc + sym), len = cw >> 27;
+                e = len + eb <= 32u ? make_uint2((cw & 0x07FFFFFFu) | (ev << len), len + eb) : make_uint2(0u, kTabSlow);
+            }
+            s_tab[i] = e;
         }
         const uint32_t tw = (bi.tree_nbits + 31u) >> 5, pw = (plen + 3u) >> 2;
         // staging: tree words, then zeros (the code words are OR-ed in)
         const uint32_t tw4 = (tw + 3u) & ~3u;
         for (uint32_t i = tid; i < tw4; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
         for (uint32_t i = (tw4 >> 2) + tid; i < ((pw + 2u + 3u) >> 2); i += blockDim.x) reinterpret_cast<uint4*>(pay)[i] = make_uint4(0, 0, 0, 0);
+        // decode index: where this block's entries go (common.cuh)
+        uint32_t* my_idx = sidecar ? sidecar + idx_slot_base(frame_off - offsets[0] + blk_off[blk] + 7u, blk) : nullptr;
+        if (my_idx && tid <= (bi.tree_nbits >> kIdxShift)) my_idx[tid] = bi.tree_nbits - (tid << kIdxShift);  // first token, output byte 0
         if (wid == kEncWarps - 1) {
             // s_after[st] = zeros between the end of step st and the next stop byte (or the block
             // end): suffix chain over the per-step leading-zero counts, 4 steps per lane
@@ -278,11 +314,9 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
 
         uint32_t base = bi.tree_nbits;  // bit offset of the group (same in every thread)
         const uint32_t ngroups = (nsteps + kEncWarps - 1) / kEncWarps;
-        const uint32_t codes_s = smem_addr(s_codes), pay_s = smem_addr(pay);  // see common.cuh
-        {
-        // ---- dense blocks: a lane owns 16 consecutive bytes (4 words) of its warp's 512-byte step
-        // (the chunk of the next group and the byte before its step are fetched one group ahead, so
-        // their latency hides behind the current group's work)
+        const uint32_t tab_s = smem_addr(s_tab), pay_s = smem_addr(pay);  // see common.cuh
+        // the chunk of the next group and the byte before its step are fetched one group ahead, so
+        // their latency hides behind the current group's work
         uint4 v_next = make_uint4(0, 0, 0, 0);
         uint32_t pstep_next = 1;
         {
@@ -294,8 +328,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             const uint32_t st = g * kEncWarps + wid;
             const uint32_t sbase = st * kStepBytes, off = sbase + lane * 16u;
             uint32_t x[4], NZ, INV = 0;
-            // zero flag of the byte before the step (lane 0 only)
-            const uint32_t pstep = pstep_next;
+            const uint32_t pstep = pstep_next;  // the byte before the step (lane 0 only)
             const uint4 v = v_next;
             {
                 const uint32_t sbn = sbase + kEncWarps * kStepBytes;
@@ -311,23 +344,25 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                 x[0] = c.v.x; x[1] = c.v.y; x[2] = c.v.z; x[3] = c.v.w;
                 NZ = c.nz;
                 INV = c.stop & ~c.nz;
+                // bytes beyond the block end: no token, and nothing in the index byte
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t iv = (INV >> (4 * r)) & 0xFu;
+                    if (iv) x[r] &= ~(((iv * 0x00204081u) & 0x01010101u) * 0xFFu);
+                }
             }
             const uint32_t STOP = NZ | INV, Z = ~STOP & 0xFFFFu;
             const uint32_t after = st < nsteps ? s_after[st] : 0u;  // zeros that follow the step
             const uint32_t z_up = __shfl_up_sync(0xFFFFFFFFu, Z, 1), z_dn = __shfl_down_sync(0xFFFFFFFFu, Z, 1);
             const uint32_t pz = lane > 0 ? z_up >> 15 : (pstep == 0u ? 1u : 0u);          // the byte before my chunk is a zero
             const uint32_t nzx = lane < 31 ? z_dn & 1u : (after ? 1u : 0u);              // the byte after my chunk is a zero
-            const uint32_t prevm = (Z << 1) | pz;
-            const uint32_t nextm = (Z >> 1) | (nzx << 15);
-            const uint32_t starts = Z & ~prevm;                  // first zero of a run
-            const uint32_t run2 = starts & nextm;                // ... of a run of >= 2
-            const uint32_t special = (Z & ~(starts & ~nextm)) | INV;  // positions that are not "one byte, one code"
-            // zeros between the end of my chunk and the next stop byte: only when a run leaves its
-            // chunk (nzx on a zero last byte) or the decode index needs a skip count
-            const bool leaves = (Z >> 15) & nzx;
-            const bool idx_lane = sc_bit && (lane & (kSegBytes / 16 - 1)) == 0u;
+            const uint32_t starts = Z & ~((Z << 1) | pz);                  // first zero of a run
+            const uint32_t run2 = starts & ((Z >> 1) | (nzx << 15));      // ... of a run of >= 2
+            const uint32_t special = (Z & ~starts) | run2 | INV;          // positions that are not "one byte, one code"
+            // zeros between the end of my chunk and the next stop byte: when a run leaves its chunk
+            const bool leaves = ((Z >> 15) & nzx) != 0u;
             uint32_t fwd = 0;
-            if (__any_sync(0xFFFFFFFFu, leaves || (idx_lane && pz))) {
+            if (__any_sync(0xFFFFFFFFu, leaves)) {
                 const uint32_t sm = __ballot_sync(0xFFFFFFFFu, STOP != 0u);
                 const uint32_t fs = STOP ? (uint32_t)__ffs(STOP) - 1u : 16u;
                 const uint32_t above = lane < 31 ? sm & ~((2u << lane) - 1u) : 0u;
@@ -335,58 +370,53 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                 const uint32_t fq = __shfl_sync(0xFFFFFFFFu, fs, q);
                 fwd = above ? 16u * (q - lane - 1u) + fq : 16u * (31u - lane) + after;
             }
-            // ---- slots and bit lengths, word by word
-            uint32_t cw[4][4], xs[4], bits[4], slow = 0;
+            // ---- index bytes of the special positions: high byte 1, low byte 0 (nothing) or run length - 1
+            uint32_t G[4] = {0, 0, 0, 0}, slow = 0;
+            if (special) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) G[r] = (((special >> (4 * r)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                uint32_t rs = run2;
+                while (rs) {
+                    const uint32_t j = __ffs(rs) - 1u;
+                    rs &= rs - 1u;
+                    const uint32_t sb = STOP >> j;
+                    const uint32_t len = sb ? (uint32_t)__ffs(sb) - 1u : 16u - j + fwd;
+                    const uint32_t r = j >> 2;
+                    const uint32_t cb = len <= kTabMaxRun ? (len - 1u) << (8u * (j & 3u)) : 0u;
+                    if (len > kTabMaxRun) slow |= 1u << r;  // generic path (also: several tokens beyond 16662)
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr)
+                        if (r == (uint32_t)rr) x[rr] |= cb;  // (the slow path masks the byte out again)
+                }
+            }
+            // ---- look-ups and slot concatenation, word by word (last slot first)
+            uint32_t lo[4], hi[4], bits[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                cw[r][0] = lds_u32(codes_s + 4u * (x[r] & 0xFFu));
-                cw[r][1] = lds_u32(codes_s + 4u * ((x[r] >> 8) & 0xFFu));
-                cw[r][2] = lds_u32(codes_s + 4u * ((x[r] >> 16) & 0xFFu));
-                cw[r][3] = lds_u32(codes_s + 4u * (x[r] >> 24));
-                xs[r] = 0;
-                const uint32_t sp = (special >> (4 * r)) & 0xFu;
-                if (sp) {
-                    // zeros inside runs and bytes beyond the block end carry no token
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if ((sp >> j) & 1u) cw[r][j] = 0;
-                    uint32_t rs = (run2 >> (4 * r)) & 0xFu;
-                    while (rs) {
-                        const uint32_t j = __ffs(rs) - 1u;
-                        rs &= rs - 1u;
-                        const uint32_t sb = STOP >> (4 * r + j);
-                        const uint32_t len = sb ? (uint32_t)__ffs(sb) - 1u : 16u - (4u * r + j) + fwd;
-                        if (len > kRunCap) {
-                            slow |= 1u << r;  // several tokens: general path
-                        } else {
-                            uint32_t c0, c1;
-                            if (len < 32u) {  // the usual case on a dense plane: both slots from the block's run table
-                                c0 = s_rc[0][len];
-                                c1 = s_rc[1][len];
-                            } else {
-                                uint32_t sym, ev, eb;
-                                run_token(len, sym, ev, eb);
-                                c0 = s_codes[sym];
-                                c1 = ev | (eb << 27);
-                            }
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                if ((uint32_t)jj == j) cw[r][jj] = c0;
-                                if ((uint32_t)jj == j + 1u) cw[r][jj] = c1;
-                            }
-                            if (j == 3u) xs[r] = c1;
-                        }
-                    }
-                }
-                bits[r] = slot_bits(cw[r][0]) + slot_bits(cw[r][1]) + slot_bits(cw[r][2]) + slot_bits(cw[r][3]) + slot_bits(xs[r]);
+                const uint2 e0 = lds_v2(tab_s + 8u * prmt(x[r], G[r], 0xCC40u)), e1 = lds_v2(tab_s + 8u * prmt(x[r], G[r], 0xDD51u));
+                const uint2 e2 = lds_v2(tab_s + 8u * prmt(x[r], G[r], 0xEE62u)), e3 = lds_v2(tab_s + 8u * prmt(x[r], G[r], 0xFF73u));
+                uint32_t l = e3.x, h = 0;
+                h = shf_l_c(l, h, e2.y); l = shl_c(l, e2.y) | e2.x;
+                h = shf_l_c(l, h, e1.y); l = shl_c(l, e1.y) | e1.x;
+                h = shf_l_c(l, h, e0.y); l = shl_c(l, e0.y) | e0.x;
+                lo[r] = l; hi[r] = h;
+                bits[r] = e0.y + e1.y + e2.y + e3.y;
                 if (bits[r] > 64u) slow |= 1u << r;
-                if ((slow >> r) & 1u) {
-                    // zeros after word r: my later words, then the chunks that follow
-                    const uint32_t sb = r < 3 ? STOP >> (4 * r + 4) : 0u;
-                    const uint32_t fw = sb ? (uint32_t)__ffs(sb) - 1u : 12u - 4u * r + fwd;
-                    LenSink ls{s_codes, 0};
-                    walk_word(x[r], (NZ >> (4 * r)) & 0xFu, (starts >> (4 * r)) & 0xFu, (STOP >> (4 * r)) & 0xFu, fw, ls);
-                    bits[r] = ls.bits;
+            }
+            if (__any_sync(0xFFFFFFFFu, slow != 0u)) {
+                // undo the run-length bytes, then measure the slow words with the generic walker
+                if (slow) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if ((slow >> r) & 1u) {
+                            const uint32_t zb = (((Z >> (4 * r)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                            x[r] &= ~(zb * 0xFFu);
+                            const uint32_t sb = r < 3 ? STOP >> (4 * r + 4) : 0u;
+                            const uint32_t fw = sb ? (uint32_t)__ffs(sb) - 1u : 12u - 4u * r + fwd;
+                            LenSink ls{s_codes, 0};
+                            walk_word(x[r], (NZ >> (4 * r)) & 0xFu, (starts >> (4 * r)) & 0xFu, (STOP >> (4 * r)) & 0xFu, fw, ls);
+                            bits[r] = ls.bits;
+                        }
                 }
             }
             // ---- bit offsets
@@ -407,10 +437,16 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             }
             uint32_t o = base + (wid ? __shfl_sync(0xFFFFFFFFu, tw2, wid - 1) : 0u) + inc - lbits;
             base += __shfl_sync(0xFFFFFFFFu, tw2, kEncWarps - 1);
-            // ---- decode index: one entry per segment of kSegBytes output bytes
-            if (idx_lane && off < n) {
-                sc_bit[(size_t)blk * kMaxSegs + off / kSegBytes] = o;
-                sc_skip[(size_t)blk * kMaxSegs + off / kSegBytes] = (uint16_t)(pz ? (STOP ? (uint32_t)__ffs(STOP) - 1u : 16u + fwd) : 0u);
+            // ---- decode index: the lane whose tokens cover the last bit before an interval boundary names the
+            // boundary behind its chunk: the next token starts at its end bit, at the first byte that follows
+            // the zeros running out of the chunk
+            if (my_idx) {
+                const uint32_t e = o + lbits;
+                if ((e >> kIdxShift) != (o >> kIdxShift)) {
+                    const uint32_t kk = e >> kIdxShift;
+                    const uint32_t P = min(off + 16u + (leaves ? fwd : 0u), n);
+                    my_idx[kk] = (e - (kk << kIdxShift)) | (P << kIdxPosShift);
+                }
             }
             // ---- emit
 #pragma unroll
@@ -423,18 +459,10 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                         walk_word(x[r], (NZ >> (4 * r)) & 0xFu, (starts >> (4 * r)) & 0xFu, (STOP >> (4 * r)) & 0xFu, fw, es);
                         es.finish();
                     } else {
-                        // <= 64 bits: concatenate the slots (last first), shift to the bit offset,
-                        // OR into <= 3 staging words
-                        uint32_t lo = xs[r] & 0x07FFFFFFu, hi = 0;
-#pragma unroll
-                        for (int j = 3; j >= 0; --j) {
-                            const uint32_t l = slot_bits(cw[r][j]);
-                            hi = __funnelshift_l(lo, hi, l);
-                            lo = (lo << l) | (cw[r][j] & 0x07FFFFFFu);
-                        }
+                        // <= 64 bits: shift to the bit offset, OR into <= 3 staging words
                         const uint32_t sh = o & 31u;
                         const uint32_t wa = pay_s + 4u * (o >> 5);
-                        const uint32_t v0 = lo << sh, v1 = __funnelshift_l(lo, hi, sh), v2 = __funnelshift_l(hi, 0u, sh);
+                        const uint32_t v0 = lo[r] << sh, v1 = __funnelshift_l(lo[r], hi[r], sh), v2 = __funnelshift_l(hi[r], 0u, sh);
                         reds_or(wa, v0);
                         if (v1) reds_or(wa + 4u, v1);
                         if (v2) reds_or(wa + 8u, v2);
@@ -442,7 +470,6 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
                 }
                 o += bits[r];
             }
-        }
         }
         __syncthreads();
     }

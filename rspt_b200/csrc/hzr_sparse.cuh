@@ -44,9 +44,7 @@ struct SparseOut {
     const uint32_t* blk_off;   // per block: offset of its header from the frame start
     uint32_t stage_bytes;      // largest payload packed here (<= kSpStageBytes; smaller values only in tests)
     const uint8_t* headers;    // per frame: the packer's header bytes (hadamard / dct means)
-    uint32_t* sc_bit;     // decode index (may be null)
-    uint16_t* sc_skip;
-    uint32_t* sc_codes;
+    uint32_t* sidecar;    // decode index (may be null), see common.cuh
 };
 
 __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, const uint8_t* __restrict__ frame_nb,
@@ -83,11 +81,11 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(list_s + 16u * i), "l"(g4 + i) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) {
-        const uint32_t cw = __ldg(codes + (size_t)blk * kSymStride + i);
-        s_codes[i] = cw;
-        if (so.sc_codes) so.sc_codes[(size_t)blk * kSymStride + i] = cw;  // decode index: the block's code table
-    }
+    for (uint32_t i = tid; i < kSymStride; i += blockDim.x) s_codes[i] = __ldg(codes + (size_t)blk * kSymStride + i);
+    // decode index: where this block's entries go (common.cuh); the first token starts behind the tree bits
+    const unsigned long long frame_off = so.offsets[f];
+    uint32_t* my_idx = so.sidecar ? so.sidecar + idx_slot_base(frame_off - so.offsets[0] + so.blk_off[blk] + 7u, blk) : nullptr;
+    if (my_idx && tid <= (bi.tree_nbits >> kIdxShift)) my_idx[tid] = bi.tree_nbits - (tid << kIdxShift);
     // staging: tree words, then zeros (the code words are OR-ed in)
     for (uint32_t i = tid; i < pw + 2u; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -146,7 +144,7 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
             if (lane >= (uint32_t)o) inc += y;
         }
-        const uint32_t o0 = base + inc - bits, o_lit = o0 + bits - slot_bits(c_lit);
+        const uint32_t o0 = base + inc - bits;
         base += __shfl_sync(0xFFFFFFFFu, inc, 31);
         if (live) {
             if (bits > 64u || gap > kRunCap) {
@@ -170,44 +168,19 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
                 if (v2) atomicOr(w + 2, v2);
             }
         }
-        if (so.sc_bit) {
-            // decode index entries of the segment boundaries B in [rs, cur], B < n: at B == rs
-            // the entry's first token starts; later boundaries lie inside the zero run and
-            // resume at the literal.  Up to 8 boundaries are written by the entry's own lane (the
-            // gaps between the bursts of a sparse plane span a few segments), the rest of a very
-            // long run by the whole warp.
-            uint32_t* my_bit = so.sc_bit + (size_t)blk * kMaxSegs;
-            uint16_t* my_skip = so.sc_skip + (size_t)blk * kMaxSegs;
-            uint32_t B = (rs + kSegBytes - 1u) & ~(uint32_t)(kSegBytes - 1);
-            const uint32_t lim = live ? min(cur, n - 1u) : 0u;  // last position a boundary may take
-            if (!live) B = 1u;                                   // nothing to write
-            if (B <= lim && B == rs) {
-                my_bit[B / kSegBytes] = o0;
-                my_skip[B / kSegBytes] = 0;
-                B += kSegBytes;
-            }
-#pragma unroll 1
-            for (int j = 0; j < 8 && B <= lim; ++j, B += kSegBytes) {
-                my_bit[B / kSegBytes] = o_lit;
-                my_skip[B / kSegBytes] = (uint16_t)(cur - B);
-            }
-            uint32_t more = __ballot_sync(0xFFFFFFFFu, B <= lim);
-            while (more) {
-                const uint32_t q = __ffs(more) - 1u;
-                more &= more - 1u;
-                const uint32_t qB = __shfl_sync(0xFFFFFFFFu, B, q), qcur = __shfl_sync(0xFFFFFFFFu, cur, q);
-                const uint32_t qlim = __shfl_sync(0xFFFFFFFFu, lim, q), qo = __shfl_sync(0xFFFFFFFFu, o_lit, q);
-                for (uint32_t Bq = qB + lane * kSegBytes; Bq <= qlim; Bq += 32u * kSegBytes) {
-                    my_bit[Bq / kSegBytes] = qo;
-                    my_skip[Bq / kSegBytes] = (uint16_t)(qcur - Bq);
-                }
+        // decode index: the entry whose tokens cover the last bit before an interval boundary names the
+        // token behind them (the next entry's run, or nothing after the last one)
+        if (my_idx && live) {
+            const uint32_t e = o0 + bits;
+            if ((e >> kIdxShift) != (o0 >> kIdxShift)) {
+                const uint32_t kk = e >> kIdxShift;
+                my_idx[kk] = (e - (kk << kIdxShift)) | ((i < m ? cur + 1u : n) << kIdxPosShift);
             }
         }
     }
     __syncthreads();
 
     // the payload goes out while warp 0 takes its CRC-32C and then writes the 7-byte block header
-    const unsigned long long frame_off = so.offsets[f];
     uint8_t* out = so.dst + frame_off + so.blk_off[blk];
     if (b == 0) write_chunk_framing(s, info, f, k, so.dst, frame_off, out, so.headers);
     copy_smem_to_global(out + 7, stg, 16, plen);

@@ -43,6 +43,9 @@ struct rspt_gpu_packer {
     uint8_t* d_blk_class;  // per block: kClassSparse / kClassDense (density probe of the histogram launches)
     cudaStream_t side;     // sparse-class histogram + trees run here, beside the dense class on `stream`
     cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2;
+    cudaStream_t place;    // multi-GPU placement (all-gather of totals + offset rebase) runs here, off the compute stream
+    cudaEvent_t ev_place;
+    uint64_t* d_all_totals;
     uint16_t* d_step_lz;   // per 512-byte step of every block: leading zero count (512 = all zero)
     rspt::BlkInfo* d_info;
     uint8_t* d_frame_nb;
@@ -59,9 +62,10 @@ struct rspt_gpu_packer {
     void* d_dec;           // block descriptors
     uint8_t* d_dec_nb;     // per-frame plane count used by the last decompress
     int32_t* d_status_tmp;
-    uint8_t* d_seg_xor;    // per 128-byte segment of every decoded plane: xor of its bytes (k_hzr_decode -> inverse transform)
-    uint32_t segs_per_plane;
-    void* d_auto_index;    // decode index built here for streams that came without one (lazy)
+    void* d_auto_index;    // decode index built here for streams that came without one
+    uint32_t* d_inv_tot;   // one-pass inverse, chained form: per (frame, round, CTA, channel) totals
+    uint32_t* d_inv_flag;  // ... and the release flags (epoch of the launch that wrote them)
+    uint32_t inv_epoch;
     double* d_fir;         // FIR kernel coefficients of the last rspt_gpu_prefilter_fir call (lazy)
     size_t fir_cap;
     int32_t* d_words2;     // second word buffer (FIR is out of place), lazy

@@ -4,6 +4,7 @@
 #include "../../include/rspt_gpu.h"
 #include "../../include/rspt_synth.h"
 
+#include <dlfcn.h>
 #include <stdlib.h>
 
 #include <atomic>
@@ -365,15 +366,18 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_redo2, F));
     A(dalloc(p->d_sub_n, F * s.nb_alloc * ch));
     A(dalloc(p->d_nb_state, 4));
+    A(dalloc(p->d_all_totals, 64));
     A(dalloc(p->d_sizes, F));
     A(dalloc(p->d_blk_off, nblocks));
     A(dalloc(p->d_headers, F * (s.hdr_bytes ? s.hdr_bytes : 1)));
     A(dalloc(p->d_ctr, 1));
     A(dalloc(p->d_status_tmp, F));
     A(dalloc(p->d_dec_nb, F));
-    p->segs_per_plane = s.nblk * (uint32_t)kMaxSegs;
-    A(dalloc(p->d_seg_xor, F * s.nb_alloc * (size_t)p->segs_per_plane));
     A(cudaMalloc(&p->d_dec, nblocks * sizeof(DecBlk) + 64));
+    A(dalloc(p->d_inv_tot, F * 2 * 8 * (ch < 32 ? 32 : ch)));
+    A(dalloc(p->d_inv_flag, F * 2 * 8));
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_inv_flag, 0, F * 2 * 8 * sizeof(uint32_t), p->stream);
+    A(cudaMalloc(&p->d_auto_index, ((F * (1 + s.hdr_bytes + (size_t)s.nb_alloc * (4 + hzr_max(s.N))) >> 7) + nblocks + 2) * sizeof(uint32_t) + 64));
     if (kind == RSPT_HADAMARD || kind == RSPT_DCT) {
         A(dalloc(p->d_words, F * (size_t)s.N));
         A(dalloc(p->d_sums, F * (size_t)s.ch));
@@ -393,6 +397,8 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_hist<1>, kHistSmem);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->place, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_place, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork2, cudaEventDisableTiming);
@@ -427,7 +433,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
-                    p->d_one_off, p->d_redo, p->d_redo2, p->d_sub_n, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2, p->d_seg_xor};
+                    p->d_one_off, p->d_redo, p->d_redo2, p->d_sub_n, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2, p->d_inv_tot, p->d_inv_flag, p->d_all_totals};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p->h_pin) cudaFreeHost(p->h_pin);
@@ -439,6 +445,8 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
         delete p->ev_free;
     }
     if (p->side) cudaStreamDestroy(p->side);
+    if (p->place) cudaStreamDestroy(p->place);
+    if (p->ev_place) cudaEventDestroy(p->ev_place);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->ev_fork2) cudaEventDestroy(p->ev_fork2);
@@ -457,10 +465,18 @@ extern "C" size_t rspt_gpu_max_compressed_size(const rspt_gpu_packer* p)
     return 1 + p->s.hdr_bytes + (size_t)p->s.nb_alloc * (4 + hzr_max(p->s.N));
 }
 
+// The decode index has one 32-bit entry per 128 bytes of stream plus one per block (common.cuh); the
+// buffer is sized for the worst-case stream, the entries of a batch occupy a prefix of it.
 extern "C" size_t rspt_gpu_sidecar_bytes(const rspt_gpu_packer* p, size_t n_frames)
 {
     if (!p) return 0;
-    return (size_t)total_blocks(p, n_frames) * (kMaxSegs * 6 + kSymStride * 4) + 64;
+    return ((n_frames * rspt_gpu_max_compressed_size(p) >> 7) + total_blocks(p, n_frames) + 2) * sizeof(uint32_t);
+}
+
+extern "C" size_t rspt_gpu_sidecar_used_bytes(const rspt_gpu_packer* p, size_t n_frames, size_t stream_bytes)
+{
+    if (!p) return 0;
+    return ((stream_bytes >> 7) + total_blocks(p, n_frames) + 2) * sizeof(uint32_t);
 }
 
 extern "C" const char* rspt_gpu_last_error(const rspt_gpu_packer* p) { return p ? p->err : "null handle"; }
@@ -587,9 +603,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     const size_t F = n_frames;
     const uint32_t nblocks = total_blocks(p, F);
     int rc = 0;
-    uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar);
-    uint16_t* sc_skip = d_sidecar ? reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs) : nullptr;
-    uint32_t* sc_codes = d_sidecar ? reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs) : nullptr;
+    uint32_t* sidecar = reinterpret_cast<uint32_t*>(d_sidecar);
     const unsigned tgrid = (nblocks + kTreeWarps - 1) / kTreeWarps;
     if (p->front_ok && !((uintptr_t)d_src & 15)) {
         // fused front end: transform + token histograms + sparse lists in one pass over the raw frames
@@ -649,7 +663,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         // sparse blocks from their lists (side stream) beside everything else from the planes: both kernels
         // decide with the same predicate which of them writes a block
         StageTimer t(p, RSPT_STAGE_ENCODE);
-        const SparseOut so{d_dst, d_offsets, p->d_blk_off, p->sp_stage, p->d_headers, sc_bit, sc_skip, sc_codes};
+        const SparseOut so{d_dst, d_offsets, p->d_blk_off, p->sp_stage, p->d_headers, sidecar};
         RSPT_CUDA_CHECK(cudaEventRecord(p->ev_fork2, p->stream));
         RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_fork2, 0));
         k_hzr_encode_sparse<<<nblocks, kSpThreads, kSparseSmem, p->side>>>(s, p->d_frame_nb, p->d_info, p->d_codes, p->d_tree, p->d_lists,
@@ -657,7 +671,7 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         RSPT_CUDA_CHECK(cudaEventRecord(p->ev_join2, p->side));
         k_hzr_encode<<<nblocks, kEncThreads, p->enc_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
                                                                         p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->sp_stage,
-                                                                        d_offsets, p->d_headers, p->d_crc, d_dst, sc_bit, sc_skip, sc_codes);
+                                                                        d_offsets, p->d_headers, p->d_crc, d_dst, sidecar);
         RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_join2, 0));
     }
     p->launches += 4;
@@ -682,12 +696,12 @@ int launch_parse_and_index(rspt_gpu_packer* p, const uint8_t* d_src, const uint6
         StageTimer t(p, RSPT_STAGE_PARSE);
         k_frame_parse<<<(unsigned)((F + 127) / 128), 128, 0, p->stream>>>(d_src, d_offsets, s, d_frame_nb, p->d_nb_state,
                                                                           (uint32_t)F, dec, p->d_headers, p->d_dec_nb, status, p->d_ctr);
-        p->launches += 1;
+        // code tables of the HUFF blocks from their in-stream trees
+        k_hzr_recover_codes<<<(nblocks + kRecoverWarps - 1) / kRecoverWarps, 32 * kRecoverWarps, 0, p->stream>>>(d_src, nblocks, dec, p->d_codes, s, status);
+        p->launches += 2;
         if (d_sidecar_out) {
-            uint32_t* sc_bit = reinterpret_cast<uint32_t*>(d_sidecar_out);
-            uint16_t* sc_skip = reinterpret_cast<uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs);
-            uint32_t* sc_codes = reinterpret_cast<uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs);
-            k_hzr_build_index<<<nblocks, kIndexThreads, p->dec_smem, p->stream>>>(d_src, s, dec, sc_bit, sc_skip, sc_codes, status);
+            k_hzr_build_index<<<nblocks, kIndexThreads, p->dec_smem, p->stream>>>(d_src, s, dec, d_offsets, p->d_codes,
+                                                                                  reinterpret_cast<uint32_t*>(d_sidecar_out), status);
             p->launches += 1;
         }
     }
@@ -736,19 +750,25 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
     void* own_index = nullptr;
     if (!d_sidecar) {
         // stream from the CPU reference: build the decode index here first (handle-owned scratch)
-        if (!p->d_auto_index) RSPT_CUDA_CHECK(cudaMalloc(&p->d_auto_index, rspt_gpu_sidecar_bytes(p, p->max_batch)));
         own_index = p->d_auto_index;
         d_sidecar = own_index;
     }
     int rc = launch_parse_and_index(p, d_src, d_offsets, F, d_frame_nb, own_index, status);
     if (rc) return rc;
-    const uint32_t* sc_bit = reinterpret_cast<const uint32_t*>(d_sidecar);
-    const uint16_t* sc_skip = reinterpret_cast<const uint16_t*>(sc_bit + (size_t)nblocks * kMaxSegs);
-    const uint32_t* sc_codes = reinterpret_cast<const uint32_t*>(sc_skip + (size_t)nblocks * kMaxSegs);
     {
         StageTimer t(p, RSPT_STAGE_DECODE);
-        k_hzr_decode<<<nblocks, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec, sc_bit, sc_skip, sc_codes, p->d_planes, status,
-                                                                          p->d_seg_xor, p->segs_per_plane, decode_pair_max_bits());
+        const uint32_t* sc = reinterpret_cast<const uint32_t*>(d_sidecar);
+        const uint32_t maxn = s.N < kBlock ? s.N : kBlock;
+        k_hzr_decode<<<nblocks, decode_class_threads(kSmallPayload), decode_class_smem(kSmallPayload), p->stream>>>(
+            d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status, decode_pair_max_bits(), 1u);
+        if (maxn > kSmallPayload) {
+            k_hzr_decode<<<nblocks, decode_class_threads(kMediumPayload), decode_class_smem(kMediumPayload), p->stream>>>(
+                d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status, decode_pair_max_bits(), 2u);
+            p->launches += 1;
+        }
+        k_hzr_decode<<<nblocks, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status,
+                                                                          decode_pair_max_bits(), 0u);
+        p->launches += 1;
     }
     p->launches += 1;
     RSPT_CUDA_CHECK(cudaGetLastError());
@@ -776,6 +796,121 @@ extern "C" int rspt_gpu_verify_batch(rspt_gpu_packer* p, const uint8_t* d_src, c
     k_hzr_verify<<<nblocks, kVerifyThreads, p->dec_smem, p->stream>>>(d_src, s, dec, p->d_crc, d_status, p->d_ctr);
     p->launches += 2;
     RSPT_CUDA_CHECK(cudaGetLastError());
+    return RSPT_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through its C API, resolved at run time (no link-time dependency)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct NcclId { char b[128]; };   // ncclUniqueId, passed by value
+
+struct NcclApi {
+    int (*get_unique_id)(void*) = nullptr;
+    int (*comm_init_rank)(void**, int, NcclId, int) = nullptr;
+    int (*comm_destroy)(void*) = nullptr;
+    int (*all_gather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi* nccl_api()
+{
+    static NcclApi api = [] {
+        NcclApi a;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy the process already has (torch's)
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return a;
+        a.get_unique_id = reinterpret_cast<decltype(a.get_unique_id)>(dlsym(h, "ncclGetUniqueId"));
+        a.comm_init_rank = reinterpret_cast<decltype(a.comm_init_rank)>(dlsym(h, "ncclCommInitRank"));
+        a.comm_destroy = reinterpret_cast<decltype(a.comm_destroy)>(dlsym(h, "ncclCommDestroy"));
+        a.all_gather = reinterpret_cast<decltype(a.all_gather)>(dlsym(h, "ncclAllGather"));
+        a.ok = a.get_unique_id && a.comm_init_rank && a.comm_destroy && a.all_gather;
+        return a;
+    }();
+    return &api;
+}
+constexpr int kNcclUint64 = 5;   // ncclUint64 (nccl.h: ncclInt8 0, ncclUint8 1, ncclInt32 2, ncclUint32 3, ncclInt64 4, ncclUint64 5)
+
+}  // namespace
+
+extern "C" int rspt_gpu_comm_unique_id(uint8_t id[128])
+{
+    NcclApi* a = nccl_api();
+    if (!id || !a->ok) return RSPT_E_ARG;
+    return a->get_unique_id(id) == 0 ? RSPT_OK : RSPT_E_CUDA;
+}
+
+extern "C" int rspt_gpu_comm_init(int world, const uint8_t id[128], int rank, int device, void** comm)
+{
+    NcclApi* a = nccl_api();
+    if (!comm || !id || !a->ok || world < 1 || rank < 0 || rank >= world) return RSPT_E_ARG;
+    DeviceGuard dg(device);
+    NcclId u;
+    memcpy(u.b, id, 128);
+    return a->comm_init_rank(comm, world, u, rank) == 0 ? RSPT_OK : RSPT_E_CUDA;
+}
+
+extern "C" int rspt_gpu_comm_destroy(void* comm)
+{
+    NcclApi* a = nccl_api();
+    if (!comm || !a->ok) return RSPT_E_ARG;
+    return a->comm_destroy(comm) == 0 ? RSPT_OK : RSPT_E_CUDA;
+}
+
+extern "C" int rspt_gpu_allgather_totals(void* comm, const uint64_t* d_total, uint64_t* d_all_totals, void* stream)
+{
+    NcclApi* a = nccl_api();
+    if (!comm || !d_total || !d_all_totals || !a->ok) return RSPT_E_ARG;
+    return a->all_gather(d_total, d_all_totals, 1, kNcclUint64, comm, (cudaStream_t)stream) == 0 ? RSPT_OK : RSPT_E_CUDA;
+}
+
+extern "C" int rspt_gpu_place_offsets_async(rspt_gpu_packer* p, void* comm, uint64_t* d_offsets, size_t n_frames, int rank, int world)
+{
+    if (!p || !d_offsets || rank < 0 || world < 1 || rank >= world || world > 64) return RSPT_E_ARG;
+    if (world == 1) return RSPT_OK;
+    DeviceGuard dg(p->device);
+    RSPT_CUDA_CHECK(cudaEventRecord(p->ev_place, p->stream));
+    RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->place, p->ev_place, 0));
+    const int rc = rspt_gpu_allgather_totals(comm, d_offsets + n_frames, p->d_all_totals, p->place);
+    if (rc) return rc;
+    return rspt_gpu_rebase_offsets(d_offsets, n_frames + 1, p->d_all_totals, rank, p->place);
+}
+
+extern "C" int rspt_gpu_place_join(rspt_gpu_packer* p)
+{
+    if (!p) return RSPT_E_ARG;
+    DeviceGuard dg(p->device);
+    RSPT_CUDA_CHECK(cudaEventRecord(p->ev_place, p->place));
+    RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_place, 0));
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_set_stream(rspt_gpu_packer* p, void* stream)
+{
+    if (!p) return RSPT_E_ARG;
+    p->stream = (cudaStream_t)stream;
+    return RSPT_OK;
+}
+
+extern "C" int rspt_gpu_set_dct_exact(rspt_gpu_packer* p, int exact)
+{
+    if (!p || p->s.kind != RSPT_DCT) return RSPT_E_ARG;
+    if (!exact && ((p->s.ns & (p->s.ns - 1)) != 0)) return fail_arg(p, "the FFT path needs a power-of-two length");
+    DeviceGuard dg(p->device);
+    if (exact && !p->d_cos) {
+        // the cosine table is built on first use (the twiddles of the FFT path are rebuilt with it)
+        RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+        if (p->d_twiddle) cudaFree(p->d_twiddle);
+        if (p->d_post) cudaFree(p->d_post);
+        p->d_twiddle = nullptr;
+        p->d_post = nullptr;
+        p->dct_direct = true;
+        RSPT_CUDA_CHECK(dct_build_tables(p));
+    }
+    p->dct_direct = exact != 0;
     return RSPT_OK;
 }
 
@@ -1061,22 +1196,6 @@ extern "C" int rspt_gpu_decompress_host(rspt_gpu_packer* p, const uint8_t* h_src
 }
 
 namespace {
-int ensure_host_batch(rspt_gpu_packer* p, size_t F)
-{
-    if (F <= p->hb_frames) return RSPT_OK;
-    if (p->d_hb_src) cudaFree(p->d_hb_src);
-    if (p->d_hb_dst) cudaFree(p->d_hb_dst);
-    if (p->d_hb_off) cudaFree(p->d_hb_off);
-    p->d_hb_src = p->d_hb_dst = nullptr;
-    p->d_hb_off = nullptr;
-    p->hb_frames = 0;
-    RSPT_CUDA_CHECK(dalloc(p->d_hb_src, F * (size_t)p->s.frame_bytes));
-    RSPT_CUDA_CHECK(dalloc(p->d_hb_dst, F * rspt_gpu_max_compressed_size(p)));
-    RSPT_CUDA_CHECK(dalloc(p->d_hb_off, F + 1));
-    p->hb_frames = F;
-    return RSPT_OK;
-}
-
 // Host-buffer compress runs as a three-stage pipeline over chunks of frames: H2D of chunk i+1,
 // the kernels of chunk i and D2H of chunk i-1 overlap on three streams with two device buffers.
 // The payload D2H of a chunk needs its byte total on the host, so the host waits for the (tiny)
@@ -1178,20 +1297,47 @@ extern "C" int rspt_gpu_compress_batch_host(rspt_gpu_packer* p, const uint8_t* h
     return status;
 }
 
+// The mirror image: H2D of the compressed bytes of chunk i+1 (with its offsets, rebased to the chunk), the
+// kernels of chunk i and D2H of the samples of chunk i-1 overlap on the same three streams and buffers.
+// The stream arrives as the reference would store it -- no decode index -- so the index is rebuilt per chunk
+// on the device (k_hzr_build_index); the call is bound by the D2H of the raw samples all the same.
 extern "C" int rspt_gpu_decompress_batch_host(rspt_gpu_packer* p, const uint8_t* h_src, const uint64_t* h_offsets,
                                               size_t n_frames, uint8_t* h_dst)
 {
     if (!p || !h_src || !h_offsets || !h_dst) return RSPT_E_ARG;
+    if (n_frames == 0) return RSPT_OK;
     DeviceGuard dg(p->device);
-    int rc = ensure_host_batch(p, n_frames);
+    int rc = ensure_host_pipe(p);
     if (rc) return rc;
-    const size_t total = (size_t)h_offsets[n_frames];
-    if (total > n_frames * rspt_gpu_max_compressed_size(p)) return fail_arg(p, "offsets exceed the frame bound"), RSPT_E_STREAM;
-    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_hb_dst, h_src, total, cudaMemcpyHostToDevice, p->stream));
-    RSPT_CUDA_CHECK(cudaMemcpyAsync(p->d_hb_off, h_offsets, (n_frames + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
-    rc = rspt_gpu_decompress_batch(p, p->d_hb_dst, p->d_hb_off, n_frames, nullptr, nullptr, p->d_hb_src, nullptr);
-    if (rc) return rc;
-    RSPT_CUDA_CHECK(cudaMemcpyAsync(h_dst, p->d_hb_src, n_frames * (size_t)p->s.frame_bytes, cudaMemcpyDeviceToHost, p->stream));
+    HostPipe& hp = p->pipe;
+    const size_t fb = p->s.frame_bytes, maxc = rspt_gpu_max_compressed_size(p), C = hp.chunk;
+    const size_t nchunks = (n_frames + C - 1) / C;
+    for (size_t f = 0; f < n_frames; ++f)
+        if (h_offsets[f + 1] < h_offsets[f] || h_offsets[f + 1] - h_offsets[f] > maxc) return fail_arg(p, "offsets exceed the frame bound"), RSPT_E_STREAM;
+    for (size_t j = 0; j < nchunks; ++j) {
+        const int b = (int)(j & 1);
+        const size_t f0 = j * C, nf = (n_frames - f0 < C) ? n_frames - f0 : C;
+        const uint64_t base = h_offsets[f0], bytes = h_offsets[f0 + nf] - base;
+        // stage 1: H2D once the kernels of chunk j-2 have released the compressed buffer; the pinned offsets
+        // staging is free once ITS copy of chunk j-2 has gone out
+        if (j >= 2) RSPT_CUDA_CHECK(cudaEventSynchronize(hp.ev_in[b]));
+        for (size_t i = 0; i <= nf; ++i) hp.h_off[b][i] = h_offsets[f0 + i] - base;
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(hp.s_in, hp.ev_comp[b], 0));
+        RSPT_CUDA_CHECK(cudaMemcpyAsync(hp.d_dst[b], h_src + base, (size_t)bytes, cudaMemcpyHostToDevice, hp.s_in));
+        RSPT_CUDA_CHECK(cudaMemcpyAsync(hp.d_off[b], hp.h_off[b], (nf + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, hp.s_in));
+        RSPT_CUDA_CHECK(cudaEventRecord(hp.ev_in[b], hp.s_in));
+        // stage 2: kernels, once the input is there and the samples of chunk j-2 have left the output buffer
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, hp.ev_in[b], 0));
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, hp.ev_out[b], 0));
+        rc = rspt_gpu_decompress_batch(p, hp.d_dst[b], hp.d_off[b], nf, nullptr, nullptr, hp.d_src[b], nullptr);
+        if (rc) return rc;
+        RSPT_CUDA_CHECK(cudaEventRecord(hp.ev_comp[b], p->stream));
+        // stage 3: D2H of the samples
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(hp.s_out, hp.ev_comp[b], 0));
+        RSPT_CUDA_CHECK(cudaMemcpyAsync(h_dst + f0 * fb, hp.d_src[b], nf * fb, cudaMemcpyDeviceToHost, hp.s_out));
+        RSPT_CUDA_CHECK(cudaEventRecord(hp.ev_out[b], hp.s_out));
+    }
+    RSPT_CUDA_CHECK(cudaStreamSynchronize(hp.s_out));
     RSPT_CUDA_CHECK(cudaStreamSynchronize(p->stream));
     return RSPT_OK;
 }

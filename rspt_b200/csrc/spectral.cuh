@@ -20,6 +20,7 @@
 
 #include "packer.cuh"
 #include "transforms.cuh"
+#include "inverse.cuh"
 
 namespace rspt {
 
@@ -881,6 +882,18 @@ inline int spectral_forward(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
 }
 
 // planes (decoded) -> samples, all four packers
+// RSPT_INV_MODE: 0 = three-pass kernel (k_planes_to_samples_fast), 1 = one pass, a cluster per frame (DSMEM),
+// 2 = one pass, chained CTAs (totals through global memory)
+inline int inverse_mode()
+{
+    static const int v = [] {
+        const char* e = getenv("RSPT_INV_MODE");
+        return e ? atoi(e) : 2;
+    }();
+    return v;
+}
+inline bool inverse_cluster_enabled() { return inverse_mode() != 0; }
+
 inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F)
 {
     const Shape& s = p->s;
@@ -889,6 +902,63 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
     const size_t sm_inv = (size_t)2 * np * 4 + tile_bytes;
     if (sm_inv > 200 * 1024 || tile_bytes > 200 * 1024) return fail_arg(p, "frame too large for the inverse kernel");
     const dim3 gf((unsigned)F);
+    // one pass over the planes: a cluster of CTAs per frame, each with a sample range of every channel (inverse.cuh)
+    if ((s.kind == 0 || s.kind == 1) && inverse_cluster_enabled() && s.bps >= 2 && (s.ch & 3) == 0 && s.ch <= (int)kInvMaxCh &&
+        (s.ns & 127) == 0 && ((uintptr_t)d_dst & 15) == 0) {
+        // S = ns / C samples per CTA, a multiple of 128; warps = (ch / 4) * (S / 128) <= 24: the largest CTA that fits
+        const uint32_t G = (uint32_t)s.ch >> 2;
+        uint32_t C = 0, S = 0;
+        for (uint32_t cc = 1; cc <= 8 && !C; cc <<= 1) {
+            if ((uint32_t)s.ns % (cc * 128u)) break;
+            const uint32_t s2 = (uint32_t)s.ns / cc;
+            if (G * (s2 >> 7) <= 24u && inverse_cluster_smem(s.bps, s.ch, s2) <= 100 * 1024) {
+                C = cc;
+                S = s2;
+            }
+        }
+        if (C) {
+            const size_t smc = inverse_cluster_smem(s.bps, s.ch, S);
+            const bool chained = inverse_mode() == 2;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(F * C));
+            cfg.blockDim = dim3(32u * G * (S >> 7));
+            cfg.dynamicSmemBytes = smc;
+            cfg.stream = p->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = C;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = chained ? 0 : 1;
+            const int scan = s.kind == 0 ? 1 : 0;
+            InvChain chain = {p->d_inv_tot, p->d_inv_flag, ++p->inv_epoch, C};
+            cudaError_t e = cudaErrorInvalidValue;
+#define INVC(B, NT, CH)                                                                                                 \
+    do {                                                                                                                \
+        e = cudaFuncSetAttribute(k_inverse_cluster<B, NT, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc);  \
+        if (e == cudaSuccess)                                                                                           \
+            e = cudaLaunchKernelEx(&cfg, k_inverse_cluster<B, NT, CH>, (const uint8_t*)p->d_planes, s, (const uint8_t*)p->d_dec_nb, d_dst, scan, S, chain); \
+    } while (0)
+#define INVC_B(B)                                                   \
+    do {                                                            \
+        if (chained) { if (s.nb_alloc <= 3) INVC(B, 3, true); else INVC(B, 4, true); }   \
+        else { if (s.nb_alloc <= 3) INVC(B, 3, false); else INVC(B, 4, false); }         \
+    } while (0)
+            switch (s.bps) {
+            case 2: INVC_B(2); break;
+            case 3: INVC_B(3); break;
+            default: INVC_B(4); break;
+            }
+#undef INVC_B
+#undef INVC
+            if (e == cudaSuccess) {
+                p->launches += 1;
+                return 0;
+            }
+            (void)cudaGetLastError();  // cluster launch not possible here: the three-pass kernel below
+        }
+    }
     // fast path: 4-channel groups, 128-sample pieces, PRMT packing (transforms.cuh)
     if ((s.kind == 0 || s.kind == 1) && (s.ch & 3) == 0 && (s.ns % (int)kInvPiece) == 0 && ((uintptr_t)d_dst & 15) == 0) {
         const size_t row = (size_t)s.ch * s.bps;
@@ -904,7 +974,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
     do {                                                                                                              \
         cudaFuncSetAttribute(k_planes_to_samples_fast<B, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf); \
         k_planes_to_samples_fast<B, SC><<<gf, kInvThreads, smf, p->stream>>>(p->d_planes, s, p->d_dec_nb, tpg, d_dst,    \
-                                                                       p->d_seg_xor, p->segs_per_plane);       \
+                                                                       nullptr, 0u);                           \
     } while (0)
             const bool sc = s.kind == 0;
             switch (s.bps) {
@@ -965,7 +1035,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
             if ((s.ns % (int)kInvPiece) == 0 && smw <= 200 * 1024) {
                 cudaFuncSetAttribute(k_planes_to_samples_fast<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);
                 k_planes_to_samples_fast<4, true, true><<<gf, kInvThreads, smw, p->stream>>>(p->d_planes, s, p->d_dec_nb, 1, nullptr,
-                                                                                             p->d_seg_xor, p->segs_per_plane, p->d_words);
+                                                                                             nullptr, 0u, p->d_words);
             } else {
                 INV_LAUNCH(4, true, false);
             }

@@ -128,12 +128,6 @@ __global__ void __launch_bounds__(256) k_xdelta_planes(const uint8_t* __restrict
 // selector), the 3-tap stencil runs in registers, and a 4 x 4 byte transpose (8 PRMT) turns four
 // consecutive y words into one 32-bit word per plane, stored coalesced (lanes run along jq).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-    return d;
-}
 
 // the 4 sign-extended samples packed in BPS consecutive words
 template <int BPS>
