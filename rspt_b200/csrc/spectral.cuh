@@ -888,7 +888,7 @@ inline int inverse_mode()
 {
     static const int v = [] {
         const char* e = getenv("RSPT_INV_MODE");
-        return e ? atoi(e) : 2;
+        return e ? atoi(e) : 0;
     }();
     return v;
 }

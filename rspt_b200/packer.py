@@ -135,6 +135,35 @@ class SignalPacker:
     def _dev(self):
         return torch.device("cuda", self.device)
 
+    def _bind_stream(self):
+        """Order the handle's work on torch's CURRENT stream (the handle was created on the stream that was
+        current then).  The switch itself is ordered: the new stream waits for what the old one still holds."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.stream_ptr:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.ExternalStream(self.stream_ptr, device=self._dev()) if self.stream_ptr else torch.cuda.default_stream(self.device))
+            cur.wait_event(ev)
+            check(self.L.rspt_gpu_set_stream(self.h, cur.cuda_stream), self.h, "rspt_gpu_set_stream")
+            self.stream_ptr = cur.cuda_stream
+
+    def sidecar_used_bytes(self, n_frames: int, stream_bytes: int) -> int:
+        """Bytes of the decode index that belong to a batch whose stream has `stream_bytes` bytes (a prefix of
+        the sidecar buffer): what has to be kept next to the stream."""
+        return int(self.L.rspt_gpu_sidecar_used_bytes(self.h, n_frames, stream_bytes))
+
+    # -- multi-GPU placement (the path's only collective), through the C ABI -------------------------
+    def place_offsets_async(self, comm, batch: "CompressedBatch", rank: int, world: int) -> None:
+        """All-gather of the ranks' byte totals + rebase of this batch's offsets into the global stream, on the
+        handle's side stream (ordered behind the compress that produced `batch`)."""
+        check(self.L.rspt_gpu_place_offsets_async(self.h, comm, batch.offsets.data_ptr(), batch.n_frames, rank, world), self.h,
+              "rspt_gpu_place_offsets_async")
+
+    def place_join(self) -> None:
+        check(self.L.rspt_gpu_place_join(self.h), self.h, "rspt_gpu_place_join")
+
+    def set_dct_exact(self, exact: bool) -> None:
+        check(self.L.rspt_gpu_set_dct_exact(self.h, int(exact)), self.h, "rspt_gpu_set_dct_exact")
+
     def alloc_output(self, n_frames: int, sidecar: bool = True) -> CompressedBatch:
         dev = self._dev()
         stream = torch.empty(n_frames * self.max_compressed_size, dtype=torch.uint8, device=dev)
@@ -144,7 +173,8 @@ class SignalPacker:
         return CompressedBatch(stream, offsets, frame_nb, sc, n_frames)
 
     def compress_batch(self, frames: torch.Tensor, out: CompressedBatch | None = None, sidecar: bool = True) -> CompressedBatch:
-        """frames: uint8 CUDA tensor of n * frame_bytes bytes.  Asynchronous on the current stream."""
+        """frames: uint8 CUDA tensor of n * frame_bytes bytes.  Asynchronous on torch's current stream (the
+        handle is re-bound to it when it changed since the last call)."""
         if not (frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous()):
             raise ValueError("frames must be a contiguous uint8 CUDA tensor")
         n = frames.numel() // self.frame_bytes
@@ -152,6 +182,11 @@ class SignalPacker:
             raise ValueError("frames is not a whole number of frames")
         if out is None:
             out = self.alloc_output(n, sidecar)
+        if out.offsets.numel() < n + 1 or out.frame_nb.numel() < n or out.stream.numel() < n * self.max_compressed_size:
+            raise ValueError("the output batch is too small for these frames")
+        if out.sidecar is not None and out.sidecar.numel() < self.L.rspt_gpu_sidecar_bytes(self.h, n):
+            raise ValueError("the output batch's sidecar is too small for these frames")
+        self._bind_stream()
         sc = out.sidecar.data_ptr() if out.sidecar is not None else None
         rc = self.L.rspt_gpu_compress_batch(self.h, frames.data_ptr(), n, out.stream.data_ptr(), out.stream.numel(),
                                             out.offsets.data_ptr(), out.frame_nb.data_ptr(), sc)
@@ -166,6 +201,7 @@ class SignalPacker:
             out = torch.empty(n * self.frame_bytes, dtype=torch.uint8, device=self._dev())
         sc = batch.sidecar.data_ptr() if (use_sidecar and batch.sidecar is not None) else None
         nbp = batch.frame_nb.data_ptr() if batch.frame_nb is not None else None
+        self._bind_stream()
         rc = self.L.rspt_gpu_decompress_batch(self.h, batch.stream.data_ptr(), batch.offsets.data_ptr(), n, nbp, sc,
                                               out.data_ptr(), status.data_ptr() if status is not None else None)
         check(rc, self.h, "rspt_gpu_decompress_batch")
@@ -175,6 +211,7 @@ class SignalPacker:
         """In place on device frames: the IIR pre-filter step of rspt_test.cpp:116-136 (i_filter::new_iir)."""
         na, da = np.ascontiguousarray(n, np.float64), np.ascontiguousarray(d, np.float64)
         dp = C.POINTER(C.c_double)
+        self._bind_stream()
         rc = self.L.rspt_gpu_prefilter_iir(self.h, frames.data_ptr(), frames.numel() // self.frame_bytes,
                                            na.ctypes.data_as(dp), da.ctypes.data_as(dp), len(na), init_nr_samples)
         check(rc, self.h, "rspt_gpu_prefilter_iir")
@@ -183,6 +220,7 @@ class SignalPacker:
     def prefilter_fir(self, frames: torch.Tensor, kernel) -> torch.Tensor:
         """In place on device frames: the same step with i_filter::new_fir(kernel)."""
         ka = np.ascontiguousarray(kernel, np.float64)
+        self._bind_stream()
         rc = self.L.rspt_gpu_prefilter_fir(self.h, frames.data_ptr(), frames.numel() // self.frame_bytes,
                                            ka.ctypes.data_as(C.POINTER(C.c_double)), len(ka))
         check(rc, self.h, "rspt_gpu_prefilter_fir")
@@ -193,6 +231,7 @@ class SignalPacker:
         n = batch.n_frames
         sc = torch.empty(self.L.rspt_gpu_sidecar_bytes(self.h, n), dtype=torch.uint8, device=self._dev())
         nbp = batch.frame_nb.data_ptr() if batch.frame_nb is not None else None
+        self._bind_stream()
         rc = self.L.rspt_gpu_build_index(self.h, batch.stream.data_ptr(), batch.offsets.data_ptr(), n, nbp, sc.data_ptr(),
                                          status.data_ptr() if status is not None else None)
         check(rc, self.h, "rspt_gpu_build_index")
@@ -205,6 +244,7 @@ class SignalPacker:
         if status is None:
             status = torch.zeros(n, dtype=torch.int32, device=self._dev())
         nbp = batch.frame_nb.data_ptr() if batch.frame_nb is not None else None
+        self._bind_stream()
         rc = self.L.rspt_gpu_verify_batch(self.h, batch.stream.data_ptr(), batch.offsets.data_ptr(), n, nbp, status.data_ptr())
         check(rc, self.h, "rspt_gpu_verify_batch")
         return status
