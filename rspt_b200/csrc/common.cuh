@@ -17,19 +17,37 @@ constexpr int kSymStride = 264;        // padded row for per-block tables
 constexpr int kTreeWords = 92;         // >= ceil((11*261-1)/32)
 constexpr uint32_t kBlock = 65536;     // HZR_MAX_BLOCK_SIZE, hzr_internal.h:109
 constexpr uint32_t kRunCap = 16662;    // hzr_encode.c:149
-// Decode index (out of band, never part of the stream): one 32-bit entry per kIdxBits payload bits of a
-// HUFF block.  Entry k names a token boundary at or shortly after bit k * kIdxBits of the block's payload:
-//   bits 0..11  start bit of that token minus k * kIdxBits     bits 12..  output byte the token starts at
+// Decode index (out of band, never part of the stream): 32-bit entries, one per INTERVAL of a HUFF block's
+// payload bits.  The interval length follows from the payload length alone (both sides know it): 512 bits,
+// or as many as it takes to cut the payload into at most 512 intervals -- one decoder thread each, so a
+// full-size block keeps a whole CTA busy and a sparse block gets a handful of short intervals.  Entry k
+// names a token boundary at or shortly after bit k * interval:
+//   bits 0..11  start bit of that token minus k * interval     bits 12..  output byte the token starts at
 // A decoder thread takes the tokens from its entry's boundary up to the next entry's.  The entries of a
-// block sit at slot (payload byte offset in the batch's stream >> 7) + block ordinal + k, so the index of
-// a batch is a prefix of the sidecar buffer whose length follows the compressed size (4 bytes per 128).
-constexpr uint32_t kIdxShift = 10;
-constexpr uint32_t kIdxBits = 1u << kIdxShift;
+// block sit at slot (payload byte offset in the batch's stream >> 6) + block ordinal + k, so the index of
+// a batch lies in a prefix of the sidecar buffer whose length follows the compressed size.
+constexpr uint32_t kIdxMinBits = 512;
 constexpr uint32_t kIdxPosShift = 12;
-constexpr int kMaxSegs = (kBlock * 8) / kIdxBits;  // 512 intervals per block at most: one decoder thread each
+constexpr int kMaxSegs = 512;             // intervals per block at most: one decoder thread each
+struct IdxGeom {
+    uint32_t bits;   // interval length
+    uint32_t inv;    // ceil(2^32 / bits): x / bits == __umulhi(x, inv) for x < 2^19
+    uint32_t n;      // intervals of the block
+};
+__host__ __device__ __forceinline__ IdxGeom idx_geom(uint32_t payload_len)
+{
+    IdxGeom g;
+    const uint32_t total = payload_len * 8u;
+    g.bits = (total + (uint32_t)kMaxSegs - 1u) / (uint32_t)kMaxSegs;
+    if (g.bits < kIdxMinBits) g.bits = kIdxMinBits;
+    g.inv = 0xFFFFFFFFu / g.bits + 1u;
+    g.n = (total + g.bits - 1u) / g.bits;
+    return g;
+}
+__device__ __forceinline__ uint32_t idx_interval_of(const IdxGeom& g, uint32_t bit) { return __umulhi(bit, g.inv); }
 __host__ __device__ __forceinline__ size_t idx_slot_base(unsigned long long payload_rel, uint32_t blk)
 {
-    return (size_t)(payload_rel >> 7) + blk;
+    return (size_t)(payload_rel >> 6) + blk;
 }
 
 enum : uint32_t { MODE_COPY = 0, MODE_HUFF = 1, MODE_FILL = 2 };  // hzr_internal.h:98-101

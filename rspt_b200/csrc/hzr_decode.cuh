@@ -22,10 +22,10 @@
 namespace rspt {
 
 constexpr int kDecodeThreads = kMaxSegs;  // one thread per decode segment
-// decode classes: HUFF payloads up to kClassPayload[c] bytes are decoded by CTAs of kClassPayload[c] * 8 / kIdxBits
-// threads; class 0 takes everything else (longer payloads, COPY / FILL blocks)
-constexpr uint32_t kSmallPayload = 8192, kMediumPayload = 32768;
-__host__ __device__ constexpr int decode_class_threads(uint32_t payload) { return (int)(payload * 8 / kIdxBits); }
+// decode classes: HUFF payloads up to kSmallPayload / kMediumPayload bytes are decoded by CTAs with one thread per
+// index interval of the largest such payload; class 0 takes everything else (longer payloads, COPY / FILL blocks)
+constexpr uint32_t kSmallPayload = 4096, kMediumPayload = 16384;
+__host__ __device__ constexpr int decode_class_threads(uint32_t payload) { return (int)(payload * 8 / kIdxMinBits); }
 __host__ __device__ constexpr size_t decode_class_smem(uint32_t payload) { return payload + 64; }
 constexpr int kLutBits = 12;
 constexpr int kPairBits = 11;  // index width of the pair table (32-bit entries in the same 8 KB)
@@ -172,12 +172,12 @@ constexpr uint32_t kLongEnd = 0x1FFu;  // flagged table entries: index of the fi
 // are that many descents to the left; after a leaf the walk resumes at the right child of the deepest
 // ancestor that was entered to the left, which is the highest zero bit of the path (code words are
 // LSB-first: bit i of the code is the turn taken at depth i).  cw[sym] = code | len << 27 (must be
-// zeroed by the caller).  Returns the number of tree bits (11 per leaf - 1), or 0xFFFFFFFF on a malformed tree;
-// the caller checks that as many code words came out as there were leaves (no symbol twice).
-__device__ __forceinline__ uint32_t recover_tree(const uint32_t* payw, uint32_t plen, uint32_t* cw)
+// zeroed by the caller; global or shared memory).  `words` / `bit0`: the word that holds the tree's first bit and
+// that bit's position in it.  Returns the number of tree bits (11 per leaf - 1), or 0xFFFFFFFF on a malformed tree.
+__device__ __forceinline__ uint32_t recover_tree(const uint32_t* words, uint32_t bit0, uint32_t plen, uint32_t* cw)
 {
     BitReader r;
-    r.init(payw, 0);
+    r.init(words, bit0);
     uint32_t leaves = 0, bits_used = 0, code = 0, depth = 0;
     const uint32_t limit = plen * 8u;
     for (;;) {
@@ -193,7 +193,7 @@ __device__ __forceinline__ uint32_t recover_tree(const uint32_t* payw, uint32_t 
         bits_used += z + 10u;
         if (bits_used > limit || sym >= (uint32_t)kNumSymbols || leaves >= (uint32_t)kNumSymbols) return 0xFFFFFFFFu;
         cw[sym] = code | (max(depth, 1u) << 27);          // lone leaf: 1-bit code (dec:306 `hzr_max(bits, 1)`)
-        ++leaves;                                         // (a symbol named twice shows up in the caller's count)
+        ++leaves;
         const uint32_t m = ~code & ((1u << depth) - 1u);  // levels entered to the left
         if (m == 0u) break;                               // the tree is complete
         const uint32_t i = 31u - (uint32_t)__clz((int)m);
@@ -203,54 +203,30 @@ __device__ __forceinline__ uint32_t recover_tree(const uint32_t* payw, uint32_t 
     return bits_used;
 }
 
-// One warp per block: the code table of every HUFF block from its in-stream tree (k_hzr_decode and
-// k_hzr_build_index read it from `codes`).  status[f] = -4 on a malformed tree; the block then decodes to zeros.
-constexpr int kRecoverWarps = 4;
-constexpr uint32_t kTreeMaxWords = (11u * kNumSymbols + 31u) / 32u + 2u;
-__global__ void __launch_bounds__(32 * kRecoverWarps) k_hzr_recover_codes(const uint8_t* __restrict__ src, uint32_t total_blocks,
-                                                                          DecBlk* __restrict__ dec, uint32_t* __restrict__ codes,
-                                                                          Shape s, int32_t* __restrict__ status)
+// One THREAD per block: the code table of every HUFF block from its in-stream tree, read straight from the
+// stream (k_hzr_decode and k_hzr_build_index read the tables from `codes`, which the host zeroes beforehand).
+// The walk is serial and latency-bound; with a thread per block a whole batch is in flight at once (a warp
+// takes as long as its block with the most leaves).  status[f] = -4 on a malformed tree; the block then
+// decodes to zeros.  A symbol named by two leaves keeps the later code (no memory safety issue: the table is
+// only ever indexed by symbol).
+constexpr int kRecoverThreads = 64;
+__global__ void __launch_bounds__(kRecoverThreads) k_hzr_recover_codes(const uint8_t* __restrict__ src, uint32_t total_blocks,
+                                                                       DecBlk* __restrict__ dec, uint32_t* __restrict__ codes,
+                                                                       Shape s, int32_t* __restrict__ status)
 {
-    __shared__ uint32_t s_w[kRecoverWarps][kTreeMaxWords + 2];
-    __shared__ uint32_t s_c[kRecoverWarps][kSymStride];
-    const uint32_t blk = blockIdx.x * kRecoverWarps + warp_id(), lane = lane_id();
+    const uint32_t blk = blockIdx.x * kRecoverThreads + threadIdx.x;
     if (blk >= total_blocks) return;
     const DecBlk d = dec[blk];
     if (d.mode != MODE_HUFF) return;
-    uint32_t* w = s_w[warp_id()];
-    uint32_t* c = s_c[warp_id()];
     const uintptr_t pa = (uintptr_t)(src + d.payload_off);
-    const uint32_t* aw = reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(pa & 3u) * 8u;
-    const uint32_t pwords = min((d.payload_len + 3u) >> 2, kTreeMaxWords), naw = (uint32_t)(((pa & 3u) + d.payload_len + 3u) >> 2);
-    for (uint32_t i = lane; i < kTreeMaxWords + 2u; i += 32) {
-        uint32_t v = 0;
-        if (i < pwords) {
-            const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
-            v = __funnelshift_r(lo, hi, sh);
-        }
-        w[i] = v;
-    }
-    for (uint32_t i = lane; i < (uint32_t)kSymStride; i += 32) c[i] = 0;
-    __syncwarp();
-    uint32_t tb = 0;
-    if (lane == 0) tb = recover_tree(w, d.payload_len, c);
-    tb = __shfl_sync(0xFFFFFFFFu, tb, 0);
-    __syncwarp();
-    uint32_t used = 0;
-    for (uint32_t i = lane; i < (uint32_t)kSymStride; i += 32) used += c[i] != 0u;
-    used = __reduce_add_sync(0xFFFFFFFFu, used);
-    if (tb != 0xFFFFFFFFu && 11u * used != tb + 1u) tb = 0xFFFFFFFFu;  // a symbol had two leaves
+    const uint32_t tb = recover_tree(reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3), (uint32_t)(pa & 3u) * 8u, d.payload_len,
+                                     codes + (size_t)blk * kSymStride);
     if (tb == 0xFFFFFFFFu) {
-        if (lane == 0) {
-            uint32_t f, k, b;
-            blk_decode(s, blk, f, k, b);
-            status[f] = -4;
-            dec[blk].mode = kModeZero;
-        }
-        return;
+        uint32_t f, k, b;
+        blk_decode(s, blk, f, k, b);
+        status[f] = -4;
+        dec[blk].mode = kModeZero;
     }
-    for (uint32_t i = lane; i < (uint32_t)kSymStride; i += 32) codes[(size_t)blk * kSymStride + i] = c[i];
 }
 
 // look-up table on the next kLutBits bits (whole CTA): a warp per symbol, lanes over the
@@ -298,6 +274,35 @@ __device__ __forceinline__ void chain_long_codes(const uint32_t* cw_tab, T* lut,
     }
 }
 
+// xor of the bytes of every 128-byte segment of a block this CTA has just written (the lines are still in L2):
+// a segment per thread-pass, read past L1 since other threads wrote them
+constexpr uint32_t kXorSeg = 128;
+__device__ __forceinline__ void block_segment_xor(const uint8_t* out, uint32_t n, uint8_t* seg)
+{
+    const uint32_t nseg = (n + kXorSeg - 1) / kXorSeg;
+    for (uint32_t sg = threadIdx.x; sg < nseg; sg += blockDim.x) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(out + (size_t)sg * kXorSeg);
+        const uint32_t chunks = min(kXorSeg / 16u, (n - sg * kXorSeg + 15u) / 16u);
+        uint32_t x = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < kXorSeg / 16u; ++i)
+            if (i < chunks) {
+                uint4 v = __ldcg(p4 + i);
+                const uint32_t left = n - sg * kXorSeg - 16u * i;   // bytes of the block in this chunk (>= 1)
+                if (left < 16u) {
+                    if (left <= 12u) v.w = 0; else v.w &= (1u << (8u * (left - 12u))) - 1u;
+                    if (left <= 8u) v.z = 0; else if (left < 12u) v.z &= (1u << (8u * (left - 8u))) - 1u;
+                    if (left <= 4u) v.y = 0; else if (left < 8u) v.y &= (1u << (8u * (left - 4u))) - 1u;
+                    if (left < 4u) v.x &= (1u << (8u * left)) - 1u;
+                }
+                x ^= v.x ^ v.y ^ v.z ^ v.w;
+            }
+        x ^= x >> 16;
+        x ^= x >> 8;
+        seg[sg] = (uint8_t)x;
+    }
+}
+
 // One CTA per hzr block.  The payload is staged in shared memory with ONE bulk asynchronous copy (the
 // 16-byte chunks of the stream that hold it, unshifted; the bit reader starts 8 * (address mod 16) bits
 // later) that lands while the tables are built; the code table comes from k_hzr_recover_codes; a 12-bit
@@ -310,7 +315,8 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                                                                    const uint32_t* __restrict__ sidecar,
                                                                    const uint32_t* __restrict__ codes,
                                                                    uint8_t* __restrict__ planes, int32_t* __restrict__ status,
-                                                                   uint32_t pair_max_bits, uint32_t small_class)
+                                                                   uint32_t pair_max_bits, uint32_t small_class,
+                                                                   uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane)
 {
     extern __shared__ __align__(16) uint32_t payw[];  // payload words (+ zero slack)
     // 8 KB of look-up table in one of two shapes, chosen per block:
@@ -338,10 +344,17 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     uint4* out4 = reinterpret_cast<uint4*>(out);
     const uint32_t n = d.out_n, nq = (n + 15u) >> 4;
     const uint8_t* pay = src + d.payload_off;
+    // xor of the bytes of every 128-byte output segment, for the inverse transform's first scan
+    // (k_planes_to_samples_fast: a segment is one of its pieces), so that it need not read the planes for it
+    uint8_t* my_xor = seg_xor ? seg_xor + ((size_t)f * s.nb_alloc + k) * segs_per_plane + (size_t)b * (kBlock / kXorSeg) : nullptr;
+    const uint32_t nseg_all = (n + kXorSeg - 1) / kXorSeg;
 
     if (d.mode == MODE_FILL || d.mode == kModeZero) {
         const uint32_t v = d.mode == MODE_FILL ? pay[0] * 0x01010101u : 0u;  // memset (dec:362-370)
         for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(v, v, v, v);
+        if (my_xor)
+            for (uint32_t i = tid; i < nseg_all; i += blockDim.x)
+                my_xor[i] = (uint8_t)((min((uint32_t)kXorSeg, n - i * kXorSeg) & 1u) ? (v & 0xFFu) : 0u);
         return;
     }
     const uintptr_t pa = (uintptr_t)pay;
@@ -349,6 +362,8 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         if (d.payload_len != n) {  // "Encoded / decoded size mismatch (COPY)" dec:351-355
             if (tid == 0) status[f] = -4;
             for (uint32_t i = tid; i < nq; i += blockDim.x) out4[i] = make_uint4(0, 0, 0, 0);
+            if (my_xor)
+                for (uint32_t i = tid; i < nseg_all; i += blockDim.x) my_xor[i] = 0;
             return;
         }
         const uint32_t* aw = reinterpret_cast<const uint32_t*>(pa & ~(uintptr_t)3);
@@ -358,6 +373,10 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         for (uint32_t i = tid; i < nw; i += blockDim.x) {
             const uint32_t lo = __ldg(aw + i), hi = (i + 1 < naw) ? __ldg(aw + i + 1) : 0u;
             out32[i] = __funnelshift_r(lo, hi, sh);
+        }
+        if (my_xor) {
+            __syncthreads();
+            block_segment_xor(out, n, my_xor);
         }
         return;
     }
@@ -417,14 +436,15 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
     }
     __syncthreads();
 
-    const uint32_t limit = plen * 8u, nint = (limit + kIdxBits - 1u) >> kIdxShift;
+    const IdxGeom ig = idx_geom(plen);
+    const uint32_t limit = plen * 8u, nint = ig.n;
     const uint32_t* my_idx = sidecar + idx_slot_base(d.payload_off - offsets[0], blk);
     uint32_t my_err = 0;
     if (tid < nint) {
         const uint32_t e0 = my_idx[tid];
-        uint32_t bitpos = (tid << kIdxShift) + (e0 & ((1u << kIdxPosShift) - 1u)), pos = e0 >> kIdxPosShift;
+        uint32_t bitpos = tid * ig.bits + (e0 & ((1u << kIdxPosShift) - 1u)), pos = e0 >> kIdxPosShift;
         uint32_t end_bit = limit;
-        if (tid + 1 < nint) end_bit = min(limit, ((tid + 1u) << kIdxShift) + (my_idx[tid + 1] & ((1u << kIdxPosShift) - 1u)));
+        if (tid + 1 < nint) end_bit = min(limit, (tid + 1u) * ig.bits + (my_idx[tid + 1] & ((1u << kIdxPosShift) - 1u)));
         if (bitpos > limit || pos > n) { my_err = 1; bitpos = end_bit; }   // an index that does not belong to this stream
         if (bitpos < end_bit && pos < n) {
             // the thread's bytes are gathered into the open word w (bytes of the word at and beyond pos are
@@ -496,12 +516,16 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
         }
     }
     if (my_err) status[f] = -4;
+    if (my_xor) {
+        __syncthreads();   // the block is complete (this CTA wrote all of it)
+        block_segment_xor(out, n, my_xor);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // Decode index for streams that arrive without one (written by the CPU reference): one CTA per
 // HUFF block.  The token stream has no sync points, but a prefix code re-synchronises by itself
-// after a few tokens, so thread k decodes from a guessed start -- bit k * kIdxBits of the payload
+// after a few tokens, so thread k decodes from a guessed start -- the first bit of index interval k
 // (the first thread that has tokens from the true start behind the tree) -- to the first token
 // boundary inside the next interval, which becomes that neighbour's start.  Threads whose start
 // moved decode again; the starts are exact once nothing moves (each round fixes at least one more
@@ -607,10 +631,11 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
     __syncthreads();
     chain_long_codes(s_cw, s_lut, s_long, s_next, s_meta[2]);
     __syncthreads();
-    const uint32_t limit = plen * 8u, nint = (limit + kIdxBits - 1u) >> kIdxShift;
+    const IdxGeom ig = idx_geom(plen);
+    const uint32_t limit = plen * 8u, nint = ig.n;
     bool bad = t0 > limit;
     // interval k: tokens that START in [lo, hi); the intervals in front of the first token have none
-    const uint32_t lo = max(tid << kIdxShift, t0), hi = min(limit, (tid + 1u) << kIdxShift);
+    const uint32_t lo = max(tid * ig.bits, t0), hi = min(limit, (tid + 1u) * ig.bits);
     const bool live = !bad && tid < nint && lo < hi;
     const TokenDecoder td{s_lut, s_cw, s_long, s_next};
     if (tid <= nint) s_start[tid] = min(lo, limit);
@@ -674,7 +699,7 @@ __global__ void __launch_bounds__(kIndexThreads, 2) k_hzr_build_index(const uint
     }
     if (tid < nint) {
         const uint32_t st = min(max(s_start[tid], lo), limit);
-        my_idx[tid] = (st - (tid << kIdxShift)) | (min(opos, n) << kIdxPosShift);
+        my_idx[tid] = (st - tid * ig.bits) | (min(opos, n) << kIdxPosShift);
     }
 }
 

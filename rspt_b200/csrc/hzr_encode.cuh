@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
         for (uint32_t i = (tw4 >> 2) + tid; i < ((pw + 2u + 3u) >> 2); i += blockDim.x) reinterpret_cast<uint4*>(pay)[i] = make_uint4(0, 0, 0, 0);
         // decode index: where this block's entries go (common.cuh)
         uint32_t* my_idx = sidecar ? sidecar + idx_slot_base(frame_off - offsets[0] + blk_off[blk] + 7u, blk) : nullptr;
-        if (my_idx && tid <= (bi.tree_nbits >> kIdxShift)) my_idx[tid] = bi.tree_nbits - (tid << kIdxShift);  // first token, output byte 0
+        const IdxGeom ig = idx_geom(plen);
+        if (my_idx && tid <= idx_interval_of(ig, bi.tree_nbits)) my_idx[tid] = bi.tree_nbits - tid * ig.bits;  // first token, output byte 0
         if (wid == kEncWarps - 1) {
             // s_after[st] = zeros between the end of step st and the next stop byte (or the block
             // end): suffix chain over the per-step leading-zero counts, 4 steps per lane
@@ -442,10 +443,10 @@ __global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __
             // the zeros running out of the chunk
             if (my_idx) {
                 const uint32_t e = o + lbits;
-                if ((e >> kIdxShift) != (o >> kIdxShift)) {
-                    const uint32_t kk = e >> kIdxShift;
+                const uint32_t kk = idx_interval_of(ig, e);
+                if (kk != idx_interval_of(ig, o)) {
                     const uint32_t P = min(off + 16u + (leaves ? fwd : 0u), n);
-                    my_idx[kk] = (e - (kk << kIdxShift)) | (P << kIdxPosShift);
+                    my_idx[kk] = (e - kk * ig.bits) | (P << kIdxPosShift);
                 }
             }
             // ---- emit

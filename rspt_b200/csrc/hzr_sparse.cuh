@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
     // decode index: where this block's entries go (common.cuh); the first token starts behind the tree bits
     const unsigned long long frame_off = so.offsets[f];
     uint32_t* my_idx = so.sidecar ? so.sidecar + idx_slot_base(frame_off - so.offsets[0] + so.blk_off[blk] + 7u, blk) : nullptr;
-    if (my_idx && tid <= (bi.tree_nbits >> kIdxShift)) my_idx[tid] = bi.tree_nbits - (tid << kIdxShift);
+    const IdxGeom ig = idx_geom(bi.payload_len);
+    if (my_idx && tid <= idx_interval_of(ig, bi.tree_nbits)) my_idx[tid] = bi.tree_nbits - tid * ig.bits;
     // staging: tree words, then zeros (the code words are OR-ed in)
     for (uint32_t i = tid; i < pw + 2u; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -172,10 +173,8 @@ __global__ void __launch_bounds__(kSpThreads, 6) k_hzr_encode_sparse(Shape s, co
         // token behind them (the next entry's run, or nothing after the last one)
         if (my_idx && live) {
             const uint32_t e = o0 + bits;
-            if ((e >> kIdxShift) != (o0 >> kIdxShift)) {
-                const uint32_t kk = e >> kIdxShift;
-                my_idx[kk] = (e - (kk << kIdxShift)) | ((i < m ? cur + 1u : n) << kIdxPosShift);
-            }
+            const uint32_t kk = idx_interval_of(ig, e);
+            if (kk != idx_interval_of(ig, o0)) my_idx[kk] = (e - kk * ig.bits) | ((i < m ? cur + 1u : n) << kIdxPosShift);
         }
     }
     __syncthreads();

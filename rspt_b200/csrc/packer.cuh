@@ -62,6 +62,8 @@ struct rspt_gpu_packer {
     void* d_dec;           // block descriptors
     uint8_t* d_dec_nb;     // per-frame plane count used by the last decompress
     int32_t* d_status_tmp;
+    uint8_t* d_seg_xor;    // per 128-byte segment of every decoded plane: xor of its bytes (k_hzr_decode -> inverse transform)
+    uint32_t segs_per_plane;
     void* d_auto_index;    // decode index built here for streams that came without one
     uint32_t* d_inv_tot;   // one-pass inverse, chained form: per (frame, round, CTA, channel) totals
     uint32_t* d_inv_flag;  // ... and the release flags (epoch of the launch that wrote them)

@@ -374,10 +374,12 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(dalloc(p->d_status_tmp, F));
     A(dalloc(p->d_dec_nb, F));
     A(cudaMalloc(&p->d_dec, nblocks * sizeof(DecBlk) + 64));
+    p->segs_per_plane = s.nblk * (kBlock / kXorSeg);
+    A(dalloc(p->d_seg_xor, F * s.nb_alloc * (size_t)p->segs_per_plane));
     A(dalloc(p->d_inv_tot, F * 2 * 8 * (ch < 32 ? 32 : ch)));
     A(dalloc(p->d_inv_flag, F * 2 * 8));
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_inv_flag, 0, F * 2 * 8 * sizeof(uint32_t), p->stream);
-    A(cudaMalloc(&p->d_auto_index, ((F * (1 + s.hdr_bytes + (size_t)s.nb_alloc * (4 + hzr_max(s.N))) >> 7) + nblocks + 2) * sizeof(uint32_t) + 64));
+    A(cudaMalloc(&p->d_auto_index, ((F * (1 + s.hdr_bytes + (size_t)s.nb_alloc * (4 + hzr_max(s.N))) >> 6) + nblocks + 2) * sizeof(uint32_t) + 64));
     if (kind == RSPT_HADAMARD || kind == RSPT_DCT) {
         A(dalloc(p->d_words, F * (size_t)s.N));
         A(dalloc(p->d_sums, F * (size_t)s.ch));
@@ -433,7 +435,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     void* ptrs[] = {p->d_planes, p->d_hist, p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class, p->d_info, p->d_frame_nb,
                     p->d_need, p->d_nb_state, p->d_sizes, p->d_blk_off, p->d_headers, p->d_words, p->d_sums, p->d_ctr,
                     p->d_dec, p->d_dec_nb, p->d_status_tmp, p->d_twiddle, p->d_post, p->d_cos, p->d_one_src, p->d_one_dst,
-                    p->d_one_off, p->d_redo, p->d_redo2, p->d_sub_n, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2, p->d_inv_tot, p->d_inv_flag, p->d_all_totals};
+                    p->d_one_off, p->d_redo, p->d_redo2, p->d_sub_n, p->d_hb_src, p->d_hb_dst, p->d_hb_off, p->d_auto_index, p->d_fir, p->d_words2, p->d_inv_tot, p->d_inv_flag, p->d_all_totals, p->d_seg_xor};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (p->h_pin) cudaFreeHost(p->h_pin);
@@ -465,18 +467,18 @@ extern "C" size_t rspt_gpu_max_compressed_size(const rspt_gpu_packer* p)
     return 1 + p->s.hdr_bytes + (size_t)p->s.nb_alloc * (4 + hzr_max(p->s.N));
 }
 
-// The decode index has one 32-bit entry per 128 bytes of stream plus one per block (common.cuh); the
-// buffer is sized for the worst-case stream, the entries of a batch occupy a prefix of it.
+// The decode index has one 32-bit slot per 64 bytes of stream plus one per block (common.cuh); the buffer is
+// sized for the worst-case stream, the entries of a batch lie in a prefix of it.
 extern "C" size_t rspt_gpu_sidecar_bytes(const rspt_gpu_packer* p, size_t n_frames)
 {
     if (!p) return 0;
-    return ((n_frames * rspt_gpu_max_compressed_size(p) >> 7) + total_blocks(p, n_frames) + 2) * sizeof(uint32_t);
+    return ((n_frames * rspt_gpu_max_compressed_size(p) >> 6) + total_blocks(p, n_frames) + 2) * sizeof(uint32_t);
 }
 
 extern "C" size_t rspt_gpu_sidecar_used_bytes(const rspt_gpu_packer* p, size_t n_frames, size_t stream_bytes)
 {
     if (!p) return 0;
-    return ((stream_bytes >> 7) + total_blocks(p, n_frames) + 2) * sizeof(uint32_t);
+    return ((stream_bytes >> 6) + total_blocks(p, n_frames) + 2) * sizeof(uint32_t);
 }
 
 extern "C" const char* rspt_gpu_last_error(const rspt_gpu_packer* p) { return p ? p->err : "null handle"; }
@@ -696,8 +698,9 @@ int launch_parse_and_index(rspt_gpu_packer* p, const uint8_t* d_src, const uint6
         StageTimer t(p, RSPT_STAGE_PARSE);
         k_frame_parse<<<(unsigned)((F + 127) / 128), 128, 0, p->stream>>>(d_src, d_offsets, s, d_frame_nb, p->d_nb_state,
                                                                           (uint32_t)F, dec, p->d_headers, p->d_dec_nb, status, p->d_ctr);
-        // code tables of the HUFF blocks from their in-stream trees
-        k_hzr_recover_codes<<<(nblocks + kRecoverWarps - 1) / kRecoverWarps, 32 * kRecoverWarps, 0, p->stream>>>(d_src, nblocks, dec, p->d_codes, s, status);
+        // code tables of the HUFF blocks from their in-stream trees (unused symbols stay 0)
+        RSPT_CUDA_CHECK(cudaMemsetAsync(p->d_codes, 0, (size_t)nblocks * kSymStride * sizeof(uint32_t), p->stream));
+        k_hzr_recover_codes<<<(nblocks + kRecoverThreads - 1) / kRecoverThreads, kRecoverThreads, 0, p->stream>>>(d_src, nblocks, dec, p->d_codes, s, status);
         p->launches += 2;
         if (d_sidecar_out) {
             k_hzr_build_index<<<nblocks, kIndexThreads, p->dec_smem, p->stream>>>(d_src, s, dec, d_offsets, p->d_codes,
@@ -759,15 +762,19 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
         StageTimer t(p, RSPT_STAGE_DECODE);
         const uint32_t* sc = reinterpret_cast<const uint32_t*>(d_sidecar);
         const uint32_t maxn = s.N < kBlock ? s.N : kBlock;
+        // per-segment xor of the decoded planes for the inverse transform's first scan: measured a wash (it
+        // takes 0.25 ms off k_planes_to_samples_fast and puts 0.25 ms onto this kernel), so off unless asked for
+        static const bool want_sxor = getenv("RSPT_DECODE_SEG_XOR") != nullptr;
+        uint8_t* sxor = (want_sxor && (s.kind == RSPT_XDELTA_HZR || s.kind == RSPT_DCT)) ? p->d_seg_xor : nullptr;
         k_hzr_decode<<<nblocks, decode_class_threads(kSmallPayload), decode_class_smem(kSmallPayload), p->stream>>>(
-            d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status, decode_pair_max_bits(), 1u);
+            d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status, decode_pair_max_bits(), 1u, sxor, p->segs_per_plane);
         if (maxn > kSmallPayload) {
             k_hzr_decode<<<nblocks, decode_class_threads(kMediumPayload), decode_class_smem(kMediumPayload), p->stream>>>(
-                d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status, decode_pair_max_bits(), 2u);
+                d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status, decode_pair_max_bits(), 2u, sxor, p->segs_per_plane);
             p->launches += 1;
         }
         k_hzr_decode<<<nblocks, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status,
-                                                                          decode_pair_max_bits(), 0u);
+                                                                          decode_pair_max_bits(), 0u, sxor, p->segs_per_plane);
         p->launches += 1;
     }
     p->launches += 1;

@@ -893,6 +893,7 @@ inline int inverse_mode()
     return v;
 }
 inline bool inverse_cluster_enabled() { return inverse_mode() != 0; }
+inline const uint8_t* inverse_seg_xor(const rspt_gpu_packer* p) { return getenv("RSPT_DECODE_SEG_XOR") ? p->d_seg_xor : nullptr; }
 
 inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F)
 {
@@ -974,7 +975,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
     do {                                                                                                              \
         cudaFuncSetAttribute(k_planes_to_samples_fast<B, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf); \
         k_planes_to_samples_fast<B, SC><<<gf, kInvThreads, smf, p->stream>>>(p->d_planes, s, p->d_dec_nb, tpg, d_dst,    \
-                                                                       nullptr, 0u);                           \
+                                                                       inverse_seg_xor(p), p->segs_per_plane); \
     } while (0)
             const bool sc = s.kind == 0;
             switch (s.bps) {
@@ -1035,7 +1036,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
             if ((s.ns % (int)kInvPiece) == 0 && smw <= 200 * 1024) {
                 cudaFuncSetAttribute(k_planes_to_samples_fast<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);
                 k_planes_to_samples_fast<4, true, true><<<gf, kInvThreads, smw, p->stream>>>(p->d_planes, s, p->d_dec_nb, 1, nullptr,
-                                                                                             nullptr, 0u, p->d_words);
+                                                                                             inverse_seg_xor(p), p->segs_per_plane, p->d_words);
             } else {
                 INV_LAUNCH(4, true, false);
             }
