@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                                                                    const uint32_t* __restrict__ codes,
                                                                    uint8_t* __restrict__ planes, int32_t* __restrict__ status,
                                                                    uint32_t pair_max_bits, uint32_t small_class,
-                                                                   uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane)
+                                                                   uint8_t* __restrict__ seg_xor, uint32_t segs_per_plane, uint32_t blk0)
 {
     extern __shared__ __align__(16) uint32_t payw[];  // payload words (+ zero slack)
     // 8 KB of look-up table in one of two shapes, chosen per block:
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
 
     const IdxGeom ig = idx_geom(plen);
     const uint32_t limit = plen * 8u, nint = ig.n;
-    const uint32_t* my_idx = sidecar + idx_slot_base(d.payload_off - offsets[0], blk);
+    const uint32_t* my_idx = sidecar + idx_slot_base(d.payload_off - offsets[0], blk0 + blk);   // blk0: a launch over part of a batch
     uint32_t my_err = 0;
     if (tid < nint) {
         const uint32_t e0 = my_idx[tid];

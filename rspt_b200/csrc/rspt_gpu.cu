@@ -758,33 +758,62 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
     }
     int rc = launch_parse_and_index(p, d_src, d_offsets, F, d_frame_nb, own_index, status);
     if (rc) return rc;
-    {
-        StageTimer t(p, RSPT_STAGE_DECODE);
-        const uint32_t* sc = reinterpret_cast<const uint32_t*>(d_sidecar);
-        const uint32_t maxn = s.N < kBlock ? s.N : kBlock;
-        // per-segment xor of the decoded planes for the inverse transform's first scan: measured a wash (it
-        // takes 0.25 ms off k_planes_to_samples_fast and puts 0.25 ms onto this kernel), so off unless asked for
-        static const bool want_sxor = getenv("RSPT_DECODE_SEG_XOR") != nullptr;
-        uint8_t* sxor = (want_sxor && (s.kind == RSPT_XDELTA_HZR || s.kind == RSPT_DCT)) ? p->d_seg_xor : nullptr;
-        k_hzr_decode<<<nblocks, decode_class_threads(kSmallPayload), decode_class_smem(kSmallPayload), p->stream>>>(
-            d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status, decode_pair_max_bits(), 1u, sxor, p->segs_per_plane);
-        if (maxn > kSmallPayload) {
-            k_hzr_decode<<<nblocks, decode_class_threads(kMediumPayload), decode_class_smem(kMediumPayload), p->stream>>>(
-                d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status, decode_pair_max_bits(), 2u, sxor, p->segs_per_plane);
-            p->launches += 1;
+    // Decode and inverse transform can run chunk by chunk (RSPT_DECODE_CHUNK_FRAMES), so that the planes a chunk's
+    // decode writes are still in the L2 when its inverse transform reads them.  Measured on B200 (profiles/
+    // r02_decode_chunks.txt): no gain at any chunk size -- the smaller grids' tails cost more than the L2 hits
+    // save -- so the default is the whole batch at once.
+    static const size_t chunk_env = [] {
+        const char* e = getenv("RSPT_DECODE_CHUNK_FRAMES");
+        return e ? (size_t)atol(e) : (size_t)0;
+    }();
+    size_t chunk = chunk_env ? chunk_env : F;
+    if (chunk > F) chunk = F;
+    const uint32_t* sc = reinterpret_cast<const uint32_t*>(d_sidecar);
+    const uint32_t maxn = s.N < kBlock ? s.N : kBlock;
+    // per-segment xor of the decoded planes for the inverse transform's first scan: measured a wash (it
+    // takes 0.25 ms off k_planes_to_samples_fast and puts 0.25 ms onto this kernel), so off unless asked for
+    static const bool want_sxor = getenv("RSPT_DECODE_SEG_XOR") != nullptr;
+    uint8_t* sxor_all = (want_sxor && (s.kind == RSPT_XDELTA_HZR || s.kind == RSPT_DCT)) ? p->d_seg_xor : nullptr;
+    struct Saved { uint8_t* planes; uint8_t* dec_nb; uint8_t* headers; int32_t* words; uint8_t* seg_xor; long long* sums; } sv =
+        {p->d_planes, p->d_dec_nb, p->d_headers, p->d_words, p->d_seg_xor, p->d_sums};
+    int rc_all = RSPT_OK;
+    for (size_t f0 = 0; f0 < F && rc_all == RSPT_OK; f0 += chunk) {
+        const size_t nf = F - f0 < chunk ? F - f0 : chunk;
+        const uint32_t blk0 = total_blocks(p, f0), nblk_c = total_blocks(p, nf);
+        // the handle's per-frame scratch, shifted to the chunk
+        p->d_planes = sv.planes + f0 * s.nb_alloc * (size_t)s.plane_stride;
+        p->d_dec_nb = sv.dec_nb + f0;
+        p->d_headers = sv.headers + f0 * (s.hdr_bytes ? s.hdr_bytes : 1);
+        if (sv.words) p->d_words = sv.words + f0 * (size_t)s.N;
+        if (sv.sums) p->d_sums = sv.sums + f0 * (size_t)s.ch;
+        p->d_seg_xor = sv.seg_xor + f0 * s.nb_alloc * (size_t)p->segs_per_plane;
+        uint8_t* sxor = sxor_all ? p->d_seg_xor : nullptr;
+        const DecBlk* dec_c = dec + blk0;
+        const uint32_t* codes_c = p->d_codes + (size_t)blk0 * kSymStride;
+        int32_t* status_c = status + f0;
+        {
+            StageTimer t(p, RSPT_STAGE_DECODE);
+            k_hzr_decode<<<nblk_c, decode_class_threads(kSmallPayload), decode_class_smem(kSmallPayload), p->stream>>>(
+                d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c, decode_pair_max_bits(), 1u, sxor, p->segs_per_plane, blk0);
+            if (maxn > kSmallPayload) {
+                k_hzr_decode<<<nblk_c, decode_class_threads(kMediumPayload), decode_class_smem(kMediumPayload), p->stream>>>(
+                    d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c, decode_pair_max_bits(), 2u, sxor, p->segs_per_plane, blk0);
+                p->launches += 1;
+            }
+            k_hzr_decode<<<nblk_c, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c,
+                                                                             decode_pair_max_bits(), 0u, sxor, p->segs_per_plane, blk0);
+            p->launches += 2;
         }
-        k_hzr_decode<<<nblocks, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec, d_offsets, sc, p->d_codes, p->d_planes, status,
-                                                                          decode_pair_max_bits(), 0u, sxor, p->segs_per_plane);
-        p->launches += 1;
+        if (cudaGetLastError() != cudaSuccess) rc_all = RSPT_E_CUDA;
+        {
+            StageTimer t(p, RSPT_STAGE_INVERSE);
+            const int rc2 = launch_inverse_transform(p, d_dst + f0 * (size_t)s.frame_bytes, nf);
+            if (rc2) rc_all = rc2;
+        }
     }
-    p->launches += 1;
-    RSPT_CUDA_CHECK(cudaGetLastError());
-    {
-        StageTimer t(p, RSPT_STAGE_INVERSE);
-        int rc2 = launch_inverse_transform(p, d_dst, F);
-        if (rc2) return rc2;
-    }
-    return RSPT_OK;
+    p->d_planes = sv.planes; p->d_dec_nb = sv.dec_nb; p->d_headers = sv.headers; p->d_words = sv.words; p->d_seg_xor = sv.seg_xor; p->d_sums = sv.sums;
+    if (rc_all == RSPT_E_CUDA) return fail_cuda(p, cudaErrorUnknown, "decode launch");
+    return rc_all;
 }
 
 extern "C" int rspt_gpu_verify_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets, size_t n_frames,
