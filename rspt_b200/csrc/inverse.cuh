@@ -72,6 +72,7 @@ __host__ __device__ inline size_t inverse_cluster_smem(int bps, int ch, uint32_t
 
 constexpr uint32_t kInvMaxPieces = 32;   // pieces of 128 samples per channel in one CTA
 constexpr uint32_t kInvMaxCh = 32;
+constexpr uint32_t kInvMaxSeg = 768;     // (channel, CTA) segments of a frame: ch * C
 
 // NBT = planes held (>= the frame's plane count); `scan` = the xdelta chain (0: plain hzr packer, y is the
 // sample).  blockDim = 32 * (ch / 4) * (S / 128); gridDim = frames * cluster size.
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(768, 2) k_inverse_cluster(const uint8_t* __res
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_px[kInvMaxCh][kInvMaxPieces];   // per (channel, piece) of this CTA: xor / sum
-    __shared__ uint32_t s_cx[kInvMaxCh * 8];              // per (channel, CTA) of the frame: totals, written by their owners
-    __shared__ uint32_t s_cs[kInvMaxCh * 8];
+    __shared__ uint32_t s_cx[kInvMaxSeg];                 // per (channel, CTA) of the frame: totals, written by their owners
+    __shared__ uint32_t s_cs[kInvMaxSeg];
 
     const uint32_t C = CHAIN ? chain.C : cluster_nctarank();
     const uint32_t r = CHAIN ? blockIdx.x % C : cluster_ctarank(), f = CHAIN ? blockIdx.x / C : cluster_id_x();

@@ -376,9 +376,9 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     A(cudaMalloc(&p->d_dec, nblocks * sizeof(DecBlk) + 64));
     p->segs_per_plane = s.nblk * (kBlock / kXorSeg);
     A(dalloc(p->d_seg_xor, F * s.nb_alloc * (size_t)p->segs_per_plane));
-    A(dalloc(p->d_inv_tot, F * 2 * 8 * (ch < 32 ? 32 : ch)));
-    A(dalloc(p->d_inv_flag, F * 2 * 8));
-    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_inv_flag, 0, F * 2 * 8 * sizeof(uint32_t), p->stream);
+    A(dalloc(p->d_inv_tot, F * 2 * 32 * (ch < 32 ? 32 : ch)));
+    A(dalloc(p->d_inv_flag, F * 2 * 32));
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_inv_flag, 0, F * 2 * 32 * sizeof(uint32_t), p->stream);
     A(cudaMalloc(&p->d_auto_index, ((F * (1 + s.hdr_bytes + (size_t)s.nb_alloc * (4 + hzr_max(s.N))) >> 6) + nblocks + 2) * sizeof(uint32_t) + 64));
     if (kind == RSPT_HADAMARD || kind == RSPT_DCT) {
         A(dalloc(p->d_words, F * (size_t)s.N));
@@ -792,16 +792,22 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
         const uint32_t* codes_c = p->d_codes + (size_t)blk0 * kSymStride;
         int32_t* status_c = status + f0;
         {
+            // the classes with short payloads (few busy threads per CTA, latency-bound) run on the side stream
+            // beside the full-size blocks
             StageTimer t(p, RSPT_STAGE_DECODE);
-            k_hzr_decode<<<nblk_c, decode_class_threads(kSmallPayload), decode_class_smem(kSmallPayload), p->stream>>>(
+            cudaEventRecord(p->ev_fork, p->stream);
+            cudaStreamWaitEvent(p->side, p->ev_fork, 0);
+            k_hzr_decode<<<nblk_c, decode_class_threads(kSmallPayload), decode_class_smem(kSmallPayload), p->side>>>(
                 d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c, decode_pair_max_bits(), 1u, sxor, p->segs_per_plane, blk0);
             if (maxn > kSmallPayload) {
-                k_hzr_decode<<<nblk_c, decode_class_threads(kMediumPayload), decode_class_smem(kMediumPayload), p->stream>>>(
+                k_hzr_decode<<<nblk_c, decode_class_threads(kMediumPayload), decode_class_smem(kMediumPayload), p->side>>>(
                     d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c, decode_pair_max_bits(), 2u, sxor, p->segs_per_plane, blk0);
                 p->launches += 1;
             }
+            cudaEventRecord(p->ev_join, p->side);
             k_hzr_decode<<<nblk_c, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c,
                                                                              decode_pair_max_bits(), 0u, sxor, p->segs_per_plane, blk0);
+            cudaStreamWaitEvent(p->stream, p->ev_join, 0);
             p->launches += 2;
         }
         if (cudaGetLastError() != cudaSuccess) rc_all = RSPT_E_CUDA;

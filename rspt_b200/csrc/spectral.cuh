@@ -906,15 +906,23 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
     // one pass over the planes: a cluster of CTAs per frame, each with a sample range of every channel (inverse.cuh)
     if ((s.kind == 0 || s.kind == 1) && inverse_cluster_enabled() && s.bps >= 2 && (s.ch & 3) == 0 && s.ch <= (int)kInvMaxCh &&
         (s.ns & 127) == 0 && ((uintptr_t)d_dst & 15) == 0) {
-        // S = ns / C samples per CTA, a multiple of 128; warps = (ch / 4) * (S / 128) <= 24: the largest CTA that fits
+        // S = ns / C samples per CTA, a multiple of 128; warps = (ch / 4) * (S / 128) <= 24.  Cluster form: the
+        // largest CTA that fits (C <= 8 CTAs per cluster).  Chained form: CTAs of about `want` warps (RSPT_INV_CHAIN_WARPS),
+        // up to 32 per frame.
         const uint32_t G = (uint32_t)s.ch >> 2;
+        const bool chained_sel = inverse_mode() == 2;
+        static const uint32_t want = [] {
+            const char* e = getenv("RSPT_INV_CHAIN_WARPS");
+            return e ? (uint32_t)atoi(e) : 12u;
+        }();
         uint32_t C = 0, S = 0;
-        for (uint32_t cc = 1; cc <= 8 && !C; cc <<= 1) {
+        for (uint32_t cc = 1; cc <= (chained_sel ? 32u : 8u); cc <<= 1) {
             if ((uint32_t)s.ns % (cc * 128u)) break;
-            const uint32_t s2 = (uint32_t)s.ns / cc;
-            if (G * (s2 >> 7) <= 24u && inverse_cluster_smem(s.bps, s.ch, s2) <= 100 * 1024) {
+            const uint32_t s2 = (uint32_t)s.ns / cc, w2 = G * (s2 >> 7);
+            if (w2 <= 24u && (uint32_t)s.ch * cc <= kInvMaxSeg && inverse_cluster_smem(s.bps, s.ch, s2) <= 100 * 1024) {
                 C = cc;
                 S = s2;
+                if (!chained_sel || w2 <= want) break;
             }
         }
         if (C) {

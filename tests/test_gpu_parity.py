@@ -703,3 +703,195 @@ def test_host_batch_pipeline_matches_device_batch(R, oracle, chunk, monkeypatch)
     out = np.empty(nfr * bps * ch * ns, np.uint8)
     p.decompress_batch_host(dst.numpy()[: total + 16], hoff, out)
     assert np.array_equal(out, raws.reshape(-1))
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: decode index v2, fused front end, one-pass inverse kernels, C-ABI collective
+# ---------------------------------------------------------------------------------------------
+def test_decode_index_is_small_and_equivalent_to_a_rebuilt_one(R, oracle):
+    """The decode index of a batch: a prefix of the sidecar buffer, about 6 % of the compressed size (one 32-bit
+    slot per 64 stream bytes), well under 6 KB per 12 ch x 3 B x 8192 frame; decoding with it, with one rebuilt
+    on the device, or with none gives the same samples."""
+    bps, ch, ns, n = 3, 12, 8192, 16
+    raws = oracle.synth_ecg(100, n, bps, ch, ns)
+    p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 3, max_batch_frames=n)
+    b = p.compress_batch(to_dev(raws))
+    torch.cuda.synchronize()
+    total = int(b.offsets[n].item())
+    used = p.sidecar_used_bytes(n, total)
+    assert used / n < 6 * 1024, used / n
+    assert used <= b.sidecar.numel()
+    d1 = p.decompress_batch(b).cpu().numpy()
+    b2 = p.build_index(R.CompressedBatch(b.stream, b.offsets, b.frame_nb, None, n))
+    d2 = p.decompress_batch(b2).cpu().numpy()
+    d3 = p.decompress_batch(b, use_sidecar=False).cpu().numpy()
+    assert np.array_equal(d1, raws.reshape(-1)) and np.array_equal(d2, d1) and np.array_equal(d3, d1)
+    # only the used prefix matters: garbage behind it changes nothing
+    b.sidecar[used:] = 0xA5
+    assert np.array_equal(p.decompress_batch(b).cpu().numpy(), d1)
+
+
+def test_wrong_decode_index_cannot_leave_its_frame(R, oracle):
+    """Entries are range-checked on use: an index that does not belong to the stream (all ones, zeros, noise)
+    gives RSPT_E_STREAM or wrong bytes in the frames it covers -- never a fault, never a write outside them.
+    The frames behind an intact part of the index stay correct."""
+    bps, ch, ns, n = 3, 12, 8192, 6
+    raws = oracle.synth_ecg(7, n, bps, ch, ns)
+    p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 3, max_batch_frames=n)
+    b = p.compress_batch(to_dev(raws))
+    torch.cuda.synchronize()
+    good = b.sidecar.clone()
+    offs = b.offsets.cpu().numpy()
+    cut = (int(offs[3]) >> 6) * 4 + 3 * 6 * 4          # slots of the frames 0..2 (4 bytes per 64 stream bytes + 1 per block)
+    rng = np.random.default_rng(1)
+    for fill in ("ones", "zeros", "noise"):
+        sc = good.clone()
+        if fill == "ones":
+            sc[:cut] = 0xFF
+        elif fill == "zeros":
+            sc[:cut] = 0
+        else:
+            sc[:cut] = torch.from_numpy(rng.integers(0, 256, cut, dtype=np.uint8)).cuda()
+        bb = R.CompressedBatch(b.stream, b.offsets, b.frame_nb, sc, n)
+        st = torch.zeros(n, dtype=torch.int32, device="cuda")
+        guard = torch.full((n * bps * ch * ns + 4096,), 0x5A, dtype=torch.uint8, device="cuda")
+        out = guard[: n * bps * ch * ns]
+        p.decompress_batch(bb, out=out, status=st)
+        torch.cuda.synchronize()
+        assert bool((guard[n * bps * ch * ns:] == 0x5A).all())
+        dec = out.cpu().numpy().reshape(n, -1)
+        assert np.array_equal(dec[4:], raws[4:].reshape(2, -1)), fill      # frames well behind the damage
+    assert np.array_equal(p.decompress_batch(R.CompressedBatch(b.stream, b.offsets, b.frame_nb, good, n)).cpu().numpy(), raws.reshape(-1))
+
+
+FRONT_CASES = [("xdelta_hzr", 3, 12, 8192, 3), ("xdelta_hzr", 4, 12, 4096, 4), ("hzr", 3, 12, 8192, 0), ("xdelta_hzr", 2, 8, 1024, 2),
+               ("xdelta_hzr", 3, 4, 512, 3), ("hzr", 4, 8, 2048, 0), ("xdelta_hzr", 4, 4, 16384, 4)]
+
+
+@pytest.mark.parametrize("kind,bps,ch,ns,nb", FRONT_CASES)
+def test_fused_front_end_streams_are_bit_exact(R, oracle, kind, bps, ch, ns, nb, monkeypatch):
+    """RSPT_FRONT=1: k_front (transform + token histograms + sparse sub-lists in one pass over the raw frames)
+    in front of the same tree builder and encoders: byte-identical streams, including frames that change
+    character half-way (a quiet first tile, then dense upper planes: the sub-lists overflow and the frame runs
+    again forced dense), all-zero frames and noise."""
+    monkeypatch.setenv("RSPT_FRONT", "1")
+    nfr = 6
+    rng = np.random.default_rng(ns + ch)
+    raws = oracle.synth_ecg(31, nfr, bps, ch, ns, amplitude=20000 if bps >= 3 else 3000)
+    fb = bps * ch * ns
+    raws[2] = 0
+    raws[3] = make_raw(rng, bps, ch, ns, kind="noise")
+    quiet_then_wild = raws[4].copy().reshape(ns, ch * bps)
+    quiet_then_wild[:600] = 0
+    quiet_then_wild[600:] = make_raw(rng, bps, ch, ns, kind="noise").reshape(ns, ch * bps)[600:]
+    raws[4] = quiet_then_wild.reshape(-1)
+    p = R.SignalPacker(kind, bps, ch, ns, nb or 3, max_batch_frames=nfr)
+    batch = p.compress_batch(to_dev(raws))
+    torch.cuda.synchronize()
+    offs = batch.offsets.cpu().numpy()
+    stream = batch.stream.cpu().numpy()
+    o = oracle.OraclePacker(kind, bps, ch, ns, nb or 3)
+    for i in range(nfr):
+        assert stream[offs[i]:offs[i + 1]].tobytes() == o.compress(raws[i]), (kind, i)
+    assert np.array_equal(p.decompress_batch(batch).cpu().numpy().reshape(nfr, fb), raws.reshape(nfr, fb))
+
+
+def test_fused_front_end_hands_oversized_lists_back(R, oracle, monkeypatch):
+    """RSPT_FRONT=1 with the list encoder's staging limit lowered: the tree kernel flags the frames whose listed
+    blocks the list encoder cannot take, and they run through k_front again with every plane dense."""
+    monkeypatch.setenv("RSPT_FRONT", "1")
+    monkeypatch.setenv("RSPT_SPARSE_STAGE_BYTES", "300")
+    bps, ch, ns, n = 3, 12, 8192, 5
+    raws = oracle.synth_ecg(40, n, bps, ch, ns)
+    p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 3, max_batch_frames=n)
+    batch = p.compress_batch(to_dev(raws))
+    torch.cuda.synchronize()
+    offs = batch.offsets.cpu().numpy()
+    stream = batch.stream.cpu().numpy()
+    o = oracle.OraclePacker("xdelta_hzr", bps, ch, ns, 3)
+    for i in range(n):
+        assert stream[offs[i]:offs[i + 1]].tobytes() == o.compress(raws[i]), i
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_one_pass_inverse_kernels(mode):
+    """RSPT_INV_MODE=1 (a cluster per frame, totals through distributed shared memory) and =2 (chained CTAs):
+    the same samples as the default three-pass kernel.  The switch is read once per process, hence a child."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from rspt_b200 import packer as R\n"
+        "for kind, bps, ch, ns in (('xdelta_hzr', 3, 12, 8192), ('hzr', 3, 12, 8192), ('xdelta_hzr', 4, 12, 4096), ('xdelta_hzr', 2, 8, 1024), ('xdelta_hzr', 4, 4, 256)):\n"
+        "    n = 7\n"
+        "    p = R.SignalPacker(kind, bps, ch, ns, 3 if bps < 4 else 4, max_batch_frames=n)\n"
+        "    x = R.synth_ecg(5, n, bps, ch, ns)\n"
+        "    assert torch.equal(p.decompress_batch(p.compress_batch(x)), x), (kind, bps, ch, ns)\n"
+        "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RSPT_INV_MODE=mode)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_host_decompress_pipeline_small_chunks(R, oracle, monkeypatch):
+    """rspt_gpu_decompress_batch_host: chunked H2D / kernels / D2H pipeline over ragged chunk counts."""
+    monkeypatch.setenv("RSPT_HOST_CHUNK_FRAMES", "3")
+    bps, ch, ns, nfr = 3, 4, 2048, 11
+    raws = oracle.synth_ecg(9, nfr, bps, ch, ns)
+    cpu = oracle.OraclePacker("xdelta_hzr", bps, ch, ns, 3)
+    frames = [cpu.compress(r) for r in raws]
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(np.uint64)
+    blob = np.frombuffer(b"".join(frames) + bytes(64), np.uint8).copy()
+    p = R.SignalPacker.new_xdelta_hzr(bps, ch, ns, 3, max_batch_frames=nfr)
+    out = np.empty(nfr * bps * ch * ns, np.uint8)
+    p.decompress_batch_host(blob, offs, out)
+    assert np.array_equal(out, raws.reshape(-1))
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_c_abi_allgather_places_two_shards():
+    """rspt_gpu_comm_* + rspt_gpu_place_offsets_async: two processes, one GPU each, no torch.distributed -- the
+    NCCL unique id travels through a file.  Every rank's offsets end up rebased by the totals of the ranks before it."""
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import ctypes as C, os, sys, time, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from rspt_b200 import packer as R, _lib\n"
+        "rank, path = int(sys.argv[1]), sys.argv[2]\n"
+        "torch.cuda.set_device(rank)\n"
+        "L = _lib.lib()\n"
+        "buf = (C.c_uint8 * 128)()\n"
+        "if rank == 0:\n"
+        "    _lib.check(L.rspt_gpu_comm_unique_id(buf), None, 'uid')\n"
+        "    open(path + '.tmp', 'wb').write(bytes(buf)); os.rename(path + '.tmp', path)\n"
+        "else:\n"
+        "    while not os.path.exists(path): time.sleep(0.05)\n"
+        "    buf = (C.c_uint8 * 128)(*open(path, 'rb').read())\n"
+        "comm = C.c_void_p()\n"
+        "_lib.check(L.rspt_gpu_comm_init(2, buf, rank, rank, C.byref(comm)), None, 'init')\n"
+        "n = 4 + rank\n"
+        "p = R.SignalPacker.new_xdelta_hzr(3, 4, 2048, 3, max_batch_frames=n)\n"
+        "x = R.synth_ecg(100 * rank, n, 3, 4, 2048)\n"
+        "b = p.compress_batch(x)\n"
+        "local = b.offsets.clone()\n"
+        "p.place_offsets_async(comm, b, rank, 2); p.place_join(); torch.cuda.synchronize()\n"
+        "print('RESULT', rank, int(local[n].item()), int(b.offsets[0].item()), int(b.offsets[n].item()))\n"
+        "L.rspt_gpu_comm_destroy(comm)\n") % root
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "uid")
+        procs = [subprocess.Popen([sys.executable, "-c", code, str(r), path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                 for r in range(2)]
+        outs = [pr.communicate(timeout=300) for pr in procs]
+    res = {}
+    for (so, se), pr in zip(outs, procs):
+        assert pr.returncode == 0, se[-2000:]
+        for ln in so.splitlines():
+            if ln.startswith("RESULT"):
+                _, r, tot, first, last = ln.split()
+                res[int(r)] = (int(tot), int(first), int(last))
+    assert res[0][1] == 0 and res[0][2] == res[0][0]
+    assert res[1][1] == res[0][0] and res[1][2] == res[0][0] + res[1][0]
