@@ -445,10 +445,12 @@ def run_ours(args):
     inputs = [R.synth_ecg(first + i * F, F, **sh) for i in range(NB)]
     outs = [p.alloc_output(F, sidecar=True) for _ in range(2)]
 
+    no_place = os.environ.get("BENCH_NO_PLACE") == "1"   # diagnosis only: leaves the collective out
+
     def step(_):
         for i in range(NB):
             b = p.compress_batch(inputs[i], out=outs[i & 1])
-            if world > 1:
+            if world > 1 and not no_place:
                 # the path's only collective: 8 bytes per rank, places this shard in the global stream;
                 # issued on the handle's side stream so that the next batch's kernels start at once
                 p.place_offsets_async(D.comm, b, rank, world)
@@ -462,6 +464,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    D.barrier()   # the sampler start takes 0.2 s on rank 0: without this the other ranks' timed region would hold that wait
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):

@@ -45,6 +45,12 @@ struct rspt_gpu_packer {
     cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2;
     cudaStream_t place;    // multi-GPU placement (all-gather of totals + offset rebase) runs here, off the compute stream
     cudaEvent_t ev_place;
+    // placements possibly still in flight, by the offsets array they rewrite: a later compress into the same
+    // array waits for its own entry only (rspt_gpu_place_offsets_async)
+    static constexpr int kPlaceRing = 4;
+    cudaEvent_t ev_placed[kPlaceRing];
+    const void* placed_ptr[kPlaceRing];
+    unsigned place_seq;
     uint64_t* d_all_totals;
     uint16_t* d_step_lz;   // per 512-byte step of every block: leading zero count (512 = all zero)
     rspt::BlkInfo* d_info;

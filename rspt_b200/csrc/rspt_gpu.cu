@@ -401,6 +401,8 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->place, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_place, cudaEventDisableTiming);
+    for (int k = 0; k < rspt_gpu_packer::kPlaceRing && e == cudaSuccess; ++k)
+        e = cudaEventCreateWithFlags(&p->ev_placed[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork2, cudaEventDisableTiming);
@@ -449,6 +451,7 @@ extern "C" int rspt_gpu_destroy(rspt_gpu_packer* p)
     if (p->side) cudaStreamDestroy(p->side);
     if (p->place) cudaStreamDestroy(p->place);
     if (p->ev_place) cudaEventDestroy(p->ev_place);
+    for (cudaEvent_t ev : p->ev_placed) if (ev) cudaEventDestroy(ev);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->ev_fork2) cudaEventDestroy(p->ev_fork2);
@@ -592,6 +595,17 @@ int launch_frame_nb(rspt_gpu_packer* p, size_t F)
 
 }  // namespace
 
+// A compress that rewrites an offsets array must not overtake a placement still rebasing it.
+static int wait_for_placement_of(rspt_gpu_packer* p, const void* d_offsets)
+{
+    for (int k = 0; k < rspt_gpu_packer::kPlaceRing; ++k)
+        if (p->placed_ptr[k] == d_offsets) {
+            RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_placed[k], 0));
+            p->placed_ptr[k] = nullptr;
+        }
+    return RSPT_OK;
+}
+
 extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src, size_t n_frames, uint8_t* d_dst,
                                        size_t dst_capacity, uint64_t* d_offsets, uint8_t* d_frame_nb, void* d_sidecar)
 {
@@ -604,7 +618,8 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
     const Shape& s = p->s;
     const size_t F = n_frames;
     const uint32_t nblocks = total_blocks(p, F);
-    int rc = 0;
+    int rc = wait_for_placement_of(p, d_offsets);
+    if (rc) return rc;
     uint32_t* sidecar = reinterpret_cast<uint32_t*>(d_sidecar);
     const unsigned tgrid = (nblocks + kTreeWarps - 1) / kTreeWarps;
     if (p->front_ok && !((uintptr_t)d_src & 15)) {
@@ -914,11 +929,19 @@ extern "C" int rspt_gpu_place_offsets_async(rspt_gpu_packer* p, void* comm, uint
     if (!p || !d_offsets || rank < 0 || world < 1 || rank >= world || world > 64) return RSPT_E_ARG;
     if (world == 1) return RSPT_OK;
     DeviceGuard dg(p->device);
+    cudaStream_t st = p->place;
     RSPT_CUDA_CHECK(cudaEventRecord(p->ev_place, p->stream));
     RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->place, p->ev_place, 0));
-    const int rc = rspt_gpu_allgather_totals(comm, d_offsets + n_frames, p->d_all_totals, p->place);
+    int rc = rspt_gpu_allgather_totals(comm, d_offsets + n_frames, p->d_all_totals, st);
     if (rc) return rc;
-    return rspt_gpu_rebase_offsets(d_offsets, n_frames + 1, p->d_all_totals, rank, p->place);
+    rc = rspt_gpu_rebase_offsets(d_offsets, n_frames + 1, p->d_all_totals, rank, st);
+    if (rc) return rc;
+    const unsigned slot = p->place_seq++ % rspt_gpu_packer::kPlaceRing;
+    if (p->placed_ptr[slot])   // the ring is full: the compute stream takes the oldest placement's completion now
+        RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_placed[slot], 0));
+    RSPT_CUDA_CHECK(cudaEventRecord(p->ev_placed[slot], st));
+    p->placed_ptr[slot] = d_offsets;
+    return RSPT_OK;
 }
 
 extern "C" int rspt_gpu_place_join(rspt_gpu_packer* p)
@@ -927,6 +950,7 @@ extern "C" int rspt_gpu_place_join(rspt_gpu_packer* p)
     DeviceGuard dg(p->device);
     RSPT_CUDA_CHECK(cudaEventRecord(p->ev_place, p->place));
     RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_place, 0));
+    for (const void*& q : p->placed_ptr) q = nullptr;
     return RSPT_OK;
 }
 
