@@ -452,65 +452,87 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
             // shared with the thread before (it is OR-ed in), and so may the last one.
             const uint32_t first_w = (pos & 3u) ? pos >> 2 : 0xFFFFFFFFu;
             uint32_t w = 0;
-            BitReader r;
-            r.init(payw, bitpos + 8u * lead16);
-            const uint32_t lut_s = smem_addr(s_lut);
+            // The reader keeps no window between tokens: the 32 bits at the bit position are fetched anew for
+            // every token (two LDS and one funnel shift, no refill branch, no 64-bit state).  bp counts from
+            // the start of the staging (payload bit 0 is bit 8 * lead16).
+            const uint32_t lut_s = smem_addr(s_lut), pay_s = smem_addr(payw), cw_s = smem_addr(s_cw);
+            const uint32_t base_bits = 8u * lead16;
+            uint32_t bp = bitpos + base_bits;
+            const uint32_t end_bp = end_bit + base_bits;
+            auto window = [&](uint32_t at) {
+                const uint32_t a = pay_s + ((at >> 3) & ~3u);
+                return __funnelshift_r(lds_u32(a), lds_u32(a + 4u), at);   // the shift uses the low 5 bits of `at`
+            };
             auto token_loop = [&](auto pairs_t) {
             constexpr bool PAIRS = decltype(pairs_t)::value;
-            while (!my_err && bitpos < end_bit && pos < n) {
-                r.refill();
-                uint32_t e = PAIRS ? lds_u32(lut_s + 4u * r.peek(kPairBits)) : lds_u16(lut_s + 2u * r.peek(kLutBits));
+            while (bp < end_bp && pos < n) {
+                uint32_t win = window(bp);
+                uint32_t e = PAIRS ? lds_u32(lut_s + 4u * (win & ((1u << kPairBits) - 1u))) : lds_u16(lut_s + 2u * (win & ((1u << kLutBits) - 1u)));
                 if (e & kLongFlag) {
                     // code longer than the table: match the few long code words (dec:418-431 walks the tree)
                     uint32_t j = e & kLongEnd;
                     e = 0;
                     while (j != kLongEnd) {
-                        const uint32_t sym = s_long[j], cw = s_cw[sym], len = cw >> 27;
-                        if (((uint32_t)r.buf & ((1u << len) - 1u)) == (cw & 0x07FFFFFFu)) {
-                            e = sym | (len << 9);
+                        const uint32_t sym = s_long[j], cw = lds_u32(cw_s + 4u * sym), len = cw >> 27;
+                        if ((win & ((1u << len) - 1u)) == (cw & 0x07FFFFFFu)) {
+                            e = sym | 0x10000u;
+                            bp += len;
                             break;
                         }
                         j = s_next[j];
                     }
                     if (e == 0u) { my_err = 1; break; }
-                    // consume it here and top the window up, so that the extra bits of a run are there
-                    r.skip(e >> 9);
-                    bitpos += e >> 9;
-                    r.refill();
+                    // consumed here (length field 0 below); the window is taken again so that the extra bits of a run are in it
                     e &= 511u;
+                    win = window(bp);
                 }
-                // two literals at once when the entry has them and both belong to this thread
-                const bool two = PAIRS && (e >> 31) != 0u && pos + 2u <= n && bitpos + ((e >> 24) & 15u) <= end_bit;
-                const uint32_t len = (two ? e >> 24 : e >> 9) & 15u, sym = e & 511u;
-                r.skip(len);  // <= kLutBits bits: at least 21 are left in the window
-                bitpos += len;
+                // two literals at once when both belong to this thread: with the pair table the entry has them;
+                // with the single-symbol table the second one comes from a second look-up into the same
+                // window (<= kLutBits bits are gone, >= 20 are left)
+                bool two = PAIRS && (e >> 31) != 0u && pos + 2u <= n && bp + ((e >> 24) & 15u) <= end_bp;
+                uint32_t len = (two ? e >> 24 : e >> 9) & 15u;
+                const uint32_t sym = e & 511u;
+                uint32_t val = two ? sym | ((e >> 8) & 0xFF00u) : sym;  // the literal byte(s)
                 const bool run = sym >= 256u;  // symbol 0 (a zero run of one) is handled as a literal
+                if (!PAIRS && !run) {
+                    const uint32_t e2 = lds_u16(lut_s + 2u * ((win >> len) & ((1u << kLutBits) - 1u)));
+                    const uint32_t len2 = len + (e2 >> 9);
+                    if (!(e2 & (kLongFlag | 0x100u)) && pos + 2u <= n && bp + len2 <= end_bp) {
+                        two = true;
+                        len = len2;
+                        val |= (e2 & 255u) << 8;
+                    }
+                }
+                bp += len;   // a run's code is <= kLutBits bits: at least 20 of the window are left for its extra bits
                 uint32_t adv = two ? 2u : 1u;
                 if (run) {
                     const uint32_t kk = sym - 256u;                              // run class 0..4 (hzr_internal.h:117-121)
                     const uint32_t eb = (0xE8420u >> (4u * kk)) & 15u;             // 0, 2, 4, 8, 14 extra bits
-                    const uint32_t ev = (uint32_t)r.buf & ((1u << eb) - 1u);
-                    r.skip(eb);
-                    bitpos += eb;
+                    const uint32_t ev = (win >> len) & ((1u << eb) - 1u);
+                    bp += eb;
                     adv = ev + (kk == 4u ? 279u : (0x17070302u >> (8u * kk)) & 255u);
                     if (pos + adv > n) { my_err = 1; break; }  // "Output buffer full" dec:473-476
+                    val = 0u;
                 }
                 const uint32_t np = pos + adv, sh = (pos & 3u) * 8u;
-                const uint32_t val = two ? sym | ((e >> 8) & 0xFF00u) : sym;  // the literal byte(s)
-                const uint32_t wv = run ? w : w | (val << sh);
-                const bool cross = (np >> 2) != (pos >> 2);
-                if (cross && wv) {
-                    uint32_t* q = reinterpret_cast<uint32_t*>(out + (pos & ~3u));
-                    if ((pos >> 2) == first_w) atomicOr(q, wv);
-                    else *q = wv;
+                const uint32_t wv = w | (val << sh);
+                const bool cross = (np ^ pos) > 3u;
+                w = wv;
+                if (cross) {
+                    if (wv) {
+                        uint32_t* q = reinterpret_cast<uint32_t*>(out + (pos & ~3u));
+                        if ((pos >> 2) == first_w) atomicOr(q, wv);
+                        else *q = wv;
+                    }
+                    // a pair that starts in a word's last byte leaves its second byte in the next word
+                    w = __funnelshift_l(val, 0u, sh);   // 0 unless the token is a pair
                 }
-                // a pair that starts in a word's last byte leaves its second byte in the next word
-                w = cross ? ((!PAIRS || run) ? 0u : __funnelshift_l(val, 0u, sh)) : wv;
                 pos = np;
             }
             };
             if (use_pairs) token_loop(std::true_type{});
             else token_loop(std::false_type{});
+            bitpos = bp - base_bits;
             if (bitpos > limit) my_err = 1;
             if (w) atomicOr(reinterpret_cast<uint32_t*>(out + (pos & ~3u)), w);
         }
