@@ -490,21 +490,40 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                 // with the single-symbol table the second one comes from a second look-up into the same
                 // window (<= kLutBits bits are gone, >= 20 are left)
                 bool two = PAIRS && (e >> 31) != 0u && pos + 2u <= n && bp + ((e >> 24) & 15u) <= end_bp;
-                uint32_t len = (two ? e >> 24 : e >> 9) & 15u;
+                uint32_t len = (two ? e >> 24 : e >> 9) & 15u, more = 0u;
                 const uint32_t sym = e & 511u;
                 uint32_t val = two ? sym | ((e >> 8) & 0xFF00u) : sym;  // the literal byte(s)
                 const bool run = sym >= 256u;  // symbol 0 (a zero run of one) is handled as a literal
                 if (!PAIRS && !run) {
+                    // up to three more literals from the same window, as long as kLutBits unread bits are left in it
                     const uint32_t e2 = lds_u16(lut_s + 2u * ((win >> len) & ((1u << kLutBits) - 1u)));
                     const uint32_t len2 = len + (e2 >> 9);
                     if (!(e2 & (kLongFlag | 0x100u)) && pos + 2u <= n && bp + len2 <= end_bp) {
                         two = true;
                         len = len2;
                         val |= (e2 & 255u) << 8;
+                        if (len <= 32u - kLutBits) {
+                            const uint32_t e3 = lds_u16(lut_s + 2u * ((win >> len) & ((1u << kLutBits) - 1u)));
+                            const uint32_t len3 = len + (e3 >> 9);
+                            if (!(e3 & (kLongFlag | 0x100u)) && pos + 3u <= n && bp + len3 <= end_bp) {
+                                more = 1u;
+                                len = len3;
+                                val |= (e3 & 255u) << 16;
+                                if (len <= 32u - kLutBits) {
+                                    const uint32_t e4 = lds_u16(lut_s + 2u * ((win >> len) & ((1u << kLutBits) - 1u)));
+                                    const uint32_t len4 = len + (e4 >> 9);
+                                    if (!(e4 & (kLongFlag | 0x100u)) && pos + 4u <= n && bp + len4 <= end_bp) {
+                                        more = 2u;
+                                        len = len4;
+                                        val |= e4 << 24;
+                                    }
+                                }
+                            }
+                        }
                     }
                 }
                 bp += len;   // a run's code is <= kLutBits bits: at least 20 of the window are left for its extra bits
-                uint32_t adv = two ? 2u : 1u;
+                uint32_t adv = (two ? 2u : 1u) + more;
                 if (run) {
                     const uint32_t kk = sym - 256u;                              // run class 0..4 (hzr_internal.h:117-121)
                     const uint32_t eb = (0xE8420u >> (4u * kk)) & 15u;             // 0, 2, 4, 8, 14 extra bits
