@@ -529,6 +529,17 @@ __global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const
         q[3] = nba > 3 ? __ldg(a + 3 * pstride) : 0u;
     };
     constexpr int U = 4;  // pieces in flight per warp
+    // four pieces at a time (np is a multiple of 4 because ch is): 16 consecutive elements per lane
+    const uint4* fpl4 = reinterpret_cast<const uint4*>(fpl);
+    const uint32_t pstride4 = s.plane_stride >> 4, nbig = np >> 2;
+    constexpr int UB = 2;
+    auto load_big = [&](uint32_t P, uint4 (&q)[4]) {
+        const uint4* a = fpl4 + P * 32u + lane;
+        q[0] = __ldg(a);
+        q[1] = nba > 1 ? __ldg(a + pstride4) : make_uint4(0, 0, 0, 0);
+        q[2] = nba > 2 ? __ldg(a + 2 * pstride4) : make_uint4(0, 0, 0, 0);
+        q[3] = nba > 3 ? __ldg(a + 3 * pstride4) : make_uint4(0, 0, 0, 0);
+    };
     if (SCAN) {
         // pass 1: xor of all words of a piece = byte-wise fold of the plane words.  k_hzr_decode leaves
         // exactly that per 128-byte segment (= piece) of every plane, so the planes are not read here.
@@ -540,48 +551,69 @@ __global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const
                 pxor[p] = (uint32_t)((int32_t)(x << sext) >> sext);
             }
         } else
-        for (uint32_t p0 = wid * U; p0 < np; p0 += nwarps * U) {
-            uint32_t q[U][4];
+        // (passes 1 and 2 walk the planes in runs of four pieces: a lane takes 16 consecutive elements with one
+        // 128-bit load per plane, eight lanes make a piece, and the warp-level steps are shared by four pieces)
+        for (uint32_t P0 = wid * UB; P0 < nbig; P0 += nwarps * UB) {
+            uint4 q[UB][4];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (p0 + u < np) load_piece(p0 + u, q[u]);
+            for (int u = 0; u < UB; ++u)
+                if (P0 + u < nbig) load_big(P0 + u, q[u]);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (p0 + u >= np) break;
+            for (int u = 0; u < UB; ++u) {
+                if (P0 + u >= nbig) break;
                 uint32_t x = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    uint32_t w = (uint32_t)k < nb ? q[u][k] : 0u;
+                    uint32_t w = (uint32_t)k < nb ? q[u][k].x ^ q[u][k].y ^ q[u][k].z ^ q[u][k].w : 0u;
                     w ^= w >> 16;
                     w ^= w >> 8;
                     x |= (w & 0xFFu) << (8 * k);
                 }
                 x = (uint32_t)((int32_t)(x << sext) >> sext);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
-                if (lane == 0) pxor[p0 + u] = x;
+                for (int o = 4; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+                if ((lane & 7u) == 0u) pxor[4u * (P0 + u) + (lane >> 3)] = x;
             }
         }
         __syncthreads();
         smem_exclusive_scan<true>(pxor, np);
         __syncthreads();
         // pass 2: sum of (prefix-xor + 128) over every piece
-        for (uint32_t p0 = wid * U; p0 < np; p0 += nwarps * U) {
-            uint32_t q[U][4];
+        for (uint32_t P0 = wid * UB; P0 < nbig; P0 += nwarps * UB) {
+            uint4 q[UB][4];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (p0 + u < np) load_piece(p0 + u, q[u]);
+            for (int u = 0; u < UB; ++u)
+                if (P0 + u < nbig) load_big(P0 + u, q[u]);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (p0 + u >= np) break;
-                uint32_t y[4];
-                planes_to_words(q[u][0], q[u][1], q[u][2], q[u][3], nb, y);
-                y[1] ^= y[0]; y[2] ^= y[1]; y[3] ^= y[2];
-                const uint32_t before = pxor[p0 + u] ^ warp_xor_inclusive(y[3]) ^ y[3];
-                uint32_t sum = (y[0] ^ before) + (y[1] ^ before) + (y[2] ^ before) + (y[3] ^ before) + 512u;
+            for (int u = 0; u < UB; ++u) {
+                if (P0 + u >= nbig) break;
+                uint32_t y[16];
+                {
+                    uint32_t t[4];
+                    planes_to_words(q[u][0].x, q[u][1].x, q[u][2].x, q[u][3].x, nb, t);
+                    y[0] = t[0]; y[1] = t[1]; y[2] = t[2]; y[3] = t[3];
+                    planes_to_words(q[u][0].y, q[u][1].y, q[u][2].y, q[u][3].y, nb, t);
+                    y[4] = t[0]; y[5] = t[1]; y[6] = t[2]; y[7] = t[3];
+                    planes_to_words(q[u][0].z, q[u][1].z, q[u][2].z, q[u][3].z, nb, t);
+                    y[8] = t[0]; y[9] = t[1]; y[10] = t[2]; y[11] = t[3];
+                    planes_to_words(q[u][0].w, q[u][1].w, q[u][2].w, q[u][3].w, nb, t);
+                    y[12] = t[0]; y[13] = t[1]; y[14] = t[2]; y[15] = t[3];
+                }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-                if (lane == 0) psum[p0 + u] = sum;
+                for (int i = 1; i < 16; ++i) y[i] ^= y[i - 1];
+                uint32_t inc = y[15];   // inclusive xor over the lanes of my piece (8 lanes)
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if ((lane & 7u) >= (uint32_t)o) inc ^= t;
+                }
+                const uint32_t before = pxor[4u * (P0 + u) + (lane >> 3)] ^ inc ^ y[15];
+                uint32_t sum = 16u * 128u;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sum += y[i] ^ before;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+                if ((lane & 7u) == 0u) psum[4u * (P0 + u) + (lane >> 3)] = sum;
             }
         }
         __syncthreads();
