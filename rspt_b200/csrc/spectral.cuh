@@ -975,7 +975,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
         uint32_t tpg = 8;  // sample tiles per output group, sized to keep 4 CTAs per SM
         size_t smf = 0;
         for (; tpg >= 1; tpg >>= 1) {
-            smf = 2 * npf * 4 + (size_t)tpg * 32 * (row + 1) * 4;
+            smf = 2 * npf * 4 + (size_t)tpg * 32 * (row + 1) * 4 + (size_t)tpg * 4;   // + one pad word per 32 quads
             if (smf <= 54 * 1024) break;
         }
         if (tpg >= 1) {

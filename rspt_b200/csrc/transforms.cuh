@@ -652,6 +652,100 @@ __global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const
 
     // pass 3: groups of `tiles_per_group` sample tiles (128 samples each); work item = (tile, channel group)
     const uint32_t row = ch * BPS, rw = row >> 2, qstride = row + 1, G = ch >> 2, cpq = row >> 2;
+    if (((ppc | tiles_per_group) & 1u) == 0u) {
+        // Two tiles per item: a lane takes 8 consecutive samples of each of the 4 channels (one 64-bit load per
+        // plane), 16 lanes make a piece, so the warp-level scan steps are shared by two pieces.  The lane's two
+        // quads lie 2 * qstride words apart: with one pad word per 32 quads the 32 lanes hit 32 banks.
+        const uint2* fpl2 = reinterpret_cast<const uint2*>(fpl);
+        const uint32_t pstride2 = s.plane_stride >> 3, half = lane >> 4;
+        for (uint32_t t0 = 0; t0 < ppc; t0 += tiles_per_group) {
+            const uint32_t nt = min(tiles_per_group, ppc - t0);
+            for (uint32_t item = wid; item < (nt >> 1) * G; item += nwarps) {
+                const uint32_t tl2 = item / G, g = item - tl2 * G, t = t0 + 2u * tl2;
+                uint2 q[4][4];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const uint2* a = fpl2 + ((4 * g + cc) * ppc + t) * 16u + lane;
+                    q[cc][0] = __ldg(a);
+                    q[cc][1] = nba > 1 ? __ldg(a + pstride2) : make_uint2(0, 0);
+                    q[cc][2] = nba > 2 ? __ldg(a + 2 * pstride2) : make_uint2(0, 0);
+                    q[cc][3] = nba > 3 ? __ldg(a + 3 * pstride2) : make_uint2(0, 0);
+                }
+                uint32_t x[4][8];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const uint32_t pp = (4 * g + cc) * ppc + t + half;   // my piece
+                    uint32_t* y = x[cc];
+                    {
+                        uint32_t tq[4];
+                        planes_to_words(q[cc][0].x, q[cc][1].x, q[cc][2].x, q[cc][3].x, nb, tq);
+                        y[0] = tq[0]; y[1] = tq[1]; y[2] = tq[2]; y[3] = tq[3];
+                        planes_to_words(q[cc][0].y, q[cc][1].y, q[cc][2].y, q[cc][3].y, nb, tq);
+                        y[4] = tq[0]; y[5] = tq[1]; y[6] = tq[2]; y[7] = tq[3];
+                    }
+                    if (SCAN) {
+#pragma unroll
+                        for (int i = 1; i < 8; ++i) y[i] ^= y[i - 1];
+                        uint32_t inc = y[7];
+#pragma unroll
+                        for (int o = 1; o < 16; o <<= 1) {
+                            const uint32_t tt = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                            if ((lane & 15u) >= (uint32_t)o) inc ^= tt;
+                        }
+                        const uint32_t before = pxor[pp] ^ inc ^ y[7];
+                        y[0] = (y[0] ^ before) + 128u;
+#pragma unroll
+                        for (int i = 1; i < 8; ++i) y[i] = (y[i] ^ before) + 128u + y[i - 1];
+                        uint32_t acc = y[7];
+#pragma unroll
+                        for (int o = 1; o < 16; o <<= 1) {
+                            const uint32_t tt = __shfl_up_sync(0xFFFFFFFFu, acc, o);
+                            if ((lane & 15u) >= (uint32_t)o) acc += tt;
+                        }
+                        const uint32_t base = psum[pp] + acc - y[7];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) y[i] += base;
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t Q = tl2 * 64u + 2u * lane + h;
+                    uint32_t* out = tile + Q * qstride + (Q >> 5) + g * BPS;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t a = x[0][4 * h + i], b = x[1][4 * h + i], c2 = x[2][4 * h + i], d = x[3][4 * h + i];
+                        if (BPS == 4) {
+                            out[i * rw + 0] = a; out[i * rw + 1] = b; out[i * rw + 2] = c2; out[i * rw + 3] = d;
+                        } else if (BPS == 3) {
+                            out[i * rw + 0] = prmt(a, b, 0x4210u);
+                            out[i * rw + 1] = prmt(b, c2, 0x5421u);
+                            out[i * rw + 2] = prmt(c2, d, 0x6542u);
+                        } else if (BPS == 2) {
+                            out[i * rw + 0] = prmt(a, b, 0x5410u);
+                            out[i * rw + 1] = prmt(c2, d, 0x5410u);
+                        } else {
+                            out[i * rw + 0] = prmt(prmt(a, b, 0x0040u), prmt(c2, d, 0x0040u), 0x5410u);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            {
+                uint4* g4 = reinterpret_cast<uint4*>(dst_raw + (size_t)f * s.frame_bytes + (size_t)t0 * kInvPiece * row);
+                const uint32_t nchunks = nt * 32u * cpq;
+                uint32_t q = threadIdx.x / cpq, r = threadIdx.x % cpq;
+                const uint32_t dq = blockDim.x / cpq, dr = blockDim.x % cpq;
+                for (uint32_t c = threadIdx.x; c < nchunks; c += blockDim.x) {
+                    const uint32_t* sp = tile + q * qstride + (q >> 5) + 4u * r;
+                    g4[c] = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                    q += dq; r += dr;
+                    if (r >= cpq) { r -= cpq; ++q; }
+                }
+            }
+            __syncthreads();
+        }
+        return;
+    }
     for (uint32_t t0 = 0; t0 < ppc; t0 += tiles_per_group) {
         const uint32_t nt = min(tiles_per_group, ppc - t0);
         for (uint32_t item = wid; item < nt * G; item += nwarps) {
