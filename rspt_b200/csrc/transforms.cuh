@@ -622,29 +622,60 @@ __global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const
     }
 
     if (WORDS) {
-        // pass 3, word output: piece by piece, 4 consecutive words per lane
+        // pass 3, word output: two pieces at a time, 8 consecutive words per lane (one 64-bit load per plane, 16 lanes
+        // make a piece; np is even because ch is a multiple of 4)
         uint4* wout = reinterpret_cast<uint4*>(dst_words + (size_t)f * s.N);
-        for (uint32_t p0 = wid * U; p0 < np; p0 += nwarps * U) {
-            uint32_t q[U][4];
+        const uint2* fpl2 = reinterpret_cast<const uint2*>(fpl);
+        const uint32_t pstride2 = s.plane_stride >> 3, half = lane >> 4;
+        for (uint32_t P0 = wid * U; P0 < (np >> 1); P0 += nwarps * U) {
+            uint2 q[U][4];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (p0 + u < np) load_piece(p0 + u, q[u]);
+                if (P0 + u < (np >> 1)) {
+                    const uint2* a = fpl2 + (P0 + u) * 32u + lane;
+                    q[u][0] = __ldg(a);
+                    q[u][1] = nba > 1 ? __ldg(a + pstride2) : make_uint2(0, 0);
+                    q[u][2] = nba > 2 ? __ldg(a + 2 * pstride2) : make_uint2(0, 0);
+                    q[u][3] = nba > 3 ? __ldg(a + 3 * pstride2) : make_uint2(0, 0);
+                }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (p0 + u >= np) break;
-                uint32_t y[4];
-                planes_to_words(q[u][0], q[u][1], q[u][2], q[u][3], nb, y);
-                if (SCAN) {
-                    y[1] ^= y[0]; y[2] ^= y[1]; y[3] ^= y[2];
-                    const uint32_t before = pxor[p0 + u] ^ warp_xor_inclusive(y[3]) ^ y[3];
-                    y[0] = (y[0] ^ before) + 128u;
-                    y[1] = (y[1] ^ before) + 128u + y[0];
-                    y[2] = (y[2] ^ before) + 128u + y[1];
-                    y[3] = (y[3] ^ before) + 128u + y[2];
-                    const uint32_t base = psum[p0 + u] + warp_add_inclusive(y[3]) - y[3];
-                    y[0] += base; y[1] += base; y[2] += base; y[3] += base;
+                if (P0 + u >= (np >> 1)) break;
+                const uint32_t pp = 2u * (P0 + u) + half;
+                uint32_t y[8];
+                {
+                    uint32_t tq[4];
+                    planes_to_words(q[u][0].x, q[u][1].x, q[u][2].x, q[u][3].x, nb, tq);
+                    y[0] = tq[0]; y[1] = tq[1]; y[2] = tq[2]; y[3] = tq[3];
+                    planes_to_words(q[u][0].y, q[u][1].y, q[u][2].y, q[u][3].y, nb, tq);
+                    y[4] = tq[0]; y[5] = tq[1]; y[6] = tq[2]; y[7] = tq[3];
                 }
-                wout[(size_t)(p0 + u) * 32u + lane] = make_uint4(y[0], y[1], y[2], y[3]);
+                if (SCAN) {
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) y[i] ^= y[i - 1];
+                    uint32_t inc = y[7];
+#pragma unroll
+                    for (int o = 1; o < 16; o <<= 1) {
+                        const uint32_t tt = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                        if ((lane & 15u) >= (uint32_t)o) inc ^= tt;
+                    }
+                    const uint32_t before = pxor[pp] ^ inc ^ y[7];
+                    y[0] = (y[0] ^ before) + 128u;
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) y[i] = (y[i] ^ before) + 128u + y[i - 1];
+                    uint32_t acc = y[7];
+#pragma unroll
+                    for (int o = 1; o < 16; o <<= 1) {
+                        const uint32_t tt = __shfl_up_sync(0xFFFFFFFFu, acc, o);
+                        if ((lane & 15u) >= (uint32_t)o) acc += tt;
+                    }
+                    const uint32_t base = psum[pp] + acc - y[7];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] += base;
+                }
+                uint4* w2 = wout + (size_t)(P0 + u) * 64u + 2u * lane;
+                w2[0] = make_uint4(y[0], y[1], y[2], y[3]);
+                w2[1] = make_uint4(y[4], y[5], y[6], y[7]);
             }
         }
         return;
