@@ -110,14 +110,17 @@ int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_src, const ui
 int rspt_gpu_verify_batch(rspt_gpu_packer* p, const uint8_t* d_src, const uint64_t* d_offsets,
                           size_t n_frames, const uint8_t* d_frame_nb, int32_t* d_status);
 
-/* Decode index ("sidecar"), out of band: one 32-bit entry per 1024 payload bits of every HUFF block (a token
- * boundary and the output byte it starts at), addressed by the block's position in the batch's stream, so it
- * is valid only together with the d_src / d_offsets layout it was produced for.  rspt_gpu_sidecar_bytes is the
- * buffer size to allocate (worst-case stream); the entries of a batch whose stream has `stream_bytes` bytes fill
- * the first rspt_gpu_sidecar_used_bytes of it (about 3 % of the compressed size) -- that prefix is what has to
- * be stored next to the stream.  Code tables are NOT part of it: the decoder recovers them from the tree bits
- * in the stream (hzr_decode.c:263-333).  Entries are range-checked on use; a wrong index yields RSPT_E_STREAM
- * or wrong bytes in that frame, never an out-of-bounds access. */
+/* Decode index ("sidecar"), out of band.  The payload bits of every HUFF block are cut into at most 512 equal
+ * intervals of at least 512 bits; the index holds one 32-bit entry per interval: where the first token that
+ * ends at or behind the interval's first bit starts (12 bits, relative to the interval) and the output byte it
+ * starts at (20 bits).  A block's entries sit at word (payload offset in the batch's stream >> 6) + block number,
+ * so the index is valid only together with the d_src / d_offsets layout it was produced for.
+ * rspt_gpu_sidecar_bytes is the buffer size to allocate (worst-case stream); the entries of a batch whose
+ * stream has `stream_bytes` bytes lie in the first rspt_gpu_sidecar_used_bytes of it (one word per 64 stream
+ * bytes + one per block: 5.4 KB for a 294 912-byte frame of 12 ch x 3 B x 8192, 6 % of its stream) -- that
+ * prefix is what has to be stored next to the stream.  Code tables are NOT part of it: the decoder recovers
+ * them from the tree bits in the stream (hzr_decode.c:263-333).  Entries are range-checked on use; a wrong
+ * index yields RSPT_E_STREAM or wrong bytes in that frame, never an out-of-bounds access. */
 size_t rspt_gpu_sidecar_bytes(const rspt_gpu_packer* p, size_t n_frames);
 size_t rspt_gpu_sidecar_used_bytes(const rspt_gpu_packer* p, size_t n_frames, size_t stream_bytes);
 
@@ -245,8 +248,9 @@ int rspt_gpu_rebase_offsets(uint64_t* d_offsets, size_t n_frames_plus_1, const u
 
 /* Both steps for the batch rspt_gpu_compress_batch has just produced into d_offsets, OFF the handle's stream:
  * they run on a side stream of the handle ordered behind the compress, so the next batch's kernels start at
- * once (its offsets must go to a different buffer).  rspt_gpu_place_join makes the handle's stream wait for
- * every placement issued so far. */
+ * once.  A later rspt_gpu_compress_batch into the SAME d_offsets array waits for that array's placement first
+ * (the handle remembers the last four placements); anything else that reads the rebased offsets needs
+ * rspt_gpu_place_join, which makes the handle's stream wait for every placement issued so far. */
 int rspt_gpu_place_offsets_async(rspt_gpu_packer* p, void* comm, uint64_t* d_offsets, size_t n_frames, int rank, int world);
 int rspt_gpu_place_join(rspt_gpu_packer* p);
 

@@ -318,6 +318,18 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (kind == RSPT_XDELTA_HZR && (nb < 1 || nb > 4)) return RSPT_E_ARG;
     if (kind == RSPT_HADAMARD && ((ns & (ns - 1)) || ns < 2 || ns > kFwhtMaxN)) return RSPT_E_ARG;  // needs 2^k (fwht.c)
     if (kind == RSPT_DCT && (ns < 2 || ns > kDctMaxN)) return RSPT_E_ARG;
+    // A shape that the tile kernels cannot stage in shared memory is refused here, not at the first call:
+    // the generic forward tile (xdelta_tile / kPiece sample rows), the inverse kernel's carries + tile.
+    {
+        Shape t{};
+        t.kind = kind; t.bps = (int)bps; t.ch = (int)ch; t.ns = (int)ns;
+        uint32_t ts;
+        size_t smem;
+        if ((kind == RSPT_XDELTA_HZR || kind == RSPT_HZR) && !xdelta_tile(t, ts, smem)) return RSPT_E_ARG;
+        const size_t tile_bytes = (size_t)kPiece * ch * bps + 48;
+        const size_t pieces = ((ns + kPiece - 1) / kPiece) * ch;
+        if (tile_bytes > 200 * 1024 || 2 * pieces * 4 + tile_bytes > 200 * 1024) return RSPT_E_ARG;
+    }
     DeviceGuard dg(device);
     int rc = ensure_device_constants(device);
     if (rc != RSPT_OK) return rc;
@@ -1100,10 +1112,10 @@ int launch_words_to_raw(rspt_gpu_packer* p, const int32_t* d_words, uint8_t* d_d
     const size_t tile_bytes = (size_t)kPiece * s.ch * s.bps + 48;
     if (tile_bytes > 200 * 1024) return fail_arg(p, "too many channels");
     switch (s.bps) {
-    case 1: cudaFuncSetAttribute(k_words_to_raw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
-    case 2: cudaFuncSetAttribute(k_words_to_raw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
-    case 3: cudaFuncSetAttribute(k_words_to_raw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
-    default: cudaFuncSetAttribute(k_words_to_raw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
+    case 1: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_words_to_raw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); break;
+    case 2: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_words_to_raw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); break;
+    case 3: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_words_to_raw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); break;
+    default: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_words_to_raw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); break;
     }
     SPECTRAL_BPS_SWITCH(k_words_to_raw, <<<(unsigned)(F * tiles), 256, tile_bytes, p->stream>>>(d_words, s, tiles, d_dst));
     p->launches += 1;
@@ -1118,10 +1130,10 @@ int launch_raw_to_words(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
     const size_t tile_smem = (size_t)kPiece * s.ch * s.bps + 48;
     if (tile_smem > 200 * 1024) return fail_arg(p, "too many channels");
     switch (s.bps) {
-    case 1: cudaFuncSetAttribute(k_raw_to_words<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
-    case 2: cudaFuncSetAttribute(k_raw_to_words<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
-    case 3: cudaFuncSetAttribute(k_raw_to_words<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
-    default: cudaFuncSetAttribute(k_raw_to_words<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    case 1: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_raw_to_words<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); break;
+    case 2: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_raw_to_words<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); break;
+    case 3: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_raw_to_words<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); break;
+    default: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_raw_to_words<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); break;
     }
     SPECTRAL_BPS_SWITCH(k_raw_to_words, <<<(unsigned)(F * tiles), 256, tile_smem, p->stream>>>(d_src, s, tiles, p->d_words, p->d_sums));
     p->launches += 1;

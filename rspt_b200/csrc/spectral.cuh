@@ -804,17 +804,17 @@ inline bool words_g4_ok(const Shape& s, const void* d_raw)
         const unsigned gr = (unsigned)(F * (s.ch >> 2));                                                          \
         if (s.ns == 4096) {                                                                                       \
             switch (s.bps) {                                                                                      \
-            case 1: cudaFuncSetAttribute(KERNEL<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<12, 1><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
-            case 2: cudaFuncSetAttribute(KERNEL<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<12, 2><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
-            case 3: cudaFuncSetAttribute(KERNEL<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<12, 3><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
-            default: cudaFuncSetAttribute(KERNEL<12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<12, 4><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
+            case 1: RSPT_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr)); KERNEL<12, 1><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
+            case 2: RSPT_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr)); KERNEL<12, 2><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
+            case 3: RSPT_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr)); KERNEL<12, 3><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
+            default: RSPT_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr)); KERNEL<12, 4><<<gr, 256, smr, p->stream>>>(__VA_ARGS__); break; \
             }                                                                                                     \
         } else {                                                                                                  \
             switch (s.bps) {                                                                                      \
-            case 1: cudaFuncSetAttribute(KERNEL<13, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<13, 1><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
-            case 2: cudaFuncSetAttribute(KERNEL<13, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<13, 2><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
-            case 3: cudaFuncSetAttribute(KERNEL<13, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<13, 3><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
-            default: cudaFuncSetAttribute(KERNEL<13, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr); KERNEL<13, 4><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
+            case 1: RSPT_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<13, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr)); KERNEL<13, 1><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
+            case 2: RSPT_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<13, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr)); KERNEL<13, 2><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
+            case 3: RSPT_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<13, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr)); KERNEL<13, 3><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
+            default: RSPT_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<13, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr)); KERNEL<13, 4><<<gr, 512, smr, p->stream>>>(__VA_ARGS__); break; \
             }                                                                                                     \
         }                                                                                                         \
     } while (0)
@@ -835,10 +835,10 @@ inline int spectral_forward(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
     RSPT_CUDA_CHECK(cudaMemsetAsync(p->d_sums, 0, F * s.ch * sizeof(long long), p->stream));
     const dim3 g1((unsigned)(F * tiles));
     switch (s.bps) {
-    case 1: cudaFuncSetAttribute(k_raw_to_words<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
-    case 2: cudaFuncSetAttribute(k_raw_to_words<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
-    case 3: cudaFuncSetAttribute(k_raw_to_words<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
-    default: cudaFuncSetAttribute(k_raw_to_words<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); break;
+    case 1: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_raw_to_words<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); break;
+    case 2: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_raw_to_words<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); break;
+    case 3: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_raw_to_words<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); break;
+    default: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_raw_to_words<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem)); break;
     }
     if (words_g4_ok(s, d_src)) {
         const unsigned gb = (unsigned)(F * (s.ch >> 2) * (size_t)(s.ns >> 2) / 256);
@@ -854,19 +854,19 @@ inline int spectral_forward(rspt_gpu_packer* p, const uint8_t* d_src, size_t F)
         } else if (s.ns == 8192) {
             k_fwht_fast_fwd<13><<<g2, 512, 0, p->stream>>>(p->d_words, p->d_sums, s, p->d_planes, p->d_headers);
         } else {
-            cudaFuncSetAttribute(k_fwht_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_fwht_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             k_fwht_fwd<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_planes, p->d_headers);
         }
         p->launches += 2;
     } else {
         if (dct_use_direct(p)) {
             const size_t sm = (size_t)s.ns * 4;
-            cudaFuncSetAttribute(k_dct_fwd_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_dct_fwd_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             k_dct_fwd_direct<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_cos, p->d_headers);
         } else {
             if (s.ns >= 16) {
                 const size_t sm = (size_t)fpad_host((uint32_t)s.ns / 2) * 16;
-                cudaFuncSetAttribute(k_dct_fwd_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_dct_fwd_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                 k_dct_fwd_half<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_sums, s, p->d_twiddle, p->d_post, p->d_headers);
             } else {
                 const size_t sm = (size_t)s.ns * 16;
@@ -981,7 +981,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
         if (tpg >= 1) {
 #define INVF_LAUNCH(B, SC)                                                                                            \
     do {                                                                                                              \
-        cudaFuncSetAttribute(k_planes_to_samples_fast<B, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf); \
+        RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_planes_to_samples_fast<B, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf)); \
         k_planes_to_samples_fast<B, SC><<<gf, kInvThreads, smf, p->stream>>>(p->d_planes, s, p->d_dec_nb, tpg, d_dst,    \
                                                                        inverse_seg_xor(p), p->segs_per_plane); \
     } while (0)
@@ -1000,7 +1000,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
     }
 #define INV_LAUNCH(B, SC, RAW)                                                                                   \
     do {                                                                                                         \
-        cudaFuncSetAttribute(k_planes_to_samples<B, SC, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_inv); \
+        RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_planes_to_samples<B, SC, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_inv)); \
         k_planes_to_samples<B, SC, RAW><<<gf, 512, sm_inv, p->stream>>>(p->d_planes, s, p->d_dec_nb, d_dst, p->d_words);  \
     } while (0)
     if (s.kind == 0 /*xdelta_hzr*/) {
@@ -1034,7 +1034,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
             } else if (s.ns == 8192) {
                 k_fwht_fast_inv<13><<<g2, 512, 0, p->stream>>>(p->d_planes, p->d_headers, p->d_dec_nb, s, p->d_words);
             } else {
-                cudaFuncSetAttribute(k_fwht_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_fwht_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                 k_fwht_inv<<<g2, 256, sm, p->stream>>>(p->d_planes, p->d_headers, p->d_dec_nb, s, p->d_words);
             }
             p->launches += 1;
@@ -1042,7 +1042,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
             // coefficient words (BPS unused for word output)
             const size_t smw = (size_t)2 * ((uint32_t)s.ns / kInvPiece) * s.ch * 4;
             if ((s.ns % (int)kInvPiece) == 0 && smw <= 200 * 1024) {
-                cudaFuncSetAttribute(k_planes_to_samples_fast<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);
+                RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_planes_to_samples_fast<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
                 k_planes_to_samples_fast<4, true, true><<<gf, kInvThreads, smw, p->stream>>>(p->d_planes, s, p->d_dec_nb, 1, nullptr,
                                                                                              inverse_seg_xor(p), p->segs_per_plane, p->d_words);
             } else {
@@ -1050,12 +1050,12 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
             }
             if (dct_use_direct(p)) {
                 const size_t sm = (size_t)s.ns * 4;
-                cudaFuncSetAttribute(k_dct_inv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_dct_inv_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                 k_dct_inv_direct<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_headers, s, p->d_cos);
             } else {
                 if (s.ns >= 16) {
                     const size_t sm = (size_t)fpad_host((uint32_t)s.ns / 2) * 16;
-                    cudaFuncSetAttribute(k_dct_inv_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                    RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_dct_inv_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                     k_dct_inv_half<<<g2, 256, sm, p->stream>>>(p->d_words, p->d_headers, s, p->d_twiddle, p->d_post);
                 } else {
                     const size_t sm = (size_t)s.ns * 16;
@@ -1066,10 +1066,10 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
         }
         const uint32_t tiles = ppc;
         switch (s.bps) {
-        case 1: cudaFuncSetAttribute(k_words_to_raw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
-        case 2: cudaFuncSetAttribute(k_words_to_raw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
-        case 3: cudaFuncSetAttribute(k_words_to_raw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
-        default: cudaFuncSetAttribute(k_words_to_raw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes); break;
+        case 1: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_words_to_raw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); break;
+        case 2: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_words_to_raw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); break;
+        case 3: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_words_to_raw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); break;
+        default: RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_words_to_raw<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); break;
         }
         if (words_g4_ok(s, d_dst)) {
             const unsigned gb = (unsigned)(F * (s.ch >> 2) * (size_t)(s.ns >> 2) / 256);

@@ -895,3 +895,17 @@ def test_c_abi_allgather_places_two_shards():
                 res[int(r)] = (int(tot), int(first), int(last))
     assert res[0][1] == 0 and res[0][2] == res[0][0]
     assert res[1][1] == res[0][0] and res[1][2] == res[0][0] + res[1][0]
+
+
+def test_create_refuses_shapes_the_tile_kernels_cannot_stage(R):
+    """A shape that would only fail at the first compress call (too many channels for the shared-memory tiles) is
+    refused by rspt_gpu_create instead (the reference has no such limit, so the refusal has to be visible early)."""
+    from rspt_b200._lib import RsptError
+    for kind, bps, ch, ns in (("xdelta_hzr", 4, 4000, 64), ("hzr", 4, 4000, 64), ("dct", 4, 4000, 64)):
+        with pytest.raises(RsptError):
+            R.SignalPacker(kind, bps, ch, ns, 3, max_batch_frames=1)
+    p = R.SignalPacker("xdelta_hzr", 2, 300, 64, 2, max_batch_frames=1)   # many channels, still feasible
+    x = np.random.default_rng(5).integers(-2000, 2000, size=(64, 300)).astype("<i2")
+    y, used = p.decompress(p.compress(x.tobytes()))
+    assert y == x.tobytes()
+    p.close()
