@@ -37,6 +37,7 @@ struct TreeWarpSmem {
     uint32_t tree[kTreeWords];
     uint16_t front[2][264];    // C: breadth-first frontiers (internal node indices)
     uint32_t hist[264];        // token histogram of a listed block, taken from its list (blocks that come from k_front)
+    uint32_t pad;              // odd word stride: the lanes of a lock-step merge (k_hzr_tree_ls) start in different banks
 };
 
 struct Counters {
@@ -408,6 +409,47 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
         // encoder packs (COPY, or a payload beyond that kernel's staging) the frame runs through k_front again
         if (redo && bi.mode != MODE_FILL && list_n[blk] != kNoList && !sparse_block_is_packed_from_list(list_n[blk], bi, sparse_stage))
             redo[f] = 1;
+    }
+}
+
+// The same, with the serial part shared: a CTA of W warps prepares W trees (one per warp, as above), then the
+// lanes 0..W-1 of warp 0 run the W two-queue merges in lock step -- one tree per LANE instead of one per warp, so
+// the merge's warp-instructions (65 % of k_hzr_tree's, issued with one active lane) are paid once per CTA -- and
+// every warp finishes its own tree.  Dynamic shared memory: W TreeWarpSmem.
+__global__ void __launch_bounds__(1024) k_hzr_tree_ls(const uint32_t* __restrict__ hist, Shape s,
+                                                      const uint8_t* __restrict__ frame_nb,
+                                                      const uint8_t* __restrict__ blk_class, uint32_t cls,
+                                                      uint32_t total_blocks,
+                                                      uint32_t* __restrict__ codes,
+                                                      uint32_t* __restrict__ tree,
+                                                      BlkInfo* __restrict__ info,
+                                                      Counters* __restrict__ ctr)
+{
+    extern __shared__ __align__(16) uint8_t s_tree_raw[];
+    TreeWarpSmem* s_all = reinterpret_cast<TreeWarpSmem*>(s_tree_raw);
+    __shared__ uint32_t s_L[32];
+    const uint32_t W = blockDim.x >> 5, wid = warp_id(), lane = lane_id();
+    TreeWarpSmem& S = s_all[wid];
+    const uint32_t blk = blockIdx.x * W + wid;
+    uint32_t f = 0, k = 0, b = 0, n = 0, L = 0;
+    bool live = blk < total_blocks, merge = false;
+    BlkInfo bi;
+    if (live) {
+        blk_decode(s, blk, f, k, b);
+        live = k < frame_nb[f] && !(blk_class && blk_class[blk] != cls);
+    }
+    if (live) {
+        n = blk_len(s, b);
+        merge = !tree_prepare(S, hist + (size_t)blk * kSymStride, codes + (size_t)blk * kSymStride, L, bi);
+    }
+    if (lane == 0) s_L[wid] = merge ? L : 0u;
+    __syncthreads();
+    if (wid == 0 && lane < W && s_L[lane]) tree_merge(s_all[lane], s_L[lane]);
+    __syncthreads();
+    if (merge) bi = tree_assign(S, L, n, codes + (size_t)blk * kSymStride, tree + (size_t)blk * kTreeWords);
+    if (live && lane == 0) {
+        info[blk] = bi;
+        count_block_mode(ctr, bi.mode);
     }
 }
 

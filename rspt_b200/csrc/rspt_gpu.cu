@@ -607,6 +607,20 @@ int launch_frame_nb(rspt_gpu_packer* p, size_t F)
 
 }  // namespace
 
+// RSPT_TREE_LS=W (2..32): trees per CTA of the lock-step tree kernel; 0 = one warp per tree (k_hzr_tree)
+static uint32_t tree_lockstep_warps()
+{
+    static const uint32_t v = [] {
+        const char* e = getenv("RSPT_TREE_LS");
+        uint32_t w = e ? (uint32_t)atoi(e) : 0u;
+        if (w > 32u) w = 32u;
+        if (w == 1u) w = 0u;
+        if (w) cudaFuncSetAttribute(k_hzr_tree_ls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(w * sizeof(TreeWarpSmem)));
+        return w;
+    }();
+    return v;
+}
+
 // A compress that rewrites an offsets array must not overtake a placement still rebasing it.
 static int wait_for_placement_of(rspt_gpu_packer* p, const void* d_offsets)
 {
@@ -669,6 +683,9 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         RSPT_CUDA_CHECK(cudaEventRecord(p->ev_fork, p->stream));
         RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
         k_hzr_hist<1><<<nblocks, kHistThreads, kHistSmem, p->side>>>(p->d_planes, s, p->d_frame_nb, p->d_hist, p->d_step_lz, p->d_lists, p->d_list_n, p->d_blk_class);
+        if (const uint32_t W = tree_lockstep_warps())
+            k_hzr_tree_ls<<<(nblocks + W - 1) / W, 32 * W, W * sizeof(TreeWarpSmem), p->side>>>(p->d_hist, s, p->d_frame_nb, p->d_blk_class, kClassSparse, nblocks, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
+        else
         k_hzr_tree<<<tgrid, 32 * kTreeWarps, 0, p->side>>>(p->d_hist, s, p->d_frame_nb, p->d_blk_class, kClassSparse, nblocks, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
         RSPT_CUDA_CHECK(cudaEventRecord(p->ev_join, p->side));
         {
@@ -677,6 +694,9 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         }
         {
             StageTimer t(p, RSPT_STAGE_TREE);
+            if (const uint32_t W = tree_lockstep_warps())
+                k_hzr_tree_ls<<<(nblocks + W - 1) / W, 32 * W, W * sizeof(TreeWarpSmem), p->stream>>>(p->d_hist, s, p->d_frame_nb, p->d_blk_class, kClassDense, nblocks, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
+            else
             k_hzr_tree<<<tgrid, 32 * kTreeWarps, 0, p->stream>>>(p->d_hist, s, p->d_frame_nb, p->d_blk_class, kClassDense, nblocks, p->d_codes, p->d_tree, p->d_info, p->d_ctr);
             RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
         }

@@ -909,3 +909,35 @@ def test_create_refuses_shapes_the_tile_kernels_cannot_stage(R):
     y, used = p.decompress(p.compress(x.tobytes()))
     assert y == x.tobytes()
     p.close()
+
+
+@pytest.mark.parametrize("warps", ["5", "32"])
+def test_lock_step_tree_kernel_streams_are_bit_exact(warps, oracle):
+    """RSPT_TREE_LS=W: W trees per CTA, their two-queue merges run one per LANE of a single warp (k_hzr_tree_ls).
+    Same streams as the oracle's, incl. blocks with few symbols, FILL blocks and ragged last CTAs.  The switch is
+    read once per process, hence a child; the oracle's streams travel as a digest."""
+    import subprocess
+    import sys
+    cases = (("xdelta_hzr", 3, 12, 2048, 5), ("hzr", 2, 4, 1024, 3), ("hadamard", 4, 4, 1024, 3), ("xdelta_hzr", 4, 3, 700, 4))
+    want = []
+    for kind, bps, ch, ns, n in cases:
+        raws = oracle.synth_ecg(21, n, bps, ch, ns)
+        raws[n - 1][:] = 0   # a frame of FILL blocks
+        cpu = oracle.OraclePacker(kind, bps, ch, ns, 3 if bps < 4 else 4)
+        want.append(hashlib.sha256(b"".join(cpu.compress(r) for r in raws)).hexdigest())
+    code = (
+        "import numpy as np, torch, sys, hashlib\n"
+        "sys.path.insert(0, %r)\n"
+        "from rspt_b200 import packer as R\n"
+        "for kind, bps, ch, ns, n in %r:\n"
+        "    p = R.SignalPacker(kind, bps, ch, ns, 3 if bps < 4 else 4, max_batch_frames=n)\n"
+        "    x = R.synth_ecg(21, n, bps, ch, ns).clone()\n"
+        "    x[(n - 1) * bps * ch * ns:] = 0\n"
+        "    b = p.compress_batch(x)\n"
+        "    torch.cuda.synchronize()\n"
+        "    print(hashlib.sha256(bytes(b.stream[: b.total_bytes()].cpu().numpy())).hexdigest())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), cases)
+    env = dict(os.environ, RSPT_TREE_LS=warps)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.split() == want

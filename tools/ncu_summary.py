@@ -1,7 +1,8 @@
 """One line per kernel launch from an ncu report (raw page)."""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
-txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# an .ncu-rep, or the `ncu -i rep --page raw --csv` dump of one (made on the GPU box when the report is too large to bring back)
+txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 hdr, units, data = rows[0], rows[1], rows[2:]
 def col(r, name):

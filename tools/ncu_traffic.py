@@ -21,11 +21,14 @@ for r in data:
             e = {"kernel": kn, "dram_bytes_per_launch": num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"),
                  "dram_read": num(r, "dram__bytes_read.sum"), "dram_write": num(r, "dram__bytes_write.sum"),
                  "duration_us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", ""))}
-            if st in res and kn not in res[st]["kernel"].split(" + "):
-                # a stage made of several kernels (encode = k_hzr_encode_sparse + k_hzr_encode): add them up
+            if st in res:
+                # a stage made of several launches (encode = k_hzr_encode_sparse + k_hzr_encode; the decoder's three
+                # payload classes; the two tree launches): add them up -- the capture holds ONE pass of the pipeline
                 for key in ("dram_bytes_per_launch", "dram_read", "dram_write", "duration_us"):
                     e[key] += res[st][key]
-                e["kernel"] = res[st]["kernel"] + " + " + kn
+                prev = res[st]["kernel"].split(" + ")
+                e["kernel"] = res[st]["kernel"] if kn in prev else res[st]["kernel"] + " + " + kn
+                e["launches"] = res[st].get("launches", 1) + 1
             res[st] = e
             break
 json.dump({"source": rep.split("/")[-1], "frames_per_launch": frames, "kernels": res}, open(out, "w"), indent=1)
