@@ -289,25 +289,29 @@ def timed(torch, fn, n):
     return e0.elapsed_time(e1) * 1e-3
 
 
-def copy_ceiling(torch, dev, h2d_bytes: int, d2h_bytes: int, reps: int = 3) -> float:
+def copy_ceiling(torch, dev, h2d_bytes: int, d2h_bytes: int, reps: int = 3, barrier=None) -> float:
     """Seconds for plain pinned H2D + D2H copies of the same sizes, both directions at once (what the link gives
-    a host-buffer call that does nothing else)."""
+    a host-buffer call that does nothing else).  At N > 1 every repetition starts behind a barrier, so that all
+    ranks copy at the same time as they do in the e2e legs; the mean of the repetitions after one warm-up."""
     hs = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
     hd = torch.empty(d2h_bytes, dtype=torch.uint8, pin_memory=True)
     ds = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
     dd = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
     s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     torch.cuda.synchronize()
-    best = 1e9
-    for _ in range(reps):
+    total = 0.0
+    for r in range(reps + 1):
+        if barrier is not None:
+            barrier()
         t0 = time.perf_counter()
         with torch.cuda.stream(s1):
             ds.copy_(hs, non_blocking=True)
         with torch.cuda.stream(s2):
             hd.copy_(dd, non_blocking=True)
         torch.cuda.synchronize()
-        best = min(best, time.perf_counter() - t0)
-    return best
+        if r > 0:
+            total += time.perf_counter() - t0
+    return total / reps
 
 
 def measure_packer(R, torch, D, kind, sh, F, nbatch, reps, hbm_peak, e2e_frames, cpu_budget, want_cpu, stage_roofline=False):
@@ -390,6 +394,7 @@ def measure_packer(R, torch, D, kind, sh, F, nbatch, reps, hbm_peak, e2e_frames,
         tot = pe.compress_batch_host(np_raw, np_cmp, np_off)
     torch.cuda.synchronize()
     tec = D.max(time.perf_counter() - t0)
+    D.barrier()
     t0 = time.perf_counter()
     for _ in range(ne):
         pe.decompress_batch_host(np_cmp, np_off, np_back)
@@ -397,8 +402,8 @@ def measure_packer(R, torch, D, kind, sh, F, nbatch, reps, hbm_peak, e2e_frames,
     ted = D.max(time.perf_counter() - t0)
     if kind in ("xdelta_hzr", "hzr"):
         r["e2e_roundtrip_bit_exact"] = bool(np.array_equal(np_back, np_raw))
-    ceil_c = D.max(copy_ceiling(torch, dev, Fe * fb, int(tot) + 8 * (Fe + 1)))
-    ceil_d = D.max(copy_ceiling(torch, dev, int(tot) + 8 * (Fe + 1), Fe * fb))
+    ceil_c = D.max(copy_ceiling(torch, dev, Fe * fb, int(tot) + 8 * (Fe + 1), barrier=D.barrier))
+    ceil_d = D.max(copy_ceiling(torch, dev, int(tot) + 8 * (Fe + 1), Fe * fb, barrier=D.barrier))
     r["compress"]["e2e"] = {"value": D.world * ne * Fe * fb / tec / 1e9, "unit": "GB/s", "h2d_bytes_per_step": Fe * fb,
                             "d2h_bytes_per_step": int(tot) + 8 * (Fe + 1), "frames_per_step": Fe,
                             "api": "rspt_gpu_compress_batch_host (pinned host buffers)",
