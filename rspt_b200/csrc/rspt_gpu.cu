@@ -30,6 +30,11 @@ constexpr int kMaxDevices = 64;
 std::mutex g_mu;
 CrcConst* g_crc[kMaxDevices] = {};
 int32_t* g_synth_tab[kMaxDevices] = {};  // beat[1024] | sine[1024]
+// 16-byte result slots of the synchronous helper calls (rspt_gpu_crc32c, rspt_gpu_prdn_terms): a ring per device,
+// so that those calls allocate nothing (64 of them may be in flight from different host threads)
+uint8_t* g_result_ring[kMaxDevices] = {};
+std::atomic<unsigned> g_result_next{0};
+void* result_slot(int dev) { return g_result_ring[dev] + 16u * (g_result_next.fetch_add(1) & 63u); }
 
 uint32_t h_multmodp(uint32_t a, uint32_t b)
 {
@@ -84,6 +89,9 @@ int ensure_device_constants(int dev)
     int32_t* dt = nullptr;
     if (cudaMalloc(&dt, tab.size() * sizeof(int32_t)) != cudaSuccess) return RSPT_E_CUDA;
     if (cudaMemcpy(dt, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) return RSPT_E_CUDA;
+    uint8_t* ring = nullptr;
+    if (cudaMalloc(&ring, 64 * 16) != cudaSuccess) return RSPT_E_CUDA;
+    g_result_ring[dev] = ring;
     g_crc[dev] = d;
     g_synth_tab[dev] = dt;
     return RSPT_OK;
@@ -1490,13 +1498,11 @@ extern "C" int rspt_gpu_crc32c(const uint8_t* d_data, size_t n, uint32_t* h_crc,
     if (cudaGetDevice(&dev) != cudaSuccess) return RSPT_E_NOGPU;
     int rc = ensure_device_constants(dev);
     if (rc) return rc;
-    uint32_t* d_out = nullptr;
-    if (cudaMalloc(&d_out, 4) != cudaSuccess) return RSPT_E_CUDA;
+    uint32_t* d_out = static_cast<uint32_t*>(result_slot(dev));
     allow_smem(k_crc32c, kEncodeSmem);
     k_crc32c<<<1, 1024, kEncodeSmem, (cudaStream_t)stream>>>(d_data, (uint32_t)n, g_crc[dev], 3, d_out);
     cudaError_t e = cudaMemcpyAsync(h_crc, d_out, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
-    cudaFree(d_out);
     return e == cudaSuccess ? RSPT_OK : RSPT_E_CUDA;
 }
 
@@ -1608,8 +1614,11 @@ extern "C" int rspt_gpu_prdn_terms(const uint8_t* d_orig, const uint8_t* d_dec, 
                                    double* h_out, void* stream)
 {
     if (!d_orig || !d_dec || !h_out || bps < 1 || bps > 4) return RSPT_E_ARG;
-    double* d_out = nullptr;
-    if (cudaMalloc(&d_out, 16) != cudaSuccess) return RSPT_E_CUDA;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RSPT_E_NOGPU;
+    int rc = ensure_device_constants(dev);
+    if (rc) return rc;
+    double* d_out = static_cast<double*>(result_slot(dev));
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(d_out, 0, 16, st);
     const dim3 grid((unsigned)(n_frames * ch));
@@ -1621,7 +1630,6 @@ extern "C" int rspt_gpu_prdn_terms(const uint8_t* d_orig, const uint8_t* d_dec, 
     }
     cudaError_t e = cudaMemcpyAsync(h_out, d_out, 16, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_out);
     return e == cudaSuccess ? RSPT_OK : RSPT_E_CUDA;
 }
 

@@ -893,6 +893,17 @@ inline int inverse_mode()
     return v;
 }
 inline bool inverse_cluster_enabled() { return inverse_mode() != 0; }
+// threads per CTA (= per frame) of the three-pass inverse kernel; the registers allow 1024 threads per SM, so this
+// sets how many frames an SM has in flight (RSPT_INV_THREADS: 256 / 512 / 1024)
+inline unsigned inverse_threads()
+{
+    static const unsigned v = [] {
+        const char* e = getenv("RSPT_INV_THREADS");
+        const unsigned t = e ? (unsigned)atoi(e) : (unsigned)kInvThreads;
+        return (t == 256u || t == 512u || t == 1024u) ? t : (unsigned)kInvThreads;
+    }();
+    return v;
+}
 inline const uint8_t* inverse_seg_xor(const rspt_gpu_packer* p) { return getenv("RSPT_DECODE_SEG_XOR") ? p->d_seg_xor : nullptr; }
 
 inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F)
@@ -982,7 +993,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
 #define INVF_LAUNCH(B, SC)                                                                                            \
     do {                                                                                                              \
         RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_planes_to_samples_fast<B, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf)); \
-        k_planes_to_samples_fast<B, SC><<<gf, kInvThreads, smf, p->stream>>>(p->d_planes, s, p->d_dec_nb, tpg, d_dst,    \
+        k_planes_to_samples_fast<B, SC><<<gf, inverse_threads(), smf, p->stream>>>(p->d_planes, s, p->d_dec_nb, tpg, d_dst,    \
                                                                        inverse_seg_xor(p), p->segs_per_plane); \
     } while (0)
             const bool sc = s.kind == 0;
@@ -1043,7 +1054,7 @@ inline int launch_inverse_transform(rspt_gpu_packer* p, uint8_t* d_dst, size_t F
             const size_t smw = (size_t)2 * ((uint32_t)s.ns / kInvPiece) * s.ch * 4;
             if ((s.ns % (int)kInvPiece) == 0 && smw <= 200 * 1024) {
                 RSPT_CUDA_CHECK(cudaFuncSetAttribute(k_planes_to_samples_fast<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
-                k_planes_to_samples_fast<4, true, true><<<gf, kInvThreads, smw, p->stream>>>(p->d_planes, s, p->d_dec_nb, 1, nullptr,
+                k_planes_to_samples_fast<4, true, true><<<gf, inverse_threads(), smw, p->stream>>>(p->d_planes, s, p->d_dec_nb, 1, nullptr,
                                                                                              inverse_seg_xor(p), p->segs_per_plane, p->d_words);
             } else {
                 INV_LAUNCH(4, true, false);

@@ -498,7 +498,7 @@ __device__ __forceinline__ uint32_t warp_add_inclusive(uint32_t v)
 }
 
 template <int BPS, bool SCAN, bool WORDS = false>
-__global__ void __launch_bounds__(kInvThreads, 4) k_planes_to_samples_fast(const uint8_t* __restrict__ planes, Shape s,
+__global__ void __launch_bounds__(1024, 1) k_planes_to_samples_fast(const uint8_t* __restrict__ planes, Shape s,
                                                                             const uint8_t* __restrict__ dec_nb,
                                                                             uint32_t tiles_per_group,
                                                                             uint8_t* __restrict__ dst_raw,

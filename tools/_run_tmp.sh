@@ -1,6 +1,2 @@
-N=8
-for c in 0 1024; do
-  if [ $c = 0 ]; then unset RSPT_HOST_CHUNK_FRAMES; else export RSPT_HOST_CHUNK_FRAMES=$c; fi
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 --quick --no-cpu 2>/dev/null > gpurun_out/r02_e2e_${N}gpu_chunk$c.json
-done
-nvidia-smi topo -m > gpurun_out/r02_topo.txt 2>&1; lscpu | head -20 >> gpurun_out/r02_topo.txt
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r02_l.log
+for t in 256 512 1024; do echo "inv threads $t" >> gpurun_out/r02_l.log; RSPT_INV_THREADS=$t timeout 300 python tools/stage_times.py 4096 2>&1 | cut -c1-75,150-240 >> gpurun_out/r02_l.log; done
