@@ -279,27 +279,30 @@ __device__ __forceinline__ void chain_long_codes(const uint32_t* cw_tab, T* lut,
 constexpr uint32_t kXorSeg = 128;
 __device__ __forceinline__ void block_segment_xor(const uint8_t* out, uint32_t n, uint8_t* seg)
 {
-    const uint32_t nseg = (n + kXorSeg - 1) / kXorSeg;
-    for (uint32_t sg = threadIdx.x; sg < nseg; sg += blockDim.x) {
-        const uint4* p4 = reinterpret_cast<const uint4*>(out + (size_t)sg * kXorSeg);
-        const uint32_t chunks = min(kXorSeg / 16u, (n - sg * kXorSeg + 15u) / 16u);
+    // eight lanes per segment, one 16-byte chunk each (consecutive lanes read consecutive chunks), folded with
+    // three shuffles; the loop bound is warp-uniform so that the shuffles see the whole warp
+    const uint32_t nchunk = (n + 15u) >> 4;
+    const uint4* p4 = reinterpret_cast<const uint4*>(out);
+    for (uint32_t c0 = (threadIdx.x & ~31u); c0 < nchunk; c0 += blockDim.x) {
+        const uint32_t c = c0 + (threadIdx.x & 31u);
         uint32_t x = 0;
-#pragma unroll
-        for (uint32_t i = 0; i < kXorSeg / 16u; ++i)
-            if (i < chunks) {
-                uint4 v = __ldcg(p4 + i);
-                const uint32_t left = n - sg * kXorSeg - 16u * i;   // bytes of the block in this chunk (>= 1)
-                if (left < 16u) {
-                    if (left <= 12u) v.w = 0; else v.w &= (1u << (8u * (left - 12u))) - 1u;
-                    if (left <= 8u) v.z = 0; else if (left < 12u) v.z &= (1u << (8u * (left - 8u))) - 1u;
-                    if (left <= 4u) v.y = 0; else if (left < 8u) v.y &= (1u << (8u * (left - 4u))) - 1u;
-                    if (left < 4u) v.x &= (1u << (8u * left)) - 1u;
-                }
-                x ^= v.x ^ v.y ^ v.z ^ v.w;
+        if (c < nchunk) {
+            uint4 v = __ldcg(p4 + c);
+            const uint32_t left = n - 16u * c;   // bytes of the block in this chunk (>= 1)
+            if (left < 16u) {
+                if (left <= 12u) v.w = 0; else v.w &= (1u << (8u * (left - 12u))) - 1u;
+                if (left <= 8u) v.z = 0; else if (left < 12u) v.z &= (1u << (8u * (left - 8u))) - 1u;
+                if (left <= 4u) v.y = 0; else if (left < 8u) v.y &= (1u << (8u * (left - 4u))) - 1u;
+                if (left < 4u) v.x &= (1u << (8u * left)) - 1u;
             }
+            x = v.x ^ v.y ^ v.z ^ v.w;
+        }
+        x ^= __shfl_xor_sync(0xFFFFFFFFu, x, 4);
+        x ^= __shfl_xor_sync(0xFFFFFFFFu, x, 2);
+        x ^= __shfl_xor_sync(0xFFFFFFFFu, x, 1);
         x ^= x >> 16;
         x ^= x >> 8;
-        seg[sg] = (uint8_t)x;
+        if ((threadIdx.x & 7u) == 0u && c < nchunk) seg[c >> 3] = (uint8_t)x;
     }
 }
 
