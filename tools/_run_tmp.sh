@@ -1,1 +1,2 @@
-for a in "hadamard 3 12 8192 4096" "hadamard 4 12 8192 2048" "hadamard 3 12 4096 8192" "hadamard 4 12 4096 4096" "dct 3 12 8192 4096"; do timeout 300 python tools/stage_times_shape.py $a 2>&1 | tail -1 >> gpurun_out/r02_m.log; done
+N=$1
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 2>gpurun_out/r02_f_bench_${N}gpu.err > gpurun_out/r02_f_bench_${N}gpu.json
