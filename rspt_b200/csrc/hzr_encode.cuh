@@ -176,7 +176,10 @@ __device__ __forceinline__ uint32_t shf_l_c(uint32_t lo, uint32_t hi, uint32_t n
 constexpr uint32_t kStgWords = 4 + kBlock / 4 + 8;
 constexpr size_t kEncodeSmem = (size_t)kStgWords * 4;
 
-__global__ void __launch_bounds__(kEncThreads, 2) k_hzr_encode(const uint8_t* __restrict__ planes, Shape s,
+// MINB = CTAs per SM the register allocation aims at: 2 (63 registers) or 3 (40 registers, 36 bytes of spills);
+// which one is faster depends on the planes (rspt_gpu.cu: encode_ctas_per_sm)
+template <int MINB>
+__global__ void __launch_bounds__(kEncThreads, MINB) k_hzr_encode(const uint8_t* __restrict__ planes, Shape s,
                                                                 const uint8_t* __restrict__ frame_nb,
                                                                 const BlkInfo* __restrict__ info,
                                                                 const uint32_t* __restrict__ blk_off,

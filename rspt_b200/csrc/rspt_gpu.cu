@@ -416,7 +416,8 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_frame_nb, (int)s.nb_init, F, p->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ctr, 0, sizeof(Counters), p->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_nb_state, &s.nb_init, 4, cudaMemcpyHostToDevice, p->stream);
-    if (e == cudaSuccess) e = allow_smem(k_hzr_encode, kEncodeSmem);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_encode<2>, kEncodeSmem);
+    if (e == cudaSuccess) e = allow_smem(k_hzr_encode<3>, kEncodeSmem);
     if (e == cudaSuccess) e = allow_smem(k_hzr_hist<1>, kHistSmem);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->place, cudaStreamNonBlocking);
@@ -615,6 +616,19 @@ int launch_frame_nb(rspt_gpu_packer* p, size_t F)
 
 }  // namespace
 
+// Dense-encoder CTAs per SM the kernel is compiled for.  Measured per 4096-frame batch: xdelta_hzr 1.075 -> 1.051 ms
+// and hadamard 1.121 -> 1.090 ms with 3 (more warps to cover the barriers), hzr 2.344 -> 2.369 and dct
+// 0.848 -> 0.890 with 3 (their planes take the spilled slow path more often).  RSPT_ENC_CTAS=2|3 overrides.
+static int encode_ctas_per_sm(const Shape& s)
+{
+    static const int forced = [] {
+        const char* e = getenv("RSPT_ENC_CTAS");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced == 2 || forced == 3) return forced;
+    return (s.kind == RSPT_XDELTA_HZR || s.kind == RSPT_HADAMARD) ? 3 : 2;
+}
+
 // RSPT_TREE_LS=W (2..32): trees per CTA of the lock-step tree kernel; 0 = one warp per tree (k_hzr_tree)
 static uint32_t tree_lockstep_warps()
 {
@@ -726,9 +740,14 @@ extern "C" int rspt_gpu_compress_batch(rspt_gpu_packer* p, const uint8_t* d_src,
         k_hzr_encode_sparse<<<nblocks, kSpThreads, kSparseSmem, p->side>>>(s, p->d_frame_nb, p->d_info, p->d_codes, p->d_tree, p->d_lists,
                                                                            p->d_list_n, p->d_crc, so);
         RSPT_CUDA_CHECK(cudaEventRecord(p->ev_join2, p->side));
-        k_hzr_encode<<<nblocks, kEncThreads, p->enc_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
-                                                                        p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->sp_stage,
-                                                                        d_offsets, p->d_headers, p->d_crc, d_dst, sidecar);
+        if (encode_ctas_per_sm(s) == 3)
+            k_hzr_encode<3><<<nblocks, kEncThreads, p->enc_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
+                                                                               p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->sp_stage,
+                                                                               d_offsets, p->d_headers, p->d_crc, d_dst, sidecar);
+        else
+            k_hzr_encode<2><<<nblocks, kEncThreads, p->enc_smem, p->stream>>>(p->d_planes, s, p->d_frame_nb, p->d_info, p->d_blk_off,
+                                                                               p->d_codes, p->d_tree, p->d_step_lz, p->d_lists, p->d_list_n, p->sp_stage,
+                                                                               d_offsets, p->d_headers, p->d_crc, d_dst, sidecar);
         RSPT_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_join2, 0));
     }
     p->launches += 4;
