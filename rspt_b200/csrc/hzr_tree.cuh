@@ -33,10 +33,9 @@ struct TreeWarpSmem {
     uint32_t key[264];         // sorted leaf keys
     uint32_t icnt[260];        // B: internal node weight (| bit 31: next node has equal weight); C: node code
     uint32_t child[260];       // child_a | child_b << 10 | leaves below << 20; ids < 512 are leaf ranks, 512 + j internal node j
-    uint32_t ninfo[260];       // C: depth | pre-order bit offset << 8
-    uint32_t tree[kTreeWords];
+    uint32_t ninfo[260];       // C: depth | pre-order bit offset << 8.  Before the build, ninfo and the first words of
+    uint32_t tree[kTreeWords]; //    tree hold the 264-word token histogram of a listed block that comes from k_front (list_hist)
     uint16_t front[2][264];    // C: breadth-first frontiers (internal node indices)
-    uint32_t hist[264];        // token histogram of a listed block, taken from its list (blocks that come from k_front)
     uint32_t pad;              // odd word stride: the lanes of a lock-step merge (k_hzr_tree_ls) start in different banks
 };
 
@@ -395,11 +394,13 @@ __global__ void __launch_bounds__(kTreeWarps * 32) k_hzr_tree(const uint32_t* __
             for (uint32_t i = lane; i < nc; i += 32) dst[at + i] = sub[i];
             at += nc;
         }
-        for (uint32_t i = lane; i < (uint32_t)kSymStride; i += 32) S.hist[i] = 0;
+        uint32_t* list_hist = S.ninfo;   // 264 words: dead before tree_prepare clears S.tree and tree_assign writes ninfo
+        static_assert(kTreeWords >= 4, "the histogram of a listed block spans ninfo[260] and tree[0..3]");
+        for (uint32_t i = lane; i < (uint32_t)kSymStride; i += 32) list_hist[i] = 0;
         __syncwarp();
-        warp_hist_from_list(dst, at, n, S.hist);
+        warp_hist_from_list(dst, at, n, list_hist);
         __syncwarp();
-        h = S.hist;
+        h = list_hist;
     }
     const BlkInfo bi = warp_build_tree(S, h, n, codes + (size_t)blk * kSymStride, tree + (size_t)blk * kTreeWords);
     if (lane_id() == 0) {
