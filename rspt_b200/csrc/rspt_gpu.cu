@@ -872,15 +872,15 @@ extern "C" int rspt_gpu_decompress_batch(rspt_gpu_packer* p, const uint8_t* d_sr
             cudaEventRecord(p->ev_fork, p->stream);
             cudaStreamWaitEvent(p->side, p->ev_fork, 0);
             k_hzr_decode<<<nblk_c, decode_class_threads(kSmallPayload), decode_class_smem(kSmallPayload), p->side>>>(
-                d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c, decode_pair_max_bits(), 1u, sxor, p->segs_per_plane, blk0);
+                d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c, decode_pair_max_bits() | (s.kind <= RSPT_HZR ? 256u : 0u), 1u, sxor, p->segs_per_plane, blk0);
             if (maxn > kSmallPayload) {
                 k_hzr_decode<<<nblk_c, decode_class_threads(kMediumPayload), decode_class_smem(kMediumPayload), p->side>>>(
-                    d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c, decode_pair_max_bits(), 2u, sxor, p->segs_per_plane, blk0);
+                    d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c, decode_pair_max_bits() | (s.kind <= RSPT_HZR ? 256u : 0u), 2u, sxor, p->segs_per_plane, blk0);
                 p->launches += 1;
             }
             cudaEventRecord(p->ev_join, p->side);
             k_hzr_decode<<<nblk_c, kDecodeThreads, p->dec_smem, p->stream>>>(d_src, s, dec_c, d_offsets, sc, codes_c, p->d_planes, status_c,
-                                                                             decode_pair_max_bits(), 0u, sxor, p->segs_per_plane, blk0);
+                                                                             decode_pair_max_bits() | (s.kind <= RSPT_HZR ? 256u : 0u), 0u, sxor, p->segs_per_plane, blk0);
             cudaStreamWaitEvent(p->stream, p->ev_join, 0);
             p->launches += 2;
         }
