@@ -470,6 +470,8 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                 return __funnelshift_r(lds_u32(a), lds_u32(a + 4u), at);   // the shift uses the low 5 bits of `at`
             };
             auto token_loop = [&](auto pairs_t, auto chain_t) {
+            // PAIRS: pair table; CHAIN: further look-ups into the same window (pair table: one more after a pair;
+            // single-symbol table: up to three more literals)
             constexpr bool PAIRS = decltype(pairs_t)::value, CHAIN = decltype(chain_t)::value;
             while (bp < end_bp && pos < n) {
                 uint32_t win = window(bp);
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                 const uint32_t sym = e & 511u;
                 uint32_t val = two ? sym | ((e >> 8) & 0xFF00u) : sym;  // the literal byte(s)
                 const bool run = sym >= 256u;  // symbol 0 (a zero run of one) is handled as a literal
-                if (!PAIRS && !run) {
+                if (!PAIRS && CHAIN && !run) {
                     // up to three more literals from the same window, as long as kLutBits unread bits are left in it
                     const uint32_t e2 = lds_u16(lut_s + 2u * ((win >> len) & ((1u << kLutBits) - 1u)));
                     const uint32_t len2 = len + (e2 >> 9);
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 3) k_hzr_decode(const uint8_t*
                 pos = np;
             }
             };
-            if (!use_pairs) token_loop(std::false_type{}, std::false_type{});
+            if (!use_pairs) token_loop(std::false_type{}, std::true_type{});
             else if (chain_pairs) token_loop(std::true_type{}, std::true_type{});
             else token_loop(std::true_type{}, std::false_type{});
             bitpos = bp - base_bits;

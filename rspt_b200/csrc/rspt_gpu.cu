@@ -804,7 +804,7 @@ static uint32_t decode_pair_max_bits()
 {
     static const uint32_t v = [] {
         const char* e = getenv("RSPT_PAIR_MAX_BITS");
-        return e ? (uint32_t)atoi(e) : 4u;
+        return e ? (uint32_t)atoi(e) & 255u : 4u;
     }();
     return v;
 }
