@@ -173,7 +173,7 @@ __device__ __forceinline__ uint32_t shf_l_c(uint32_t lo, uint32_t hi, uint32_t n
     return d;
 }
 
-constexpr uint32_t kStgWords = 4 + kBlock / 4 + 8;
+constexpr uint32_t kStgWords = 12 + kBlock / 4 + 8;   // header + payload at an offset of 16 .. 31 + 7 bytes, + slack
 constexpr size_t kEncodeSmem = (size_t)kStgWords * 4;
 
 // MINB = CTAs per SM the register allocation aims at: 2 (63 registers) or 3 (40 registers, 36 bytes of spills);
@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(kEncThreads, MINB) k_hzr_encode(const uint8_t*
                                                                 uint8_t* __restrict__ dst,
                                                                 uint32_t* __restrict__ sidecar)
 {
-    extern __shared__ __align__(16) uint32_t stg[];  // header at bytes 9..15, payload from byte 16
+    // The block (7 header bytes + payload) is staged at an offset CONGRUENT to its address in the output stream mod 16,
+    // so that it leaves with one bulk asynchronous store: header at byte hoff = 16 + (address & 15), payload at
+    // poff = hoff + 7, i.e. `lead` = poff & 3 bytes into the word array `pay`; every bit offset below counts from pay[0].
+    extern __shared__ __align__(16) uint32_t stg[];
     __shared__ uint32_t s_codes[kSymStride];
     __shared__ __align__(8) uint2 s_tab[kTabSize];
     __shared__ __align__(16) uint32_t s_zt[1024];
@@ -230,16 +233,31 @@ __global__ void __launch_bounds__(kEncThreads, MINB) k_hzr_encode(const uint8_t*
 
     uint8_t* sbytes = reinterpret_cast<uint8_t*>(stg);
     const uint32_t plen = bi.payload_len;
-    uint32_t* pay = stg + 4;
+    const uint32_t hoff = 16u + (uint32_t)((uintptr_t)out & 15u), poff = hoff + 7u;
+    const uint32_t lead = poff & 3u, lead_bits = 8u * lead, pw0 = poff >> 2;
+    uint32_t* pay = stg + pw0;
     for (uint32_t i = tid; i < 256; i += blockDim.x)
         reinterpret_cast<uint4*>(s_zt)[i] = __ldg(reinterpret_cast<const uint4*>(&cc->zt[kEncZtSel][0][0]) + i);
     const uint8_t* src = blk_ptr(planes, s, f, k, b);
 
     if (bi.mode == MODE_COPY) {
         // raw plane bytes are the payload (PlainCopy); rows are 16-byte aligned
+        // (moved `lead` bytes up: word w of the staging = bytes 4w - lead .. 4w - lead + 3 of the plane)
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
         const uint4* s4 = reinterpret_cast<const uint4*>(src);
-        uint4* d4 = reinterpret_cast<uint4*>(pay);
-        for (uint32_t i = tid; i < (n + 15) / 16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+        const uint32_t nq = (n + 15u) >> 4;   // 16-byte chunks of the plane row (rows are padded to 16 bytes)
+        for (uint32_t i = tid; i <= nq; i += blockDim.x) {
+            const uint32_t prev = i ? __ldg(s32 + 4u * i - 1u) : 0u;
+            const uint4 v = i < nq ? __ldg(s4 + i) : make_uint4(0, 0, 0, 0);
+            uint32_t* d = pay + 4u * i;
+            d[0] = __funnelshift_l(prev, v.x, lead_bits);
+            if (i < nq) {
+                d[1] = __funnelshift_l(v.x, v.y, lead_bits);
+                d[2] = __funnelshift_l(v.y, v.z, lead_bits);
+                d[3] = __funnelshift_l(v.z, v.w, lead_bits);
+            }
+        }
+        for (uint32_t w = tid; w < pw0; w += blockDim.x) stg[w] = 0;   // header bytes: zero until the CRC is taken
         __syncthreads();
     } else {
         const uint32_t nsteps = (n + kStepBytes - 1) / kStepBytes;
@@ -262,9 +280,19 @@ __global__ void __launch_bounds__(kEncThreads, MINB) k_hzr_encode(const uint8_t*
         }
         const uint32_t tw = (bi.tree_nbits + 31u) >> 5, pw = (plen + 3u) >> 2;
         // staging: tree words, then zeros (the code words are OR-ed in)
-        const uint32_t tw4 = (tw + 3u) & ~3u;
-        for (uint32_t i = tid; i < tw4; i += blockDim.x) pay[i] = i < tw ? __ldg(tree + (size_t)blk * kTreeWords + i) : 0u;
-        for (uint32_t i = (tw4 >> 2) + tid; i < ((pw + 2u + 3u) >> 2); i += blockDim.x) reinterpret_cast<uint4*>(pay)[i] = make_uint4(0, 0, 0, 0);
+        // (stg words 0 .. pw0 - 1 are zero: the header is written after the CRC has been taken; the tree words
+        // are moved up by `lead` bytes and spill into one more word)
+        const uint32_t tw4 = (pw0 + tw + 1u + 3u) & ~3u;
+        const uint32_t* gt = tree + (size_t)blk * kTreeWords;
+        for (uint32_t i = tid; i < tw4; i += blockDim.x) {
+            uint32_t v = 0;
+            if (i >= pw0 && i <= pw0 + tw) {
+                const uint32_t j = i - pw0;
+                v = __funnelshift_l(j ? __ldg(gt + j - 1) : 0u, j < tw ? __ldg(gt + j) : 0u, lead_bits);
+            }
+            stg[i] = v;
+        }
+        for (uint32_t i = (tw4 >> 2) + tid; i < ((pw0 + pw + 3u + 3u) >> 2); i += blockDim.x) reinterpret_cast<uint4*>(stg)[i] = make_uint4(0, 0, 0, 0);
         // decode index: where this block's entries go (common.cuh)
         uint32_t* my_idx = sidecar ? sidecar + idx_slot_base(frame_off - offsets[0] + blk_off[blk] + 7u, blk) : nullptr;
         const IdxGeom ig = idx_geom(plen);
@@ -316,7 +344,7 @@ __global__ void __launch_bounds__(kEncThreads, MINB) k_hzr_encode(const uint8_t*
         }
         __syncthreads();
 
-        uint32_t base = bi.tree_nbits;  // bit offset of the group (same in every thread)
+        uint32_t base = bi.tree_nbits + lead_bits;  // bit offset of the group from pay[0] (same in every thread)
         const uint32_t ngroups = (nsteps + kEncWarps - 1) / kEncWarps;
         const uint32_t tab_s = smem_addr(s_tab), pay_s = smem_addr(pay);  // see common.cuh
         // the chunk of the next group and the byte before its step are fetched one group ahead, so
@@ -445,9 +473,9 @@ __global__ void __launch_bounds__(kEncThreads, MINB) k_hzr_encode(const uint8_t*
             // boundary behind its chunk: the next token starts at its end bit, at the first byte that follows
             // the zeros running out of the chunk
             if (my_idx) {
-                const uint32_t e = o + lbits;
+                const uint32_t e = o + lbits - lead_bits;   // payload bit offsets
                 const uint32_t kk = idx_interval_of(ig, e);
-                if (kk != idx_interval_of(ig, o)) {
+                if (kk != idx_interval_of(ig, o - lead_bits)) {
                     const uint32_t P = min(off + 16u + (leaves ? fwd : 0u), n);
                     my_idx[kk] = (e - kk * ig.bits) | (P << kIdxPosShift);
                 }
@@ -477,14 +505,16 @@ __global__ void __launch_bounds__(kEncThreads, MINB) k_hzr_encode(const uint8_t*
         }
         __syncthreads();
     }
-    const uint32_t crc = block_crc32c(pay, plen, s_zt, cc, s_red);
+    const uint32_t crc = block_crc32c(pay, plen, s_zt, cc, s_red, lead);
     if (tid == 0) {
-        sbytes[9] = (uint8_t)(plen - 1); sbytes[10] = (uint8_t)((plen - 1) >> 8);
-        sbytes[11] = (uint8_t)crc; sbytes[12] = (uint8_t)(crc >> 8); sbytes[13] = (uint8_t)(crc >> 16); sbytes[14] = (uint8_t)(crc >> 24);
-        sbytes[15] = (uint8_t)bi.mode;
+        uint8_t* hb = sbytes + hoff;
+        hb[0] = (uint8_t)(plen - 1); hb[1] = (uint8_t)((plen - 1) >> 8);
+        hb[2] = (uint8_t)crc; hb[3] = (uint8_t)(crc >> 8); hb[4] = (uint8_t)(crc >> 16); hb[5] = (uint8_t)(crc >> 24);
+        hb[6] = (uint8_t)bi.mode;
     }
+    fence_async_smem();   // the staging was written by ordinary stores and reductions; the bulk store reads it
     __syncthreads();
-    copy_smem_to_global(out, stg, 9, 7u + plen);
+    copy_smem_to_global_bulk(out, sbytes + hoff, 7u + plen);
 }
 
 // stand-alone CRC-32C of a global buffer of <= 65536 bytes (tests / rspt_gpu_crc32c)

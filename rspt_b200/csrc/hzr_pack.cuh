@@ -3,6 +3,7 @@
 // WriteBits / FlushBitCache: lib_hzr/hzr_encode.c:63-113; CRC-32C: lib_hzr/hzr_crc32c.c:77-97.
 #pragma once
 
+#include "bulk.cuh"
 #include "common.cuh"
 
 namespace rspt {
@@ -29,22 +30,27 @@ __device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b)
     return p;
 }
 
-// CRC-32C of `len` bytes that start at the WORD-ALIGNED shared-memory address `words`
-// (hzr_crc32c.c:77-84 semantics: init ~0, final ~).  All threads of the CTA must call it;
-// the result is returned to every thread.  s_zt is the CTA's copy of zt[log2(T/128)],
+// CRC-32C of `len` bytes that start `lead` (0..3) bytes into the WORD-ALIGNED shared-memory array `words`; the
+// `lead` bytes in front of them must be zero (leading zeros leave a zero CRC register unchanged, so the message
+// can be folded word by word from words[0]).  hzr_crc32c.c:77-84 semantics: init ~0, final ~.  All threads of the
+// CTA must call it; the result is returned to every thread.  s_zt is the CTA's copy of zt[log2(T/128)],
 // s_red holds 33 words.  blockDim.x must be 128, 256, 512 or 1024.
 __device__ __forceinline__ uint32_t block_crc32c(const uint32_t* words, uint32_t len, const uint32_t* s_zt,
-                                                 const CrcConst* __restrict__ cc, uint32_t* s_red)
+                                                 const CrcConst* __restrict__ cc, uint32_t* s_red, uint32_t lead = 0)
 {
     const uint32_t T = blockDim.x, j = threadIdx.x;
+    const uint32_t tot = lead + len;
+    // init 0xFFFFFFFF == complement of the first four bytes of the message: bytes lead .. lead + 3
+    const uint32_t m0 = 0xFFFFFFFFu << (8u * lead), m1 = ~m0;
     uint32_t part = 0;
-    if (len >= 8) {
-        const uint32_t W = len >> 2;
+    if (tot >= 8) {
+        const uint32_t W = tot >> 2;
         if (j < W) {
             uint32_t S = 0;
             for (uint32_t i = (W - 1 - j) % T; i < W; i += T) {
                 uint32_t w = words[i];
-                if (i == 0) w = ~w;  // init 0xFFFFFFFF == complement of the first four bytes
+                if (i == 0) w ^= m0;
+                if (i == 1) w ^= m1;
                 S = s_zt[S & 255u] ^ s_zt[256 + ((S >> 8) & 255u)] ^ s_zt[512 + ((S >> 16) & 255u)] ^
                     s_zt[768 + (S >> 24)] ^ w;
             }
@@ -60,12 +66,12 @@ __device__ __forceinline__ uint32_t block_crc32c(const uint32_t* words, uint32_t
         uint32_t s = 0;
         for (uint32_t w = 0; w < (T >> 5); ++w) s ^= s_red[w];
         const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
-        uint32_t q = len & ~3u;
-        if (len < 8) {
+        uint32_t q = tot & ~3u;
+        if (tot < 8) {
             s = 0xFFFFFFFFu;
-            q = 0;
+            q = lead;
         }
-        for (; q < len; ++q) s = (s >> 8) ^ __ldg(&cc->byte_tab[(s ^ bytes[q]) & 255u]);
+        for (; q < tot; ++q) s = (s >> 8) ^ __ldg(&cc->byte_tab[(s ^ bytes[q]) & 255u]);
         s_red[32] = ~s;
     }
     __syncthreads();
@@ -175,6 +181,25 @@ __device__ __forceinline__ void copy_smem_to_global(uint8_t* __restrict__ dst, c
         dw[i] = __funnelshift_r(sw[wbase + i], sw[wbase + i + 1], sh);
     const uint32_t done = head + (nw << 2);
     if (threadIdx.x < len - done) dst[done + threadIdx.x] = sb[soff + done + threadIdx.x];
+}
+
+// The same when the shared-memory bytes sit at an offset congruent to the global address mod 16 (the caller staged
+// them that way): the 16-byte-aligned middle leaves with ONE bulk asynchronous store (cp.async.bulk shared -> global,
+// issued by thread 0), the <= 15 bytes on either side with byte stores.  Every thread must have fenced its writes
+// (fence_async_smem) and the CTA synchronised before the call; thread 0 waits for the store to complete before
+// returning, so the CTA may exit.
+__device__ __forceinline__ void copy_smem_to_global_bulk(uint8_t* __restrict__ dst, const uint8_t* sb, uint32_t len)
+{
+    uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+    if (head > len) head = len;
+    const uint32_t mid = (len - head) & ~15u, tail = len - head - mid;
+    if (threadIdx.x < head) dst[threadIdx.x] = sb[threadIdx.x];
+    if (threadIdx.x < tail) dst[head + mid + threadIdx.x] = sb[head + mid + threadIdx.x];
+    if (threadIdx.x == 0 && mid) {
+        bulk_s2g(dst + head, sb + head, mid);
+        bulk_commit();
+        bulk_wait<0>();
+    }
 }
 
 }  // namespace rspt

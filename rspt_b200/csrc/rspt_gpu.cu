@@ -364,7 +364,7 @@ extern "C" int rspt_gpu_create(int kind, size_t bps, size_t ch, size_t ns, size_
     p->max_batch = max_batch_frames;
     p->d_crc = g_crc[device];
     const uint32_t maxn = s.N < kBlock ? s.N : kBlock;
-    p->enc_smem = (size_t)(4 + (maxn + 3) / 4 + 8) * 4;  // staging of the largest block: header words + payload + slack
+    p->enc_smem = (size_t)(12 + (maxn + 3) / 4 + 8) * 4;  // staging of the largest block: header + payload at an offset of <= 38 bytes, + slack
     p->dec_smem = ((size_t)(maxn + 30) / 16 + 2) * 16;   // the 16-byte chunks that hold the largest payload (any alignment) + zero slack
     p->stream = (cudaStream_t)stream;  // NULL = the CUDA default stream
     p->own_stream = false;
