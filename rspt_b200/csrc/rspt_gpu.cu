@@ -163,6 +163,19 @@ bool xdelta_fast_tile(const Shape& s, const uint8_t* d_src, uint32_t& tsq, size_
 // ---- fused front end (front.cuh) ----------------------------------------------------------------
 #define RSPT_FRONT_SHAPES(X) X(2, 4) X(2, 8) X(2, 12) X(3, 4) X(3, 8) X(3, 12) X(4, 4) X(4, 8) X(4, 12)
 
+// shapes k_xdelta_planes_tma is compiled for (RSPT_FRONT_SHAPES), whole tiles of 128 quads, 16-byte aligned input;
+// RSPT_TMA_TRANSFORM=0 keeps k_xdelta_planes_fast (A/B runs)
+bool tma_transform_ok(const Shape& s, const uint8_t* d_src)
+{
+    static const bool off = [] {
+        const char* e = getenv("RSPT_TMA_TRANSFORM");
+        return e && atoi(e) == 0;
+    }();
+    if (off || ((uintptr_t)d_src & 15)) return false;
+    if (s.bps < 2 || s.bps > 4 || (s.ch != 4 && s.ch != 8 && s.ch != 12)) return false;
+    return s.ns % (4 * kFrontQuads) == 0 && s.ns >= 4 * kFrontQuads;
+}
+
 bool front_shape_ok(const Shape& s)
 {
     if (s.kind != RSPT_XDELTA_HZR && s.kind != RSPT_HZR) return false;
@@ -560,6 +573,28 @@ int launch_forward_transform(rspt_gpu_packer* p, const uint8_t* d_src, size_t F,
         uint32_t* need = p->can_escalate ? p->d_need : nullptr;
         if (need) RSPT_CUDA_CHECK(cudaMemsetAsync(need, 0, F * sizeof(uint32_t), p->stream));
         const bool st = s.kind == RSPT_XDELTA_HZR;
+        // TMA-fed tile kernel (front.cuh: k_xdelta_planes_tma) for the shapes it is compiled for; it has no
+        // plane-count probe (need) and no frame filter (only): those cases keep k_xdelta_planes_fast
+        if (!need && !only && tma_transform_ok(s, d_src)) {
+            const uint32_t tiles = (uint32_t)s.ns / (4u * kFrontQuads);
+            const size_t tsm = (size_t)(kFrontQuads + 2) * 4u * s.ch * s.bps;
+            const dim3 grid((unsigned)(F * tiles));
+#define X(B, C)                                                                                                          \
+    if (s.bps == B && s.ch == C) {                                                                                       \
+        if (st) {                                                                                                        \
+            RSPT_CUDA_CHECK(allow_smem(k_xdelta_planes_tma<B, C, true>, tsm));                                           \
+            k_xdelta_planes_tma<B, C, true><<<grid, kFrontThreads, tsm, p->stream>>>(d_src, s, tiles, p->d_planes);       \
+        } else {                                                                                                         \
+            RSPT_CUDA_CHECK(allow_smem(k_xdelta_planes_tma<B, C, false>, tsm));                                          \
+            k_xdelta_planes_tma<B, C, false><<<grid, kFrontThreads, tsm, p->stream>>>(d_src, s, tiles, p->d_planes);      \
+        }                                                                                                                \
+    }
+            RSPT_FRONT_SHAPES(X)
+#undef X
+            p->launches += 1;
+            RSPT_CUDA_CHECK(cudaGetLastError());
+            return RSPT_OK;
+        }
         uint32_t tsq;
         size_t fsmem;
         if (xdelta_fast_tile(s, d_src, tsq, fsmem)) {
