@@ -519,7 +519,7 @@ def run_ours(args):
                     traffic = traffic * Fp / tj["frames_per_launch"]
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": {"transform": "k_xdelta_planes_fast", "hist": "k_hzr_hist", "tree": "k_hzr_tree",
+    roofline = {"bound": "hbm", "kernel": {"transform": "k_xdelta_planes_tma", "hist": "k_hzr_hist", "tree": "k_hzr_tree",
                                            "layout": "k_scan_offsets", "encode": "k_hzr_encode_sparse + k_hzr_encode"}[dom],
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "ms_per_launch": comp_stages[dom],
