@@ -236,14 +236,25 @@ template <class T, int BITS = kLutBits>
 __device__ __forceinline__ void build_lut(const uint32_t* cw_tab, T* lut, uint16_t* longs, uint32_t* nlong)
 {
     const uint32_t lane = lane_id();
+    // A symbol's entries lie 2^len apart.  Short codes (len <= 5, at most 32 of them): a warp per symbol, lanes over
+    // the entries (neighbouring lanes are <= 64 bytes apart: at most two per bank).  Longer codes would put all 32
+    // lanes into ONE bank that way (entries >= 128 bytes apart), so they get a thread per symbol instead: the 32
+    // lanes then write into 32 unrelated places, and neighbouring symbols have similar lengths (<= 64 entries each).
     for (uint32_t sym = warp_id(); sym < (uint32_t)kNumSymbols; sym += (blockDim.x >> 5)) {
         const uint32_t cw = cw_tab[sym];
-        if (cw == 0u) continue;
         const uint32_t len = cw >> 27, code = cw & 0x07FFFFFFu;
+        if (cw == 0u || len > 5u) continue;
+        const T e = (T)(sym | (len << 9));
+        for (uint32_t i = lane; i < (1u << (BITS - len)); i += 32) lut[(i << len) | code] = e;
+    }
+    for (uint32_t sym = threadIdx.x; sym < (uint32_t)kNumSymbols; sym += blockDim.x) {
+        const uint32_t cw = cw_tab[sym];
+        const uint32_t len = cw >> 27, code = cw & 0x07FFFFFFu;
+        if (cw == 0u || len <= 5u) continue;
         if (len <= (uint32_t)BITS) {
             const T e = (T)(sym | (len << 9));
-            for (uint32_t i = lane; i < (1u << (BITS - len)); i += 32) lut[(i << len) | code] = e;
-        } else if (lane == 0) {
+            for (uint32_t i = 0; i < (1u << (BITS - len)); ++i) lut[(i << len) | code] = e;
+        } else {
             longs[atomicAdd(nlong, 1u)] = (uint16_t)sym;
         }
     }
