@@ -911,11 +911,13 @@ def test_create_refuses_shapes_the_tile_kernels_cannot_stage(R):
     p.close()
 
 
-@pytest.mark.parametrize("warps", ["5", "32"])
-def test_lock_step_tree_kernel_streams_are_bit_exact(warps, oracle):
-    """RSPT_TREE_LS=W: W trees per CTA, their two-queue merges run one per LANE of a single warp (k_hzr_tree_ls).
-    Same streams as the oracle's, incl. blocks with few symbols, FILL blocks and ragged last CTAs.  The switch is
-    read once per process, hence a child; the oracle's streams travel as a digest."""
+@pytest.mark.parametrize("switch", ["RSPT_TREE_LS=5", "RSPT_TREE_LS=32", "RSPT_TMA_TRANSFORM=0", "RSPT_ENC_CTAS=2", "RSPT_ENC_CTAS=3"])
+def test_alternative_kernels_streams_are_bit_exact(switch, oracle):
+    """The kernels behind the A/B switches write the oracle's streams too.  RSPT_TREE_LS=W: W trees per CTA, their
+    two-queue merges run one per LANE of a single warp (k_hzr_tree_ls), incl. blocks with few symbols, FILL blocks and
+    ragged last CTAs; RSPT_TMA_TRANSFORM=0: k_xdelta_planes_fast instead of the TMA-fed transform; RSPT_ENC_CTAS: either
+    build of the dense encoder for every packer.  The switches are read once per process, hence a child; the oracle's
+    streams travel as a digest."""
     import subprocess
     import sys
     cases = (("xdelta_hzr", 3, 12, 2048, 5), ("hzr", 2, 4, 1024, 3), ("hadamard", 4, 4, 1024, 3), ("xdelta_hzr", 4, 3, 700, 4))
@@ -937,7 +939,8 @@ def test_lock_step_tree_kernel_streams_are_bit_exact(warps, oracle):
         "    torch.cuda.synchronize()\n"
         "    print(hashlib.sha256(bytes(b.stream[: b.total_bytes()].cpu().numpy())).hexdigest())\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), cases)
-    env = dict(os.environ, RSPT_TREE_LS=warps)
+    name, value = switch.split("=")
+    env = dict(os.environ, **{name: value})
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.split() == want
